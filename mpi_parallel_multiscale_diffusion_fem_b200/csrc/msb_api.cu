@@ -1,0 +1,643 @@
+// msb_api.cu -- the C ABI declared in include/msfem_basis.h.
+//
+// One handle = one shard of coarse cells on one GPU.  The construction loop
+// diffusion_problem_ms.tpp:50-73 becomes msb_create, the hot loop :81-87 becomes
+// msb_run / msb_run_async, the accessors of diffusion_problem_basis.hpp:72-138 become the
+// msb_get_* / msb_set_* calls.  There is no CPU fallback anywhere in this file.
+#include <limits.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "msb_internal.cuh"
+
+using namespace msb;
+
+struct msb_handle_s
+{
+  Shard s;
+};
+
+static thread_local char g_err[512] = "";
+
+static int
+fail(int code, const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(call)                                                                        \
+  do                                                                                          \
+    {                                                                                         \
+      cudaError_t e_ = (call);                                                                \
+      if (e_ != cudaSuccess)                                                                  \
+        return fail(MSB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),    \
+                    __FILE__, __LINE__);                                                      \
+    }                                                                                         \
+  while (0)
+
+extern "C" const char *
+msb_last_error(void)
+{
+  return g_err;
+}
+
+extern "C" const char *
+msb_version(void)
+{
+  return "msfem_basis 0.1 (sm_100a)";
+}
+
+extern "C" int
+msb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return 0;
+    }
+  return n;
+}
+
+// BasisQ1<2> coefficient matrix (basis_q1.tpp:26-47): inverse of the point matrix
+// [1, x, y, xy] at the four vertices, by Gauss-Jordan with partial pivoting.
+static bool
+basis_q1_matrix(const double *corners, double *coef)
+{
+  double a[4][8];
+  for (int i = 0; i < 4; ++i)
+    {
+      const double x = corners[2 * i], y = corners[2 * i + 1];
+      a[i][0] = 1.0, a[i][1] = x, a[i][2] = y, a[i][3] = x * y;
+      for (int j = 0; j < 4; ++j)
+        a[i][4 + j] = i == j ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < 4; ++c)
+    {
+      int piv = c;
+      for (int r = c + 1; r < 4; ++r)
+        if (fabs(a[r][c]) > fabs(a[piv][c]))
+          piv = r;
+      if (a[piv][c] == 0.0)
+        return false;
+      if (piv != c)
+        for (int j = 0; j < 8; ++j)
+          {
+            const double t = a[c][j];
+            a[c][j]        = a[piv][j];
+            a[piv][j]      = t;
+          }
+      const double inv = 1.0 / a[c][c];
+      for (int j = 0; j < 8; ++j)
+        a[c][j] *= inv;
+      for (int r = 0; r < 4; ++r)
+        if (r != c)
+          {
+            const double f = a[r][c];
+            if (f != 0.0)
+              for (int j = 0; j < 8; ++j)
+                a[r][j] -= f * a[c][j];
+          }
+    }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      coef[4 * i + j] = a[i][4 + j];
+  return true;
+}
+
+static void
+free_shard(Shard &s)
+{
+  cudaSetDevice(s.device);
+  void *ptrs[] = {s.d_corners, s.d_q1coef, s.d_table, s.d_sten, s.d_phi,  s.d_M,    s.d_b,
+                  s.d_iters,   s.d_res,    s.d_fail,  s.d_dofmap, s.d_invmap, s.d_gsol, s.d_tmp,
+                  s.d_wr,      s.d_wp,     s.d_wq,    s.d_scal, s.d_part, s.d_flags};
+  for (void *p : ptrs)
+    if (p)
+      cudaFree(p);
+  for (auto &e : s.ev)
+    if (e)
+      cudaEventDestroy(e);
+  if (s.stream)
+    cudaStreamDestroy(s.stream);
+}
+
+extern "C" int
+msb_create(const msb_config *cfg, const double *corners, const double *coeff_table, msb_handle *out)
+{
+  if (!cfg || !corners || !out)
+    return fail(MSB_ERR_INVALID_ARG, "msb_create: null argument");
+  *out = nullptr;
+  if (cfg->abi_version != MSB_ABI_VERSION)
+    return fail(MSB_ERR_INVALID_ARG, "msb_create: abi_version %d, library has %d", cfg->abi_version,
+                MSB_ABI_VERSION);
+  if (cfg->dim != 2)
+    return fail(MSB_ERR_UNSUPPORTED, "msb_create: dim=%d (only the 2D path is built)", cfg->dim);
+  if (cfg->n_refine_local < 1 || cfg->n_refine_local > 9)
+    return fail(MSB_ERR_UNSUPPORTED, "msb_create: n_refine_local=%d outside 1..9", cfg->n_refine_local);
+  if (cfg->n_cells < 1)
+    return fail(MSB_ERR_INVALID_ARG, "msb_create: n_cells=%d", cfg->n_cells);
+  if (cfg->coeff.kind < MSB_COEFF_REFERENCE || cfg->coeff.kind > MSB_COEFF_TABLE)
+    return fail(MSB_ERR_INVALID_ARG, "msb_create: coefficient kind %d", cfg->coeff.kind);
+  if (cfg->coeff.kind == MSB_COEFF_TABLE && !coeff_table)
+    return fail(MSB_ERR_INVALID_ARG, "msb_create: MSB_COEFF_TABLE needs coeff_table");
+  if (cfg->coeff.kind == MSB_COEFF_PERIODIC && !(cfg->coeff.par[0] > 0.0))
+    return fail(MSB_ERR_INVALID_ARG, "msb_create: periodic coefficient needs eps > 0");
+  if (cfg->coeff.kind == MSB_COEFF_INCLUSIONS && !(cfg->coeff.par[0] > 0.0))
+    return fail(MSB_ERR_INVALID_ARG, "msb_create: inclusion coefficient needs block size > 0");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+      cudaGetLastError();
+      return fail(MSB_ERR_NO_DEVICE, "msb_create: no CUDA device (this library has no CPU path)");
+    }
+  if (cfg->device_id < 0 || cfg->device_id >= ndev)
+    return fail(MSB_ERR_NO_DEVICE, "msb_create: device %d of %d", cfg->device_id, ndev);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device_id));
+  if (prop.major != 10)
+    return fail(MSB_ERR_NO_DEVICE, "msb_create: device %d is sm_%d%d, kernels are built for sm_100a",
+                cfg->device_id, prop.major, prop.minor);
+  CUDA_TRY(cudaSetDevice(cfg->device_id));
+
+  msb_handle h = new (std::nothrow) msb_handle_s();
+  if (!h)
+    return fail(MSB_ERR_INVALID_ARG, "msb_create: out of host memory");
+  Shard &s    = h->s;
+  s.l         = cfg->n_refine_local;
+  s.n         = 1 << s.l;
+  s.np        = s.n + 1;
+  s.N         = s.np * s.np;
+  s.n_cells   = cfg->n_cells;
+  s.device    = cfg->device_id;
+  s.variant   = cfg->variant;
+  s.coeff     = cfg->coeff;
+  s.rhs_value = cfg->rhs_value;
+  s.tier      = cfg->tier;
+  if (s.tier == MSB_TIER_AUTO)
+    s.tier = smem_tier_supported(s.l) ? MSB_TIER_SMEM : MSB_TIER_STREAMED;
+  if (s.tier == MSB_TIER_SMEM && !smem_tier_supported(s.l))
+    {
+      delete h;
+      return fail(MSB_ERR_UNSUPPORTED, "msb_create: shared-memory tier needs 3 <= n_refine_local <= 6");
+    }
+
+  const size_t C = (size_t)s.n_cells, N = (size_t)s.N;
+  std::vector<double> q1(16 * C);
+  for (size_t c = 0; c < C; ++c)
+    if (!basis_q1_matrix(corners + 8 * c, q1.data() + 16 * c))
+      {
+        delete h;
+        return fail(MSB_ERR_INVALID_ARG, "msb_create: coarse cell %zu is degenerate", c);
+      }
+
+#define ALLOC(ptr, count)                                                                      \
+  do                                                                                           \
+    {                                                                                          \
+      cudaError_t e_ = cudaMalloc((void **)&(ptr), sizeof(*(ptr)) * (size_t)(count));          \
+      if (e_ != cudaSuccess)                                                                   \
+        {                                                                                      \
+          free_shard(s);                                                                       \
+          delete h;                                                                            \
+          return fail(MSB_ERR_CUDA, "cudaMalloc(%s, %zu bytes) failed: %s", #ptr,              \
+                      sizeof(*(ptr)) * (size_t)(count), cudaGetErrorString(e_));               \
+        }                                                                                      \
+    }                                                                                          \
+  while (0)
+
+  ALLOC(s.d_corners, 8 * C);
+  ALLOC(s.d_q1coef, 16 * C);
+  ALLOC(s.d_sten, C * ST_NARR * N);
+  ALLOC(s.d_phi, C * 4 * N);
+  ALLOC(s.d_M, 16 * C);
+  ALLOC(s.d_b, 4 * C);
+  ALLOC(s.d_iters, 4 * C);
+  ALLOC(s.d_res, 4 * C);
+  ALLOC(s.d_fail, 2);
+  ALLOC(s.d_dofmap, N);
+  ALLOC(s.d_invmap, N);
+  ALLOC(s.d_tmp, 3 * N);
+  ALLOC(s.d_flags, 4);
+  if (s.coeff.kind == MSB_COEFF_TABLE)
+    ALLOC(s.d_table, C * (size_t)s.n * s.n * 16);
+  if (s.tier == MSB_TIER_STREAMED)
+    {
+      ALLOC(s.d_wr, C * 4 * N);
+      ALLOC(s.d_wp, C * 4 * N);
+      ALLOC(s.d_wq, C * 4 * N);
+      ALLOC(s.d_scal, 4 * C);
+      ALLOC(s.d_part, 4 * C * 2 * 3 * 32);
+    }
+#undef ALLOC
+
+  cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+    e = cudaEventCreate(&s.ev[i]);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(s.d_corners, corners, sizeof(double) * 8 * C, cudaMemcpyHostToDevice, s.stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(s.d_q1coef, q1.data(), sizeof(double) * 16 * C, cudaMemcpyHostToDevice, s.stream);
+  if (e == cudaSuccess && s.d_table)
+    e = cudaMemcpyAsync(s.d_table, coeff_table, sizeof(double) * C * (size_t)s.n * s.n * 16,
+                        cudaMemcpyHostToDevice, s.stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(s.stream);
+  if (e == cudaSuccess)
+    e = launch_dofmap(s, s.stream);
+  if (e != cudaSuccess)
+    {
+      free_shard(s);
+      delete h;
+      return fail(MSB_ERR_CUDA, "msb_create: device setup failed: %s", cudaGetErrorString(e));
+    }
+  *out = h;
+  return MSB_OK;
+}
+
+extern "C" int
+msb_set_cells(msb_handle h, const double *corners, const double *coeff_table)
+{
+  if (!h || !corners)
+    return fail(MSB_ERR_INVALID_ARG, "msb_set_cells: null argument");
+  Shard &s = h->s;
+  if (s.coeff.kind == MSB_COEFF_TABLE && !coeff_table)
+    return fail(MSB_ERR_INVALID_ARG, "msb_set_cells: MSB_COEFF_TABLE needs coeff_table");
+  CUDA_TRY(cudaSetDevice(s.device));
+  if (s.run_pending)
+    CUDA_TRY(cudaStreamSynchronize(s.run_stream));
+  const size_t        C = (size_t)s.n_cells;
+  std::vector<double> q1(16 * C);
+  for (size_t c = 0; c < C; ++c)
+    if (!basis_q1_matrix(corners + 8 * c, q1.data() + 16 * c))
+      return fail(MSB_ERR_INVALID_ARG, "msb_set_cells: coarse cell %zu is degenerate", c);
+  CUDA_TRY(cudaMemcpyAsync(s.d_corners, corners, sizeof(double) * 8 * C, cudaMemcpyHostToDevice, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(s.d_q1coef, q1.data(), sizeof(double) * 16 * C, cudaMemcpyHostToDevice, s.stream));
+  if (s.d_table)
+    CUDA_TRY(cudaMemcpyAsync(s.d_table, coeff_table, sizeof(double) * C * (size_t)s.n * s.n * 16,
+                             cudaMemcpyHostToDevice, s.stream));
+  CUDA_TRY(cudaStreamSynchronize(s.stream));
+  s.assembled = s.ran = s.weights_set = s.run_pending = false;
+  return MSB_OK;
+}
+
+extern "C" int
+msb_destroy(msb_handle h)
+{
+  if (!h)
+    return MSB_OK;
+  cudaSetDevice(h->s.device);
+  cudaDeviceSynchronize();
+  free_shard(h->s);
+  delete h;
+  return MSB_OK;
+}
+
+// the stage: assemble_system -> 2^dim x (condense, PCG, distribute) -> element matrices
+extern "C" int
+msb_run_async(msb_handle h, double tol_abs, int32_t max_iter, void *cuda_stream)
+{
+  if (!h)
+    return fail(MSB_ERR_INVALID_ARG, "msb_run: null handle");
+  if (!(tol_abs >= 0.0) || max_iter < 0)
+    return fail(MSB_ERR_INVALID_ARG, "msb_run: tol_abs=%g max_iter=%d", tol_abs, max_iter);
+  Shard &s = h->s;
+  CUDA_TRY(cudaSetDevice(s.device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s.stream;
+  s.run_stream    = st;
+  s.n_launches    = 0;
+  s.ran           = false;
+  const int32_t init_fail[2] = {INT_MAX, 0};
+  CUDA_TRY(cudaMemcpyAsync(s.d_fail, init_fail, sizeof init_fail, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(s.ev[0], st));
+  CUDA_TRY(launch_assemble(s, st, &s.n_launches));
+  s.assembled = true;
+  CUDA_TRY(cudaEventRecord(s.ev[1], st));
+  if (s.tier == MSB_TIER_SMEM)
+    CUDA_TRY(launch_solve_smem(s, tol_abs, max_iter, st, &s.n_launches));
+  else
+    CUDA_TRY(launch_solve_streamed(s, tol_abs, max_iter, st, &s.n_launches));
+  s.tier_used = s.tier;
+  CUDA_TRY(cudaEventRecord(s.ev[2], st));
+  CUDA_TRY(launch_element_matrices(s, st, &s.n_launches));
+  CUDA_TRY(cudaEventRecord(s.ev[3], st));
+  s.run_pending = true;
+  s.weights_set = false;
+  return MSB_OK;
+}
+
+extern "C" int
+msb_sync(msb_handle h)
+{
+  if (!h)
+    return fail(MSB_ERR_INVALID_ARG, "msb_sync: null handle");
+  Shard &s = h->s;
+  if (!s.run_pending)
+    return s.last_status;
+  CUDA_TRY(cudaSetDevice(s.device));
+  CUDA_TRY(cudaStreamSynchronize(s.run_stream));
+  int32_t f[2];
+  CUDA_TRY(cudaMemcpy(f, s.d_fail, sizeof f, cudaMemcpyDeviceToHost));
+  s.run_pending = false;
+  s.ran         = true;
+  s.last_status = MSB_OK;
+  if (f[0] != INT_MAX)
+    s.last_status = fail(MSB_ERR_NO_CONVERGENCE,
+                         "local solve (cell %d, basis %d) did not reach the tolerance within max_iter "
+                         "(the reference throws SolverControl::NoConvergence here)",
+                         f[0] / 4, f[0] % 4);
+  return s.last_status;
+}
+
+extern "C" int
+msb_run(msb_handle h, double tol_abs, int32_t max_iter)
+{
+  const int rc = msb_run_async(h, tol_abs, max_iter, nullptr);
+  if (rc != MSB_OK)
+    return rc;
+  return msb_sync(h);
+}
+
+static int
+need_ran(msb_handle h, const char *who)
+{
+  if (!h)
+    return fail(MSB_ERR_INVALID_ARG, "%s: null handle", who);
+  if (h->s.run_pending)
+    {
+      const int rc = msb_sync(h);
+      if (rc != MSB_OK && rc != MSB_ERR_NO_CONVERGENCE)
+        return rc;
+    }
+  if (!h->s.ran)
+    return fail(MSB_ERR_STATE, "%s: msb_run has not been called", who);
+  cudaError_t e = cudaSetDevice(h->s.device);
+  if (e != cudaSuccess)
+    return fail(MSB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  return MSB_OK;
+}
+
+extern "C" int
+msb_get_failure(msb_handle h, int32_t *cell, int32_t *index_basis, double *residual)
+{
+  int rc = need_ran(h, "msb_get_failure");
+  if (rc != MSB_OK)
+    return rc;
+  int32_t f[2];
+  CUDA_TRY(cudaMemcpy(f, h->s.d_fail, sizeof f, cudaMemcpyDeviceToHost));
+  if (f[0] == INT_MAX)
+    {
+      if (cell)
+        *cell = -1;
+      if (index_basis)
+        *index_basis = -1;
+      if (residual)
+        *residual = 0.0;
+      return MSB_OK;
+    }
+  if (cell)
+    *cell = f[0] / 4;
+  if (index_basis)
+    *index_basis = f[0] % 4;
+  if (residual)
+    CUDA_TRY(cudaMemcpy(residual, h->s.d_res + f[0], sizeof(double), cudaMemcpyDeviceToHost));
+  return MSB_OK;
+}
+
+extern "C" int
+msb_get_element_matrices(msb_handle h, double *M, double *b)
+{
+  int rc = need_ran(h, "msb_get_element_matrices");
+  if (rc != MSB_OK)
+    return rc;
+  const size_t C = (size_t)h->s.n_cells;
+  if (M)
+    CUDA_TRY(cudaMemcpy(M, h->s.d_M, sizeof(double) * 16 * C, cudaMemcpyDeviceToHost));
+  if (b)
+    CUDA_TRY(cudaMemcpy(b, h->s.d_b, sizeof(double) * 4 * C, cudaMemcpyDeviceToHost));
+  return MSB_OK;
+}
+
+extern "C" int
+msb_get_iteration_counts(msb_handle h, int32_t *iters, double *residuals)
+{
+  int rc = need_ran(h, "msb_get_iteration_counts");
+  if (rc != MSB_OK)
+    return rc;
+  const size_t C = (size_t)h->s.n_cells;
+  if (iters)
+    CUDA_TRY(cudaMemcpy(iters, h->s.d_iters, sizeof(int32_t) * 4 * C, cudaMemcpyDeviceToHost));
+  if (residuals)
+    CUDA_TRY(cudaMemcpy(residuals, h->s.d_res, sizeof(double) * 4 * C, cudaMemcpyDeviceToHost));
+  return MSB_OK;
+}
+
+static int
+check_cell(msb_handle h, int32_t cell, int32_t ib, const char *who)
+{
+  if (cell < 0 || cell >= h->s.n_cells || ib < 0 || ib > 3)
+    return fail(MSB_ERR_INVALID_ARG, "%s: cell %d / basis %d out of range", who, cell, ib);
+  return MSB_OK;
+}
+
+extern "C" int
+msb_get_basis(msb_handle h, int32_t cell, int32_t ib, double *out)
+{
+  int rc = need_ran(h, "msb_get_basis");
+  if (rc != MSB_OK)
+    return rc;
+  if ((rc = check_cell(h, cell, ib, "msb_get_basis")) != MSB_OK || !out)
+    return rc != MSB_OK ? rc : fail(MSB_ERR_INVALID_ARG, "msb_get_basis: null out");
+  Shard &s = h->s;
+  CUDA_TRY(launch_permute(s, s.d_phi + ((size_t)cell * 4 + ib) * s.N, s.d_tmp, true, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(out, s.d_tmp, sizeof(double) * s.N, cudaMemcpyDeviceToHost, s.stream));
+  CUDA_TRY(cudaStreamSynchronize(s.stream));
+  return MSB_OK;
+}
+
+extern "C" int
+msb_get_dof_map(msb_handle h, uint32_t *dof_of_vertex)
+{
+  if (!h || !dof_of_vertex)
+    return fail(MSB_ERR_INVALID_ARG, "msb_get_dof_map: null argument");
+  CUDA_TRY(cudaSetDevice(h->s.device));
+  CUDA_TRY(cudaMemcpy(dof_of_vertex, h->s.d_dofmap, sizeof(uint32_t) * h->s.N, cudaMemcpyDeviceToHost));
+  return MSB_OK;
+}
+
+extern "C" int
+msb_get_constraints(msb_handle h, int32_t cell, int32_t ib, uint32_t *dofs, double *values)
+{
+  if (!h || !dofs || !values)
+    return fail(MSB_ERR_INVALID_ARG, "msb_get_constraints: null argument");
+  int rc = check_cell(h, cell, ib, "msb_get_constraints");
+  if (rc != MSB_OK)
+    return rc;
+  Shard &s = h->s;
+  CUDA_TRY(cudaSetDevice(s.device));
+  const int nb    = 4 * s.n;
+  uint32_t *d_dof = reinterpret_cast<uint32_t *>(s.d_tmp);       // nb uint32 <= N doubles
+  double   *d_val = s.d_tmp + s.N;
+  CUDA_TRY(launch_constraints(s, cell, ib, d_dof, d_val, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(dofs, d_dof, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(values, d_val, sizeof(double) * nb, cudaMemcpyDeviceToHost, s.stream));
+  CUDA_TRY(cudaStreamSynchronize(s.stream));
+  return MSB_OK;
+}
+
+static int
+ensure_assembled(msb_handle h)
+{
+  Shard &s = h->s;
+  if (s.run_pending)
+    {
+      const int rc = msb_sync(h);
+      if (rc != MSB_OK && rc != MSB_ERR_NO_CONVERGENCE)
+        return rc;
+    }
+  if (!s.assembled)
+    {
+      int nl = 0;
+      CUDA_TRY(launch_assemble(s, s.stream, &nl));
+      CUDA_TRY(cudaStreamSynchronize(s.stream));
+      s.assembled = true;
+    }
+  return MSB_OK;
+}
+
+extern "C" int
+msb_apply_operator(msb_handle h, int32_t cell, const double *x, double *y)
+{
+  if (!h || !x || !y)
+    return fail(MSB_ERR_INVALID_ARG, "msb_apply_operator: null argument");
+  int rc = check_cell(h, cell, 0, "msb_apply_operator");
+  if (rc != MSB_OK)
+    return rc;
+  Shard &s = h->s;
+  CUDA_TRY(cudaSetDevice(s.device));
+  if ((rc = ensure_assembled(h)) != MSB_OK)
+    return rc;
+  double *d_in = s.d_tmp, *d_lex = s.d_tmp + s.N, *d_out = s.d_tmp + 2 * (size_t)s.N;
+  CUDA_TRY(cudaMemcpyAsync(d_in, x, sizeof(double) * s.N, cudaMemcpyHostToDevice, s.stream));
+  CUDA_TRY(launch_permute(s, d_in, d_lex, false, s.stream));      // dof order -> lex
+  CUDA_TRY(launch_apply_operator(s, cell, d_lex, d_out, s.stream));
+  CUDA_TRY(launch_permute(s, d_out, d_in, true, s.stream));       // lex -> dof order
+  CUDA_TRY(cudaMemcpyAsync(y, d_in, sizeof(double) * s.N, cudaMemcpyDeviceToHost, s.stream));
+  CUDA_TRY(cudaStreamSynchronize(s.stream));
+  return MSB_OK;
+}
+
+extern "C" int
+msb_get_load_vector(msb_handle h, int32_t cell, double *F)
+{
+  if (!h || !F)
+    return fail(MSB_ERR_INVALID_ARG, "msb_get_load_vector: null argument");
+  int rc = check_cell(h, cell, 0, "msb_get_load_vector");
+  if (rc != MSB_OK)
+    return rc;
+  Shard &s = h->s;
+  CUDA_TRY(cudaSetDevice(s.device));
+  if ((rc = ensure_assembled(h)) != MSB_OK)
+    return rc;
+  CUDA_TRY(launch_permute(s, s.d_sten + ((size_t)cell * ST_NARR + ST_F) * s.N, s.d_tmp, true, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(F, s.d_tmp, sizeof(double) * s.N, cudaMemcpyDeviceToHost, s.stream));
+  CUDA_TRY(cudaStreamSynchronize(s.stream));
+  return MSB_OK;
+}
+
+extern "C" int
+msb_set_global_weights(msb_handle h, const double *w)
+{
+  int rc = need_ran(h, "msb_set_global_weights");
+  if (rc != MSB_OK)
+    return rc;
+  if (!w)
+    return fail(MSB_ERR_INVALID_ARG, "msb_set_global_weights: null weights");
+  Shard       &s = h->s;
+  const size_t C = (size_t)s.n_cells;
+  if (!s.d_gsol)
+    CUDA_TRY(cudaMalloc((void **)&s.d_gsol, sizeof(double) * C * s.N));
+  double *d_w = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&d_w, sizeof(double) * 4 * C));
+  cudaError_t e = cudaMemcpyAsync(d_w, w, sizeof(double) * 4 * C, cudaMemcpyHostToDevice, s.stream);
+  if (e == cudaSuccess)
+    e = launch_global_solution(s, d_w, s.stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(s.stream);
+  cudaFree(d_w);
+  if (e != cudaSuccess)
+    return fail(MSB_ERR_CUDA, "msb_set_global_weights: %s", cudaGetErrorString(e));
+  s.weights_set = true;
+  return MSB_OK;
+}
+
+extern "C" int
+msb_get_global_solution(msb_handle h, int32_t cell, double *out)
+{
+  int rc = need_ran(h, "msb_get_global_solution");
+  if (rc != MSB_OK)
+    return rc;
+  if ((rc = check_cell(h, cell, 0, "msb_get_global_solution")) != MSB_OK)
+    return rc;
+  Shard &s = h->s;
+  // the reference asserts is_set_global_weights (basis.tpp:425-426)
+  if (!s.weights_set)
+    return fail(MSB_ERR_STATE, "msb_get_global_solution: global weights must be set first");
+  if (!out)
+    return fail(MSB_ERR_INVALID_ARG, "msb_get_global_solution: null out");
+  CUDA_TRY(launch_permute(s, s.d_gsol + (size_t)cell * s.N, s.d_tmp, true, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(out, s.d_tmp, sizeof(double) * s.N, cudaMemcpyDeviceToHost, s.stream));
+  CUDA_TRY(cudaStreamSynchronize(s.stream));
+  return MSB_OK;
+}
+
+extern "C" int
+msb_get_run_stats(msb_handle h, float *ms_total, float *ms_solve, int32_t *n_launches, int32_t *tier_used)
+{
+  int rc = need_ran(h, "msb_get_run_stats");
+  if (rc != MSB_OK)
+    return rc;
+  Shard &s = h->s;
+  if (ms_total)
+    CUDA_TRY(cudaEventElapsedTime(ms_total, s.ev[0], s.ev[3]));
+  if (ms_solve)
+    CUDA_TRY(cudaEventElapsedTime(ms_solve, s.ev[1], s.ev[2]));
+  if (n_launches)
+    *n_launches = s.n_launches;
+  if (tier_used)
+    *tier_used = s.tier_used;
+  return MSB_OK;
+}
+
+extern "C" int
+msb_get_algorithmic_bytes(msb_handle h, double *bytes, double *mean_iterations)
+{
+  int rc = need_ran(h, "msb_get_algorithmic_bytes");
+  if (rc != MSB_OK)
+    return rc;
+  Shard               &s = h->s;
+  const size_t         n = 4 * (size_t)s.n_cells;
+  std::vector<int32_t> it(n);
+  CUDA_TRY(cudaMemcpy(it.data(), s.d_iters, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+  // W = N (96 k + 16) bytes per solve
+  double tot = 0.0, ksum = 0.0;
+  for (size_t i = 0; i < n; ++i)
+    {
+      tot += (double)s.N * (96.0 * it[i] + 16.0);
+      ksum += it[i];
+    }
+  if (bytes)
+    *bytes = tot;
+  if (mean_iterations)
+    *mean_iterations = ksum / (double)n;
+  return MSB_OK;
+}

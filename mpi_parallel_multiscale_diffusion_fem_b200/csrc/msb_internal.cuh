@@ -1,0 +1,136 @@
+// msb_internal.cuh -- shared declarations of the sm_100a multiscale-basis library.
+//
+// Data layout in HBM (one shard = the coarse cells owned by one GPU), all FP64,
+// node index "lex" = jy*(n+1)+jx on the implicit structured fine grid:
+//   corners  [C][4][2]      coarse-cell vertices, deal.II vertex order
+//   q1coef   [C][16]        BasisQ1 coefficient matrix (basis_q1.tpp:26-47)
+//   sten     [C][6][np*np]  symmetric 9-point stencil of the unconstrained fine
+//                           stiffness matrix + load vector:
+//                           0 KC diag, 1 KE (jx,jy)-(jx+1,jy), 2 KN (jx,jy)-(jx,jy+1),
+//                           3 KD1 (jx,jy)-(jx+1,jy+1), 4 KD2 (jx+1,jy)-(jx,jy+1), 5 F
+//   phi      [C][4][np*np]  the multiscale bases, lexicographic node order
+//   M [C][16], b [C][4], iters [C][4], res [C][4]
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "msfem_basis.h"
+
+namespace msb
+{
+  enum
+  {
+    ST_KC  = 0,
+    ST_KE  = 1,
+    ST_KN  = 2,
+    ST_KD1 = 3,
+    ST_KD2 = 4,
+    ST_F   = 5,
+    ST_NARR = 6
+  };
+
+  struct Shard
+  {
+    int     l, n, np, N; // n = 2^l, np = n+1, N = np*np
+    int     n_cells;
+    int     device;
+    int     tier, variant;
+    msb_coeff_desc coeff;
+    double  rhs_value;
+
+    double       *d_corners = nullptr;
+    double       *d_q1coef  = nullptr;
+    double       *d_table   = nullptr;
+    double       *d_sten    = nullptr;
+    double       *d_phi     = nullptr;
+    double       *d_M       = nullptr;
+    double       *d_b       = nullptr;
+    int32_t      *d_iters   = nullptr;
+    double       *d_res     = nullptr;
+    int32_t      *d_fail    = nullptr; // [2]: first failing solve index (cell*4+ib) or INT_MAX, flag
+    uint32_t     *d_dofmap  = nullptr; // lex -> deal.II dof
+    uint32_t     *d_invmap  = nullptr; // deal.II dof -> lex
+    double       *d_gsol    = nullptr; // [C][N] global solution (after set_global_weights)
+    double       *d_tmp     = nullptr; // 2*N scratch for single-vector calls
+    // streamed tier work vectors [C][4][N] each
+    double       *d_wr = nullptr, *d_wp = nullptr, *d_wq = nullptr;
+    double       *d_scal = nullptr;   // streamed tier per-solve scalars
+    double       *d_part = nullptr;   // streamed tier partial sums
+    int32_t      *d_flags = nullptr;  // streamed tier per-solve state
+
+    cudaStream_t stream = nullptr;    // library-owned stream
+    cudaStream_t run_stream = nullptr;
+    cudaEvent_t  ev[4]  = {nullptr, nullptr, nullptr, nullptr};
+    bool         assembled = false, ran = false, weights_set = false, run_pending = false;
+    int          n_launches = 0;
+    int          tier_used  = 0;
+    int          last_status = 0;
+  };
+
+  // ---- launchers implemented in the .cu files -------------------------------------------
+  cudaError_t launch_dofmap(const Shard &s, cudaStream_t st);
+  cudaError_t launch_assemble(const Shard &s, cudaStream_t st, int *n_launches);
+  cudaError_t launch_solve_smem(const Shard &s, double tol, int max_iter, cudaStream_t st,
+                                int *n_launches);
+  cudaError_t launch_solve_streamed(Shard &s, double tol, int max_iter, cudaStream_t st,
+                                    int *n_launches);
+  cudaError_t launch_element_matrices(const Shard &s, cudaStream_t st, int *n_launches);
+  cudaError_t launch_apply_operator(const Shard &s, int cell, const double *d_x_lex, double *d_y_lex,
+                                    cudaStream_t st);
+  cudaError_t launch_permute(const Shard &s, const double *d_src, double *d_dst, bool lex_to_dof,
+                             cudaStream_t st);
+  cudaError_t launch_global_solution(const Shard &s, const double *d_w, cudaStream_t st);
+  cudaError_t launch_constraints(const Shard &s, int cell, int ib, uint32_t *d_dofs, double *d_vals,
+                                 cudaStream_t st);
+  bool        smem_tier_supported(int l);
+  size_t      streamed_workspace_doubles(const Shard &s);
+
+  // ---- small device helpers -----------------------------------------------------------------
+  __host__ __device__ inline uint32_t
+  morton_compact(uint32_t m)
+  {
+    uint32_t x = m & 0x55555555u;
+    x          = (x | (x >> 1)) & 0x33333333u;
+    x          = (x | (x >> 2)) & 0x0f0f0f0fu;
+    x          = (x | (x >> 4)) & 0x00ff00ffu;
+    x          = (x | (x >> 8)) & 0x0000ffffu;
+    return x;
+  }
+
+  __host__ __device__ inline uint32_t
+  morton_spread(uint32_t x)
+  {
+    x &= 0x0000ffffu;
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+  }
+
+  // Morton index of fine cell (ix,iy), x the low bit (deal.II child order)
+  __host__ __device__ inline uint32_t
+  morton_encode(uint32_t ix, uint32_t iy)
+  {
+    return morton_spread(ix) | (morton_spread(iy) << 1);
+  }
+
+  // fine vertex (jx,jy) of the refined general_cell (basis.tpp:94-98): bilinear image of
+  // the uniform grid, exact for axis-aligned dyadic cells
+  __device__ inline void
+  fine_vertex(const double *__restrict__ c, int n, int jx, int jy, double &px, double &py)
+  {
+    const double s = (double)jx / (double)n, t = (double)jy / (double)n;
+    const double st = s * t;
+    px = c[0] + s * (c[2] - c[0]) + t * (c[4] - c[0]) + st * ((c[6] - c[4]) - (c[2] - c[0]));
+    py = c[1] + s * (c[3] - c[1]) + t * (c[5] - c[1]) + st * ((c[7] - c[5]) - (c[3] - c[1]));
+  }
+
+  // BasisQ1<2>::value (basis_q1.tpp:86-96), coef[r*4+ib]
+  __device__ inline double
+  basis_q1_value(const double *__restrict__ coef, int ib, double x, double y)
+  {
+    return coef[0 * 4 + ib] + coef[1 * 4 + ib] * x + coef[2 * 4 + ib] * y + coef[3 * 4 + ib] * x * y;
+  }
+} // namespace msb

@@ -1,0 +1,609 @@
+// msb_setup.cu -- everything around the solve: DoF map, stencil assembly, the
+// coarse element matrices, operator application, reordering, reconstruction.
+//
+// Reference lines restated here (never copied):
+//   DoF numbering          diffusion_problem_basis.tpp:106   
+//   assemble_system        diffusion_problem_basis.tpp:159-242
+//   MatrixCoeff            include/coefficients/matrix_coeff.tpp:17-25,66-91
+//   constraints            diffusion_problem_basis.tpp:119-135
+//   element matrix / rhs   diffusion_problem_basis.tpp:245-285
+//   set_global_weights     diffusion_problem_basis.tpp:352-377
+#include <math.h>
+
+#include "msb_internal.cuh"
+
+namespace msb
+{
+  // ======================================================================================
+  // DoF map: closed form of deal.II's first-touch numbering.  A vertex is first touched by
+  // the adjacent fine cell with the smallest Morton index; its DoF index is the number of
+  // vertices first touched earlier = (exclusive scan over cells of #new vertices) + rank
+  // inside its cell.
+  // ======================================================================================
+  __device__ inline uint32_t
+  first_touch_cell(int n, int jx, int jy, int &lv)
+  {
+    uint32_t best = 0xffffffffu;
+    lv            = 0;
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      {
+        // cell for which (jx,jy) is local vertex v
+        const int ix = jx - (v & 1), iy = jy - (v >> 1);
+        if (ix < 0 || iy < 0 || ix >= n || iy >= n)
+          continue;
+        const uint32_t m = morton_encode((uint32_t)ix, (uint32_t)iy);
+        if (m < best)
+          {
+            best = m;
+            lv   = v;
+          }
+      }
+    return best;
+  }
+
+  __global__ void
+  dofmap_count_kernel(int n, uint32_t *__restrict__ cnt, uint32_t *__restrict__ mask)
+  {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= (uint32_t)(n * n))
+      return;
+    const int ix = (int)morton_compact(m), iy = (int)morton_compact(m >> 1);
+    uint32_t  msk = 0;
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      {
+        int lv;
+        if (first_touch_cell(n, ix + (v & 1), iy + (v >> 1), lv) == m)
+          msk |= 1u << v;
+      }
+    mask[m] = msk;
+    cnt[m]  = __popc(msk);
+  }
+
+  // single-block exclusive scan (n*n <= 2^18 entries)
+  __global__ void
+  dofmap_scan_kernel(int total, const uint32_t *__restrict__ cnt, uint32_t *__restrict__ base)
+  {
+    __shared__ uint32_t part[1024];
+    const int           T     = blockDim.x;
+    const int           chunk = (total + T - 1) / T;
+    const int           lo    = min(total, (int)threadIdx.x * chunk), hi = min(total, lo + chunk);
+    uint32_t            s = 0;
+    for (int i = lo; i < hi; ++i)
+      s += cnt[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0)
+      {
+        uint32_t run = 0;
+        for (int t = 0; t < T; ++t)
+          {
+            const uint32_t v = part[t];
+            part[t]          = run;
+            run += v;
+          }
+      }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (int i = lo; i < hi; ++i)
+      {
+        base[i] = run;
+        run += cnt[i];
+      }
+  }
+
+  __global__ void
+  dofmap_assign_kernel(int n, const uint32_t *__restrict__ base, const uint32_t *__restrict__ mask,
+                       uint32_t *__restrict__ dofmap, uint32_t *__restrict__ invmap)
+  {
+    const int np  = n + 1;
+    const int lex = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lex >= np * np)
+      return;
+    const int      jx = lex % np, jy = lex / np;
+    int            lv;
+    const uint32_t m   = first_touch_cell(n, jx, jy, lv);
+    const uint32_t dof = base[m] + __popc(mask[m] & ((1u << lv) - 1u));
+    dofmap[lex]        = dof;
+    invmap[dof]        = (uint32_t)lex;
+  }
+
+  cudaError_t
+  launch_dofmap(const Shard &s, cudaStream_t st)
+  {
+    const int  ncell = s.n * s.n;
+    uint32_t  *tmp   = nullptr;
+    cudaError_t e    = cudaMalloc(&tmp, sizeof(uint32_t) * 3 * (size_t)ncell);
+    if (e != cudaSuccess)
+      return e;
+    uint32_t *cnt = tmp, *mask = tmp + ncell, *base = tmp + 2 * (size_t)ncell;
+    dofmap_count_kernel<<<(ncell + 255) / 256, 256, 0, st>>>(s.n, cnt, mask);
+    dofmap_scan_kernel<<<1, 1024, 0, st>>>(ncell, cnt, base);
+    dofmap_assign_kernel<<<(s.N + 255) / 256, 256, 0, st>>>(s.n, base, mask, s.d_dofmap, s.d_invmap);
+    e = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    return e != cudaSuccess ? e : cudaGetLastError();
+  }
+
+  // ======================================================================================
+  // Coefficient evaluation (device twins of include/coefficients/matrix_coeff.tpp and of
+  // the BASELINE.md synthetic coefficients).
+  // ======================================================================================
+  __device__ inline uint64_t
+  mix64(uint64_t z)
+  {
+    z ^= z >> 33;
+    z *= 0xff51afd7ed558ccdULL;
+    z ^= z >> 33;
+    z *= 0xc4ceb9fe1a85ec53ULL;
+    z ^= z >> 33;
+    return z;
+  }
+
+  struct CoeffEval
+  {
+    int    kind, seed;
+    double par[6];
+    double rot00, rot01, rot10, rot11; // reference rotation (matrix_coeff.tpp:17-25)
+
+    __device__ inline void
+    operator()(double x, double y, double &a00, double &a01, double &a10, double &a11) const
+    {
+      if (kind == MSB_COEFF_REFERENCE)
+        {
+          // coefficients.h:21 (sic) and matrix_coeff.hpp:45-46
+          const double PI_D = 3.14592653509793218403;
+          const double a =
+            1.0 * (1.0 - 0.9999 * (0.5 * sin(2 * PI_D * 57 * x) + 0.5 * sin(2 * PI_D * 57 * y)));
+          // values = rot * (a I) * transpose(rot), evaluated in that order
+          const double t00 = rot00 * a, t01 = rot01 * a, t10 = rot10 * a, t11 = rot11 * a;
+          a00 = t00 * rot00 + t01 * rot01;
+          a01 = t00 * rot10 + t01 * rot11;
+          a10 = t10 * rot00 + t11 * rot01;
+          a11 = t10 * rot10 + t11 * rot11;
+        }
+      else if (kind == MSB_COEFF_PERIODIC)
+        {
+          const double PI = 3.14159265358979323846;
+          const double a =
+            1.0 - par[1] * (0.5 * sin(2 * PI * x / par[0]) + 0.5 * sin(2 * PI * y / par[0]));
+          a00 = a, a01 = 0.0, a10 = 0.0, a11 = a;
+        }
+      else if (kind == MSB_COEFF_INCLUSIONS)
+        {
+          const long long bx = (long long)floor(x / par[0]), by = (long long)floor(y / par[0]);
+          uint64_t        h  = (uint64_t)bx * 0x9E3779B97F4A7C15ULL;
+          h ^= mix64((uint64_t)by + 0xC2B2AE3D27D4EB4FULL * (uint64_t)(uint32_t)seed);
+          h = mix64(h);
+          const bool   in = (double)(h >> 11) * (1.0 / 9007199254740992.0) < par[1];
+          const double a  = in ? par[2] : par[3];
+          a00 = a, a01 = 0.0, a10 = 0.0, a11 = a;
+        }
+      else
+        {
+          a00 = par[0], a01 = 0.0, a10 = 0.0, a11 = par[0];
+        }
+    }
+  };
+
+  // ======================================================================================
+  // Stencil assembly.  One CTA handles a strip of node rows of one coarse cell: it first
+  // computes the 10 unique entries of every fine element matrix K_e (2x2 Gauss, Q1 mapping,
+  // full tensor coefficient) plus the element load F_e for the R+1 rows of fine cells the
+  // strip touches into shared memory, then gathers them per node into the symmetric
+  // 9-point stencil.  The coefficient is evaluated once per quadrature point (+1/R halo).
+  // ======================================================================================
+  struct AssembleParams
+  {
+    int           n, R, n_cells;
+    const double *corners;
+    const double *table;
+    double       *sten;
+    double        rhs_value;
+    CoeffEval     coef;
+  };
+
+  __global__ void __launch_bounds__(256)
+  assemble_kernel(AssembleParams P)
+  {
+    extern __shared__ double ke[]; // [14][(R+1)*n]
+    const int n = P.n, np = n + 1, N = np * np, R = P.R;
+    const int cell  = blockIdx.y;
+    const int jy0   = blockIdx.x * R; // first node row of the strip
+    const int rows  = min(R, np - jy0);
+    const int slab  = (R + 1) * n;
+    const double *c = P.corners + 8 * (size_t)cell;
+
+    const double g0 = 0.5 - 0.5 / sqrt(3.0), g1 = 0.5 + 0.5 / sqrt(3.0);
+
+    // ---- phase 1: element matrices of cell rows jy0-1 .. jy0+rows-1
+    for (int t = threadIdx.x; t < (rows + 1) * n; t += blockDim.x)
+      {
+        const int lr = t / n, ix = t % n;
+        const int iy = jy0 - 1 + lr;
+        double    K[10], Fe[4];
+#pragma unroll
+        for (int e = 0; e < 10; ++e)
+          K[e] = 0.0;
+        Fe[0] = Fe[1] = Fe[2] = Fe[3] = 0.0;
+        if (iy >= 0 && iy < n)
+          {
+            double Px[4], Py[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              fine_vertex(c, n, ix + (v & 1), iy + (v >> 1), Px[v], Py[v]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              {
+                const double xi = (q & 1) ? g1 : g0, eta = (q >> 1) ? g1 : g0;
+                const double Nv[4]  = {(1 - xi) * (1 - eta), xi * (1 - eta), (1 - xi) * eta, xi * eta};
+                const double dNx[4] = {-(1 - eta), (1 - eta), -eta, eta};
+                const double dNy[4] = {-(1 - xi), -xi, (1 - xi), xi};
+                double       J00 = 0, J01 = 0, J10 = 0, J11 = 0, xq = 0, yq = 0;
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                  {
+                    xq += Px[v] * Nv[v];
+                    yq += Py[v] * Nv[v];
+                    J00 += Px[v] * dNx[v];
+                    J01 += Px[v] * dNy[v];
+                    J10 += Py[v] * dNx[v];
+                    J11 += Py[v] * dNy[v];
+                  }
+                const double det = J00 * J11 - J01 * J10;
+                const double i00 = J11 / det, i01 = -J01 / det, i10 = -J10 / det, i11 = J00 / det;
+                const double JxW = det * 0.25;
+                double       Gx[4], Gy[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                  {
+                    Gx[v] = i00 * dNx[v] + i10 * dNy[v];
+                    Gy[v] = i01 * dNx[v] + i11 * dNy[v];
+                  }
+                double a00, a01, a10, a11;
+                if (P.table)
+                  {
+                    const double *tp =
+                      P.table + (((size_t)cell * n * n + (size_t)iy * n + ix) * 4 + q) * 4;
+                    a00 = tp[0], a01 = tp[1], a10 = tp[2], a11 = tp[3];
+                  }
+                else
+                  P.coef(xq, yq, a00, a01, a10, a11);
+                // K is symmetrised: only the symmetric part of A enters x^T K x, and the
+                // reference tensor is symmetric up to 1e-17
+                const double as = 0.5 * (a01 + a10);
+                int          e  = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  {
+                    const double t0 = Gx[i] * a00 + Gy[i] * as, t1 = Gx[i] * as + Gy[i] * a11;
+#pragma unroll
+                    for (int j = i; j < 4; ++j)
+                      K[e++] += (t0 * Gx[j] + t1 * Gy[j]) * JxW;
+                    Fe[i] += Nv[i] * P.rhs_value * JxW;
+                  }
+              }
+          }
+#pragma unroll
+        for (int e = 0; e < 10; ++e)
+          ke[e * slab + t] = K[e];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          ke[(10 + e) * slab + t] = Fe[e];
+      }
+    __syncthreads();
+
+    // ---- phase 2: gather per node.  K index of (i,j), i<=j: 00:0 01:1 02:2 03:3 11:4 12:5 13:6 22:7 23:8 33:9
+    double *out = P.sten + (size_t)cell * ST_NARR * N;
+    for (int t = threadIdx.x; t < rows * np; t += blockDim.x)
+      {
+        const int ly = t / np, jx = t % np;
+        const int jy = jy0 + ly;
+        // local slab rows: cell row jy-1 -> ly, cell row jy -> ly+1
+        const bool hasW = jx > 0, hasE = jx < n, hasS = jy > 0, hasN = jy < n;
+        const int  sw = ly * n + jx - 1, se = ly * n + jx, nw = (ly + 1) * n + jx - 1,
+                  ne = (ly + 1) * n + jx;
+        double kc = 0, kE = 0, kN = 0, kd1 = 0, kd2 = 0, f = 0;
+        if (hasS && hasW)
+          {
+            kc += ke[9 * slab + sw];
+            f += ke[13 * slab + sw];
+          }
+        if (hasS && hasE)
+          {
+            kc += ke[7 * slab + se];
+            kE += ke[8 * slab + se];
+            f += ke[12 * slab + se];
+          }
+        if (hasN && hasW)
+          {
+            kc += ke[4 * slab + nw];
+            kN += ke[6 * slab + nw];
+            f += ke[11 * slab + nw];
+          }
+        if (hasN && hasE)
+          {
+            kc += ke[0 * slab + ne];
+            kE += ke[1 * slab + ne];
+            kN += ke[2 * slab + ne];
+            kd1 = ke[3 * slab + ne];
+            kd2 = ke[5 * slab + ne];
+            f += ke[10 * slab + ne];
+          }
+        const int lex           = jy * np + jx;
+        out[ST_KC * N + lex]    = kc;
+        out[ST_KE * N + lex]    = kE;
+        out[ST_KN * N + lex]    = kN;
+        out[ST_KD1 * N + lex]   = kd1;
+        out[ST_KD2 * N + lex]   = kd2;
+        out[ST_F * N + lex]     = f;
+      }
+  }
+
+  cudaError_t
+  launch_assemble(const Shard &s, cudaStream_t st, int *n_launches)
+  {
+    AssembleParams P;
+    P.n         = s.n;
+    P.n_cells   = s.n_cells;
+    P.corners   = s.d_corners;
+    P.table     = s.coeff.kind == MSB_COEFF_TABLE ? s.d_table : nullptr;
+    P.sten      = s.d_sten;
+    P.rhs_value = s.rhs_value;
+    P.coef.kind = s.coeff.kind;
+    P.coef.seed = s.coeff.seed;
+    for (int i = 0; i < 6; ++i)
+      P.coef.par[i] = s.coeff.par[i];
+    {
+      // matrix_coeff.hpp:48, matrix_coeff.tpp:17-25: alpha = PI_D/3
+      const double alpha = 3.14592653509793218403 / 3;
+      P.coef.rot00 = cos(alpha), P.coef.rot01 = sin(alpha);
+      P.coef.rot10 = -sin(alpha), P.coef.rot11 = cos(alpha);
+    }
+    // strip height: as many node rows as fit ~96 KB of element data, at most 16
+    int R = (int)(96 * 1024 / (14 * sizeof(double) * (size_t)s.n)) - 1;
+    R     = R < 1 ? 1 : (R > 16 ? 16 : R);
+    P.R   = R;
+    const size_t smem = sizeof(double) * 14 * (size_t)(R + 1) * s.n;
+    cudaError_t  e =
+      cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+      return e;
+    // gridDim.y is limited to 65535: loop over slices of cells
+    const int strips = (s.np + R - 1) / R;
+    for (int c0 = 0; c0 < s.n_cells; c0 += 65535)
+      {
+        const int      nc = s.n_cells - c0 < 65535 ? s.n_cells - c0 : 65535;
+        AssembleParams Q  = P;
+        Q.corners += 8 * (size_t)c0;
+        Q.sten += (size_t)c0 * ST_NARR * s.N;
+        if (Q.table)
+          Q.table += (size_t)c0 * s.n * s.n * 16;
+        assemble_kernel<<<dim3(strips, nc), 256, smem, st>>>(Q);
+        ++*n_launches;
+      }
+    return cudaGetLastError();
+  }
+
+  // ======================================================================================
+  // y = K x for one vector on one cell's stencil (lexicographic order).
+  // ======================================================================================
+  __device__ inline double
+  stencil_apply(const double *__restrict__ S, const double *__restrict__ x, int n, int jx, int jy)
+  {
+    const int  np = n + 1, N = np * np, i = jy * np + jx;
+    const bool hasW = jx > 0, hasE = jx < n, hasS = jy > 0, hasN = jy < n;
+    double     y = S[ST_KC * N + i] * x[i];
+    if (hasE)
+      y += S[ST_KE * N + i] * x[i + 1];
+    if (hasW)
+      y += S[ST_KE * N + i - 1] * x[i - 1];
+    if (hasN)
+      y += S[ST_KN * N + i] * x[i + np];
+    if (hasS)
+      y += S[ST_KN * N + i - np] * x[i - np];
+    if (hasN && hasE)
+      y += S[ST_KD1 * N + i] * x[i + np + 1];
+    if (hasS && hasW)
+      y += S[ST_KD1 * N + i - np - 1] * x[i - np - 1];
+    if (hasN && hasW)
+      y += S[ST_KD2 * N + i - 1] * x[i + np - 1];
+    if (hasS && hasE)
+      y += S[ST_KD2 * N + i - np] * x[i - np + 1];
+    return y;
+  }
+
+  __global__ void
+  apply_operator_kernel(int n, const double *__restrict__ S, const double *__restrict__ x,
+                        double *__restrict__ y)
+  {
+    const int np = n + 1, lex = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lex < np * np)
+      y[lex] = stencil_apply(S, x, n, lex % np, lex / np);
+  }
+
+  cudaError_t
+  launch_apply_operator(const Shard &s, int cell, const double *d_x, double *d_y, cudaStream_t st)
+  {
+    apply_operator_kernel<<<(s.N + 255) / 256, 256, 0, st>>>(
+      s.n, s.d_sten + (size_t)cell * ST_NARR * s.N, d_x, d_y);
+    return cudaGetLastError();
+  }
+
+  // ======================================================================================
+  // assemble_global_element_matrix (basis.tpp:245-285): M_ij = phi_i . (K phi_j) with the
+  // UNCONSTRAINED K over all N DoFs, b_i = phi_i . F.  One CTA per coarse cell, fixed
+  // summation order (deterministic).
+  // ======================================================================================
+  __global__ void __launch_bounds__(256)
+  element_matrix_kernel(int n, const double *__restrict__ sten, const double *__restrict__ phi,
+                        double *__restrict__ M, double *__restrict__ b)
+  {
+    const int     np = n + 1, N = np * np, cell = blockIdx.x;
+    const double *S = sten + (size_t)cell * ST_NARR * N;
+    const double *P = phi + (size_t)cell * 4 * N;
+    double        acc[20];
+#pragma unroll
+    for (int k = 0; k < 20; ++k)
+      acc[k] = 0.0;
+    for (int lex = threadIdx.x; lex < N; lex += blockDim.x)
+      {
+        const int jx = lex % np, jy = lex / np;
+        double    kp[4], ph[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          {
+            kp[j] = stencil_apply(S, P + (size_t)j * N, n, jx, jy);
+            ph[j] = P[(size_t)j * N + lex];
+          }
+        const double f = S[ST_F * N + lex];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              acc[4 * i + j] += ph[i] * kp[j];
+            acc[16 + i] += ph[i] * f;
+          }
+      }
+    __shared__ double red[8][20];
+    const int         lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 20; ++k)
+      {
+        double v = acc[k];
+        for (int off = 16; off > 0; off >>= 1)
+          v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0)
+          red[warp][k] = v;
+      }
+    __syncthreads();
+    if (threadIdx.x < 20)
+      {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w)
+          v += red[w][threadIdx.x];
+        if (threadIdx.x < 16)
+          M[16 * (size_t)cell + threadIdx.x] = v;
+        else
+          b[4 * (size_t)cell + threadIdx.x - 16] = v;
+      }
+  }
+
+  cudaError_t
+  launch_element_matrices(const Shard &s, cudaStream_t st, int *n_launches)
+  {
+    element_matrix_kernel<<<s.n_cells, 256, 0, st>>>(s.n, s.d_sten, s.d_phi, s.d_M, s.d_b);
+    ++*n_launches;
+    return cudaGetLastError();
+  }
+
+  // ======================================================================================
+  // reordering between the lexicographic device layout and the deal.II DoF order
+  // ======================================================================================
+  __global__ void
+  permute_kernel(int N, const uint32_t *__restrict__ dofmap, const double *__restrict__ src,
+                 double *__restrict__ dst, int lex_to_dof)
+  {
+    const int lex = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lex >= N)
+      return;
+    if (lex_to_dof)
+      dst[dofmap[lex]] = src[lex];
+    else
+      dst[lex] = src[dofmap[lex]];
+  }
+
+  cudaError_t
+  launch_permute(const Shard &s, const double *d_src, double *d_dst, bool lex_to_dof, cudaStream_t st)
+  {
+    permute_kernel<<<(s.N + 255) / 256, 256, 0, st>>>(s.N, s.d_dofmap, d_src, d_dst, lex_to_dof ? 1 : 0);
+    return cudaGetLastError();
+  }
+
+  // ======================================================================================
+  // set_global_weights (basis.tpp:352-377) for all cells: gsol = sum_i w_i phi_i.
+  // Purely bandwidth bound: reads 4N, writes N doubles per cell.
+  // ======================================================================================
+  __global__ void __launch_bounds__(256)
+  global_solution_kernel(int N, const double *__restrict__ phi, const double *__restrict__ w,
+                         double *__restrict__ out)
+  {
+    const int     cell = blockIdx.y;
+    const double *P    = phi + (size_t)cell * 4 * N;
+    const double  w0 = w[4 * cell], w1 = w[4 * cell + 1], w2 = w[4 * cell + 2], w3 = w[4 * cell + 3];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+      {
+        // same accumulation order as Vector::sadd(1, w_i, phi_i) for i = 0..3
+        double v = 0.0;
+        v        = v + w0 * P[i];
+        v        = v + w1 * P[(size_t)N + i];
+        v        = v + w2 * P[2 * (size_t)N + i];
+        v        = v + w3 * P[3 * (size_t)N + i];
+        out[(size_t)cell * N + i] = v;
+      }
+  }
+
+  cudaError_t
+  launch_global_solution(const Shard &s, const double *d_w, cudaStream_t st)
+  {
+    const int bx = (s.N + 255) / 256 < 8 ? (s.N + 255) / 256 : 8;
+    for (int c0 = 0; c0 < s.n_cells; c0 += 65535)
+      {
+        const int nc = s.n_cells - c0 < 65535 ? s.n_cells - c0 : 65535;
+        global_solution_kernel<<<dim3(bx, nc), 256, 0, st>>>(
+          s.N, s.d_phi + (size_t)c0 * 4 * s.N, d_w + 4 * (size_t)c0, s.d_gsol + (size_t)c0 * s.N);
+      }
+    return cudaGetLastError();
+  }
+
+  // ======================================================================================
+  // constraint set of one (cell, basis): boundary DoFs ascending + BasisQ1 values
+  // (basis.tpp:119-135).  The sorted order is produced by ranking: a boundary DoF's
+  // position is the number of boundary DoFs with a smaller index.
+  // ======================================================================================
+  __global__ void
+  constraints_kernel(int n, const uint32_t *__restrict__ dofmap, const double *__restrict__ corners,
+                     const double *__restrict__ q1coef, int ib, uint32_t *__restrict__ dofs,
+                     double *__restrict__ vals)
+  {
+    const int nb = 4 * n, np = n + 1;
+    const int t  = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb)
+      return;
+    // boundary node t: walk the four sides
+    auto node_of = [&](int k, int &jx, int &jy) {
+      if (k < n)
+        jx = k, jy = 0;
+      else if (k < 2 * n)
+        jx = n, jy = k - n;
+      else if (k < 3 * n)
+        jx = n - (k - 2 * n), jy = n;
+      else
+        jx = 0, jy = n - (k - 3 * n);
+    };
+    int jx, jy;
+    node_of(t, jx, jy);
+    const uint32_t d    = dofmap[jy * np + jx];
+    int            rank = 0;
+    for (int k = 0; k < nb; ++k)
+      {
+        int kx, ky;
+        node_of(k, kx, ky);
+        rank += dofmap[ky * np + kx] < d;
+      }
+    double px, py;
+    fine_vertex(corners, n, jx, jy, px, py);
+    dofs[rank] = d;
+    vals[rank] = basis_q1_value(q1coef, ib, px, py);
+  }
+
+  cudaError_t
+  launch_constraints(const Shard &s, int cell, int ib, uint32_t *d_dofs, double *d_vals, cudaStream_t st)
+  {
+    constraints_kernel<<<(4 * s.n + 127) / 128, 128, 0, st>>>(
+      s.n, s.d_dofmap, s.d_corners + 8 * (size_t)cell, s.d_q1coef + 16 * (size_t)cell, ib, d_dofs, d_vals);
+    return cudaGetLastError();
+  }
+} // namespace msb

@@ -1,0 +1,301 @@
+"""Parity of the sm_100a basis stage (through the C ABI) with the CPU oracle.
+
+Tolerances (BASELINE.json north_star): DoF maps and constraint index sets bit-exact;
+multiscale basis vectors within 1e-8 relative L2 of the oracle's SSOR-PCG solution of the
+same condensed systems (both sides converged to ||r||_2 <= 1e-12 absolute, the
+reference's SolverControl(1000, 1e-12) rule); M, b within 1e-8 relative.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL_PHI = 1e-8  # relative L2, north_star
+TOL_MB = 1e-8
+
+
+def _morton(ix, iy, r):
+    m = 0
+    for bit in range(r):
+        m |= ((ix >> bit) & 1) << (2 * bit) | ((iy >> bit) & 1) << (2 * bit + 1)
+    return m
+
+
+def _coeffs(msb, oracle, kind, par=(), seed=0):
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
+    return coeff_desc(kind, par, seed), oracle.coeff(kind, par, seed)
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b))
+
+
+# ---------------------------------------------------------------------------- integers
+@pytest.mark.parametrize("l", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_dof_map_bit_exact(msb, oracle, l):
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_CONSTANT, (1.0,))
+    with msb.BasisShard(l, msb.coarse_corners(1, 0, 1), cd) as sh:
+        assert np.array_equal(sh.dof_map(), oracle.dof_map(l))
+
+
+@pytest.mark.parametrize("l", [3, 5, 6])
+def test_constraint_sets(msb, oracle, l):
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    cor = msb.coarse_corners(8, 777, 779)
+    with msb.BasisShard(l, cor, cd) as sh:
+        for cell in range(2):
+            for ib in range(4):
+                dofs, vals = sh.constraints(cell, ib)
+                assert np.array_equal(dofs, oracle.boundary_dofs(l))          # bit-exact index set
+                ref = oracle.constraint_values(l, cor[cell], ib)
+                # values differ only through the 4x4 inverse (~eps/H^2)
+                assert np.abs(vals - ref).max() < 1e-9
+
+
+# ---------------------------------------------------------------------------- operator
+@pytest.mark.parametrize("l,kind,par,seed", [
+    (5, 0, (), 0), (6, 1, (1.0 / 64, 0.9999), 0), (5, 2, (2.0 ** -11, 0.2, 1e4, 1.0), 1234),
+    (7, 0, (), 0), (3, 3, (2.5,), 0)])
+def test_matrix_free_operator_matches_csr_vmult(msb, oracle, l, kind, par, seed):
+    """y = K(a) x against the oracle's CSR vmult, ~1e-14 relative."""
+    import scipy.sparse as sp
+    cd, co = _coeffs(msb, oracle, kind, par, seed)
+    r = 8 if kind == 2 else 3
+    cor = msb.coarse_corners(r, 37, 38)
+    rowptr, col, val, F = oracle.assemble(l, cor[0], co)
+    N = oracle.n_dofs(l)
+    K = sp.csr_matrix((val, col.astype(np.int64), rowptr.astype(np.int64)), shape=(N, N))
+    rng = np.random.default_rng(l)
+    with msb.BasisShard(l, cor, cd) as sh:
+        for _ in range(2):
+            x = rng.standard_normal(N)
+            y = sh.apply_operator(0, x)
+            assert _rel(y, K @ x) < 5e-14
+        assert np.abs(sh.load_vector(0) - F).max() < 1e-15 * max(1.0, np.abs(F).max() / 1e-6)
+
+
+def test_table_coefficient_equals_analytic(msb, oracle):
+    """MSB_COEFF_TABLE: tensor values as a host TensorFunction::value_list would produce."""
+    l, r = 4, 3
+    n = 1 << l
+    cor = msb.coarse_corners(r, 10, 12)
+    co = oracle.coeff(oracle.COEFF_REFERENCE)
+    g = [0.5 - 0.5 / np.sqrt(3.0), 0.5 + 0.5 / np.sqrt(3.0)]
+    table = np.empty((2, n * n, 4, 4))
+    for c in range(2):
+        x0, y0 = cor[c, 0]
+        h = (cor[c, 1, 0] - x0) / n
+        for iy in range(n):
+            for ix in range(n):
+                for q in range(4):
+                    A = oracle.coeff_eval(co, x0 + (ix + g[q & 1]) * h, y0 + (iy + g[q >> 1]) * h)
+                    table[c, iy * n + ix, q] = A.ravel()
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
+    with msb.BasisShard(l, cor, coeff_desc(msb.COEFF_TABLE), table=table) as a, \
+            msb.BasisShard(l, cor, coeff_desc(msb.COEFF_REFERENCE)) as b:
+        a.run()
+        b.run()
+        Ma, ba = a.element_matrices()
+        Mb, bb = b.element_matrices()
+        assert _rel(Ma, Mb) < 1e-12 and _rel(ba, bb) < 1e-12
+
+
+# ---------------------------------------------------------------------------- bases
+CASES = json.load(open(os.path.join(GOLD, "oracle_golden.json")))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_bases_match_oracle_and_goldens(msb, oracle, name):
+    g = CASES[name]
+    l, r, m = g["l"], g["r"], g["morton"]
+    cd, co = _coeffs(msb, oracle, g["kind"], g["par"], g["seed"])
+    cor = msb.coarse_corners(r, m, m + 1)
+    ref = oracle.run_cells(l, cor, co)
+    with msb.BasisShard(l, cor, cd) as sh:
+        sh.run(1e-12, 5000)
+        M, b = sh.element_matrices()
+        it, res = sh.iteration_counts()
+        assert np.all(res <= 1e-12) and np.all(it > 0)
+        for ib in range(4):
+            phi = sh.basis(0, ib)
+            assert _rel(phi, ref["phi"][0][ib]) < TOL_PHI, (name, ib)
+        assert _rel(M[0], ref["M"][0]) < TOL_MB and _rel(b[0], ref["b"][0]) < TOL_MB
+        # committed goldens
+        assert _rel(M[0], np.array(g["M"])) < TOL_MB and _rel(b[0], np.array(g["b"])) < TOL_MB
+        d = oracle.dof_map(l)
+        for (jx, jy), vals in zip(g["probes"], g["phi_probes"]):
+            got = np.array([sh.basis(0, i)[d[jy, jx]] for i in range(4)])
+            assert np.abs(got - np.array(vals)).max() < 1e-9
+        # the GPU iterates Jacobi-preconditioned CG: same counts as the oracle's Jacobi run
+        assert np.abs(it[0] - np.array(g["iters_jacobi"])).max() <= 3, (it[0], g["iters_jacobi"])
+
+
+def test_survey_crosscheck_on_gpu(msb, oracle):
+    """The only numbers that come from outside this repo's oracle."""
+    sv = json.load(open(os.path.join(GOLD, "survey_crosscheck.json")))
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    with msb.BasisShard(7, msb.coarse_corners(3, 0, 1), cd) as sh:
+        sh.run(1e-12, 5000)
+        M, b = sh.element_matrices()
+        assert np.abs(M[0] - np.array(sv["M"])).max() < 1e-9
+        assert np.abs(b[0] - np.array(sv["b"])).max() < 1e-11
+        d = oracle.dof_map(7)
+        assert abs(sh.basis(0, 0)[d[64, 64]] - sv["phi0_centre"]) < 1e-9
+        assert abs(sh.basis(0, 3)[d[64, 64]] - sv["phi3_centre"]) < 1e-9
+
+
+@pytest.mark.parametrize("l,variant", [(6, 0), (6, 1), (6, 2), (6, 3), (5, 0), (5, 1), (5, 2)])
+def test_kernel_variants_agree(msb, oracle, l, variant):
+    cd, co = _coeffs(msb, oracle, msb.COEFF_PERIODIC, (1.0 / 64, 0.9999))
+    cor = msb.coarse_corners(7, 1000, 1003)
+    ref = oracle.run_cells(l, cor, co)
+    with msb.BasisShard(l, cor, cd, variant=variant) as sh:
+        sh.run(1e-12, 5000)
+        for c in range(3):
+            for ib in range(4):
+                assert _rel(sh.basis(c, ib), ref["phi"][c][ib]) < TOL_PHI
+        M, b = sh.element_matrices()
+        assert _rel(M, ref["M"]) < TOL_MB and _rel(b, ref["b"]) < TOL_MB
+
+
+@pytest.mark.parametrize("l", [5, 6])
+def test_streamed_tier_equals_smem_tier(msb, oracle, l):
+    cd, co = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    cor = msb.coarse_corners(4, 20, 25)
+    with msb.BasisShard(l, cor, cd, tier=msb.TIER_SMEM) as a, \
+            msb.BasisShard(l, cor, cd, tier=msb.TIER_STREAMED) as b:
+        a.run(1e-12, 5000)
+        b.run(1e-12, 5000)
+        ita, _ = a.iteration_counts()
+        itb, _ = b.iteration_counts()
+        assert np.abs(ita - itb).max() <= 2
+        for c in (0, 4):
+            for ib in range(4):
+                assert _rel(a.basis(c, ib), b.basis(c, ib)) < 1e-10
+        Ma, ba = a.element_matrices()
+        Mb, bb = b.element_matrices()
+        assert _rel(Ma, Mb) < 1e-10 and _rel(ba, bb) < 1e-10
+
+
+def test_default_run_all_64_cells(msb, oracle):
+    """BASELINE cfg1: the reference's default MsFEM run (main.cxx:23-25), streamed tier."""
+    cd, co = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    cor = msb.coarse_corners(3)
+    with msb.BasisShard(7, cor, cd) as sh:
+        sh.run(1e-12, 5000)
+        M, b = sh.element_matrices()
+        it, res = sh.iteration_counts()
+        assert np.all(res <= 1e-12)
+        ref = oracle.run_cells(7, cor[[0, 29, 63]], co, n_threads=3)
+        for k, c in enumerate([0, 29, 63]):
+            assert _rel(M[c], ref["M"][k]) < TOL_MB and _rel(b[c], ref["b"][k]) < TOL_MB
+            for ib in (0, 3):
+                assert _rel(sh.basis(c, ib), ref["phi"][k][ib]) < TOL_PHI
+        # invariants on every cell
+        assert np.abs(M.sum(axis=2)).max() < 1e-9
+        assert np.abs(M - M.transpose(0, 2, 1)).max() < 1e-9
+        assert np.abs(b.sum(axis=1) - 2.0 / 64).max() < 1e-13
+
+
+# ---------------------------------------------------------------------------- edge cases
+def test_no_convergence_is_an_error_code_not_an_exception_across_the_abi(msb, oracle):
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    with msb.BasisShard(5, msb.coarse_corners(3, 0, 3), cd) as sh:
+        with pytest.raises(msb.MsbError) as e:
+            sh.run(1e-12, 7)
+        assert e.value.code == -5
+        cell, ib, res = sh.failure()
+        assert (cell, ib) == (0, 0) and res > 1e-12
+        it, _ = sh.iteration_counts()
+        assert np.all(it == 7)
+        # and the handle stays usable
+        sh.run(1e-12, 5000)
+        assert sh.failure()[0] == -1
+
+
+def test_call_order_errors(msb, oracle):
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    with msb.BasisShard(4, msb.coarse_corners(2, 0, 2), cd) as sh:
+        with pytest.raises(msb.MsbError) as e:
+            sh.element_matrices()
+        assert e.value.code == -6
+        sh.run()
+        with pytest.raises(msb.MsbError) as e:
+            sh.global_solution(0)           # the reference asserts is_set_global_weights
+        assert e.value.code == -6
+        with pytest.raises(msb.MsbError):
+            sh.basis(5, 0)
+
+
+def test_zero_right_hand_side_edge_case(msb, oracle):
+    """Constant coefficient: the Q1 data is discretely harmonic only up to rounding, so CG
+    still iterates; a loose tolerance must stop at k = 0 like SolverCG's initial check."""
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_CONSTANT, (1.0,))
+    with msb.BasisShard(5, msb.coarse_corners(2, 0, 1), cd) as sh:
+        sh.run(1e3, 1000)
+        it, _ = sh.iteration_counts()
+        assert np.all(it == 0)
+
+
+def test_set_global_weights_reconstruction(msb, oracle):
+    cd, co = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    cor = msb.coarse_corners(3, 8, 12)
+    rng = np.random.default_rng(1)
+    w = rng.standard_normal((4, 4))
+    ref = oracle.run_cells(5, cor, co)
+    with msb.BasisShard(5, cor, cd) as sh:
+        sh.run()
+        sh.set_global_weights(w)
+        for c in range(4):
+            want = oracle.global_solution(ref["phi"][c], w[c])
+            assert _rel(sh.global_solution(c), want) < TOL_PHI
+
+
+# ---------------------------------------------------------------------------- full sizes
+@pytest.mark.parametrize("name,r,l,kind,par,seed,lo,hi", [
+    ("cfg2", 5, 5, 1, (1.0 / 64, 0.9999), 0, 0, 1024),
+    ("cfg3-slice", 7, 6, 1, (1.0 / 64, 0.9999), 0, 4096, 4096 + 2048),
+    ("cfg4-slice", 8, 5, 2, (2.0 ** -11, 0.2, 1e4, 1.0), 1234, 30000, 30000 + 4096),
+    ("target-slice", 8, 6, 1, (1.0 / 64, 0.9999), 0, 50000, 50000 + 2048),
+])
+def test_full_size_invariants(msb, oracle, name, r, l, kind, par, seed, lo, hi):
+    """Size-independent properties at BASELINE sizes, plus oracle
+    parity on a few sampled cells."""
+    cd, co = _coeffs(msb, oracle, kind, par, seed)
+    cor = msb.coarse_corners(r, lo, hi)
+    H = 1.0 / (1 << r)
+    with msb.BasisShard(l, cor, cd) as sh:
+        sh.run(1e-12, 5000)
+        M, b = sh.element_matrices()
+        it, res = sh.iteration_counts()
+        assert np.all(res <= 1e-12)
+        scale = np.abs(M).max()
+        assert np.abs(M.sum(axis=2)).max() < 1e-9 * scale          # zero row sums
+        assert np.abs(M - M.transpose(0, 2, 1)).max() < 1e-9 * scale
+        assert np.abs(b.sum(axis=1) - 2.0 * H * H).max() < 1e-12 * H * H * 1e3
+        sample = [0, (hi - lo) // 2, hi - lo - 1]
+        ref = oracle.run_cells(l, cor[sample], co, n_threads=3)
+        for k, c in enumerate(sample):
+            phis = np.stack([sh.basis(c, ib) for ib in range(4)])
+            assert np.abs(phis.sum(axis=0) - 1.0).max() < 1e-9   # partition of unity
+            assert _rel(phis, ref["phi"][k]) < TOL_PHI
+            assert _rel(M[c], ref["M"][k]) < TOL_MB
+
+
+def test_streamed_tier_256x256_local_mesh(msb, oracle):
+    """BASELINE cfg5 local size (n=256: beyond one SM's shared memory)."""
+    cd, co = _coeffs(msb, oracle, msb.COEFF_PERIODIC, (1.0 / 64, 0.9999))
+    cor = msb.coarse_corners(6, 1234, 1236)
+    ref = oracle.run_cells(8, cor[:1], co)
+    with msb.BasisShard(8, cor, cd) as sh:
+        sh.run(1e-12, 5000)
+        it, res = sh.iteration_counts()
+        assert np.all(res <= 1e-12)
+        for ib in range(4):
+            assert _rel(sh.basis(0, ib), ref["phi"][0][ib]) < TOL_PHI
+        M, b = sh.element_matrices()
+        assert _rel(M[0], ref["M"][0]) < TOL_MB and _rel(b[0], ref["b"][0]) < TOL_MB

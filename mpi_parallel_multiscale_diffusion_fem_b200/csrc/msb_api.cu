@@ -322,8 +322,10 @@ msb_run_async(msb_handle h, double tol_abs, int32_t max_iter, void *cuda_stream)
   CUDA_TRY(launch_assemble(s, st, &s.n_launches));
   s.assembled = true;
   CUDA_TRY(cudaEventRecord(s.ev[1], st));
-  if (s.tier == MSB_TIER_SMEM)
-    CUDA_TRY(launch_solve_smem(s, tol_abs, max_iter, st, &s.n_launches));
+  if (s.tier == MSB_TIER_SMEM && s.variant < 100)
+    CUDA_TRY(launch_solve_bpx(s, tol_abs, max_iter, st, &s.n_launches)); // multilevel PCG (default)
+  else if (s.tier == MSB_TIER_SMEM)
+    CUDA_TRY(launch_solve_smem(s, tol_abs, max_iter, st, &s.n_launches)); // Jacobi PCG (variant >= 100)
   else
     CUDA_TRY(launch_solve_streamed(s, tol_abs, max_iter, st, &s.n_launches));
   s.tier_used = s.tier;

@@ -73,6 +73,8 @@ namespace msb
   cudaError_t launch_assemble(const Shard &s, cudaStream_t st, int *n_launches);
   cudaError_t launch_solve_smem(const Shard &s, double tol, int max_iter, cudaStream_t st,
                                 int *n_launches);
+  cudaError_t launch_solve_bpx(const Shard &s, double tol, int max_iter, cudaStream_t st,
+                               int *n_launches);
   cudaError_t launch_solve_streamed(Shard &s, double tol, int max_iter, cudaStream_t st,
                                     int *n_launches);
   cudaError_t launch_element_matrices(const Shard &s, cudaStream_t st, int *n_launches);

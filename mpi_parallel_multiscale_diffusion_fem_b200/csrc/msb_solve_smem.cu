@@ -524,6 +524,7 @@ namespace msb
     P.max_iter = max_iter;
     P.n_cells  = s.n_cells;
     ++*n_launches;
+    const int variant = s.variant >= 100 ? s.variant - 100 : s.variant;
     switch (s.l)
       {
         case 3:
@@ -531,17 +532,17 @@ namespace msb
         case 4:
           return launch_one<4, 4, 128>(P, st);
         case 5:
-          if (s.variant == 1)
+          if (variant == 1)
             return launch_one<5, 2, 256>(P, st);
-          if (s.variant == 2)
+          if (variant == 2)
             return launch_one<5, 4, 128>(P, st);
           return launch_one<5, 4, 256>(P, st);
         case 6:
-          if (s.variant == 1)
+          if (variant == 1)
             return launch_one<6, 2, 512>(P, st);
-          if (s.variant == 2)
+          if (variant == 2)
             return launch_one<6, 2, 256>(P, st);
-          if (s.variant == 3)
+          if (variant == 3)
             return launch_one<6, 1, 256>(P, st);
           return launch_one<6, 1, 512>(P, st);
         default:

@@ -108,14 +108,16 @@ def test_table_coefficient_equals_analytic(msb, oracle):
 CASES = json.load(open(os.path.join(GOLD, "oracle_golden.json")))
 
 
+@pytest.mark.parametrize("variant", [0, 100])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_bases_match_oracle_and_goldens(msb, oracle, name):
+def test_bases_match_oracle_and_goldens(msb, oracle, name, variant):
+    """variant 0: multilevel-preconditioned CG (default); 100: Jacobi-preconditioned CG."""
     g = CASES[name]
     l, r, m = g["l"], g["r"], g["morton"]
     cd, co = _coeffs(msb, oracle, g["kind"], g["par"], g["seed"])
     cor = msb.coarse_corners(r, m, m + 1)
     ref = oracle.run_cells(l, cor, co)
-    with msb.BasisShard(l, cor, cd) as sh:
+    with msb.BasisShard(l, cor, cd, variant=variant) as sh:
         sh.run(1e-12, 5000)
         M, b = sh.element_matrices()
         it, res = sh.iteration_counts()
@@ -130,8 +132,13 @@ def test_bases_match_oracle_and_goldens(msb, oracle, name):
         for (jx, jy), vals in zip(g["probes"], g["phi_probes"]):
             got = np.array([sh.basis(0, i)[d[jy, jx]] for i in range(4)])
             assert np.abs(got - np.array(vals)).max() < 1e-9
-        # the GPU iterates Jacobi-preconditioned CG: same counts as the oracle's Jacobi run
-        assert np.abs(it[0] - np.array(g["iters_jacobi"])).max() <= 3, (it[0], g["iters_jacobi"])
+        tier = sh.run_stats()["tier"]
+        if variant == 100 or tier == msb.TIER_STREAMED:
+            # Jacobi-preconditioned CG: same counts as the oracle's Jacobi run
+            assert np.abs(it[0] - np.array(g["iters_jacobi"])).max() <= 3, (it[0], g["iters_jacobi"])
+        else:
+            # the multilevel preconditioner must beat Jacobi by a wide margin
+            assert np.all(it[0] * 2 <= np.array(g["iters_jacobi"])), (it[0], g["iters_jacobi"])
 
 
 def test_survey_crosscheck_on_gpu(msb, oracle):
@@ -148,7 +155,8 @@ def test_survey_crosscheck_on_gpu(msb, oracle):
         assert abs(sh.basis(0, 3)[d[64, 64]] - sv["phi3_centre"]) < 1e-9
 
 
-@pytest.mark.parametrize("l,variant", [(6, 0), (6, 1), (6, 2), (6, 3), (5, 0), (5, 1), (5, 2)])
+@pytest.mark.parametrize("l,variant", [(6, 0), (6, 1), (6, 100), (6, 101), (6, 102), (6, 103),
+                                       (5, 0), (5, 1), (5, 100), (5, 101), (5, 102), (4, 0), (3, 0)])
 def test_kernel_variants_agree(msb, oracle, l, variant):
     cd, co = _coeffs(msb, oracle, msb.COEFF_PERIODIC, (1.0 / 64, 0.9999))
     cor = msb.coarse_corners(7, 1000, 1003)
@@ -172,7 +180,7 @@ def test_streamed_tier_equals_smem_tier(msb, oracle, l):
         b.run(1e-12, 5000)
         ita, _ = a.iteration_counts()
         itb, _ = b.iteration_counts()
-        assert np.abs(ita - itb).max() <= 2
+        assert np.all(ita <= itb)   # multilevel PCG (smem tier) vs Jacobi PCG (streamed tier)
         for c in (0, 4):
             for ib in range(4):
                 assert _rel(a.basis(c, ib), b.basis(c, ib)) < 1e-10

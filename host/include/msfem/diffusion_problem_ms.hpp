@@ -1,0 +1,360 @@
+// diffusion_problem_ms.hpp -- the caller of the basis stage, shaped like the reference's
+// DiffusionProblemMultiscale<dim> (/root/reference/include/base/diffusion_problem_ms.{hpp,tpp})
+// so that the GPU path can be exercised end to end on a machine without deal.II, MPI,
+// p4est and Trilinos.  Method names and the order of run() follow ms.tpp:445-491.
+//
+// What is NOT the reference here (and is out of the accelerated path):
+// the coarse mesh is the structured 2^r x 2^r refinement of hyper_cube(0,1,colorize) held
+// as plain arrays in Morton / CellId order (ms.tpp:97-99), the coarse matrix is a host CSR,
+// and the coarse system is solved by a host Jacobi-PCG to the reference's tolerance
+// (SolverControl(n_dofs, 1e-12), ms.tpp:264) instead of Trilinos AMG-CG.  One process
+// drives one GPU; with several GPUs each rank owns a contiguous Morton range (ms.tpp:52).
+#pragma once
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "msfem/coefficients.hpp"
+#include "msfem/diffusion_problem_basis.hpp"
+
+namespace DiffusionProblem
+{
+  using namespace msfem;
+
+  template <int dim>
+  class DiffusionProblemMultiscale
+  {
+    static_assert(dim == 2, "only the 2D path is built");
+
+  public:
+    DiffusionProblemMultiscale(unsigned int n_refine, unsigned int n_refine_local, int device_id = 0)
+      : n_refine(n_refine)
+      , n_refine_local(n_refine_local)
+      , device_id(device_id)
+    {}
+
+    void set_coefficient(const Coefficients::TensorCoefficient<dim> *c) { matrix_coeff = c; }
+    void set_output(bool coarse_and_fine) { write_output = coarse_and_fine; }
+
+    // ms.tpp:445-491
+    void run()
+    {
+      std::cout << std::endl
+                << "===========================================" << std::endl
+                << "Solving >> MULTISCALE << problem in " << dim << "D." << std::endl;
+      std::cout << "Running with the B200 basis stage on 1 rank(s)..." << std::endl;
+      make_grid();
+      setup_system();
+      timed("basis initialization and computation", [&] { initialize_and_compute_basis(); });
+      timed("global multiscale assembly", [&] { assemble_system(); });
+      timed("global iterative solver", [&] { solve_iterative(); });
+      send_global_weights_to_cell();
+      if (write_output)
+        {
+          timed("coarse output vtu", [&] { output_global_coarse(); });
+          timed("fine output vtu", [&] { output_global_fine(); });
+        }
+      print_summary();
+      std::cout << std::endl << "===========================================" << std::endl;
+    }
+
+    const std::vector<double> &get_solution() const { return solution; }
+    unsigned int                n_dofs() const { return n_coarse_dofs; }
+    const std::vector<unsigned> &get_dof_map() const { return dof_of_vertex; }
+    double basis_seconds() const { return timings.count("basis initialization and computation") ?
+                                            timings.at("basis initialization and computation") : 0.0; }
+    std::map<CellId, DiffusionProblemBasis<dim>> &get_cell_basis_map() { return cell_basis_map; }
+
+  private:
+    template <class F>
+    void timed(const std::string &name, F f)
+    {
+      const auto t0 = std::chrono::steady_clock::now();
+      f();
+      timings[name] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+
+    static unsigned compact(unsigned m)
+    {
+      unsigned x = m & 0x55555555u;
+      x          = (x | (x >> 1)) & 0x33333333u;
+      x          = (x | (x >> 2)) & 0x0f0f0f0fu;
+      x          = (x | (x >> 4)) & 0x00ff00ffu;
+      x          = (x | (x >> 8)) & 0x0000ffffu;
+      return x;
+    }
+
+    // ms.tpp:91-103: hyper_cube(0,1,colorize=true), refine_global(n_refine); active cells in
+    // Morton order (= CellId order = p4est order)
+    void make_grid()
+    {
+      nc = 1u << n_refine;
+      H  = 1.0 / nc;
+      cells.resize((std::size_t)nc * nc);
+      for (unsigned m = 0; m < nc * nc; ++m)
+        {
+          const unsigned   ix = compact(m), iy = compact(m >> 1);
+          CoarseCell<dim> &c = cells[m];
+          for (unsigned v = 0; v < 4; ++v)
+            c.vertices[v] = Point<dim>((ix + (v & 1)) * H, (iy + (v >> 1)) * H);
+          c.cell_id        = CellId(n_refine, m);
+          c.boundary_id[0] = ix == 0 ? 0 : 255;      // x = 0
+          c.boundary_id[1] = ix == nc - 1 ? 1 : 255; // x = 1
+          c.boundary_id[2] = iy == 0 ? 2 : 255;      // y = 0
+          c.boundary_id[3] = iy == nc - 1 ? 3 : 255; // y = 1
+        }
+      std::cout << "Number of active global cells: " << cells.size() << std::endl;
+    }
+
+    // ms.tpp:106-156: first-touch DoF numbering, Dirichlet values on boundary ids 0 and 2
+    void setup_system()
+    {
+      const unsigned np = nc + 1;
+      dof_of_vertex.assign((std::size_t)np * np, ~0u);
+      unsigned next = 0;
+      for (unsigned m = 0; m < nc * nc; ++m)
+        {
+          const unsigned ix = compact(m), iy = compact(m >> 1);
+          for (unsigned v = 0; v < 4; ++v)
+            {
+              unsigned &d = dof_of_vertex[(iy + (v >> 1)) * np + ix + (v & 1)];
+              if (d == ~0u)
+                d = next++;
+            }
+        }
+      n_coarse_dofs = next;
+      is_constrained.assign(n_coarse_dofs, 0);
+      constraint_value.assign(n_coarse_dofs, 0.0);
+      const Coefficients::DirichletBC<dim> dirichlet_bc;
+      for (unsigned jy = 0; jy < np; ++jy)
+        for (unsigned jx = 0; jx < np; ++jx)
+          if (jx == 0 || jy == 0) // boundary ids 0 (x=0) and 2 (y=0), ms.tpp:130-137
+            {
+              const unsigned d    = dof_of_vertex[jy * np + jx];
+              is_constrained[d]   = 1;
+              constraint_value[d] = dirichlet_bc.value(Point<dim>(jx * H, jy * H));
+            }
+      solution.assign(n_coarse_dofs, 0.0);
+    }
+
+    // ms.tpp:40-88 -- THE stage.  Construction loop as in the reference; the serial run()
+    // loop (ms.tpp:81-87) is replaced by one batched call.
+    void initialize_and_compute_basis()
+    {
+      for (std::size_t m = 0; m < cells.size(); ++m)
+        {
+          DiffusionProblemBasis<dim> current_cell_problem(n_refine_local, cells[m], /*subdomain*/ 0, 0);
+          cell_basis_map.insert(std::make_pair(cells[m].id(), current_cell_problem));
+        }
+      if (matrix_coeff)
+        DiffusionProblemBasis<dim>::run_all(cell_basis_map, *matrix_coeff, BasisSolverControl(), device_id);
+      else
+        DiffusionProblemBasis<dim>::run_all(cell_basis_map);
+    }
+
+    void cell_dofs(std::size_t m, unsigned (&ld)[4]) const
+    {
+      const unsigned np = nc + 1, ix = compact((unsigned)m), iy = compact((unsigned)m >> 1);
+      for (unsigned v = 0; v < 4; ++v)
+        ld[v] = dof_of_vertex[(iy + (v >> 1)) * np + ix + (v & 1)];
+    }
+
+    // ms.tpp:159-255: element matrices from the basis objects, Neumann face terms on boundary
+    // ids 1 and 3 (QGauss<1>(2), standard Q1 face shape values), scatter into the coarse system
+    void assemble_system()
+    {
+      rows.assign(n_coarse_dofs, {});
+      system_rhs.assign(n_coarse_dofs, 0.0);
+      const Coefficients::NeumannBC<dim> neumann_bc;
+      const double g[2] = {0.5 - 0.5 / std::sqrt(3.0), 0.5 + 0.5 / std::sqrt(3.0)};
+      std::size_t  m    = 0;
+      for (auto &kv : cell_basis_map)
+        {
+          const FullMatrix<double> &cell_matrix = kv.second.get_global_element_matrix();
+          Vector<double>            cell_rhs    = kv.second.get_global_element_rhs();
+          const CoarseCell<dim>    &c           = cells[m];
+          // face 1: x = x1 (vertices 1,3); face 3: y = y1 (vertices 2,3)
+          for (int face = 1; face <= 3; face += 2)
+            if (c.boundary_id[face] == (unsigned)face)
+              for (int q = 0; q < 2; ++q)
+                {
+                  const Point<dim> &a  = c.vertex(face == 1 ? 1 : 2), &b = c.vertex(3);
+                  const Point<dim>  xq(a(0) + g[q] * (b(0) - a(0)), a(1) + g[q] * (b(1) - a(1)));
+                  const double      JxW = 0.5 * H, val = neumann_bc.value(xq);
+                  cell_rhs(face == 1 ? 1 : 2) += val * (1.0 - g[q]) * JxW;
+                  cell_rhs(3) += val * g[q] * JxW;
+                }
+          unsigned ld[4];
+          cell_dofs(m, ld);
+          for (int i = 0; i < 4; ++i)
+            {
+              for (int j = 0; j < 4; ++j)
+                rows[ld[i]][ld[j]] += cell_matrix(i, j);
+              system_rhs[ld[i]] += cell_rhs(i);
+            }
+          ++m;
+        }
+    }
+
+    // ms.tpp:258-296: CG to ||r||_2 <= 1e-12 on the system with the Dirichlet DoFs eliminated,
+    // then constraints.distribute
+    void solve_iterative()
+    {
+      const unsigned      n = n_coarse_dofs;
+      std::vector<double> b(n, 0.0), x(n, 0.0), r(n), z(n), p(n), q(n), dinv(n, 1.0);
+      for (unsigned i = 0; i < n; ++i)
+        {
+          if (is_constrained[i])
+            continue;
+          double bi = system_rhs[i];
+          for (auto &e : rows[i])
+            if (is_constrained[e.first])
+              bi -= e.second * constraint_value[e.first];
+          b[i]    = bi;
+          dinv[i] = 1.0 / rows[i][i];
+        }
+      auto vmult = [&](const std::vector<double> &in, std::vector<double> &out) {
+        for (unsigned i = 0; i < n; ++i)
+          {
+            double s = 0.0;
+            if (!is_constrained[i])
+              for (auto &e : rows[i])
+                if (!is_constrained[e.first])
+                  s += e.second * in[e.first];
+            out[i] = s;
+          }
+      };
+      auto dot = [&](const std::vector<double> &a, const std::vector<double> &c) {
+        double s = 0.0;
+        for (unsigned i = 0; i < n; ++i)
+          s += a[i] * c[i];
+        return s;
+      };
+      r = b;
+      for (unsigned i = 0; i < n; ++i)
+        z[i] = dinv[i] * r[i];
+      p          = z;
+      double   rz = dot(r, z);
+      unsigned it = 0;
+      while (std::sqrt(dot(r, r)) > 1e-12 && it < 10 * n)
+        {
+          ++it;
+          vmult(p, q);
+          const double alpha = rz / dot(p, q);
+          for (unsigned i = 0; i < n; ++i)
+            x[i] += alpha * p[i], r[i] -= alpha * q[i];
+          for (unsigned i = 0; i < n; ++i)
+            z[i] = dinv[i] * r[i];
+          const double rz_new = dot(r, z), beta = rz_new / rz;
+          rz                  = rz_new;
+          for (unsigned i = 0; i < n; ++i)
+            p[i] = z[i] + beta * p[i];
+        }
+      std::cout << "   Global problem solved in " << it << " iterations." << std::endl;
+      for (unsigned i = 0; i < n; ++i)
+        solution[i] = is_constrained[i] ? constraint_value[i] : x[i];
+    }
+
+    // ms.tpp:299-325
+    void send_global_weights_to_cell()
+    {
+      std::size_t m = 0;
+      for (auto &kv : cell_basis_map)
+        {
+          unsigned ld[4];
+          cell_dofs(m++, ld);
+          std::vector<double> extracted_weights(4);
+          for (int i = 0; i < 4; ++i)
+            extracted_weights[i] = solution[ld[i]];
+          kv.second.set_global_weights(extracted_weights);
+        }
+    }
+
+    // ms.tpp:328-379 (one rank: a single VTU)
+    void output_global_coarse() const
+    {
+      const unsigned np = nc + 1;
+      std::ofstream  out("solution-ms_coarse-2d_refinements-" + std::to_string(n_refine) + ".0000.vtu");
+      out.precision(17);
+      out << "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" "
+             "byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n<Piece NumberOfPoints=\""
+          << np * np << "\" NumberOfCells=\"" << nc * nc << "\">\n<Points>\n<DataArray type=\"Float64\" "
+             "NumberOfComponents=\"3\" format=\"ascii\">\n";
+      for (unsigned jy = 0; jy < np; ++jy)
+        for (unsigned jx = 0; jx < np; ++jx)
+          out << jx * H << " " << jy * H << " 0\n";
+      out << "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int32\" Name=\"connectivity\" "
+             "format=\"ascii\">\n";
+      for (unsigned iy = 0; iy < nc; ++iy)
+        for (unsigned ix = 0; ix < nc; ++ix)
+          out << iy * np + ix << " " << iy * np + ix + 1 << " " << (iy + 1) * np + ix + 1 << " "
+              << (iy + 1) * np + ix << "\n";
+      out << "</DataArray>\n<DataArray type=\"Int32\" Name=\"offsets\" format=\"ascii\">\n";
+      for (unsigned k = 1; k <= nc * nc; ++k)
+        out << 4 * k << "\n";
+      out << "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n";
+      for (unsigned k = 0; k < nc * nc; ++k)
+        out << "9\n";
+      out << "</DataArray>\n</Cells>\n<PointData Scalars=\"scalars\">\n<DataArray type=\"Float64\" "
+             "Name=\"u\" format=\"ascii\">\n";
+      for (unsigned i = 0; i < np * np; ++i)
+        out << solution[dof_of_vertex[i]] << "\n";
+      out << "</DataArray>\n</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n";
+    }
+
+    // ms.tpp:382-423: one VTU per coarse cell + a PVTU record naming them
+    void output_global_fine()
+    {
+      std::vector<std::string> filenames;
+      for (auto &kv : cell_basis_map)
+        {
+          kv.second.output_global_solution_in_cell();
+          filenames.push_back(kv.second.get_filename_global());
+        }
+      std::ofstream out("solution-ms_fine-2d.pvtu");
+      out << "<?xml version=\"1.0\"?>\n<VTKFile type=\"PUnstructuredGrid\" version=\"0.1\" "
+             "byte_order=\"LittleEndian\">\n<PUnstructuredGrid GhostLevel=\"0\">\n<PPointData "
+             "Scalars=\"scalars\">\n<PDataArray type=\"Float64\" Name=\"solution\" format=\"ascii\"/>\n"
+             "</PPointData>\n<PPoints>\n<PDataArray type=\"Float64\" NumberOfComponents=\"3\"/>\n"
+             "</PPoints>\n";
+      for (auto &f : filenames)
+        out << "<Piece Source=\"" << f << "\"/>\n";
+      out << "</PUnstructuredGrid>\n</VTKFile>\n";
+    }
+
+    void print_summary() const
+    {
+      std::cout << "\n+---------------------------------------------+------------+\n"
+                << "| Section                                     | wall time  |\n"
+                << "+---------------------------------------------+------------+\n";
+      for (auto &kv : timings)
+        {
+          std::string name = kv.first;
+          name.resize(43, ' ');
+          std::cout << "| " << name << " | " << kv.second << "s |\n";
+        }
+      std::cout << "+---------------------------------------------+------------+\n";
+    }
+
+    unsigned int n_refine, n_refine_local;
+    int          device_id;
+    unsigned     nc = 0, n_coarse_dofs = 0;
+    double       H = 1.0;
+    bool         write_output = false;
+    const Coefficients::TensorCoefficient<dim> *matrix_coeff = nullptr;
+
+    std::vector<CoarseCell<dim>>                 cells;
+    std::vector<unsigned>                        dof_of_vertex;
+    std::vector<char>                            is_constrained;
+    std::vector<double>                          constraint_value, system_rhs, solution;
+    std::vector<std::map<unsigned, double>>      rows;
+    std::map<CellId, DiffusionProblemBasis<dim>> cell_basis_map;
+    std::map<std::string, double>                timings;
+  };
+} // namespace DiffusionProblem

@@ -19,6 +19,8 @@
 // staging/restriction/prolongation 7, direction update 2) and executes 7 block barriers.
 #include <math.h>
 
+#include <type_traits>
+
 #include "msb_internal.cuh"
 
 namespace msb
@@ -156,6 +158,28 @@ namespace msb
           }
     }
 
+    // compile-time loops over levels (ascending / descending, inclusive bounds)
+    template <int L0, int L1, class F>
+    __device__ __forceinline__ void
+    for_levels(F &&f)
+    {
+      if constexpr (L0 <= L1)
+        {
+          f(std::integral_constant<int, L0>{});
+          for_levels<L0 + 1, L1>(f);
+        }
+    }
+    template <int L1, int L0, class F>
+    __device__ __forceinline__ void
+    for_levels_down(F &&f)
+    {
+      if constexpr (L1 >= L0)
+        {
+          f(std::integral_constant<int, L1>{});
+          for_levels_down<L1 - 1, L0>(f);
+        }
+    }
+
     template <int NL, int NRHS, int THREADS>
     struct Cfg
     {
@@ -167,6 +191,8 @@ namespace msb
       static constexpr int WY    = NWARP / WX;
       static constexpr int RPT   = (n - 1 + WY - 1) / WY;
       static constexpr int LEVELS = NL - 1; // coarse levels 1..NL-1 (the last has one unknown)
+      // levels 1..LW have >= 15x15 unknowns and are swept by the whole CTA
+      static constexpr int LW = NL >= 4 ? NL - 4 : 0;
       // coarse level arrays, all levels packed: level l has (n>>l)+1 nodes per direction
       __host__ __device__ static constexpr int
       lvl_np(int l)
@@ -354,13 +380,21 @@ namespace msb
               }
           }
         __syncthreads();
-        // restriction 0 -> 1 by all threads (full weighting = P^T)
-        {
-          constexpr int np1 = C::lvl_np(1), nin = np1 - 2;
-          for (int t = tid; t < nin * nin; t += THREADS)
+        // Level sweeps.  "Wide" levels (>= 15x15 unknowns) are done by the whole CTA with a block
+        // barrier each; the remaining tiny levels form a short serial chain on warp 0.
+        // restrict(l): r_l = P^T r_{l-1} (full weighting); source of level 1 is the staged u.
+        auto restrict_level = [&](auto lc, int first, int nthr) {
+          constexpr int l   = decltype(lc)::value;
+          constexpr int W   = n >> l, LG = NL - l, npl = W + 1;
+          constexpr int npf = (n >> (l - 1)) + 1;
+          const double *Vf  = l == 1 ? sU : sV + (size_t)NRHS * C::lvl_off(l - 1);
+          double       *Vl  = sV + (size_t)NRHS * C::lvl_off(l);
+          for (int t = first; t < W * W; t += nthr)
             {
-              const int cx = 1 + t % nin, cy = 1 + t / nin;
-              double    acc[NRHS];
+              const int cx = 1 + (t & (W - 1)), cy = 1 + (t >> LG);
+              if (cx > W - 1 || cy > W - 1)
+                continue;
+              double acc[NRHS];
 #pragma unroll
               for (int k = 0; k < NRHS; ++k)
                 acc[k] = 0.0;
@@ -371,126 +405,78 @@ namespace msb
                   {
                     const double w = (ax == 0 ? 1.0 : 0.5) * (ay == 0 ? 1.0 : 0.5);
                     double       u[NRHS];
-                    ldv<NRHS>(sU, (2 * cy + ay) * np + 2 * cx + ax, u);
+                    ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx + ax, u);
 #pragma unroll
                     for (int k = 0; k < NRHS; ++k)
                       acc[k] = fma(w, u[k], acc[k]);
                   }
-              stv<NRHS>(sV, cy * np1 + cx, acc);
+              stv<NRHS>(Vl, cy * npl + cx, acc);
             }
-        }
-        __syncthreads();
-        // levels 2..LEVELS down and back up to level 2: tiny, done by warp 0 alone
-        if (warp == 0)
-          {
-#pragma unroll
-            for (int l = 2; l <= C::LEVELS; ++l)
-              {
-                const int     npl = C::lvl_np(l), nin = npl - 2, npf = C::lvl_np(l - 1);
-                double       *Vl  = sV + (size_t)NRHS * C::lvl_off(l);
-                const double *Vf  = sV + (size_t)NRHS * C::lvl_off(l - 1);
-                for (int t = lane; t < nin * nin; t += 32)
-                  {
-                    const int cx = 1 + t % nin, cy = 1 + t / nin;
-                    double    acc[NRHS];
-#pragma unroll
-                    for (int k = 0; k < NRHS; ++k)
-                      acc[k] = 0.0;
-#pragma unroll
-                    for (int ay = -1; ay <= 1; ++ay)
-#pragma unroll
-                      for (int ax = -1; ax <= 1; ++ax)
-                        {
-                          const double w = (ax == 0 ? 1.0 : 0.5) * (ay == 0 ? 1.0 : 0.5);
-                          double       u[NRHS];
-                          ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx + ax, u);
-#pragma unroll
-                          for (int k = 0; k < NRHS; ++k)
-                            acc[k] = fma(w, u[k], acc[k]);
-                        }
-                    stv<NRHS>(Vl, cy * npl + cx, acc);
-                  }
-                __syncwarp();
-              }
-            // coarsest level: z = r / D
+        };
+        // prolong(l): z_l = r_l / D_l + P z_{l+1}  (coarsest level: z = r / D)
+        auto prolong_level = [&](auto lc, int first, int nthr) {
+          constexpr int l   = decltype(lc)::value;
+          constexpr int W   = n >> l, LG = NL - l, npl = W + 1;
+          double       *Vl  = sV + (size_t)NRHS * C::lvl_off(l);
+          const double *Dl  = sDi + C::lvl_off(l);
+          for (int t = first; t < W * W; t += nthr)
             {
-              constexpr int l   = C::LEVELS;
-              const int     npl = C::lvl_np(l), nin = npl - 2;
-              double       *Vl  = sV + (size_t)NRHS * C::lvl_off(l);
-              const double *Dl  = sDi + C::lvl_off(l);
-              for (int t = lane; t < nin * nin; t += 32)
+              const int fx = 1 + (t & (W - 1)), fy = 1 + (t >> LG);
+              if (fx > W - 1 || fy > W - 1)
+                continue;
+              const int i = fy * npl + fx;
+              double    v[NRHS];
+              ldv<NRHS>(Vl, i, v);
+              const double di = Dl[i];
+              if constexpr (l < C::LEVELS)
                 {
-                  const int i = (1 + t / nin) * npl + 1 + t % nin;
-                  double    v[NRHS];
-                  ldv<NRHS>(Vl, i, v);
+                  constexpr int npc = (n >> (l + 1)) + 1;
+                  const double *Vc  = sV + (size_t)NRHS * C::lvl_off(l + 1);
+                  const int xl = fx >> 1, xh = (fx + 1) >> 1, yl = fy >> 1, yh = (fy + 1) >> 1;
+                  double    a[NRHS], b[NRHS], c[NRHS], d[NRHS];
+                  ldv<NRHS>(Vc, yl * npc + xl, a);
+                  ldv<NRHS>(Vc, yl * npc + xh, b);
+                  ldv<NRHS>(Vc, yh * npc + xl, c);
+                  ldv<NRHS>(Vc, yh * npc + xh, d);
 #pragma unroll
                   for (int k = 0; k < NRHS; ++k)
-                    v[k] *= Dl[i];
-                  stv<NRHS>(Vl, i, v);
+                    v[k] = fma(v[k], di, 0.25 * ((a[k] + b[k]) + (c[k] + d[k])));
                 }
-              __syncwarp();
+              else
+                {
+#pragma unroll
+                  for (int k = 0; k < NRHS; ++k)
+                    v[k] *= di;
+                }
+              stv<NRHS>(Vl, i, v);
             }
-#pragma unroll
-            for (int l = C::LEVELS - 1; l >= 2; --l)
-              {
-                const int     npl = C::lvl_np(l), nin = npl - 2, npc = C::lvl_np(l + 1);
-                double       *Vl  = sV + (size_t)NRHS * C::lvl_off(l);
-                const double *Vc  = sV + (size_t)NRHS * C::lvl_off(l + 1);
-                const double *Dl  = sDi + C::lvl_off(l);
-                for (int t = lane; t < nin * nin; t += 32)
-                  {
-                    const int fx = 1 + t % nin, fy = 1 + t / nin, i = fy * npl + fx;
-                    const int xl = fx >> 1, xh = (fx + 1) >> 1, yl = fy >> 1, yh = (fy + 1) >> 1;
-                    double    v[NRHS], a[NRHS], b[NRHS], c[NRHS], d[NRHS];
-                    ldv<NRHS>(Vl, i, v);
-                    ldv<NRHS>(Vc, yl * npc + xl, a);
-                    ldv<NRHS>(Vc, yl * npc + xh, b);
-                    ldv<NRHS>(Vc, yh * npc + xl, c);
-                    ldv<NRHS>(Vc, yh * npc + xh, d);
-                    const double di = Dl[i];
-#pragma unroll
-                    for (int k = 0; k < NRHS; ++k)
-                      v[k] = fma(v[k], di, 0.25 * ((a[k] + b[k]) + (c[k] + d[k])));
-                    stv<NRHS>(Vl, i, v);
-                  }
-                __syncwarp();
-              }
-          }
-        __syncthreads();
-        // level 1: z_1 = r_1 / D_1 + P z_2, all threads
-        if constexpr (C::LEVELS >= 1)
+        };
+        // down: wide levels
+        for_levels<1, C::LW>([&](auto lc) {
+          restrict_level(lc, tid, THREADS);
+          __syncthreads();
+        });
+        // the tiny levels: down, coarsest scale, and back up, on warp 0
+        if constexpr (C::LEVELS > C::LW)
           {
-            constexpr int np1 = C::lvl_np(1), nin = np1 - 2;
-            for (int t = tid; t < nin * nin; t += THREADS)
+            if (warp == 0)
               {
-                const int fx = 1 + t % nin, fy = 1 + t / nin, i = fy * np1 + fx;
-                double    v[NRHS];
-                ldv<NRHS>(sV, i, v);
-                const double di = sDi[i];
-                if constexpr (C::LEVELS >= 2)
-                  {
-                    constexpr int npc = C::lvl_np(2);
-                    const double *Vc  = sV + (size_t)NRHS * C::lvl_off(2);
-                    const int xl = fx >> 1, xh = (fx + 1) >> 1, yl = fy >> 1, yh = (fy + 1) >> 1;
-                    double    a[NRHS], b[NRHS], c[NRHS], d[NRHS];
-                    ldv<NRHS>(Vc, yl * npc + xl, a);
-                    ldv<NRHS>(Vc, yl * npc + xh, b);
-                    ldv<NRHS>(Vc, yh * npc + xl, c);
-                    ldv<NRHS>(Vc, yh * npc + xh, d);
-#pragma unroll
-                    for (int k = 0; k < NRHS; ++k)
-                      v[k] = fma(v[k], di, 0.25 * ((a[k] + b[k]) + (c[k] + d[k])));
-                  }
-                else
-                  {
-#pragma unroll
-                    for (int k = 0; k < NRHS; ++k)
-                      v[k] *= di;
-                  }
-                stv<NRHS>(sV, i, v);
+                for_levels<C::LW + 1, C::LEVELS>([&](auto lc) {
+                  restrict_level(lc, lane, 32);
+                  __syncwarp();
+                });
+                for_levels_down<C::LEVELS, C::LW + 1>([&](auto lc) {
+                  prolong_level(lc, lane, 32);
+                  __syncwarp();
+                });
               }
+            __syncthreads();
           }
-        __syncthreads();
+        // up: wide levels
+        for_levels_down<C::LW, 1>([&](auto lc) {
+          prolong_level(lc, tid, THREADS);
+          __syncthreads();
+        });
         // level 0: zhat = rhat + D^1/2 (P z_1)
         {
           constexpr int np1 = C::lvl_np(1);

@@ -273,11 +273,7 @@ def main():
     # ---- end-to-end leg: host buffers in, host buffers out, through the C ABI -------------
     e2e = None
     if not args.no_e2e:
-        gathered = None
-        if world > 1:
-            d_pack = torch.empty((n_local, 20), dtype=torch.float64, device="cuda")
-            counts = [pkg.morton_partition(total_cells, q, world) for q in range(world)]
-            gathered = [torch.empty((b - a, 20), dtype=torch.float64, device="cuda") for a, b in counts]
+        from mpi_parallel_multiscale_diffusion_fem_b200 import parallel
 
         def e2e_step():
             sh.set_cells_ptr(h_corners.data_ptr())                 # H2D corners (+ BasisQ1 data)
@@ -287,10 +283,8 @@ def main():
             sh.iteration_counts_into(h_it.data_ptr())
             if world > 1:
                 # the reference's compress(add) exchange (ms.tpp:253-254): every rank obtains the
-                # per-cell coarse contributions of all ranks over NVLink
-                d_pack[:, :16].copy_(h_M.view(n_local, 16), non_blocking=True)
-                d_pack[:, 16:].copy_(h_b, non_blocking=True)
-                dist.all_gather(gathered, d_pack)
+                # per-cell coarse contributions of all ranks over NVLink (NCCL all_gather)
+                parallel.gather_coarse_contributions(h_M, h_b, total_cells, device="cuda")
 
         e2e_step()
         barrier()
@@ -348,14 +342,14 @@ def main():
                        "l2": "working set (stencil + bases = %.1f GB per GPU) far larger than L2; "
                              "no flush needed" % (n_local * 10 * N * 8 / 1e9),
                        "mean_pcg_iterations": iters_all / n_solves,
-                       "preconditioner": "Jacobi (symmetric diagonal scaling)",
+                       "preconditioner": ("multilevel diagonal scaling (BPX), exact Galerkin diagonals" if args.variant < 100 else "Jacobi (symmetric diagonal scaling)"),
                        "variant": args.variant},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches_all,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "solve_smem_kernel" if sh.run_stats()["tier"] == 1 else "stream_k*",
+                         "kernel": ("solve_bpx_kernel" if args.variant < 100 else "solve_smem_kernel") if sh.run_stats()["tier"] == 1 else "stream_k*",
                          "kernel_ms_per_launch": solve_ms_max,
                          "peak_source": peak_src,
                          "note": "achieved = ALGORITHMIC streaming bytes N(96k+16)/solve (SURVEY 8d) / "

@@ -147,15 +147,34 @@ namespace msb
     double par[6];
     double rot00, rot01, rot10, rot11; // reference rotation (matrix_coeff.tpp:17-25)
 
-    __device__ inline void
-    operator()(double x, double y, double &a00, double &a01, double &a10, double &a11) const
+    // REFERENCE and PERIODIC are a(x,y) = 1 - c (sin(kx)/2 + sin(ky)/2): separable sines
+    __device__ inline bool
+    separable() const
+    {
+      return kind == MSB_COEFF_REFERENCE || kind == MSB_COEFF_PERIODIC;
+    }
+
+    // the 1-D sine term of coordinate t, evaluated exactly as the reference writes it
+    __device__ inline double
+    sine_term(double t) const
     {
       if (kind == MSB_COEFF_REFERENCE)
         {
-          // coefficients.h:21 (sic) and matrix_coeff.hpp:45-46
+          // coefficients.h:21 (sic) and matrix_coeff.hpp:45: sin(2 * PI_D * k * p(d))
           const double PI_D = 3.14592653509793218403;
-          const double a =
-            1.0 * (1.0 - 0.9999 * (0.5 * sin(2 * PI_D * 57 * x) + 0.5 * sin(2 * PI_D * 57 * y)));
+          return sin(2 * PI_D * 57 * t);
+        }
+      const double PI = 3.14159265358979323846;
+      return sin(2 * PI * t / par[0]);
+    }
+
+    __device__ inline void
+    from_sines(double sx, double sy, double &a00, double &a01, double &a10, double &a11) const
+    {
+      if (kind == MSB_COEFF_REFERENCE)
+        {
+          // matrix_coeff.hpp:46, matrix_coeff.tpp:78-89
+          const double a = 1.0 * (1.0 - 0.9999 * (0.5 * sx + 0.5 * sy));
           // values = rot * (a I) * transpose(rot), evaluated in that order
           const double t00 = rot00 * a, t01 = rot01 * a, t10 = rot10 * a, t11 = rot11 * a;
           a00 = t00 * rot00 + t01 * rot01;
@@ -163,13 +182,18 @@ namespace msb
           a10 = t10 * rot00 + t11 * rot01;
           a11 = t10 * rot10 + t11 * rot11;
         }
-      else if (kind == MSB_COEFF_PERIODIC)
+      else
         {
-          const double PI = 3.14159265358979323846;
-          const double a =
-            1.0 - par[1] * (0.5 * sin(2 * PI * x / par[0]) + 0.5 * sin(2 * PI * y / par[0]));
+          const double a = 1.0 - par[1] * (0.5 * sx + 0.5 * sy);
           a00 = a, a01 = 0.0, a10 = 0.0, a11 = a;
         }
+    }
+
+    __device__ inline void
+    operator()(double x, double y, double &a00, double &a01, double &a10, double &a11) const
+    {
+      if (separable())
+        from_sines(sine_term(x), sine_term(y), a00, a01, a10, a11);
       else if (kind == MSB_COEFF_INCLUSIONS)
         {
           const long long bx = (long long)floor(x / par[0]), by = (long long)floor(y / par[0]);
@@ -207,7 +231,7 @@ namespace msb
   __global__ void __launch_bounds__(256)
   assemble_kernel(AssembleParams P)
   {
-    extern __shared__ double ke[]; // [14][(R+1)*n]
+    extern __shared__ double ke[]; // [14][(R+1)*n] + sine tables [4n] + [4(R+1)]
     const int n = P.n, np = n + 1, N = np * np, R = P.R;
     const int cell  = blockIdx.y;
     const int jy0   = blockIdx.x * R; // first node row of the strip
@@ -216,6 +240,41 @@ namespace msb
     const double *c = P.corners + 8 * (size_t)cell;
 
     const double g0 = 0.5 - 0.5 / sqrt(3.0), g1 = 0.5 + 0.5 / sqrt(3.0);
+
+    // ---- phase 0: on an axis-aligned coarse cell (the only kind the reference's refined
+    // hyper_cube produces) a separable coefficient needs its sines only once per fine column
+    // and per fine row of the strip: 4n + 4(R+1) evaluations instead of 8 per fine cell.  The
+    // quadrature abscissae are computed by the same expressions as in the general path.
+    double    *tsx = ke + 14 * slab, *tsy = tsx + 4 * n;
+    const bool fast = !P.table && P.coef.separable() && c[0] == c[4] && c[2] == c[6] && c[1] == c[3] &&
+                      c[5] == c[7];
+    if (fast)
+      {
+        for (int t = threadIdx.x; t < 4 * n + 4 * (rows + 1); t += blockDim.x)
+          {
+            const bool isx = t < 4 * n;
+            const int  u = isx ? t : t - 4 * n, k = u >> 2, q = u & 3;
+            const int  ix = isx ? k : 0, iy = isx ? 0 : jy0 - 1 + k;
+            double     v = 0.0;
+            if (isx || (iy >= 0 && iy < n))
+              {
+                const double xi = (q & 1) ? g1 : g0, eta = (q >> 1) ? g1 : g0;
+                const double Nv[4] = {(1 - xi) * (1 - eta), xi * (1 - eta), (1 - xi) * eta, xi * eta};
+                double       xq = 0, yq = 0;
+#pragma unroll
+                for (int vv = 0; vv < 4; ++vv)
+                  {
+                    double px, py;
+                    fine_vertex(c, n, ix + (vv & 1), iy + (vv >> 1), px, py);
+                    xq += px * Nv[vv];
+                    yq += py * Nv[vv];
+                  }
+                v = P.coef.sine_term(isx ? xq : yq);
+              }
+            (isx ? tsx : tsy)[u] = v;
+          }
+        __syncthreads();
+      }
 
     // ---- phase 1: element matrices of cell rows jy0-1 .. jy0+rows-1
     for (int t = threadIdx.x; t < (rows + 1) * n; t += blockDim.x)
@@ -268,6 +327,8 @@ namespace msb
                       P.table + (((size_t)cell * n * n + (size_t)iy * n + ix) * 4 + q) * 4;
                     a00 = tp[0], a01 = tp[1], a10 = tp[2], a11 = tp[3];
                   }
+                else if (fast)
+                  P.coef.from_sines(tsx[4 * ix + q], tsy[4 * lr + q], a00, a01, a10, a11);
                 else
                   P.coef(xq, yq, a00, a01, a10, a11);
                 // K is symmetrised: only the symmetric part of A enters x^T K x, and the
@@ -365,7 +426,7 @@ namespace msb
     int R = (int)(96 * 1024 / (14 * sizeof(double) * (size_t)s.n)) - 1;
     R     = R < 1 ? 1 : (R > 16 ? 16 : R);
     P.R   = R;
-    const size_t smem = sizeof(double) * 14 * (size_t)(R + 1) * s.n;
+    const size_t smem = sizeof(double) * (14 * (size_t)(R + 1) * s.n + 4 * (size_t)s.n + 4 * (size_t)(R + 1));
     cudaError_t  e =
       cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)

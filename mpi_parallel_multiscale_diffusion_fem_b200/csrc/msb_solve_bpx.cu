@@ -237,7 +237,7 @@ namespace msb
       double *sRed = sDi + CN;                // 2 reduction buffers
 
       const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-      const int cell = blockIdx.x / GROUPS, rhs0 = (blockIdx.x % GROUPS) * NRHS;
+      const int cell = blockIdx.x; // one CTA per coarse cell; its 4/NRHS groups of bases run in turn
 
       const double *S   = P.sten + (size_t)cell * ST_NARR * N;
       const double *KC  = S + ST_KC * N;
@@ -303,6 +303,12 @@ namespace msb
           sD2[i] = S[ST_KD2 * N + g] * s10 * s01;
         }
       __syncthreads();
+      // The prologue above (scaled operator + Galerkin diagonals) is shared by all 2^dim bases
+      // of the cell: they are solved one group of NRHS after the other by this CTA.
+#pragma unroll 1
+      for (int grp = 0; grp < GROUPS; ++grp)
+      {
+      const int rhs0 = grp * NRHS;
       // (d) clear p, u and the coarse vectors (their halos stay zero for the whole solve)
       for (int i = tid; i < 2 * NRHS * N + NRHS * CN; i += THREADS)
         sP[i] = 0.0;
@@ -713,6 +719,8 @@ namespace msb
                 atomicMin(P.fail, sidx);
             }
         }
+      __syncthreads(); // shared buffers are reused by the next group of bases
+      } // grp
     }
 
     template <int NL, int NRHS, int THREADS>
@@ -725,7 +733,7 @@ namespace msb
       cudaError_t  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
       if (e != cudaSuccess)
         return e;
-      kern<<<P.n_cells * (4 / NRHS), THREADS, bytes, st>>>(P);
+      kern<<<P.n_cells, THREADS, bytes, st>>>(P);
       return cudaGetLastError();
     }
   } // namespace bpx

@@ -123,7 +123,8 @@ namespace msb
   __device__ inline void
   fine_vertex(const double *__restrict__ c, int n, int jx, int jy, double &px, double &py)
   {
-    const double s = (double)jx / (double)n, t = (double)jy / (double)n;
+    // n is a power of two: multiplying by 1/n is exact and avoids two FP64 divisions
+    const double rn = 1.0 / (double)n, s = (double)jx * rn, t = (double)jy * rn;
     const double st = s * t;
     px = c[0] + s * (c[2] - c[0]) + t * (c[4] - c[0]) + st * ((c[6] - c[4]) - (c[2] - c[0]));
     py = c[1] + s * (c[3] - c[1]) + t * (c[5] - c[1]) + st * ((c[7] - c[5]) - (c[3] - c[1]));

@@ -311,7 +311,8 @@ namespace msb
                     J11 += Py[v] * dNy[v];
                   }
                 const double det = J00 * J11 - J01 * J10;
-                const double i00 = J11 / det, i01 = -J01 / det, i10 = -J10 / det, i11 = J00 / det;
+                const double idet = 1.0 / det;
+                const double i00 = J11 * idet, i01 = -J01 * idet, i10 = -J10 * idet, i11 = J00 * idet;
                 const double JxW = det * 0.25;
                 double       Gx[4], Gy[4];
 #pragma unroll

@@ -67,16 +67,21 @@ def test_no_cpu_fallback_without_a_device(msb):
 
 
 def test_product_package_never_touches_the_oracle():
-    pkg = os.path.join(ROOT, "mpi_parallel_multiscale_diffusion_fem_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
-                src = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in src.replace("no oracle", "").lower() or f == "__init__.py" or \
-                    "imports or calls oracle" in src, f
-    for dirpath, _, files in os.walk(os.path.join(ROOT, "host")):
-        for f in files:
-            assert "msfem_oracle" not in open(os.path.join(dirpath, f)).read(), f
+    """The product (package, CUDA sources, C ABI header, C++ host mirror) never imports, links or
+    calls anything under oracle/."""
+    bad = re.compile(r"(import\s+oracle|from\s+oracle|msfem_oracle|orc_[a-z_]+\s*\(|oracle/_build)")
+    roots = [os.path.join(ROOT, "mpi_parallel_multiscale_diffusion_fem_b200"),
+             os.path.join(ROOT, "host"), os.path.join(ROOT, "include")]
+    n = 0
+    for root in roots:
+        for dirpath, dirs, files in os.walk(root):
+            dirs[:] = [d for d in dirs if d not in ("_build", "__pycache__")]
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp", ".cxx", "Makefile")):
+                    src = open(os.path.join(dirpath, f), errors="ignore").read()
+                    assert not bad.search(src), f
+                    n += 1
+    assert n >= 12
 
 
 def test_coarse_mesh_helpers(msb):

@@ -45,7 +45,8 @@ class Config(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libmsfem_basis.so")
+    # MSB_LIBRARY selects another build of the SAME library (e.g. the stage-timer profiling build)
+    return os.environ.get("MSB_LIBRARY") or os.path.join(_HERE, "libmsfem_basis.so")
 
 
 _lib = None

@@ -23,6 +23,38 @@
 
 #include "msb_internal.cuh"
 
+// Optional per-stage cycle timers (profiling build only: make EXTRA=-DMSB_STAGE_TIMERS).
+#ifdef MSB_STAGE_TIMERS
+__device__ unsigned long long g_msb_stage_cycles[16];
+#  define ST_DECL long long st_t0 = clock64(), st_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#  define ST_MARK(i)                       \
+    if (threadIdx.x == 0)                  \
+      {                                    \
+        const long long st_t1 = clock64(); \
+        st_acc[i] += st_t1 - st_t0;        \
+        st_t0 = st_t1;                     \
+      }
+#  define ST_FLUSH                                                              \
+    if (threadIdx.x == 0)                                                       \
+      for (int st_i = 0; st_i < 12; ++st_i)                                     \
+        atomicAdd(&g_msb_stage_cycles[st_i], (unsigned long long)st_acc[st_i]);
+extern "C" int
+msb_debug_stage_cycles(unsigned long long *out, int reset)
+{
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_msb_stage_cycles, sizeof(unsigned long long) * 16);
+  if (e == cudaSuccess && reset)
+    {
+      unsigned long long z[16] = {0};
+      e = cudaMemcpyToSymbol(g_msb_stage_cycles, z, sizeof z);
+    }
+  return (int)e;
+}
+#else
+#  define ST_DECL
+#  define ST_MARK(i)
+#  define ST_FLUSH
+#endif
+
 namespace msb
 {
   struct BpxParams
@@ -105,6 +137,48 @@ namespace msb
           // lanes >= NWARP hold partial garbage sums of zeros and real values: broadcast lane 0
           v[k] = __shfl_sync(0xffffffffu, s, 0);
         }
+    }
+
+    // a / b for finite b > 0 without the FP64 division sequence (every thread needs alpha and
+    // beta each iteration): 20-bit hardware reciprocal seed, three Newton steps (>= 53 bits),
+    // one correction step on the quotient
+    __device__ __forceinline__ double
+    fast_div(double a, double b)
+    {
+      double y;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+      double e = fma(-b, y, 1.0);
+      y        = fma(y, e, y);
+      e        = fma(-b, y, 1.0);
+      y        = fma(y, e, y);
+      e        = fma(-b, y, 1.0);
+      y        = fma(y, e, y);
+      const double q = a * y;
+      return fma(fma(-b, q, a), y, q);
+    }
+
+    // block-wide sums of TWO values with half the shuffles of two separate reductions: after
+    // the first exchange the lower half-warp carries value 0, the upper half-warp value 1
+    template <int NWARP>
+    __device__ __forceinline__ void
+    block_sum2(double &v0, double &v1, double *buf, int warp, int lane)
+    {
+      static_assert(NWARP <= 16, "one half-warp lane per warp partial");
+      const bool   up   = lane & 16;
+      const double recv = __shfl_xor_sync(0xffffffffu, up ? v0 : v1, 16);
+      double       s    = (up ? v1 : v0) + recv;
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+      if ((lane & 15) == 0)
+        buf[(lane >> 4) * NWARP + warp] = s;
+      __syncthreads();
+      double t = (lane & 15) < NWARP ? buf[(lane >> 4) * NWARP + (lane & 15)] : 0.0;
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1)
+        t += __shfl_xor_sync(0xffffffffu, t, off);
+      v0 = __shfl_sync(0xffffffffu, t, 0);
+      v1 = __shfl_sync(0xffffffffu, t, 16);
     }
 
     // symmetric 9-point stencil storage (the layout of Shard::d_sten, any level):
@@ -216,7 +290,7 @@ namespace msb
     };
 
     template <int NL, int NRHS, int THREADS>
-    __global__ void __launch_bounds__(THREADS, 1)
+    __global__ void __launch_bounds__(THREADS, (NL <= 5 && NRHS == 1 && THREADS <= 128) ? 3 : 1)
     solve_bpx_kernel(BpxParams P)
     {
       using C             = Cfg<NL, NRHS, THREADS>;
@@ -244,6 +318,7 @@ namespace msb
       const double *crn = P.corners + 8 * (size_t)cell;
       const double *q1  = P.q1coef + 16 * (size_t)cell;
 
+      ST_DECL
       // ---------------------------------------------------------------- prologue
       // (a) Galerkin hierarchy of the UNSCALED interior operator; scratch = p/u buffers.
       //     Level 1 reads the raw stencil from global memory, level l+1 reads level l.
@@ -303,6 +378,7 @@ namespace msb
           sD2[i] = S[ST_KD2 * N + g] * s10 * s01;
         }
       __syncthreads();
+      ST_MARK(0)
       // The prologue above (scaled operator + Galerkin diagonals) is shared by all 2^dim bases
       // of the cell: they are solved one group of NRHS after the other by this CTA.
 #pragma unroll 1
@@ -386,6 +462,7 @@ namespace msb
               }
           }
         __syncthreads();
+        ST_MARK(4)
         // Level sweeps.  "Wide" levels (>= 15x15 unknowns) are done by the whole CTA with a block
         // barrier each; the remaining tiny levels form a short serial chain on warp 0.
         // restrict(l): r_l = P^T r_{l-1} (full weighting); source of level 1 is the staged u.
@@ -400,22 +477,22 @@ namespace msb
               const int cx = 1 + (t & (W - 1)), cy = 1 + (t >> LG);
               if (cx > W - 1 || cy > W - 1)
                 continue;
-              double acc[NRHS];
-#pragma unroll
-              for (int k = 0; k < NRHS; ++k)
-                acc[k] = 0.0;
+              // three independent row sums, then combined (short dependency chains)
+              double row[3][NRHS], acc[NRHS];
 #pragma unroll
               for (int ay = -1; ay <= 1; ++ay)
+                {
+                  double a[NRHS], b[NRHS], c[NRHS];
+                  ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx - 1, a);
+                  ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx, b);
+                  ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx + 1, c);
 #pragma unroll
-                for (int ax = -1; ax <= 1; ++ax)
-                  {
-                    const double w = (ax == 0 ? 1.0 : 0.5) * (ay == 0 ? 1.0 : 0.5);
-                    double       u[NRHS];
-                    ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx + ax, u);
+                  for (int k = 0; k < NRHS; ++k)
+                    row[ay + 1][k] = fma(0.5, a[k] + c[k], b[k]);
+                }
 #pragma unroll
-                    for (int k = 0; k < NRHS; ++k)
-                      acc[k] = fma(w, u[k], acc[k]);
-                  }
+              for (int k = 0; k < NRHS; ++k)
+                acc[k] = fma(0.5, row[0][k] + row[2][k], row[1][k]);
               stv<NRHS>(Vl, cy * npl + cx, acc);
             }
         };
@@ -462,27 +539,151 @@ namespace msb
           restrict_level(lc, tid, THREADS);
           __syncthreads();
         });
-        // the tiny levels: down, coarsest scale, and back up, on warp 0
-        if constexpr (C::LEVELS > C::LW)
+        ST_MARK(5)
+        // the three tiny levels below the 15x15 level B = LW (7x7, 3x3, 1x1 unknowns)
+        if constexpr (C::LW >= 1)
           {
+            // No serial chain: their residuals are restricted DIRECTLY from level B (a product
+            // of full-weighting restrictions is the restriction with the nested hat function) by
+            // different warps in parallel, and their corrections are interpolated DIRECTLY back
+            // to level B (a product of bilinear interpolations is bilinear on the coarser grid).
+            static_assert(C::LEVELS == C::LW + 3, "levels below the 15x15 level");
+            constexpr int B   = C::LW, npB = 17;
+            double       *VB  = sV + (size_t)NRHS * C::lvl_off(B);
+            double       *V1  = sV + (size_t)NRHS * C::lvl_off(B + 1); // 9x9 nodes
+            double       *V2  = sV + (size_t)NRHS * C::lvl_off(B + 2); // 5x5 nodes
+            double       *V3  = sV + (size_t)NRHS * C::lvl_off(B + 3); // 3x3 nodes
+            const double *DB  = sDi + C::lvl_off(B), *D1 = sDi + C::lvl_off(B + 1);
+            const double *D2  = sDi + C::lvl_off(B + 2), *D3 = sDi + C::lvl_off(B + 3);
+            for (int task = warp; task < 12; task += NWARP)
+              {
+                if (task >= 10)
+                  {
+                    // level B+1: one thread per node, 3x3 window; stores t = r / D
+                    const int t = (task - 10) * 32 + lane;
+                    if (t < 49)
+                      {
+                        const int cx = 1 + t % 7, cy = 1 + t / 7, i = cy * 9 + cx;
+                        double    row[3][NRHS];
+#pragma unroll
+                        for (int ay = -1; ay <= 1; ++ay)
+                          {
+                            double a[NRHS], b[NRHS], c[NRHS];
+                            ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx - 1, a);
+                            ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx, b);
+                            ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx + 1, c);
+#pragma unroll
+                            for (int k = 0; k < NRHS; ++k)
+                              row[ay + 1][k] = fma(0.5, a[k] + c[k], b[k]);
+                          }
+                        const double di = D1[i];
+                        double       o[NRHS];
+#pragma unroll
+                        for (int k = 0; k < NRHS; ++k)
+                          o[k] = fma(0.5, row[0][k] + row[2][k], row[1][k]) * di;
+                        stv<NRHS>(V1, i, o);
+                      }
+                  }
+                else
+                  {
+                    // level B+2 (task 0..8: node of the 3x3 grid, 7x7 window, hat of width 4) or
+                    // level B+3 (task 9: the single node, 15x15 window, hat of width 8):
+                    // one warp per node, lanes stride over the window, shuffle reduction
+                    const bool   top = task == 9;
+                    const int    W = top ? 15 : 7, half = top ? 7 : 3, cx = top ? 8 : 4 * (1 + task % 3),
+                              cy = top ? 8 : 4 * (1 + task / 3);
+                    const double inv = top ? 0.125 : 0.25;
+                    double       acc[NRHS];
+#pragma unroll
+                    for (int k = 0; k < NRHS; ++k)
+                      acc[k] = 0.0;
+                    for (int e = lane; e < W * W; e += 32)
+                      {
+                        const int    ax = e % W - half, ay = e / W - half;
+                        const double w  = (1.0 - abs(ax) * inv) * (1.0 - abs(ay) * inv);
+                        double       u[NRHS];
+                        ldv<NRHS>(VB, (cy + ay) * npB + cx + ax, u);
+#pragma unroll
+                        for (int k = 0; k < NRHS; ++k)
+                          acc[k] = fma(w, u[k], acc[k]);
+                      }
+#pragma unroll
+                    for (int k = 0; k < NRHS; ++k)
+#pragma unroll
+                      for (int off = 16; off > 0; off >>= 1)
+                        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+                    if (lane == 0)
+                      {
+                        const int    i  = top ? 4 : (1 + task / 3) * 5 + 1 + task % 3;
+                        const double di = top ? D3[4] : D2[i];
+#pragma unroll
+                        for (int k = 0; k < NRHS; ++k)
+                          acc[k] *= di;
+                        stv<NRHS>(top ? V3 : V2, i, acc);
+                      }
+                  }
+              }
+            __syncthreads();
+            // z_B = r_B / D_B + interpolants of t_{B+1}, t_{B+2}, t_{B+3} at the level-B nodes
+            for (int t = tid; t < 256; t += THREADS)
+              {
+                const int fx = 1 + (t & 15), fy = 1 + (t >> 4);
+                if (fx > 15 || fy > 15)
+                  continue;
+                const int i = fy * npB + fx;
+                double    v[NRHS];
+                ldv<NRHS>(VB, i, v);
+                const double di = DB[i];
+#pragma unroll
+                for (int k = 0; k < NRHS; ++k)
+                  v[k] *= di;
+#pragma unroll
+                for (int m = 1; m <= 3; ++m)
+                  {
+                    const int     R = 1 << m, npm = (16 >> m) + 1;
+                    const double *Vm = m == 1 ? V1 : (m == 2 ? V2 : V3);
+                    const int     cx = fx >> m, cy = fy >> m;
+                    const double  gx = (fx & (R - 1)) * (1.0 / R), gy = (fy & (R - 1)) * (1.0 / R);
+                    double        a[NRHS], b[NRHS], c[NRHS], d[NRHS];
+                    ldv<NRHS>(Vm, cy * npm + cx, a);
+                    ldv<NRHS>(Vm, cy * npm + cx + 1, b);
+                    ldv<NRHS>(Vm, (cy + 1) * npm + cx, c);
+                    ldv<NRHS>(Vm, (cy + 1) * npm + cx + 1, d);
+#pragma unroll
+                    for (int k = 0; k < NRHS; ++k)
+                      {
+                        const double lo = fma(gx, b[k] - a[k], a[k]), hi = fma(gx, d[k] - c[k], c[k]);
+                        v[k] += fma(gy, hi - lo, lo);
+                      }
+                  }
+                stv<NRHS>(VB, i, v);
+              }
+            __syncthreads();
+            ST_MARK(6)
+            // up: the wide levels above B
+            for_levels_down<C::LW - 1, 1>([&](auto lc) {
+              prolong_level(lc, tid, THREADS);
+              __syncthreads();
+            });
+          }
+        else
+          {
+            // small local meshes (n <= 16): every coarse level on warp 0, serially
             if (warp == 0)
               {
-                for_levels<C::LW + 1, C::LEVELS>([&](auto lc) {
+                for_levels<1, C::LEVELS>([&](auto lc) {
                   restrict_level(lc, lane, 32);
                   __syncwarp();
                 });
-                for_levels_down<C::LEVELS, C::LW + 1>([&](auto lc) {
+                for_levels_down<C::LEVELS, 1>([&](auto lc) {
                   prolong_level(lc, lane, 32);
                   __syncwarp();
                 });
               }
             __syncthreads();
+            ST_MARK(6)
           }
-        // up: wide levels
-        for_levels_down<C::LW, 1>([&](auto lc) {
-          prolong_level(lc, tid, THREADS);
-          __syncthreads();
-        });
+        ST_MARK(7)
         // level 0: zhat = rhat + D^1/2 (P z_1)
         {
           constexpr int np1 = C::lvl_np(1);
@@ -522,7 +723,10 @@ namespace msb
 #pragma unroll
         for (int k = 0; k < NRHS; ++k)
           both[k] = rz[k], both[NRHS + k] = rr[k];
-        block_sum<2 * NRHS, NWARP>(both, sRed, warp, lane);
+        if constexpr (NRHS == 1 && NWARP <= 16)
+          block_sum2<NWARP>(both[0], both[1], sRed, warp, lane);
+        else
+          block_sum<2 * NRHS, NWARP>(both, sRed, warp, lane);
 #pragma unroll
         for (int k = 0; k < NRHS; ++k)
           rho[k] = both[k], exact[k] = both[NRHS + k];
@@ -536,6 +740,7 @@ namespace msb
       }
       __syncthreads();
 
+      ST_MARK(1)
       bool done[NRHS];
       int  kit[NRHS];
       bool all_done = true;
@@ -604,12 +809,14 @@ namespace msb
                     }
                 }
             }
+          ST_MARK(2)
           block_sum<NRHS, NWARP>(pq, sRed, warp, lane);
+          ST_MARK(3)
 
           double alpha[NRHS];
 #pragma unroll
           for (int k = 0; k < NRHS; ++k)
-            alpha[k] = done[k] ? 0.0 : rho[k] / pq[k];
+            alpha[k] = done[k] ? 0.0 : fast_div(rho[k], pq[k]);
 
           // ---- r -= alpha q ; z = M^-1 r ; rho' = r.z ; ||r||^2
 #pragma unroll
@@ -627,18 +834,22 @@ namespace msb
 #pragma unroll
             for (int k = 0; k < NRHS; ++k)
               both[k] = rz[k], both[NRHS + k] = rr[k];
-            block_sum<2 * NRHS, NWARP>(both, sRed + C::RED, warp, lane);
+            if constexpr (NRHS == 1 && NWARP <= 16)
+              block_sum2<NWARP>(both[0], both[1], sRed + C::RED, warp, lane);
+            else
+              block_sum<2 * NRHS, NWARP>(both, sRed + C::RED, warp, lane);
 #pragma unroll
             for (int k = 0; k < NRHS; ++k)
               rz[k] = both[k], rr[k] = both[NRHS + k];
           }
 
+          ST_MARK(8)
           double beta[NRHS];
           all_done = true;
 #pragma unroll
           for (int k = 0; k < NRHS; ++k)
             {
-              beta[k] = done[k] ? 0.0 : rz[k] / rho[k];
+              beta[k] = done[k] ? 0.0 : fast_div(rz[k], rho[k]);
               if (!done[k])
                 {
                   rho[k]   = rz[k];
@@ -673,6 +884,7 @@ namespace msb
                 }
             }
           __syncthreads();
+          ST_MARK(9)
         }
 
       // ---------------------------------------------------------------- epilogue
@@ -720,7 +932,9 @@ namespace msb
             }
         }
       __syncthreads(); // shared buffers are reused by the next group of bases
+      ST_MARK(10)
       } // grp
+      ST_FLUSH
     }
 
     template <int NL, int NRHS, int THREADS>
@@ -762,6 +976,10 @@ namespace msb
         case 5:
           if (s.variant == 1)
             return bpx::launch_one<5, 2, 256>(P, st);
+          if (s.variant == 2)
+            return bpx::launch_one<5, 1, 128>(P, st); // 3 CTAs per SM
+          if (s.variant == 3)
+            return bpx::launch_one<5, 2, 128>(P, st);
           return bpx::launch_one<5, 4, 256>(P, st);
         case 6:
           if (s.variant == 1)

@@ -156,7 +156,7 @@ def test_survey_crosscheck_on_gpu(msb, oracle):
 
 
 @pytest.mark.parametrize("l,variant", [(6, 0), (6, 1), (6, 100), (6, 101), (6, 102), (6, 103),
-                                       (5, 0), (5, 1), (5, 100), (5, 101), (5, 102), (4, 0), (3, 0)])
+                                       (5, 0), (5, 1), (5, 2), (5, 3), (5, 100), (5, 101), (5, 102), (4, 0), (3, 0)])
 def test_kernel_variants_agree(msb, oracle, l, variant):
     cd, co = _coeffs(msb, oracle, msb.COEFF_PERIODIC, (1.0 / 64, 0.9999))
     cor = msb.coarse_corners(7, 1000, 1003)

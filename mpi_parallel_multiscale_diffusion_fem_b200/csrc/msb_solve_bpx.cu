@@ -587,25 +587,58 @@ namespace msb
                 else
                   {
                     // level B+2 (task 0..8: node of the 3x3 grid, 7x7 window, hat of width 4) or
-                    // level B+3 (task 9: the single node, 15x15 window, hat of width 8):
-                    // one warp per node, lanes stride over the window, shuffle reduction
-                    const bool   top = task == 9;
-                    const int    W = top ? 15 : 7, half = top ? 7 : 3, cx = top ? 8 : 4 * (1 + task % 3),
-                              cy = top ? 8 : 4 * (1 + task / 3);
-                    const double inv = top ? 0.125 : 0.25;
-                    double       acc[NRHS];
+                    // level B+3 (task 9: the single node, 15x15 window, hat of width 8): one warp
+                    // per node, lane <-> (window column, row group), constant trip counts, then a
+                    // shuffle reduction.  The hat weights are separable: w = hx(ax) * hy(ay).
+                    const bool top = task == 9;
+                    double     acc[NRHS];
 #pragma unroll
                     for (int k = 0; k < NRHS; ++k)
                       acc[k] = 0.0;
-                    for (int e = lane; e < W * W; e += 32)
+                    if (top)
                       {
-                        const int    ax = e % W - half, ay = e / W - half;
-                        const double w  = (1.0 - abs(ax) * inv) * (1.0 - abs(ay) * inv);
-                        double       u[NRHS];
-                        ldv<NRHS>(VB, (cy + ay) * npB + cx + ax, u);
+                        // 30 lanes: column ax = lane % 15 - 7, rows [-7,0] (lanes < 15) or [1,7]
+                        const int  col = lane % 15, grp = lane / 15;
+                        if (grp < 2)
+                          {
+                            const double hx = 1.0 - abs(col - 7) * 0.125;
 #pragma unroll
-                        for (int k = 0; k < NRHS; ++k)
-                          acc[k] = fma(w, u[k], acc[k]);
+                            for (int j = 0; j < 8; ++j)
+                              {
+                                const int ay = grp ? 1 + j : j - 7;
+                                if (grp && j == 7)
+                                  break;
+                                const double hy = grp ? 1.0 - (1 + j) * 0.125 : 1.0 - (7 - j) * 0.125;
+                                double       u[NRHS];
+                                ldv<NRHS>(VB, (8 + ay) * npB + 1 + col, u);
+#pragma unroll
+                                for (int k = 0; k < NRHS; ++k)
+                                  acc[k] = fma(hy * hx, u[k], acc[k]);
+                              }
+                          }
+                      }
+                    else
+                      {
+                        // 28 lanes: column ax = lane % 7 - 3, rows ay = -3 + grp + 4 j, j = 0,1
+                        const int col = lane % 7, grp = lane / 7;
+                        const int cx = 4 * (1 + task % 3), cy = 4 * (1 + task / 3);
+                        if (grp < 4)
+                          {
+                            const double hx = 1.0 - abs(col - 3) * 0.25;
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+                              {
+                                const int ay = -3 + grp + 4 * j;
+                                if (ay > 3)
+                                  break;
+                                const double hy = 1.0 - abs(ay) * 0.25;
+                                double       u[NRHS];
+                                ldv<NRHS>(VB, (cy + ay) * npB + cx - 3 + col, u);
+#pragma unroll
+                                for (int k = 0; k < NRHS; ++k)
+                                  acc[k] = fma(hy * hx, u[k], acc[k]);
+                              }
+                          }
                       }
 #pragma unroll
                     for (int k = 0; k < NRHS; ++k)
@@ -684,27 +717,41 @@ namespace msb
             ST_MARK(6)
           }
         ST_MARK(7)
-        // level 0: zhat = rhat + D^1/2 (P z_1)
+        // level 0: zhat = rhat + D^1/2 (P z_1).  The strip of RPT fine rows (first row odd, RPT
+        // even) lies under RPT/2+1 coarse rows: their horizontal averages are loaded once and kept
+        // in registers (2 loads per coarse row instead of 4 per fine row).
         {
+          static_assert(RPT % 2 == 0, "strip must start on an odd row");
           constexpr int np1 = C::lvl_np(1);
-#pragma unroll
-          for (int j = 0; j < RPT; ++j)
+          if (colok)
             {
-              const int y = Y0 + j;
-              if (colok && y <= n - 1)
+              const int xl = X >> 1, xh = (X + 1) >> 1, cr0 = (Y0 - 1) >> 1;
+              double    h[RPT / 2 + 1][NRHS]; // 0.5 * (V1[cr][xl] + V1[cr][xh]); rows beyond n/2 are halo zeros
+#pragma unroll
+              for (int c = 0; c <= RPT / 2; ++c)
                 {
-                  const int xl = X >> 1, xh = (X + 1) >> 1, yl = y >> 1, yh = (y + 1) >> 1;
-                  double    a[NRHS], b[NRHS], c[NRHS], d[NRHS];
-                  ldv<NRHS>(sV, yl * np1 + xl, a);
-                  ldv<NRHS>(sV, yl * np1 + xh, b);
-                  ldv<NRHS>(sV, yh * np1 + xl, c);
-                  ldv<NRHS>(sV, yh * np1 + xh, d);
+                  const int cr = cr0 + c <= n / 2 ? cr0 + c : n / 2;
+                  double    a[NRHS], b[NRHS];
+                  ldv<NRHS>(sV, cr * np1 + xl, a);
+                  ldv<NRHS>(sV, cr * np1 + xh, b);
 #pragma unroll
                   for (int k = 0; k < NRHS; ++k)
+                    h[c][k] = 0.5 * (a[k] + b[k]);
+                }
+#pragma unroll
+              for (int j = 0; j < RPT; ++j)
+                {
+                  const int y = Y0 + j;
+                  if (y <= n - 1)
                     {
-                      const double cc = 0.25 * ((a[k] + b[k]) + (c[k] + d[k]));
-                      z[j][k]         = fma(sq[j], cc, r[j][k]);
-                      rz[k]           = fma(r[j][k], z[j][k], rz[k]);
+#pragma unroll
+                      for (int k = 0; k < NRHS; ++k)
+                        {
+                          // j even: y odd, between coarse rows j/2 and j/2+1; j odd: y even, on row (j+1)/2
+                          const double cc = (j & 1) ? h[(j + 1) / 2][k] : 0.5 * (h[j / 2][k] + h[j / 2 + 1][k]);
+                          z[j][k]         = fma(sq[j], cc, r[j][k]);
+                          rz[k]           = fma(r[j][k], z[j][k], rz[k]);
+                        }
                     }
                 }
             }
@@ -974,13 +1021,15 @@ namespace msb
         case 4:
           return bpx::launch_one<4, 4, 128>(P, st);
         case 5:
+          // small CTAs, two resident per SM, hide the barrier latency (measured: 1.52M vs 1.03M
+          // solves/s on cfg4 against one 256-thread CTA with all four bases)
           if (s.variant == 1)
             return bpx::launch_one<5, 2, 256>(P, st);
           if (s.variant == 2)
             return bpx::launch_one<5, 1, 128>(P, st); // 3 CTAs per SM
           if (s.variant == 3)
-            return bpx::launch_one<5, 2, 128>(P, st);
-          return bpx::launch_one<5, 4, 256>(P, st);
+            return bpx::launch_one<5, 4, 256>(P, st);
+          return bpx::launch_one<5, 2, 128>(P, st);
         case 6:
           if (s.variant == 1)
             return bpx::launch_one<6, 1, 256>(P, st);

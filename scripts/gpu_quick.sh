@@ -3,10 +3,8 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -x > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -12 gpurun_out/pytest_gpu.log
-python scripts/stage_timers.py target 1184
-python scripts/stage_timers.py cfg4 2368 0
-for wv in "target 0" "target 1" "cfg4 0" "cfg4 2" "cfg4 3" "cfg2 0" "cfg2 3"; do
+tail -6 gpurun_out/pytest_gpu.log
+for wv in "target 0" "cfg4 0" "cfg2 0" "cfg3 0"; do
   set -- $wv
   timeout 300 python bench.py --workload $1 --cells 5920 --variant $2 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/sweep_$1_v$2.json 2> gpurun_out/sweep_$1_v$2.err
   python - <<PY

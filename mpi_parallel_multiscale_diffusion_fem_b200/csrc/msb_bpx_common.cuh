@@ -1,0 +1,523 @@
+// msb_bpx_common.cuh -- device helpers shared by the shared-memory-resident multilevel PCG
+// kernels (msb_solve_bpx.cu: one right-hand side per pass; msb_solve_bpx_tm.cu: two, with
+// tensor memory as per-thread spill space).
+#pragma once
+
+#include <math.h>
+
+#include <type_traits>
+
+#include "msb_internal.cuh"
+
+// Optional per-stage cycle timers (profiling build only: make EXTRA=-DMSB_STAGE_TIMERS).
+#ifdef MSB_STAGE_TIMERS
+// the including .cu defines MSB_STAGE_ARRAY (its own __device__ unsigned long long [16])
+#  define ST_DECL long long st_t0 = clock64(), st_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#  define ST_MARK(i)                       \
+    if (threadIdx.x == 0)                  \
+      {                                    \
+        const long long st_t1 = clock64(); \
+        st_acc[i] += st_t1 - st_t0;        \
+        st_t0 = st_t1;                     \
+      }
+#  define ST_FLUSH                                                              \
+    if (threadIdx.x == 0)                                                       \
+      for (int st_i = 0; st_i < 12; ++st_i)                                     \
+        atomicAdd(&MSB_STAGE_ARRAY[st_i], (unsigned long long)st_acc[st_i]);
+#else
+#  define ST_DECL
+#  define ST_MARK(i)
+#  define ST_FLUSH
+#endif
+
+namespace msb
+{
+  struct BpxParams
+  {
+    const double *corners; // [C][8]
+    const double *q1coef;  // [C][16]
+    const double *sten;    // [C][6][N]
+    double       *phi;     // [C][4][N]
+    int32_t      *iters;   // [C][4]
+    double       *res;     // [C][4]
+    int32_t      *fail;
+    double        tol2;
+    int           max_iter;
+    int           n_cells;
+  };
+
+  // two right-hand sides per pass with tensor memory as spill space (msb_solve_bpx_tm.cu)
+  cudaError_t launch_solve_bpx_tm(const BpxParams &P, int threads, cudaStream_t st);
+
+  namespace bpx
+  {
+    template <int NRHS>
+    __device__ __forceinline__ void
+    ldv(const double *p, int idx, double (&o)[NRHS])
+    {
+      if constexpr (NRHS == 1)
+        o[0] = p[idx];
+      else
+        {
+#pragma unroll
+          for (int k = 0; k < NRHS; k += 2)
+            {
+              const double2 t = *reinterpret_cast<const double2 *>(p + (size_t)idx * NRHS + k);
+              o[k]     = t.x;
+              o[k + 1] = t.y;
+            }
+        }
+    }
+
+    template <int NRHS>
+    __device__ __forceinline__ void
+    stv(double *p, int idx, const double (&o)[NRHS])
+    {
+      if constexpr (NRHS == 1)
+        p[idx] = o[0];
+      else
+        {
+#pragma unroll
+          for (int k = 0; k < NRHS; k += 2)
+            *reinterpret_cast<double2 *>(p + (size_t)idx * NRHS + k) = make_double2(o[k], o[k + 1]);
+        }
+    }
+
+    // deterministic block-wide sums; stage 2 is one load per lane plus a shuffle butterfly
+    // (every thread ends with bitwise identical totals)
+    template <int NV, int NWARP>
+    __device__ __forceinline__ void
+    block_sum(double (&v)[NV], double *buf, int warp, int lane)
+    {
+      static_assert(NWARP <= 32, "one lane per warp partial");
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1)
+            v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+        }
+      if (lane == 0)
+        {
+#pragma unroll
+          for (int k = 0; k < NV; ++k)
+            buf[k * NWARP + warp] = v[k];
+        }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        {
+          double s = lane < NWARP ? buf[k * NWARP + lane] : 0.0;
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1)
+            if (off < NWARP || NWARP == 32)
+              s += __shfl_xor_sync(0xffffffffu, s, off);
+          // lanes >= NWARP hold partial garbage sums of zeros and real values: broadcast lane 0
+          v[k] = __shfl_sync(0xffffffffu, s, 0);
+        }
+    }
+
+    // a / b for finite b > 0 without the FP64 division sequence (every thread needs alpha and
+    // beta each iteration): 20-bit hardware reciprocal seed, three Newton steps (>= 53 bits),
+    // one correction step on the quotient
+    __device__ __forceinline__ double
+    fast_div(double a, double b)
+    {
+      double y;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+      double e = fma(-b, y, 1.0);
+      y        = fma(y, e, y);
+      e        = fma(-b, y, 1.0);
+      y        = fma(y, e, y);
+      e        = fma(-b, y, 1.0);
+      y        = fma(y, e, y);
+      const double q = a * y;
+      return fma(fma(-b, q, a), y, q);
+    }
+
+    // block-wide sums of TWO values with half the shuffles of two separate reductions: after
+    // the first exchange the lower half-warp carries value 0, the upper half-warp value 1
+    template <int NWARP>
+    __device__ __forceinline__ void
+    block_sum2(double &v0, double &v1, double *buf, int warp, int lane)
+    {
+      static_assert(NWARP <= 16, "one half-warp lane per warp partial");
+      const bool   up   = lane & 16;
+      const double recv = __shfl_xor_sync(0xffffffffu, up ? v0 : v1, 16);
+      double       s    = (up ? v1 : v0) + recv;
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+      if ((lane & 15) == 0)
+        buf[(lane >> 4) * NWARP + warp] = s;
+      __syncthreads();
+      double t = (lane & 15) < NWARP ? buf[(lane >> 4) * NWARP + (lane & 15)] : 0.0;
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1)
+        t += __shfl_xor_sync(0xffffffffu, t, off);
+      v0 = __shfl_sync(0xffffffffu, t, 0);
+      v1 = __shfl_sync(0xffffffffu, t, 16);
+    }
+
+    // symmetric 9-point stencil storage (the layout of Shard::d_sten, any level):
+    // entry of row node (x,y) towards (x+ex, y+ey); np = nodes per direction, N = np*np
+    __device__ __forceinline__ double
+    sten_get(const double *S, int np, int N, int x, int y, int ex, int ey)
+    {
+      const int i = y * np + x;
+      if (ey == 0)
+        return ex == 0 ? S[ST_KC * N + i] : S[ST_KE * N + (ex > 0 ? i : i - 1)];
+      if (ex == 0)
+        return S[ST_KN * N + (ey > 0 ? i : i - np)];
+      if (ex == ey)
+        return S[ST_KD1 * N + (ex > 0 ? i : i - np - 1)];
+      return S[ST_KD2 * N + (ey > 0 ? i - 1 : i - np)];
+    }
+
+    // One row of the Galerkin coarse operator P^T A P for bilinear P: the five entries of
+    // coarse node I = (X,Y) towards d = (0,0) (1,0) (0,1) (1,1) (-1,1).  Every fine stencil
+    // entry A(i, i+e), i = 2I + a, is loaded once and scattered (at compile time) into the
+    // entries it contributes to: (P^T A P)(I, I+d) = sum_a sum_e w(a) w(b) A(2I+a, 2I+a+e)
+    // with b = a + e - 2d, |b| <= 1.
+    __device__ __forceinline__ void
+    galerkin_row(const double *Sf, int npf, int Nf, int X, int Y, double (&acc)[5])
+    {
+      constexpr int ddx[5] = {0, 1, 0, 1, -1}, ddy[5] = {0, 0, 1, 1, 1};
+#pragma unroll
+      for (int d = 0; d < 5; ++d)
+        acc[d] = 0.0;
+#pragma unroll
+      for (int ay = -1; ay <= 1; ++ay)
+#pragma unroll
+        for (int ax = -1; ax <= 1; ++ax)
+          {
+            const double wa = (ax == 0 ? 1.0 : 0.5) * (ay == 0 ? 1.0 : 0.5);
+            const int    ix = 2 * X + ax, iy = 2 * Y + ay;
+#pragma unroll
+            for (int ey = -1; ey <= 1; ++ey)
+#pragma unroll
+              for (int ex = -1; ex <= 1; ++ex)
+                {
+                  const double v = wa * sten_get(Sf, npf, Nf, ix, iy, ex, ey);
+#pragma unroll
+                  for (int d = 0; d < 5; ++d)
+                    {
+                      const int bx = ax + ex - 2 * ddx[d], by = ay + ey - 2 * ddy[d];
+                      if (bx >= -1 && bx <= 1 && by >= -1 && by <= 1)
+                        acc[d] = fma((bx == 0 ? 1.0 : 0.5) * (by == 0 ? 1.0 : 0.5), v, acc[d]);
+                    }
+                }
+          }
+    }
+
+    // compile-time loops over levels (ascending / descending, inclusive bounds)
+    template <int L0, int L1, class F>
+    __device__ __forceinline__ void
+    for_levels(F &&f)
+    {
+      if constexpr (L0 <= L1)
+        {
+          f(std::integral_constant<int, L0>{});
+          for_levels<L0 + 1, L1>(f);
+        }
+    }
+    template <int L1, int L0, class F>
+    __device__ __forceinline__ void
+    for_levels_down(F &&f)
+    {
+      if constexpr (L1 >= L0)
+        {
+          f(std::integral_constant<int, L1>{});
+          for_levels_down<L1 - 1, L0>(f);
+        }
+    }
+
+
+    // level bookkeeping of the coarsened interior grids of an n = 2^NL local mesh
+    template <int NL>
+    struct Levels
+    {
+      static constexpr int n      = 1 << NL;
+      static constexpr int LEVELS = NL - 1;               // coarse levels 1..NL-1 (last: one unknown)
+      static constexpr int LW     = NL >= 4 ? NL - 4 : 0; // levels 1..LW have >= 15x15 unknowns
+      __host__ __device__ static constexpr int
+      lvl_np(int l)
+      {
+        return (n >> l) + 1;
+      }
+      __host__ __device__ static constexpr int
+      lvl_off(int l) // offset (in nodes) of level l >= 1 inside the packed level arrays
+      {
+        int o = 0;
+        for (int k = 1; k < l; ++k)
+          o += lvl_np(k) * lvl_np(k);
+        return o;
+      }
+      static constexpr int CN = lvl_off(NL); // total coarse nodes
+    };
+
+    // The coarse part of the multilevel preconditioner, entirely in shared memory:
+    // on entry sU holds the staged unscaled fine residual (stored and block-synchronised);
+    // on exit level 1 of sV holds z_1 = sum_{l>=1} P_{l->1} D_l^-1 P_l^T u (block-synchronised).
+    // sDi: reciprocal Galerkin diagonals of all levels (double or float storage).
+    template <int NL, int NRHS, int THREADS, class DiT>
+    __device__ __forceinline__ void
+    coarse_correction(const double *sU, double *sV, const DiT *sDi, int tid, int warp, int lane)
+    {
+      using L             = Levels<NL>;
+      constexpr int NWARP = THREADS / 32;
+      constexpr int n     = L::n;
+      constexpr int np    = n + 1;
+        // Level sweeps.  "Wide" levels (>= 15x15 unknowns) are done by the whole CTA with a block
+      // barrier each; the remaining tiny levels form a short serial chain on warp 0.
+      // restrict(l): r_l = P^T r_{l-1} (full weighting); source of level 1 is the staged u.
+      auto restrict_level = [&](auto lc, int first, int nthr) {
+        constexpr int l   = decltype(lc)::value;
+        constexpr int W   = n >> l, LG = NL - l, npl = W + 1;
+        constexpr int npf = (n >> (l - 1)) + 1;
+        const double *Vf  = l == 1 ? sU : sV + (size_t)NRHS * L::lvl_off(l - 1);
+        double       *Vl  = sV + (size_t)NRHS * L::lvl_off(l);
+        for (int t = first; t < W * W; t += nthr)
+          {
+            const int cx = 1 + (t & (W - 1)), cy = 1 + (t >> LG);
+            if (cx > W - 1 || cy > W - 1)
+              continue;
+            // three independent row sums, then combined (short dependency chains)
+            double row[3][NRHS], acc[NRHS];
+#pragma unroll
+            for (int ay = -1; ay <= 1; ++ay)
+              {
+                double a[NRHS], b[NRHS], c[NRHS];
+                ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx - 1, a);
+                ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx, b);
+                ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx + 1, c);
+#pragma unroll
+                for (int k = 0; k < NRHS; ++k)
+                  row[ay + 1][k] = fma(0.5, a[k] + c[k], b[k]);
+              }
+#pragma unroll
+            for (int k = 0; k < NRHS; ++k)
+              acc[k] = fma(0.5, row[0][k] + row[2][k], row[1][k]);
+            stv<NRHS>(Vl, cy * npl + cx, acc);
+          }
+      };
+      // prolong(l): z_l = r_l / D_l + P z_{l+1}  (coarsest level: z = r / D)
+      auto prolong_level = [&](auto lc, int first, int nthr) {
+        constexpr int l   = decltype(lc)::value;
+        constexpr int W   = n >> l, LG = NL - l, npl = W + 1;
+        double       *Vl  = sV + (size_t)NRHS * L::lvl_off(l);
+        const DiT *Dl  = sDi + L::lvl_off(l);
+        for (int t = first; t < W * W; t += nthr)
+          {
+            const int fx = 1 + (t & (W - 1)), fy = 1 + (t >> LG);
+            if (fx > W - 1 || fy > W - 1)
+              continue;
+            const int i = fy * npl + fx;
+            double    v[NRHS];
+            ldv<NRHS>(Vl, i, v);
+            const double di = Dl[i];
+            if constexpr (l < L::LEVELS)
+              {
+                constexpr int npc = (n >> (l + 1)) + 1;
+                const double *Vc  = sV + (size_t)NRHS * L::lvl_off(l + 1);
+                const int xl = fx >> 1, xh = (fx + 1) >> 1, yl = fy >> 1, yh = (fy + 1) >> 1;
+                double    a[NRHS], b[NRHS], c[NRHS], d[NRHS];
+                ldv<NRHS>(Vc, yl * npc + xl, a);
+                ldv<NRHS>(Vc, yl * npc + xh, b);
+                ldv<NRHS>(Vc, yh * npc + xl, c);
+                ldv<NRHS>(Vc, yh * npc + xh, d);
+#pragma unroll
+                for (int k = 0; k < NRHS; ++k)
+                  v[k] = fma(v[k], di, 0.25 * ((a[k] + b[k]) + (c[k] + d[k])));
+              }
+            else
+              {
+#pragma unroll
+                for (int k = 0; k < NRHS; ++k)
+                  v[k] *= di;
+              }
+            stv<NRHS>(Vl, i, v);
+          }
+      };
+      // down: wide levels
+      for_levels<1, L::LW>([&](auto lc) {
+        restrict_level(lc, tid, THREADS);
+        __syncthreads();
+      });
+      // the three tiny levels below the 15x15 level B = LW (7x7, 3x3, 1x1 unknowns)
+      if constexpr (L::LW >= 1)
+        {
+          // No serial chain: their residuals are restricted DIRECTLY from level B (a product
+          // of full-weighting restrictions is the restriction with the nested hat function) by
+          // different warps in parallel, and their corrections are interpolated DIRECTLY back
+          // to level B (a product of bilinear interpolations is bilinear on the coarser grid).
+          static_assert(L::LEVELS == L::LW + 3, "levels below the 15x15 level");
+          constexpr int B   = L::LW, npB = 17;
+          double       *VB  = sV + (size_t)NRHS * L::lvl_off(B);
+          double       *V1  = sV + (size_t)NRHS * L::lvl_off(B + 1); // 9x9 nodes
+          double       *V2  = sV + (size_t)NRHS * L::lvl_off(B + 2); // 5x5 nodes
+          double       *V3  = sV + (size_t)NRHS * L::lvl_off(B + 3); // 3x3 nodes
+          const DiT *DB  = sDi + L::lvl_off(B), *D1 = sDi + L::lvl_off(B + 1);
+          const DiT *D2  = sDi + L::lvl_off(B + 2), *D3 = sDi + L::lvl_off(B + 3);
+          for (int task = warp; task < 12; task += NWARP)
+            {
+              if (task >= 10)
+                {
+                  // level B+1: one thread per node, 3x3 window; stores t = r / D
+                  const int t = (task - 10) * 32 + lane;
+                  if (t < 49)
+                    {
+                      const int cx = 1 + t % 7, cy = 1 + t / 7, i = cy * 9 + cx;
+                      double    row[3][NRHS];
+#pragma unroll
+                      for (int ay = -1; ay <= 1; ++ay)
+                        {
+                          double a[NRHS], b[NRHS], c[NRHS];
+                          ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx - 1, a);
+                          ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx, b);
+                          ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx + 1, c);
+#pragma unroll
+                          for (int k = 0; k < NRHS; ++k)
+                            row[ay + 1][k] = fma(0.5, a[k] + c[k], b[k]);
+                        }
+                      const double di = D1[i];
+                      double       o[NRHS];
+#pragma unroll
+                      for (int k = 0; k < NRHS; ++k)
+                        o[k] = fma(0.5, row[0][k] + row[2][k], row[1][k]) * di;
+                      stv<NRHS>(V1, i, o);
+                    }
+                }
+              else
+                {
+                  // level B+2 (task 0..8: node of the 3x3 grid, 7x7 window, hat of width 4) or
+                  // level B+3 (task 9: the single node, 15x15 window, hat of width 8): one warp
+                  // per node, lane <-> (window column, row group), constant trip counts, then a
+                  // shuffle reduction.  The hat weights are separable: w = hx(ax) * hy(ay).
+                  const bool top = task == 9;
+                  double     acc[NRHS];
+#pragma unroll
+                  for (int k = 0; k < NRHS; ++k)
+                    acc[k] = 0.0;
+                  if (top)
+                    {
+                      // 30 lanes: column ax = lane % 15 - 7, rows [-7,0] (lanes < 15) or [1,7]
+                      const int  col = lane % 15, grp = lane / 15;
+                      if (grp < 2)
+                        {
+                          const double hx = 1.0 - abs(col - 7) * 0.125;
+#pragma unroll
+                          for (int j = 0; j < 8; ++j)
+                            {
+                              const int ay = grp ? 1 + j : j - 7;
+                              if (grp && j == 7)
+                                break;
+                              const double hy = grp ? 1.0 - (1 + j) * 0.125 : 1.0 - (7 - j) * 0.125;
+                              double       u[NRHS];
+                              ldv<NRHS>(VB, (8 + ay) * npB + 1 + col, u);
+#pragma unroll
+                              for (int k = 0; k < NRHS; ++k)
+                                acc[k] = fma(hy * hx, u[k], acc[k]);
+                            }
+                        }
+                    }
+                  else
+                    {
+                      // 28 lanes: column ax = lane % 7 - 3, rows ay = -3 + grp + 4 j, j = 0,1
+                      const int col = lane % 7, grp = lane / 7;
+                      const int cx = 4 * (1 + task % 3), cy = 4 * (1 + task / 3);
+                      if (grp < 4)
+                        {
+                          const double hx = 1.0 - abs(col - 3) * 0.25;
+#pragma unroll
+                          for (int j = 0; j < 2; ++j)
+                            {
+                              const int ay = -3 + grp + 4 * j;
+                              if (ay > 3)
+                                break;
+                              const double hy = 1.0 - abs(ay) * 0.25;
+                              double       u[NRHS];
+                              ldv<NRHS>(VB, (cy + ay) * npB + cx - 3 + col, u);
+#pragma unroll
+                              for (int k = 0; k < NRHS; ++k)
+                                acc[k] = fma(hy * hx, u[k], acc[k]);
+                            }
+                        }
+                    }
+#pragma unroll
+                  for (int k = 0; k < NRHS; ++k)
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1)
+                      acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+                  if (lane == 0)
+                    {
+                      const int    i  = top ? 4 : (1 + task / 3) * 5 + 1 + task % 3;
+                      const double di = top ? D3[4] : D2[i];
+#pragma unroll
+                      for (int k = 0; k < NRHS; ++k)
+                        acc[k] *= di;
+                      stv<NRHS>(top ? V3 : V2, i, acc);
+                    }
+                }
+            }
+          __syncthreads();
+          // z_B = r_B / D_B + interpolants of t_{B+1}, t_{B+2}, t_{B+3} at the level-B nodes
+          for (int t = tid; t < 256; t += THREADS)
+            {
+              const int fx = 1 + (t & 15), fy = 1 + (t >> 4);
+              if (fx > 15 || fy > 15)
+                continue;
+              const int i = fy * npB + fx;
+              double    v[NRHS];
+              ldv<NRHS>(VB, i, v);
+              const double di = DB[i];
+#pragma unroll
+              for (int k = 0; k < NRHS; ++k)
+                v[k] *= di;
+#pragma unroll
+              for (int m = 1; m <= 3; ++m)
+                {
+                  const int     R = 1 << m, npm = (16 >> m) + 1;
+                  const double *Vm = m == 1 ? V1 : (m == 2 ? V2 : V3);
+                  const int     cx = fx >> m, cy = fy >> m;
+                  const double  gx = (fx & (R - 1)) * (1.0 / R), gy = (fy & (R - 1)) * (1.0 / R);
+                  double        a[NRHS], b[NRHS], c[NRHS], d[NRHS];
+                  ldv<NRHS>(Vm, cy * npm + cx, a);
+                  ldv<NRHS>(Vm, cy * npm + cx + 1, b);
+                  ldv<NRHS>(Vm, (cy + 1) * npm + cx, c);
+                  ldv<NRHS>(Vm, (cy + 1) * npm + cx + 1, d);
+#pragma unroll
+                  for (int k = 0; k < NRHS; ++k)
+                    {
+                      const double lo = fma(gx, b[k] - a[k], a[k]), hi = fma(gx, d[k] - c[k], c[k]);
+                      v[k] += fma(gy, hi - lo, lo);
+                    }
+                }
+              stv<NRHS>(VB, i, v);
+            }
+          __syncthreads();
+          // up: the wide levels above B
+          for_levels_down<L::LW - 1, 1>([&](auto lc) {
+            prolong_level(lc, tid, THREADS);
+            __syncthreads();
+          });
+        }
+      else
+        {
+          // small local meshes (n <= 16): every coarse level on warp 0, serially
+          if (warp == 0)
+            {
+              for_levels<1, L::LEVELS>([&](auto lc) {
+                restrict_level(lc, lane, 32);
+                __syncwarp();
+              });
+              for_levels_down<L::LEVELS, 1>([&](auto lc) {
+                prolong_level(lc, lane, 32);
+                __syncwarp();
+              });
+            }
+          __syncthreads();
+        }
+    }
+  } // namespace bpx
+} // namespace msb

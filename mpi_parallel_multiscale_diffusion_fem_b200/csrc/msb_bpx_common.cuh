@@ -12,7 +12,7 @@
 // Optional per-stage cycle timers (profiling build only: make EXTRA=-DMSB_STAGE_TIMERS).
 #ifdef MSB_STAGE_TIMERS
 // the including .cu defines MSB_STAGE_ARRAY (its own __device__ unsigned long long [16])
-#  define ST_DECL long long st_t0 = clock64(), st_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#  define ST_DECL long long st_t0 = clock64(), st_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #  define ST_MARK(i)                       \
     if (threadIdx.x == 0)                  \
       {                                    \
@@ -22,7 +22,7 @@
       }
 #  define ST_FLUSH                                                              \
     if (threadIdx.x == 0)                                                       \
-      for (int st_i = 0; st_i < 12; ++st_i)                                     \
+      for (int st_i = 0; st_i < 16; ++st_i)                                     \
         atomicAdd(&MSB_STAGE_ARRAY[st_i], (unsigned long long)st_acc[st_i]);
 #else
 #  define ST_DECL
@@ -260,9 +260,10 @@ namespace msb
     // on entry sU holds the staged unscaled fine residual (stored and block-synchronised);
     // on exit level 1 of sV holds z_1 = sum_{l>=1} P_{l->1} D_l^-1 P_l^T u (block-synchronised).
     // sDi: reciprocal Galerkin diagonals of all levels (double or float storage).
-    template <int NL, int NRHS, int THREADS, class DiT>
+    // mark(i): optional stage-timer hook (a no-op lambda in production builds)
+    template <int NL, int NRHS, int THREADS, class DiT, class Mark>
     __device__ __forceinline__ void
-    coarse_correction(const double *sU, double *sV, const DiT *sDi, int tid, int warp, int lane)
+    coarse_correction(const double *sU, double *sV, const DiT *sDi, int tid, int warp, int lane, Mark &&mark)
     {
       using L             = Levels<NL>;
       constexpr int NWARP = THREADS / 32;
@@ -344,6 +345,7 @@ namespace msb
         restrict_level(lc, tid, THREADS);
         __syncthreads();
       });
+      mark(5);
       // the three tiny levels below the 15x15 level B = LW (7x7, 3x3, 1x1 unknowns)
       if constexpr (L::LW >= 1)
         {
@@ -461,6 +463,7 @@ namespace msb
                 }
             }
           __syncthreads();
+          mark(6);
           // z_B = r_B / D_B + interpolants of t_{B+1}, t_{B+2}, t_{B+3} at the level-B nodes
           for (int t = tid; t < 256; t += THREADS)
             {
@@ -496,6 +499,7 @@ namespace msb
               stv<NRHS>(VB, i, v);
             }
           __syncthreads();
+          mark(7);
           // up: the wide levels above B
           for_levels_down<L::LW - 1, 1>([&](auto lc) {
             prolong_level(lc, tid, THREADS);

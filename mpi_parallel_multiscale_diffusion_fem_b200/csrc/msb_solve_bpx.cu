@@ -249,8 +249,11 @@ namespace msb
         __syncthreads();
         ST_MARK(4)
         ST_MARK(5)
-        coarse_correction<NL, NRHS, THREADS>(sU, sV, sDi, tid, warp, lane);
-        ST_MARK(7)
+        coarse_correction<NL, NRHS, THREADS>(sU, sV, sDi, tid, warp, lane, [&](int st_k) {
+          (void)st_k;
+          ST_MARK(st_k)
+        });
+        ST_MARK(11)
         // level 0: zhat = rhat + D^1/2 (P z_1).  The strip of RPT fine rows (first row odd, RPT
         // even) lies under RPT/2+1 coarse rows: their horizontal averages are loaded once and kept
         // in registers (2 loads per coarse row instead of 4 per fine row).
@@ -565,13 +568,15 @@ namespace msb
             return bpx::launch_one<5, 4, 256>(P, st);
           return bpx::launch_one<5, 2, 128>(P, st);
         case 6:
-          if (s.variant == 4)
-            return launch_solve_bpx_tm(P, 512, st);
+          // default: two bases in flight per CTA, tensor memory as spill space (1.07M vs 0.89M
+          // solves/s on the target configuration against one basis per pass)
           if (s.variant == 5)
             return launch_solve_bpx_tm(P, 256, st);
+          if (s.variant == 6)
+            return bpx::launch_one<6, 1, 512>(P, st);
           if (s.variant == 1)
             return bpx::launch_one<6, 1, 256>(P, st);
-          return bpx::launch_one<6, 1, 512>(P, st);
+          return launch_solve_bpx_tm(P, 512, st);
         default:
           return cudaErrorInvalidValue;
       }

@@ -345,8 +345,11 @@ namespace msb
               }
             __syncthreads();
             ST_MARK(4)
-            coarse_correction<NL, NRHS, THREADS>(sP, sV, sDi, tid, warp, lane);
-            ST_MARK(5)
+            coarse_correction<NL, NRHS, THREADS>(sP, sV, sDi, tid, warp, lane, [&](int st_k) {
+              (void)st_k;
+              ST_MARK(st_k)
+            });
+            ST_MARK(11)
             // level 0: zhat = rhat + D^1/2 (P z_1), coarse-row averages cached in registers
             {
               constexpr int np1 = L::lvl_np(1);

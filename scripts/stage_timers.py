@@ -14,10 +14,11 @@ import mpi_parallel_multiscale_diffusion_fem_b200 as pkg  # noqa: E402
 from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc  # noqa: E402
 from bench import WORKLOADS  # noqa: E402
 
-NAMES = ["prologue (scale + Galerkin)", "rhs init + z0", "stencil q=Ap", "reduce p.q",
-         "r update + stage u (+barrier)", "restrict wide levels", "warp-0 coarse chain",
-         "prolong wide levels", "fine prolong + reduce r.z,|r|", "p update (+barrier)",
-         "epilogue (write phi)"]
+NAMES = {0: "prologue (scale + Galerkin)", 1: "rhs init + z0", 2: "stencil q=Ap", 3: "reduce p.q",
+         4: "r update + stage u (+barrier)", 5: "restrict 0->1->2 (wide levels)",
+         6: "direct restrict to 7x7/3x3/1x1", 7: "direct interpolate to 15x15", 11: "prolong 2->1 (wide)",
+         8: "fine prolong + reduce r.z,|r|", 9: "p update (+barrier)", 10: "epilogue (write phi)"}
+ORDER = [0, 1, 2, 3, 4, 5, 6, 7, 11, 8, 9, 10]
 
 
 def main():
@@ -29,19 +30,23 @@ def main():
     out = (C.c_ulonglong * 16)()
     with pkg.BasisShard(l, pkg.coarse_corners(r, 0, cells), coeff_desc(kind, par, seed), variant=variant) as sh:
         sh.run(1e-12, 5000)
-        lib.msb_debug_stage_cycles(out, 1)
+        fn = lib.msb_debug_stage_cycles_tm if (l == 6 and variant in (0, 5)) else lib.msb_debug_stage_cycles
+        fn(out, 1)
         sh.run(1e-12, 5000)
-        lib.msb_debug_stage_cycles(out, 1)
+        fn(out, 1)
         it, _ = sh.iteration_counts()
         st = sh.run_stats()
-    cyc = np.array(out[:11], dtype=np.float64)
+    cyc = np.array(out[:12], dtype=np.float64)
     tot = cyc.sum()
     n_iter = it.sum() / (4.0 / max(1, 4 // (4 if l <= 5 and variant == 0 else 1)))  # per solve-group iterations
     print("workload %s cells %d l=%d variant %d: solve kernel %.3f ms, mean k %.1f" %
           (wl, cells, l, variant, st["ms_solve"], it.mean()))
-    print("cycles per CTA: %.0f  (per group-iteration: %.0f)" % (tot / cells, tot / it[:, 0].sum() if l <= 5 else tot / it.sum()))
-    for nm, c in zip(NAMES, cyc):
-        per_it = c / (it[:, 0].sum() if l <= 5 else it.sum())
+    nrhs = 2 if (l == 6 and variant in (0, 5)) or (l == 5 and variant == 0) else (4 if l <= 5 and variant == 3 else 1)
+    group_its = it.sum() / nrhs
+    print("cycles per CTA: %.0f  (per pass-iteration of %d bases: %.0f)" % (tot / cells, nrhs, tot / group_its))
+    for idx in ORDER:
+        nm, c = NAMES[idx], cyc[idx]
+        per_it = c / group_its
         print("  %-34s %5.1f%%   %8.0f cycles/iteration" % (nm, 100 * c / tot, per_it))
 
 

@@ -260,8 +260,71 @@ namespace msb
     // on entry sU holds the staged unscaled fine residual (stored and block-synchronised);
     // on exit level 1 of sV holds z_1 = sum_{l>=1} P_{l->1} D_l^-1 P_l^T u (block-synchronised).
     // sDi: reciprocal Galerkin diagonals of all levels (double or float storage).
-    // mark(i): optional stage-timer hook (a no-op lambda in production builds)
-    template <int NL, int NRHS, int THREADS, class DiT, class Mark>
+    // Staging of the fine residual for the restriction to level 1 (local meshes with n >= 32):
+    // the thread that owns column X and fine rows Y0 .. Y0+RPT-1 (Y0 odd, RPT even) forms the
+    // VERTICAL full-weighting sums of its own strip in registers and stores
+    //   - the RPT/2-1 complete coarse rows and the partial sum of the coarse row on the upper
+    //     strip edge into T[cy][col(X)],
+    //   - half its first row (the missing part of the coarse row on the lower strip edge)
+    //     into TB[strip][col(X)],
+    // with the columns de-interleaved (odd X in the upper half of a row) so that the horizontal
+    // 3-point combination of the level-1 stage reads consecutive addresses.
+    template <int NL, int NRHS, int RPT>
+    struct Presum
+    {
+      static constexpr int n = 1 << NL, ROW = n, HALF = RPT / 2;
+      static constexpr int TB = (n / 2) * ROW; // entry offset of the strip-edge contributions
+      __device__ static __forceinline__ int
+      col(int X)
+      {
+        return (X & 1) * (n / 2) + (X >> 1);
+      }
+      // Streaming form: call for j = 0 .. RPT-1 in order (j is a compile-time constant after
+      // unrolling) with u_j = the unscaled residual of row Y0+j (zero beyond the mesh); `acc`
+      // carries the running vertical sum, so only one row is live at a time.
+      __device__ static __forceinline__ void
+      push(double *sT, int j, const double (&uj)[NRHS], double (&acc)[NRHS], int c, int wy, bool colok)
+      {
+        const int cr0 = HALF * wy;
+        if ((j & 1) == 0)
+          {
+            if (j > 0)
+              {
+                // row j closes coarse row cr0 + j/2:  0.5 u[j-2] + u[j-1] + 0.5 u[j]
+                double v[NRHS];
+#pragma unroll
+                for (int k = 0; k < NRHS; ++k)
+                  v[k] = fma(0.5, uj[k], acc[k]);
+                if (colok && cr0 + j / 2 <= n / 2 - 1)
+                  stv<NRHS>(sT, (cr0 + j / 2) * ROW + c, v);
+              }
+            else if (colok && wy >= 1)
+              {
+                // half the first row: the missing part of the coarse row on the lower strip edge
+                double v[NRHS];
+#pragma unroll
+                for (int k = 0; k < NRHS; ++k)
+                  v[k] = 0.5 * uj[k];
+                stv<NRHS>(sT, TB + wy * ROW + c, v);
+              }
+#pragma unroll
+            for (int k = 0; k < NRHS; ++k)
+              acc[k] = 0.5 * uj[k];
+          }
+        else
+          {
+#pragma unroll
+            for (int k = 0; k < NRHS; ++k)
+              acc[k] += uj[k];
+            if (j == RPT - 1 && colok && cr0 + HALF <= n / 2 - 1)
+              stv<NRHS>(sT, (cr0 + HALF) * ROW + c, acc); // partial sum of the upper strip edge
+          }
+      }
+    };
+
+    // mark(i): optional stage-timer hook (a no-op lambda in production builds).
+    // RPT > 0: sU holds the pre-summed strips of Presum<NL,NRHS,RPT>; RPT == 0: sU holds u itself.
+    template <int NL, int NRHS, int THREADS, int RPT, class DiT, class Mark>
     __device__ __forceinline__ void
     coarse_correction(const double *sU, double *sV, const DiT *sDi, int tid, int warp, int lane, Mark &&mark)
     {
@@ -341,10 +404,52 @@ namespace msb
           }
       };
       // down: wide levels
-      for_levels<1, L::LW>([&](auto lc) {
-        restrict_level(lc, tid, THREADS);
-        __syncthreads();
-      });
+      if constexpr (RPT > 0)
+        {
+          // level 1 from the pre-summed strips: horizontal 3-point combination, conflict-free
+          static_assert(L::LW >= 1, "pre-summed staging needs a wide level 1");
+          using PS          = Presum<NL, NRHS, RPT>;
+          constexpr int W   = n >> 1, LG = NL - 1, np1 = W + 1;
+          for (int t = tid; t < W * W; t += THREADS)
+            {
+              const int cx = 1 + (t & (W - 1)), cy = 1 + (t >> LG);
+              if (cx > W - 1 || cy > W - 1)
+                continue;
+              const double *row = sU + (size_t)NRHS * (cy * PS::ROW);
+              double        a[NRHS], b[NRHS], c[NRHS];
+              ldv<NRHS>(row, W + cx - 1, a); // X = 2cx-1
+              ldv<NRHS>(row, cx, b);         // X = 2cx
+              ldv<NRHS>(row, W + cx, c);     // X = 2cx+1
+              if (cy % PS::HALF == 0)
+                {
+                  const double *rb = sU + (size_t)NRHS * (PS::TB + (cy / PS::HALF) * PS::ROW);
+                  double        a2[NRHS], b2[NRHS], c2[NRHS];
+                  ldv<NRHS>(rb, W + cx - 1, a2);
+                  ldv<NRHS>(rb, cx, b2);
+                  ldv<NRHS>(rb, W + cx, c2);
+#pragma unroll
+                  for (int k = 0; k < NRHS; ++k)
+                    a[k] += a2[k], b[k] += b2[k], c[k] += c2[k];
+                }
+              double o[NRHS];
+#pragma unroll
+              for (int k = 0; k < NRHS; ++k)
+                o[k] = fma(0.5, a[k] + c[k], b[k]);
+              stv<NRHS>(sV, cy * np1 + cx, o);
+            }
+          __syncthreads();
+          for_levels<2, L::LW>([&](auto lc) {
+            restrict_level(lc, tid, THREADS);
+            __syncthreads();
+          });
+        }
+      else
+        {
+          for_levels<1, L::LW>([&](auto lc) {
+            restrict_level(lc, tid, THREADS);
+            __syncthreads();
+          });
+        }
       mark(5);
       // the three tiny levels below the 15x15 level B = LW (7x7, 3x3, 1x1 unknowns)
       if constexpr (L::LW >= 1)

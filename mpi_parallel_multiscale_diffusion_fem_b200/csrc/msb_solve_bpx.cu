@@ -82,6 +82,7 @@ namespace msb
       constexpr int n     = C::n, np = C::np, N = C::N;
       constexpr int NWARP = C::NWARP, WX = C::WX, RPT = C::RPT;
       constexpr int GROUPS = 4 / NRHS;
+      constexpr int PRESUM_RPT = C::LW >= 1 ? RPT : 0; // pre-summed residual staging (n >= 32)
       constexpr int CN     = C::CN;
 
       extern __shared__ __align__(16) double smem[];
@@ -229,27 +230,33 @@ namespace msb
       // ------------------------------------------------ the preconditioner zhat = Mhat^-1 rhat
       // returns z in `q` (register array reuse), accumulates rz = rhat.zhat and rr = ||r||^2
       auto precondition = [&](double (&z)[RPT][NRHS], double (&rz)[NRHS], double (&rr)[NRHS]) {
-        // u = D^1/2 rhat = unscaled residual, staged for the restriction
+        // u = D^1/2 rhat = unscaled residual, staged for the restriction: as pre-summed strips
+        // (Presum) when level 1 is a wide level, else as plain values
+        {
+          using PS = Presum<NL, NRHS, RPT>;
+          double    acc[NRHS];
+          const int pc = PS::col(X);
 #pragma unroll
-        for (int j = 0; j < RPT; ++j)
-          {
-            const int y = Y0 + j;
-            if (colok && y <= n - 1)
-              {
-                double u[NRHS];
+          for (int j = 0; j < RPT; ++j)
+            {
+              double u[NRHS];
 #pragma unroll
-                for (int k = 0; k < NRHS; ++k)
-                  {
-                    u[k]  = sq[j] * r[j][k];
-                    rr[k] = fma(u[k], u[k], rr[k]);
-                  }
-                stv<NRHS>(sU, y * np + X, u);
-              }
-          }
+              for (int k = 0; k < NRHS; ++k)
+                {
+                  u[k]  = sq[j] * r[j][k]; // zero on rows / columns beyond the mesh
+                  rr[k] = fma(u[k], u[k], rr[k]);
+                }
+              if constexpr (PRESUM_RPT > 0)
+                PS::push(sU, j, u, acc, pc, wy, colok);
+              else if (colok && Y0 + j <= n - 1)
+                stv<NRHS>(sU, (Y0 + j) * np + X, u);
+            }
+          (void)acc, (void)pc;
+        }
         __syncthreads();
         ST_MARK(4)
         ST_MARK(5)
-        coarse_correction<NL, NRHS, THREADS>(sU, sV, sDi, tid, warp, lane, [&](int st_k) {
+        coarse_correction<NL, NRHS, THREADS, PRESUM_RPT>(sU, sV, sDi, tid, warp, lane, [&](int st_k) {
           (void)st_k;
           ST_MARK(st_k)
         });

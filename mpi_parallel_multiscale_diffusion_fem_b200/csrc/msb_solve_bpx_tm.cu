@@ -275,6 +275,24 @@ namespace msb
           __syncthreads();
 
           double r[RPT][NRHS], q[RPT][NRHS];
+          // the pre-summed residual strips share the vector buffer with p and overwrite parts of
+          // p's zero halo: restore the halo whenever p is rewritten
+          auto zero_halo = [&]() {
+            const double zero2[NRHS] = {0.0, 0.0};
+            for (int t = tid; t < 4 * n; t += THREADS)
+              {
+                int jx, jy;
+                if (t < n)
+                  jx = t, jy = 0;
+                else if (t < 2 * n)
+                  jx = n, jy = t - n;
+                else if (t < 3 * n)
+                  jx = n - (t - 2 * n), jy = n;
+                else
+                  jx = 0, jy = n - (t - 3 * n);
+                stv<NRHS>(sP, jy * np + jx, zero2);
+              }
+          };
 
           // (e) rhat_0 = -D^-1/2 K_IB g_B ; x = 0 in tensor memory
 #pragma unroll
@@ -320,32 +338,34 @@ namespace msb
 
           // ------------------------------------------ zhat = Mhat^-1 rhat (into z), r.z and ||r||^2
           auto precondition = [&](double (&z)[RPT][NRHS], double (&rz)[NRHS], double (&rr)[NRHS]) {
-            // u = D^1/2 rhat staged into the vector buffer (p is dead: saved in tensor memory)
+            // u = D^1/2 rhat, pre-summed per strip (Presum) into the vector buffer (p is dead there:
+            // it is saved in tensor memory)
+            {
+              using PS = Presum<NL, NRHS, RPT>;
+              double    acc[NRHS];
+              const int pc = PS::col(X);
 #pragma unroll
-            for (int c = 0; c < RPT / 8; ++c)
-              {
-                double sq8[8];
-                tmem_ld8(tm + C::SOFF + 16 * c, sq8);
+              for (int c = 0; c < RPT / 8; ++c)
+                {
+                  double sq8[8];
+                  tmem_ld8(tm + C::SOFF + 16 * c, sq8);
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                  {
-                    const int j = 8 * c + jj, y = Y0 + j;
-                    if (colok && y <= n - 1)
-                      {
-                        double u[NRHS];
+                  for (int jj = 0; jj < 8; ++jj)
+                    {
+                      double u[NRHS];
 #pragma unroll
-                        for (int k = 0; k < NRHS; ++k)
-                          {
-                            u[k]  = sq8[jj] * r[j][k];
-                            rr[k] = fma(u[k], u[k], rr[k]);
-                          }
-                        stv<NRHS>(sP, y * np + X, u);
-                      }
-                  }
-              }
+                      for (int k = 0; k < NRHS; ++k)
+                        {
+                          u[k]  = sq8[jj] * r[8 * c + jj][k]; // zero beyond the mesh
+                          rr[k] = fma(u[k], u[k], rr[k]);
+                        }
+                      PS::push(sP, 8 * c + jj, u, acc, pc, wy, colok);
+                    }
+                }
+            }
             __syncthreads();
             ST_MARK(4)
-            coarse_correction<NL, NRHS, THREADS>(sP, sV, sDi, tid, warp, lane, [&](int st_k) {
+            coarse_correction<NL, NRHS, THREADS, RPT>(sP, sV, sDi, tid, warp, lane, [&](int st_k) {
               (void)st_k;
               ST_MARK(st_k)
             });
@@ -417,6 +437,7 @@ namespace msb
                   }
                 tmem_st8(tm + C::POFF + 16 * c, p8);
               }
+            zero_halo();
             tmem_wait_st();
           }
           __syncthreads();
@@ -557,6 +578,7 @@ namespace msb
                   tmem_st8(tm + C::XOFF + 16 * c, x8);
                   tmem_st8(tm + C::POFF + 16 * c, p8);
                 }
+              zero_halo();
               tmem_wait_st();
               __syncthreads();
               ST_MARK(9)

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -x > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -6 gpurun_out/pytest_gpu.log
-for wv in "target 0" "target 4" "target 5" "cfg3 4"; do
+for wv in "target 0" "target 6" "cfg4 0" "cfg2 0"; do
   set -- $wv
   timeout 300 python bench.py --workload $1 --cells 5920 --variant $2 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/sweep_$1_v$2.json 2> gpurun_out/sweep_$1_v$2.err
   python - <<PY
@@ -19,3 +19,4 @@ done
 timeout 900 python bench.py > gpurun_out/bench_target.json 2> gpurun_out/bench_target.err
 cut -c1-300 gpurun_out/bench_target.json
 tail -3 gpurun_out/bench_target.err
+python scripts/stage_timers.py target 1184 0

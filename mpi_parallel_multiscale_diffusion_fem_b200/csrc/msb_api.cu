@@ -120,7 +120,8 @@ free_shard(Shard &s)
   cudaSetDevice(s.device);
   void *ptrs[] = {s.d_corners, s.d_q1coef, s.d_table, s.d_sten, s.d_phi,  s.d_M,    s.d_b,
                   s.d_iters,   s.d_res,    s.d_fail,  s.d_dofmap, s.d_invmap, s.d_gsol, s.d_tmp,
-                  s.d_wr,      s.d_wp,     s.d_wq,    s.d_scal, s.d_part, s.d_flags};
+                  s.d_wr,      s.d_wp,     s.d_wq,    s.d_scal, s.d_part, s.d_flags,
+                  s.d_wz,      s.d_wv,     s.d_dinv,  s.d_gal};
   for (void *p : ptrs)
     if (p)
       cudaFree(p);
@@ -235,6 +236,10 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
       ALLOC(s.d_wr, C * 4 * N);
       ALLOC(s.d_wp, C * 4 * N);
       ALLOC(s.d_wq, C * 4 * N);
+      ALLOC(s.d_wz, C * 4 * N);
+      ALLOC(s.d_wv, C * 4 * streamed_coarse_nodes(s.l));
+      ALLOC(s.d_dinv, C * streamed_coarse_nodes(s.l));
+      ALLOC(s.d_gal, streamed_galerkin_scratch_doubles(s.l, s.n_cells));
       ALLOC(s.d_scal, 4 * C);
       ALLOC(s.d_part, 4 * C * 2 * 3 * 32);
     }

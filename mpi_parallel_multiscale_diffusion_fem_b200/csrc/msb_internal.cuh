@@ -54,7 +54,10 @@ namespace msb
     double       *d_gsol    = nullptr; // [C][N] global solution (after set_global_weights)
     double       *d_tmp     = nullptr; // 2*N scratch for single-vector calls
     // streamed tier work vectors [C][4][N] each
-    double       *d_wr = nullptr, *d_wp = nullptr, *d_wq = nullptr;
+    double       *d_wr = nullptr, *d_wp = nullptr, *d_wq = nullptr, *d_wz = nullptr;
+    double       *d_wv = nullptr;     // streamed tier coarse-level vectors [C][4][cn]
+    double       *d_dinv = nullptr;   // streamed tier reciprocal Galerkin diagonals [C][cn]
+    double       *d_gal = nullptr;    // streamed tier Galerkin scratch (two coarse stencil buffers)
     double       *d_scal = nullptr;   // streamed tier per-solve scalars
     double       *d_part = nullptr;   // streamed tier partial sums
     int32_t      *d_flags = nullptr;  // streamed tier per-solve state
@@ -86,7 +89,8 @@ namespace msb
   cudaError_t launch_constraints(const Shard &s, int cell, int ib, uint32_t *d_dofs, double *d_vals,
                                  cudaStream_t st);
   bool        smem_tier_supported(int l);
-  size_t      streamed_workspace_doubles(const Shard &s);
+  size_t      streamed_coarse_nodes(int l);
+  size_t      streamed_galerkin_scratch_doubles(int l, int n_cells);
 
   // ---- small device helpers -----------------------------------------------------------------
   __host__ __device__ inline uint32_t

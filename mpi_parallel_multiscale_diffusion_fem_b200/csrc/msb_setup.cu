@@ -246,8 +246,8 @@ namespace msb
     // and per fine row of the strip: 4n + 4(R+1) evaluations instead of 8 per fine cell.  The
     // quadrature abscissae are computed by the same expressions as in the general path.
     double    *tsx = ke + 14 * slab, *tsy = tsx + 4 * n;
-    const bool fast = !P.table && P.coef.separable() && c[0] == c[4] && c[2] == c[6] && c[1] == c[3] &&
-                      c[5] == c[7];
+    const bool aligned = c[0] == c[4] && c[2] == c[6] && c[1] == c[3] && c[5] == c[7];
+    const bool fast    = aligned && !P.table && P.coef.separable();
     if (fast)
       {
         for (int t = threadIdx.x; t < 4 * n + 4 * (rows + 1); t += blockDim.x)
@@ -286,7 +286,49 @@ namespace msb
         for (int e = 0; e < 10; ++e)
           K[e] = 0.0;
         Fe[0] = Fe[1] = Fe[2] = Fe[3] = 0.0;
-        if (iy >= 0 && iy < n)
+        if (iy >= 0 && iy < n && aligned)
+          {
+            // Axis-aligned coarse cell: the fine cells are hx x hy rectangles, the Jacobian is
+            // diag(hx, hy) and  K_ij = sum_q [dNx_i dNx_j a00 hy/hx + (dNx_i dNy_j + dNy_i dNx_j) a_s
+            //                               + dNy_i dNy_j a11 hx/hy] / 4
+            // with the reference-cell gradients at the Gauss points folded at compile time.
+            const double hx = (c[2] - c[0]) / n, hy = (c[5] - c[1]) / n;
+            const double rxx = 0.25 * hy / hx, ryy = 0.25 * hx / hy;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              {
+                constexpr double G0 = 0.21132486540518711775, G1 = 0.78867513459481288225;
+                const double     xi = (q & 1) ? G1 : G0, eta = (q >> 1) ? G1 : G0;
+                const double     dNx[4] = {-(1 - eta), (1 - eta), -eta, eta};
+                const double     dNy[4] = {-(1 - xi), -xi, (1 - xi), xi};
+                double           a00, a01, a10, a11;
+                if (P.table)
+                  {
+                    const double *tp =
+                      P.table + (((size_t)cell * n * n + (size_t)iy * n + ix) * 4 + q) * 4;
+                    a00 = tp[0], a01 = tp[1], a10 = tp[2], a11 = tp[3];
+                  }
+                else if (fast)
+                  P.coef.from_sines(tsx[4 * ix + q], tsy[4 * lr + q], a00, a01, a10, a11);
+                else
+                  P.coef(c[0] + (ix + xi) * hx, c[1] + (iy + eta) * hy, a00, a01, a10, a11);
+                const double c00 = a00 * rxx, c01 = 0.125 * (a01 + a10), c11 = a11 * ryy;
+                int          e   = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                  for (int j = i; j < 4; ++j)
+                    {
+                      K[e] = fma(dNx[i] * dNx[j], c00, K[e]);
+                      K[e] = fma(dNx[i] * dNy[j] + dNy[i] * dNx[j], c01, K[e]);
+                      K[e] = fma(dNy[i] * dNy[j], c11, K[e]);
+                      ++e;
+                    }
+              }
+            // sum_q N_i(q) w_q = 1/4: every vertex receives a quarter of f |cell|
+            Fe[0] = Fe[1] = Fe[2] = Fe[3] = P.rhs_value * hx * hy * 0.25;
+          }
+        else if (iy >= 0 && iy < n)
           {
             double Px[4], Py[4];
 #pragma unroll
@@ -498,7 +540,10 @@ namespace msb
   // UNCONSTRAINED K over all N DoFs, b_i = phi_i . F.  One CTA per coarse cell, fixed
   // summation order (deterministic).
   // ======================================================================================
-  __global__ void __launch_bounds__(256)
+  // Every thread owns one node column and a band of rows and marches up the band with a 3x3
+  // register window per basis, so each phi value is loaded three times (by the three column
+  // neighbours, from the same cache lines) instead of nine and each stencil coefficient once.
+  __global__ void __launch_bounds__(256, 2)
   element_matrix_kernel(int n, const double *__restrict__ sten, const double *__restrict__ phi,
                         double *__restrict__ M, double *__restrict__ b)
   {
@@ -509,25 +554,80 @@ namespace msb
 #pragma unroll
     for (int k = 0; k < 20; ++k)
       acc[k] = 0.0;
-    for (int lex = threadIdx.x; lex < N; lex += blockDim.x)
+    // thread -> (column X, band of rows); with np > blockDim.x the columns are swept in passes
+    const int nb = blockDim.x >= np ? blockDim.x / np : 1; // bands
+    const int rb = (np + nb - 1) / nb;                     // rows per band
+    for (int col0 = 0; col0 < np; col0 += (nb > 1 || blockDim.x >= np ? np : blockDim.x))
       {
-        const int jx = lex % np, jy = lex / np;
-        double    kp[4], ph[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
+        const int X    = blockDim.x >= np ? threadIdx.x % np : col0 + threadIdx.x;
+        const int band = blockDim.x >= np ? threadIdx.x / np : 0;
+        const int y0 = band * rb, y1 = min(np, y0 + rb);
+        if (X < np && band < nb && y0 < y1)
           {
-            kp[j] = stencil_apply(S, P + (size_t)j * N, n, jx, jy);
-            ph[j] = P[(size_t)j * N + lex];
-          }
-        const double f = S[ST_F * N + lex];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          {
+            const bool hasW = X > 0, hasE = X < n;
+            const int  xm = hasW ? X - 1 : X, xp = hasE ? X + 1 : X;
+            // window rows a = y-1, c = y, d = y+1; columns m (x-1), 0 (x), p (x+1).  Values read
+            // through clamped indices are always multiplied by a zero coupling.
+            double a0[4], cm[4], c0[4], cp[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              acc[4 * i + j] += ph[i] * kp[j];
-            acc[16 + i] += ph[i] * f;
+              {
+                const double *Pj = P + (size_t)j * N;
+                const int     ra = (y0 > 0 ? y0 - 1 : y0) * np, rc = y0 * np;
+                a0[j] = Pj[ra + X];
+                cm[j] = Pj[rc + xm], c0[j] = Pj[rc + X], cp[j] = Pj[rc + xp];
+              }
+            for (int y = y0; y < y1; ++y)
+              {
+                const int  i    = y * np + X;
+                const bool hasS = y > 0, hasN = y < n;
+                const int  rd = (hasN ? y + 1 : y) * np, ra = (hasS ? y - 1 : y) * np;
+                // symmetric stencil row of node (X, y); couplings that leave the mesh are zero
+                const double kc = S[ST_KC * N + i], f = S[ST_F * N + i];
+                const double kE = hasE ? S[ST_KE * N + i] : 0.0, kW = hasW ? S[ST_KE * N + i - 1] : 0.0;
+                const double kN = hasN ? S[ST_KN * N + i] : 0.0, kS = hasS ? S[ST_KN * N + i - np] : 0.0;
+                const double kNE = hasN && hasE ? S[ST_KD1 * N + i] : 0.0;
+                const double kSW = hasS && hasW ? S[ST_KD1 * N + i - np - 1] : 0.0;
+                const double kNW = hasN && hasW ? S[ST_KD2 * N + i - 1] : 0.0;
+                const double kSE = hasS && hasE ? S[ST_KD2 * N + i - np] : 0.0;
+                double       kp[4], dm[4], d0[4], dp[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  {
+                    const double *Pj = P + (size_t)j * N;
+                    dm[j] = Pj[rd + xm], d0[j] = Pj[rd + X], dp[j] = Pj[rd + xp];
+                    // the two lower diagonal neighbours are re-read (L1 hits) to keep the window
+                    // small enough for two resident CTAs per SM
+                    const double am = Pj[ra + xm], ap = Pj[ra + xp];
+                    double       t  = kc * c0[j];
+                    t     = fma(kE, cp[j], t);
+                    t     = fma(kW, cm[j], t);
+                    t     = fma(kN, d0[j], t);
+                    t     = fma(kS, a0[j], t);
+                    t     = fma(kNE, dp[j], t);
+                    t     = fma(kSW, am, t);
+                    t     = fma(kNW, dm[j], t);
+                    t     = fma(kSE, ap, t);
+                    kp[j] = t;
+                  }
+#pragma unroll
+                for (int i2 = 0; i2 < 4; ++i2)
+                  {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                      acc[4 * i2 + j] = fma(c0[i2], kp[j], acc[4 * i2 + j]);
+                    acc[16 + i2] = fma(c0[i2], f, acc[16 + i2]);
+                  }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  {
+                    a0[j] = c0[j];
+                    cm[j] = dm[j], c0[j] = d0[j], cp[j] = dp[j];
+                  }
+              }
           }
+        if (blockDim.x >= np)
+          break;
       }
     __shared__ double red[8][20];
     const int         lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -1,46 +1,65 @@
-// msb_solve_stream.cu -- HBM/L2-streamed tier: batched Jacobi-PCG for local meshes that do
-// not fit the shared-memory tier (n >= 128; BASELINE cfg1 and cfg5).
+// msb_solve_stream.cu -- HBM/L2-streamed tier: batched multilevel-preconditioned CG for local
+// meshes that do not fit the shared-memory tier (n >= 128: BASELINE cfg1 -- the reference's
+// default run -- and cfg5).
 //
-// Same mathematics as the reference's per-basis sequence (diffusion_problem_basis.tpp:
-// 450-465 + solve_iterative :293-317) on the condensed system: unknowns are the interior
-// DoFs, the boundary DoFs carry the BasisQ1 data g (distribute(), :308) and never move.
-// All (cell, basis) solves of the shard advance together, three kernels per iteration:
-//     K1  p = D^-1 r + beta p                (beta from the previous iteration's dots)
-//     K2  q = K p  (matrix-free 9-point stencil, coefficients shared by the 4 bases),  p.q
-//     K3  x += alpha p ; r -= alpha q ; r.D^-1 r and r.r
-// Dot products are two-level and deterministic: every CTA writes one partial per basis,
-// every consumer CTA re-adds the partials of its cell in a fixed order, so all CTAs of a
-// cell take bitwise identical decisions and no atomics are needed.  The stopping rule is
-// the reference's: ||r||_2 <= tol every iteration (basis.tpp:297); a converged solve is
-// frozen (its CTAs exit at once) and its iteration count recorded on the device.
+// Same mathematics as the reference's per-basis sequence (diffusion_problem_basis.tpp:450-465
+// + solve_iterative :293-317) on the condensed system: unknowns are the interior DoFs, the
+// boundary DoFs carry the BasisQ1 data g (distribute(), :308) and never move.  All
+// (cell, basis) solves of the shard advance together; vectors live in HBM / L2 in the
+// lexicographic layout [cell][basis][node].  One PCG iteration is a fixed sequence of batched
+// kernels over all cells:
+//     K1        p = z + beta p
+//     K2        q = K p (matrix-free 9-point stencil, coefficients shared by the 4 bases), p.q
+//     K3        x += alpha p ; r -= alpha q ; r.r
+//     restrict  r_l = P^T r_{l-1}                      for every coarse level l = 1..L
+//     prolong   z_l = r_l / D_l + P z_{l+1}            for l = L..1
+//     fine      z = r / D + P z_1 ; r.z
+// i.e. the same additive multilevel preconditioner (exact Galerkin diagonals D_l, computed by
+// batched RAP kernels in the setup) as the shared-memory tier; k drops from ~460 (Jacobi) to ~39
+// at n = 128.  Dot products are two-level and deterministic: every CTA writes one partial per
+// basis, every consumer CTA re-adds the partials of its cell in a fixed order, so all CTAs of a
+// cell take bitwise identical decisions and no atomics are needed.  Partials are double
+// buffered by iteration parity so that a CTA never reads a partial a sibling is rewriting.
+// The stopping rule is the reference's: ||r||_2 <= tol every iteration (basis.tpp:297); a
+// converged solve is frozen and its iteration count recorded on the device.
 #include <limits.h>
 #include <math.h>
 
-#include "msb_internal.cuh"
+#include <vector>
+
+#include "msb_bpx_common.cuh"
 
 namespace msb
 {
   constexpr int STREAM_THREADS = 256;
-  constexpr int STREAM_MAXBLK  = 32; // max CTAs per coarse cell
+  constexpr int STREAM_MAXBLK  = 32;                    // max CTAs per coarse cell (fine kernels)
+  constexpr int PART_STRIDE    = 2 * 3 * STREAM_MAXBLK; // doubles per solve: [parity][rz|pq|rr][blk]
+  constexpr int MAX_LEVELS     = 10;
+
+  struct LevelInfo
+  {
+    int npl[MAX_LEVELS + 1]; // nodes per direction of level l (level 0 = fine)
+    int off[MAX_LEVELS + 2]; // node offset of level l >= 1 inside the packed coarse arrays
+    int levels;              // coarse levels 1..levels
+    int cn;                  // total coarse nodes
+  };
 
   struct StreamParams
   {
-    int           n, nblk, rows; // rows of nodes per CTA
+    int           n, nblk, rows; // fine kernels: rows of nodes per CTA
     const double *corners, *q1coef, *sten;
     double       *x;             // phi buffer [C][4][N]
-    double       *r, *p, *q;     // [C][4][N]
-    double       *part;          // [C][4][2 parity][3][STREAM_MAXBLK]: 0 rz, 1 pq, 2 rr;
-                                 // iteration `it` reads parity (it-1)&1 and writes it&1, so the
-                                 // CTAs of one cell never read partials a sibling is rewriting
+    double       *r, *p, *q, *z; // [C][4][N]
+    double       *v;             // [C][4][cn] coarse residuals / corrections
+    const double *dinv;          // [C][cn] reciprocal Galerkin diagonals
+    double       *part;          // [C][4][PART_STRIDE]
     double       *rzprev;        // [C][4]
     int32_t      *iters;         // [C][4]  (-1 while running)
     double       *res;           // [C][4]
-    int32_t      *remaining;     // cells with an unfinished solve
     double        tol2;
-    int           it;            // iteration about to be executed (1-based)
+    int           it;            // iteration being executed (1-based); 0 = initialisation
+    LevelInfo     L;
   };
-
-  constexpr int PART_STRIDE = 2 * 3 * STREAM_MAXBLK; // doubles per solve
 
   __device__ __forceinline__ double *
   part_ptr(double *part, int sidx, int parity, int which)
@@ -57,7 +76,29 @@ namespace msb
     return s;
   }
 
-  // block-wide deterministic sums of NV values -> written by thread 0
+  // done(solve) as seen by every CTA of a cell: either recorded in an earlier launch
+  // (iters >= 0) or implied by the r.r partials of parity `parity`.  A CTA that races with the
+  // recording CTA re-derives the same answer from the partials.
+  __device__ __forceinline__ int
+  solve_done(const StreamParams &P, int sidx, int parity, double *rr_out)
+  {
+    const double rr = sum_part(part_ptr(P.part, sidx, parity, 2), P.nblk);
+    if (rr_out)
+      *rr_out = rr;
+    return (P.iters[sidx] >= 0) || (rr <= P.tol2);
+  }
+
+  // all four solves of a cell done?  (four threads evaluate, the block shares the answer)
+  __device__ __forceinline__ bool
+  cell_done(const StreamParams &P, int cell, int parity, int *sdone /*shared[4]*/)
+  {
+    if (threadIdx.x < 4)
+      sdone[threadIdx.x] = solve_done(P, cell * 4 + threadIdx.x, parity, nullptr);
+    __syncthreads();
+    return sdone[0] && sdone[1] && sdone[2] && sdone[3];
+  }
+
+  // block-wide deterministic sums of NV values -> valid on thread 0
   template <int NV>
   __device__ __forceinline__ void
   block_sum_to(double (&v)[NV], double *sbuf /*[8][NV]*/)
@@ -86,20 +127,38 @@ namespace msb
       }
   }
 
-  // done(solve) as seen by every CTA of a cell during iteration `it`: either recorded in an
-  // earlier launch (iters >= 0) or implied by the r.r partials of iteration it-1.  A CTA
-  // that races with the recording CTA re-derives the same answer from the partials.
-  __device__ __forceinline__ int
-  solve_done(const StreamParams &P, int sidx, int parity, double *rr_out)
+  // ------------------------------------------------------------------------------ setup
+  // One level of the Galerkin hierarchy of the unscaled interior operator for every cell:
+  // Sc = P^T Sf P (symmetric 9-point storage, same layout as Shard::d_sten), dinv = 1/diag.
+  __global__ void __launch_bounds__(STREAM_THREADS)
+  stream_galerkin_kernel(const double *__restrict__ Sf_all, size_t sf_stride, int npf,
+                         double *__restrict__ Sc_all, size_t sc_stride, int npc,
+                         double *__restrict__ dinv_all, size_t dinv_stride, int dinv_off)
   {
-    const double rr = sum_part(part_ptr(P.part, sidx, parity, 2), P.nblk);
-    if (rr_out)
-      *rr_out = rr;
-    return (P.iters[sidx] >= 0) || (rr <= P.tol2);
+    const int     cell = blockIdx.y, nin = npc - 2, Nf = npf * npf, Nc = npc * npc;
+    const double *Sf   = Sf_all + (size_t)cell * sf_stride;
+    double       *Sc   = Sc_all + (size_t)cell * sc_stride;
+    double       *di   = dinv_all + (size_t)cell * dinv_stride + dinv_off;
+    const int     t    = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nin * nin)
+      return;
+    const int X = 1 + t % nin, Y = 1 + t / nin, i = Y * npc + X;
+    double    a[5];
+    bpx::galerkin_row(Sf, npf, Nf, X, Y, a);
+    Sc[ST_KC * Nc + i] = a[0];
+    if (X < nin)
+      Sc[ST_KE * Nc + i] = a[1];
+    if (Y < nin)
+      Sc[ST_KN * Nc + i] = a[2];
+    if (X < nin && Y < nin)
+      Sc[ST_KD1 * Nc + i] = a[3];
+    if (X > 1 && Y < nin)
+      Sc[ST_KD2 * Nc + i - 1] = a[4];
+    di[i] = 1.0 / a[0];
   }
 
   // r = b = -K_IB g_B on interior rows, 0 on constrained rows (condense);
-  // x = g on the boundary, 0 inside; p = 0; partial r.z and r.r into parity 0
+  // x = g on the boundary, 0 inside; p = 0; partial r.r into parity 0
   __global__ void __launch_bounds__(STREAM_THREADS)
   stream_init_kernel(StreamParams P)
   {
@@ -107,10 +166,7 @@ namespace msb
     const double *S = P.sten + (size_t)cell * ST_NARR * N;
     const double *c = P.corners + 8 * (size_t)cell, *q1 = P.q1coef + 16 * (size_t)cell;
     const int     y0 = blk * P.rows, y1 = min(np, y0 + P.rows);
-    double        acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      acc[k] = 0.0;
+    double        acc[4] = {0, 0, 0, 0};
     for (int t = y0 * np + threadIdx.x; t < y1 * np; t += STREAM_THREADS)
       {
         const int  jx = t % np, jy = t / np;
@@ -132,28 +188,16 @@ namespace msb
                   const int bx = jx + dx, by = jy + dy;
                   if ((dx == 0 && dy == 0) || !(bx == 0 || bx == n || by == 0 || by == n))
                     continue;
-                  double kij;
-                  if (dy == 0)
-                    kij = S[ST_KE * N + (dx > 0 ? t : t - 1)];
-                  else if (dx == 0)
-                    kij = S[ST_KN * N + (dy > 0 ? t : t - np)];
-                  else if (dx == dy)
-                    kij = S[ST_KD1 * N + (dx > 0 ? t : t - np - 1)];
-                  else
-                    kij = S[ST_KD2 * N + (dy > 0 ? t - 1 : t - np)];
-                  double px, py;
+                  const double kij = bpx::sten_get(S, np, N, jx, jy, dx, dy);
+                  double       px, py;
                   fine_vertex(c, n, bx, by, px, py);
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
                     rv[k] -= kij * basis_q1_value(q1, k, px, py);
                 }
-            const double dinv = 1.0 / S[ST_KC * N + t];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              {
-                acc[k] += rv[k] * rv[k] * dinv;
-                acc[4 + k] += rv[k] * rv[k];
-              }
+              acc[k] += rv[k] * rv[k];
           }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -164,19 +208,17 @@ namespace msb
             P.p[o]         = 0.0;
           }
       }
-    __shared__ double sbuf[8 * 8];
-    block_sum_to<8>(acc, sbuf);
+    __shared__ double sbuf[8 * 4];
+    block_sum_to<4>(acc, sbuf);
     if (threadIdx.x == 0)
       {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          {
-            part_ptr(P.part, cell * 4 + k, 0, 0)[blk] = acc[k];
-            part_ptr(P.part, cell * 4 + k, 0, 2)[blk] = acc[4 + k];
-          }
+          part_ptr(P.part, cell * 4 + k, 0, 2)[blk] = acc[k];
       }
   }
 
+  // ------------------------------------------------------------------------------ iteration
   // K1: convergence bookkeeping of the previous iteration, then p = z + beta p
   __global__ void __launch_bounds__(STREAM_THREADS)
   stream_k1_kernel(StreamParams P)
@@ -202,21 +244,19 @@ namespace msb
     __syncthreads();
     if (sdone[0] && sdone[1] && sdone[2] && sdone[3])
       return;
-    const double *KC = P.sten + (size_t)cell * ST_NARR * N + ST_KC * N;
-    const int     y0 = blk * P.rows, y1 = min(np, y0 + P.rows);
+    const int y0 = blk * P.rows, y1 = min(np, y0 + P.rows);
     for (int t = y0 * np + threadIdx.x; t < y1 * np; t += STREAM_THREADS)
       {
         const int jx = t % np, jy = t / np;
         if (jx == 0 || jy == 0 || jx == n || jy == n)
           continue;
-        const double dinv = 1.0 / KC[t];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           {
             if (sdone[k])
               continue;
             const size_t o = ((size_t)cell * 4 + k) * N + t;
-            P.p[o]         = fma(sbeta[k], P.p[o], P.r[o] * dinv);
+            P.p[o]         = fma(sbeta[k], P.p[o], P.z[o]);
           }
       }
   }
@@ -229,10 +269,7 @@ namespace msb
     const int par = (P.it - 1) & 1;
     __shared__ int    sdone[4];
     __shared__ double sbuf[8 * 4];
-    if (threadIdx.x < 4)
-      sdone[threadIdx.x] = solve_done(P, cell * 4 + threadIdx.x, par, nullptr);
-    __syncthreads();
-    if (sdone[0] && sdone[1] && sdone[2] && sdone[3])
+    if (cell_done(P, cell, par, sdone))
       return;
     const double *S  = P.sten + (size_t)cell * ST_NARR * N;
     const int     y0 = blk * P.rows, y1 = min(np, y0 + P.rows);
@@ -277,7 +314,7 @@ namespace msb
       }
   }
 
-  // K3: alpha = rz/pq ; x += alpha p ; r -= alpha q ; partial r.z and r.r
+  // K3: alpha = rz/pq ; x += alpha p ; r -= alpha q ; partial r.r
   __global__ void __launch_bounds__(STREAM_THREADS)
   stream_k3_kernel(StreamParams P)
   {
@@ -285,7 +322,7 @@ namespace msb
     const int par = (P.it - 1) & 1;
     __shared__ int    sdone[4];
     __shared__ double salpha[4];
-    __shared__ double sbuf[8 * 8];
+    __shared__ double sbuf[8 * 4];
     if (threadIdx.x < 4)
       {
         const int sidx      = cell * 4 + threadIdx.x;
@@ -298,18 +335,13 @@ namespace msb
     __syncthreads();
     if (sdone[0] && sdone[1] && sdone[2] && sdone[3])
       return;
-    const double *KC = P.sten + (size_t)cell * ST_NARR * N + ST_KC * N;
-    const int     y0 = blk * P.rows, y1 = min(np, y0 + P.rows);
-    double        acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      acc[k] = 0.0;
+    const int y0 = blk * P.rows, y1 = min(np, y0 + P.rows);
+    double    acc[4] = {0, 0, 0, 0};
     for (int t = y0 * np + threadIdx.x; t < y1 * np; t += STREAM_THREADS)
       {
         const int jx = t % np, jy = t / np;
         if (jx == 0 || jy == 0 || jx == n || jy == n)
           continue;
-        const double dinv = 1.0 / KC[t];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           {
@@ -320,11 +352,10 @@ namespace msb
             P.x[o]          = fma(a, P.p[o], P.x[o]);
             const double rn = fma(-a, P.q[o], P.r[o]);
             P.r[o]          = rn;
-            acc[k]          = fma(rn * dinv, rn, acc[k]);
-            acc[4 + k]      = fma(rn, rn, acc[4 + k]);
+            acc[k]          = fma(rn, rn, acc[k]);
           }
       }
-    block_sum_to<8>(acc, sbuf);
+    block_sum_to<4>(acc, sbuf);
     if (threadIdx.x == 0)
       {
 #pragma unroll
@@ -332,13 +363,114 @@ namespace msb
           if (!sdone[k])
             {
               const int sidx = cell * 4 + k;
-              part_ptr(P.part, sidx, P.it & 1, 0)[blk] = acc[k];
-              part_ptr(P.part, sidx, P.it & 1, 2)[blk] = acc[4 + k];
+              part_ptr(P.part, sidx, P.it & 1, 2)[blk] = acc[k];
               // r.z of the iteration just consumed becomes "previous" for the next K1
-              // (every CTA of the cell writes the same value; nobody reads it in this launch)
               if (blk == 0)
                 P.rzprev[sidx] = sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
             }
+      }
+  }
+
+  // ---- the preconditioner z = M^-1 r on the residual whose r.r partials are in parity `rpar`
+  // restriction r_l = P^T r_{l-1} (full weighting) for all cells and the four bases
+  __global__ void __launch_bounds__(STREAM_THREADS)
+  stream_restrict_kernel(StreamParams P, int l, int rpar)
+  {
+    const int cell = blockIdx.y, npl = P.L.npl[l], nin = npl - 2, npf = P.L.npl[l - 1];
+    __shared__ int sdone[4];
+    if (cell_done(P, cell, rpar, sdone))
+      return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nin * nin)
+      return;
+    const int    cx = 1 + t % nin, cy = 1 + t / nin;
+    const size_t Nf = (size_t)npf * npf;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      {
+        const double *src = l == 1 ? P.r + ((size_t)cell * 4 + k) * Nf :
+                                     P.v + ((size_t)cell * 4 + k) * P.L.cn + P.L.off[l - 1];
+        double row[3];
+#pragma unroll
+        for (int ay = -1; ay <= 1; ++ay)
+          {
+            const double *s = src + (size_t)(2 * cy + ay) * npf + 2 * cx;
+            row[ay + 1]     = fma(0.5, s[-1] + s[1], s[0]);
+          }
+        P.v[((size_t)cell * 4 + k) * P.L.cn + P.L.off[l] + cy * npl + cx] = fma(0.5, row[0] + row[2], row[1]);
+      }
+  }
+
+  // prolongation z_l = r_l / D_l + P z_{l+1}  (coarsest level: z = r / D), in place
+  __global__ void __launch_bounds__(STREAM_THREADS)
+  stream_prolong_kernel(StreamParams P, int l, int rpar)
+  {
+    const int cell = blockIdx.y, npl = P.L.npl[l], nin = npl - 2;
+    __shared__ int sdone[4];
+    if (cell_done(P, cell, rpar, sdone))
+      return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nin * nin)
+      return;
+    const int    fx = 1 + t % nin, fy = 1 + t / nin, i = fy * npl + fx;
+    const double di = P.dinv[(size_t)cell * P.L.cn + P.L.off[l] + i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      {
+        double *vl = P.v + ((size_t)cell * 4 + k) * P.L.cn + P.L.off[l];
+        double  v  = vl[i] * di;
+        if (l < P.L.levels)
+          {
+            const int     npc = P.L.npl[l + 1];
+            const double *vc  = P.v + ((size_t)cell * 4 + k) * P.L.cn + P.L.off[l + 1];
+            const int     xl = fx >> 1, xh = (fx + 1) >> 1, yl = fy >> 1, yh = (fy + 1) >> 1;
+            v += 0.25 * ((vc[yl * npc + xl] + vc[yl * npc + xh]) + (vc[yh * npc + xl] + vc[yh * npc + xh]));
+          }
+        vl[i] = v;
+      }
+  }
+
+  // fine level: z = r / D + P z_1 on interior rows; partial r.z into parity `rpar`
+  __global__ void __launch_bounds__(STREAM_THREADS)
+  stream_fine_kernel(StreamParams P, int rpar)
+  {
+    const int n = P.n, np = n + 1, N = np * np, cell = blockIdx.y, blk = blockIdx.x;
+    __shared__ int    sdone[4];
+    __shared__ double sbuf[8 * 4];
+    if (cell_done(P, cell, rpar, sdone))
+      return;
+    const double *KC  = P.sten + (size_t)cell * ST_NARR * N + ST_KC * N;
+    const int     np1 = P.L.npl[1];
+    const int     y0 = blk * P.rows, y1 = min(np, y0 + P.rows);
+    double        acc[4] = {0, 0, 0, 0};
+    for (int t = y0 * np + threadIdx.x; t < y1 * np; t += STREAM_THREADS)
+      {
+        const int jx = t % np, jy = t / np;
+        if (jx == 0 || jy == 0 || jx == n || jy == n)
+          continue;
+        const double dinv = 1.0 / KC[t];
+        const int    xl = jx >> 1, xh = (jx + 1) >> 1, yl = jy >> 1, yh = (jy + 1) >> 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          {
+            if (sdone[k])
+              continue;
+            const size_t  o  = ((size_t)cell * 4 + k) * N + t;
+            const double *v1 = P.v + ((size_t)cell * 4 + k) * P.L.cn + P.L.off[1];
+            const double  c =
+              0.25 * ((v1[yl * np1 + xl] + v1[yl * np1 + xh]) + (v1[yh * np1 + xl] + v1[yh * np1 + xh]));
+            const double rv = P.r[o], zv = fma(rv, dinv, c);
+            P.z[o]          = zv;
+            acc[k]          = fma(rv, zv, acc[k]);
+          }
+      }
+    block_sum_to<4>(acc, sbuf);
+    if (threadIdx.x == 0)
+      {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (!sdone[k])
+            part_ptr(P.part, cell * 4 + k, rpar, 0)[blk] = acc[k];
       }
   }
 
@@ -367,20 +499,50 @@ namespace msb
       atomicAdd(remaining, 1);
   }
 
-  size_t
-  streamed_workspace_doubles(const Shard &s)
+  // ------------------------------------------------------------------------------ host side
+  static LevelInfo
+  make_levels(int l)
   {
-    return 3 * (size_t)s.n_cells * 4 * s.N;
+    LevelInfo L;
+    const int n = 1 << l;
+    L.levels    = l - 1;
+    L.npl[0]    = n + 1;
+    int off     = 0;
+    for (int k = 1; k <= L.levels; ++k)
+      {
+        L.npl[k] = (n >> k) + 1;
+        L.off[k] = off;
+        off += L.npl[k] * L.npl[k];
+      }
+    L.off[L.levels + 1] = off;
+    L.cn                = off;
+    return L;
   }
 
+  size_t
+  streamed_coarse_nodes(int l)
+  {
+    return (size_t)make_levels(l).cn;
+  }
+
+  size_t
+  streamed_galerkin_scratch_doubles(int l, int n_cells)
+  {
+    // level 1 and level 2 stencils (5 arrays each); deeper levels reuse the two buffers
+    const LevelInfo L  = make_levels(l);
+    const size_t    n1 = (size_t)L.npl[1] * L.npl[1], n2 = L.levels >= 2 ? (size_t)L.npl[2] * L.npl[2] : 0;
+    return 5 * (n1 + n2) * (size_t)n_cells;
+  }
+
+  // cells are processed in slices of at most 65535 (gridDim.y): all per-cell pointers shift
   static StreamParams
   shifted(const StreamParams &P, const Shard &s, int c0)
   {
-    // all per-cell pointers are indexed by blockIdx.y inside the kernels
     StreamParams Q = P;
     Q.corners += 8 * (size_t)c0, Q.q1coef += 16 * (size_t)c0, Q.sten += (size_t)c0 * ST_NARR * s.N;
     Q.x += (size_t)c0 * 4 * s.N, Q.r += (size_t)c0 * 4 * s.N, Q.p += (size_t)c0 * 4 * s.N;
-    Q.q += (size_t)c0 * 4 * s.N, Q.part += (size_t)c0 * 4 * PART_STRIDE;
+    Q.q += (size_t)c0 * 4 * s.N, Q.z += (size_t)c0 * 4 * s.N, Q.v += (size_t)c0 * 4 * P.L.cn;
+    Q.dinv += (size_t)c0 * P.L.cn, Q.part += (size_t)c0 * 4 * PART_STRIDE;
     Q.rzprev += 4 * (size_t)c0, Q.iters += 4 * (size_t)c0, Q.res += 4 * (size_t)c0;
     return Q;
   }
@@ -394,72 +556,135 @@ namespace msb
     int rows = 16;
     while ((s.np + rows - 1) / rows > STREAM_MAXBLK)
       rows *= 2;
-    P.rows      = rows;
-    P.nblk      = (s.np + rows - 1) / rows;
-    P.corners   = s.d_corners;
-    P.q1coef    = s.d_q1coef;
-    P.sten      = s.d_sten;
-    P.x         = s.d_phi;
-    P.r         = s.d_wr;
-    P.p         = s.d_wp;
-    P.q         = s.d_wq;
-    P.part      = s.d_part;
-    P.rzprev    = s.d_scal;
-    P.iters     = s.d_iters;
-    P.res       = s.d_res;
-    P.remaining = s.d_flags;
-    P.tol2      = tol * tol;
-    P.it        = 0;
-    const int   n_solves = 4 * s.n_cells;
-    cudaError_t e;
-    if ((e = cudaMemsetAsync(s.d_iters, 0xff, sizeof(int32_t) * n_solves, st)) != cudaSuccess)
-      return e;
-    if ((e = cudaMemsetAsync(s.d_part, 0, sizeof(double) * (size_t)n_solves * PART_STRIDE, st)) !=
-        cudaSuccess)
-      return e;
-    for (int c0 = 0; c0 < s.n_cells; c0 += 65535)
-      {
-        const int nc = s.n_cells - c0 < 65535 ? s.n_cells - c0 : 65535;
-        stream_init_kernel<<<dim3(P.nblk, nc), STREAM_THREADS, 0, st>>>(shifted(P, s, c0));
-        ++*n_launches;
-      }
+    P.rows    = rows;
+    P.nblk    = (s.np + rows - 1) / rows;
+    P.corners = s.d_corners;
+    P.q1coef  = s.d_q1coef;
+    P.sten    = s.d_sten;
+    P.x       = s.d_phi;
+    P.r       = s.d_wr;
+    P.p       = s.d_wp;
+    P.q       = s.d_wq;
+    P.z       = s.d_wz;
+    P.v       = s.d_wv;
+    P.dinv    = s.d_dinv;
+    P.part    = s.d_part;
+    P.rzprev  = s.d_scal;
+    P.iters   = s.d_iters;
+    P.res     = s.d_res;
+    P.tol2    = tol * tol;
+    P.it      = 0;
+    P.L       = make_levels(s.l);
+    const LevelInfo &L        = P.L;
+    const int        n_solves = 4 * s.n_cells;
+    const int        C        = s.n_cells;
+    cudaError_t      e;
+
+#define TRY(call)                  \
+  if ((e = (call)) != cudaSuccess) \
+  return e
+
+    TRY(cudaMemsetAsync(s.d_iters, 0xff, sizeof(int32_t) * n_solves, st));
+    TRY(cudaMemsetAsync(s.d_part, 0, sizeof(double) * (size_t)n_solves * PART_STRIDE, st));
+    TRY(cudaMemsetAsync(s.d_wv, 0, sizeof(double) * (size_t)n_solves * L.cn, st));
+    TRY(cudaMemsetAsync(s.d_dinv, 0, sizeof(double) * (size_t)C * L.cn, st));
+
+    // ---- setup: Galerkin diagonals of every level, level by level, for all cells
+    {
+      const size_t  n1        = (size_t)L.npl[1] * L.npl[1];
+      double       *buf[2]    = {s.d_gal, s.d_gal + 5 * n1 * (size_t)C};
+      const double *Sf        = s.d_sten;
+      size_t        sf_stride = (size_t)ST_NARR * s.N;
+      for (int l = 1; l <= L.levels; ++l)
+        {
+          const int    npc = L.npl[l], nin = npc - 2, npf = L.npl[l - 1];
+          const size_t Nc  = (size_t)npc * npc;
+          double      *Sc  = buf[(l - 1) & 1];
+          TRY(cudaMemsetAsync(Sc, 0, sizeof(double) * 5 * Nc * (size_t)C, st));
+          for (int c0 = 0; c0 < C; c0 += 65535)
+            {
+              const int nc = C - c0 < 65535 ? C - c0 : 65535;
+              stream_galerkin_kernel<<<dim3((nin * nin + STREAM_THREADS - 1) / STREAM_THREADS, nc),
+                                       STREAM_THREADS, 0, st>>>(
+                Sf + (size_t)c0 * sf_stride, sf_stride, npf, Sc + (size_t)c0 * 5 * Nc, 5 * Nc, npc,
+                s.d_dinv + (size_t)c0 * L.cn, (size_t)L.cn, L.off[l]);
+              ++*n_launches;
+            }
+          Sf        = Sc;
+          sf_stride = 5 * Nc;
+        }
+    }
+
+    auto for_slices = [&](auto &&launch) {
+      for (int c0 = 0; c0 < C; c0 += 65535)
+        {
+          const int nc = C - c0 < 65535 ? C - c0 : 65535;
+          launch(shifted(P, s, c0), nc);
+          ++*n_launches;
+        }
+    };
+    // z = M^-1 r and r.z for the residual whose r.r partials sit in parity `rpar`
+    auto precondition = [&](int rpar) {
+      for (int l = 1; l <= L.levels; ++l)
+        {
+          const int nin = L.npl[l] - 2;
+          for_slices([&](const StreamParams &Q, int nc) {
+            stream_restrict_kernel<<<dim3((nin * nin + STREAM_THREADS - 1) / STREAM_THREADS, nc),
+                                     STREAM_THREADS, 0, st>>>(Q, l, rpar);
+          });
+        }
+      for (int l = L.levels; l >= 1; --l)
+        {
+          const int nin = L.npl[l] - 2;
+          for_slices([&](const StreamParams &Q, int nc) {
+            stream_prolong_kernel<<<dim3((nin * nin + STREAM_THREADS - 1) / STREAM_THREADS, nc),
+                                    STREAM_THREADS, 0, st>>>(Q, l, rpar);
+          });
+        }
+      for_slices([&](const StreamParams &Q, int nc) {
+        stream_fine_kernel<<<dim3(P.nblk, nc), STREAM_THREADS, 0, st>>>(Q, rpar);
+      });
+    };
+
+    for_slices([&](const StreamParams &Q, int nc) {
+      stream_init_kernel<<<dim3(P.nblk, nc), STREAM_THREADS, 0, st>>>(Q);
+    });
+    precondition(0);
+
     int32_t   h_remaining = 1;
     int       it          = 0;
-    const int check_every = 8;
+    const int check_every = 4;
     while (it < max_iter)
       {
         // host poll: how many solves are still running after iteration `it`?
         if (it % check_every == 0)
           {
             P.it = it;
-            if ((e = cudaMemsetAsync(s.d_flags, 0, sizeof(int32_t), st)) != cudaSuccess)
-              return e;
+            TRY(cudaMemsetAsync(s.d_flags, 0, sizeof(int32_t), st));
             stream_count_kernel<<<(n_solves + 255) / 256, 256, 0, st>>>(P, n_solves, s.d_flags);
             ++*n_launches;
-            if ((e = cudaMemcpyAsync(&h_remaining, s.d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                     st)) != cudaSuccess)
-              return e;
-            if ((e = cudaStreamSynchronize(st)) != cudaSuccess)
-              return e;
+            TRY(cudaMemcpyAsync(&h_remaining, s.d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            TRY(cudaStreamSynchronize(st));
             if (h_remaining == 0)
               break;
           }
         ++it;
         P.it = it;
-        for (int c0 = 0; c0 < s.n_cells; c0 += 65535)
-          {
-            const int          nc = s.n_cells - c0 < 65535 ? s.n_cells - c0 : 65535;
-            const StreamParams Q  = shifted(P, s, c0);
-            const dim3         g(P.nblk, nc);
-            stream_k1_kernel<<<g, STREAM_THREADS, 0, st>>>(Q);
-            stream_k2_kernel<<<g, STREAM_THREADS, 0, st>>>(Q);
-            stream_k3_kernel<<<g, STREAM_THREADS, 0, st>>>(Q);
-            *n_launches += 3;
-          }
+        for_slices([&](const StreamParams &Q, int nc) {
+          stream_k1_kernel<<<dim3(P.nblk, nc), STREAM_THREADS, 0, st>>>(Q);
+        });
+        for_slices([&](const StreamParams &Q, int nc) {
+          stream_k2_kernel<<<dim3(P.nblk, nc), STREAM_THREADS, 0, st>>>(Q);
+        });
+        for_slices([&](const StreamParams &Q, int nc) {
+          stream_k3_kernel<<<dim3(P.nblk, nc), STREAM_THREADS, 0, st>>>(Q);
+        });
+        precondition(it & 1);
       }
     P.it = it;
     stream_finalize_kernel<<<(n_solves + 255) / 256, 256, 0, st>>>(P, n_solves, s.d_fail);
     ++*n_launches;
+#undef TRY
     return cudaGetLastError();
   }
 } // namespace msb

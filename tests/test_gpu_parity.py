@@ -134,7 +134,7 @@ def test_bases_match_oracle_and_goldens(msb, oracle, name, variant):
             got = np.array([sh.basis(0, i)[d[jy, jx]] for i in range(4)])
             assert np.abs(got - np.array(vals)).max() < 1e-9
         tier = sh.run_stats()["tier"]
-        if variant == 100 or tier == msb.TIER_STREAMED:
+        if variant == 100 and tier == msb.TIER_SMEM:
             # Jacobi-preconditioned CG: same counts as the oracle's Jacobi run
             # (rounding-level differences of the operator shift high-contrast counts by a few)
             ref_it = np.array(g["iters_jacobi"])
@@ -183,7 +183,7 @@ def test_streamed_tier_equals_smem_tier(msb, oracle, l):
         b.run(1e-12, 5000)
         ita, _ = a.iteration_counts()
         itb, _ = b.iteration_counts()
-        assert np.all(ita <= itb)   # multilevel PCG (smem tier) vs Jacobi PCG (streamed tier)
+        assert np.abs(ita - itb).max() <= 2   # the same multilevel PCG in both tiers
         for c in (0, 4):
             for ib in range(4):
                 assert _rel(a.basis(c, ib), b.basis(c, ib)) < 1e-10

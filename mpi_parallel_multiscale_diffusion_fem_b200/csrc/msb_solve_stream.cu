@@ -457,7 +457,7 @@ namespace msb
               continue;
             const size_t  o  = ((size_t)cell * 4 + k) * N + t;
             const double *v1 = P.v + ((size_t)cell * 4 + k) * P.L.cn + P.L.off[1];
-            const double  c =
+            const double  c = P.L.levels < 1 ? 0.0 : // n = 2 has no coarse level: plain Jacobi
               0.25 * ((v1[yl * np1 + xl] + v1[yl * np1 + xh]) + (v1[yh * np1 + xl] + v1[yh * np1 + xh]));
             const double rv = P.r[o], zv = fma(rv, dinv, c);
             P.z[o]          = zv;
@@ -503,7 +503,7 @@ namespace msb
   static LevelInfo
   make_levels(int l)
   {
-    LevelInfo L;
+    LevelInfo L = {};
     const int n = 1 << l;
     L.levels    = l - 1;
     L.npl[0]    = n + 1;
@@ -522,7 +522,8 @@ namespace msb
   size_t
   streamed_coarse_nodes(int l)
   {
-    return (size_t)make_levels(l).cn;
+    const size_t cn = (size_t)make_levels(l).cn;
+    return cn ? cn : 1; // l = 1 has no coarse level
   }
 
   size_t
@@ -530,6 +531,8 @@ namespace msb
   {
     // level 1 and level 2 stencils (5 arrays each); deeper levels reuse the two buffers
     const LevelInfo L  = make_levels(l);
+    if (L.levels < 1)
+      return 1;
     const size_t    n1 = (size_t)L.npl[1] * L.npl[1], n2 = L.levels >= 2 ? (size_t)L.npl[2] * L.npl[2] : 0;
     return 5 * (n1 + n2) * (size_t)n_cells;
   }

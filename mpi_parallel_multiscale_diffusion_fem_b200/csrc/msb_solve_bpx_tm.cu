@@ -62,6 +62,34 @@ namespace msb
         d[i] = __hiloint2double((int)v[2 * i + 1], (int)v[2 * i]);
     }
 
+    // two independent loads in flight, one wait
+    __device__ __forceinline__ void
+    tmem_ld8x2(uint32_t ta, uint32_t tb, double (&da)[8], double (&db)[8])
+    {
+      uint32_t v[16], w[16];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                   "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                     "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                     "=r"(v[14]), "=r"(v[15])
+                   : "r"(ta)
+                   : "memory");
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                   "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]),
+                     "=r"(w[7]), "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]),
+                     "=r"(w[14]), "=r"(w[15])
+                   : "r"(tb)
+                   : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        {
+          da[i] = __hiloint2double((int)v[2 * i + 1], (int)v[2 * i]);
+          db[i] = __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]);
+        }
+    }
+
     __device__ __forceinline__ void
     tmem_st8(uint32_t taddr, const double (&d)[8])
     {
@@ -557,6 +585,7 @@ namespace msb
               for (int c = 0; c < NCH; ++c)
                 {
                   double x8[8], p8[8];
+                  // (two loads in flight would need 32 more live registers and spill: measured slower)
                   tmem_ld8(tm + C::XOFF + 16 * c, x8);
                   tmem_ld8(tm + C::POFF + 16 * c, p8);
 #pragma unroll
@@ -592,8 +621,7 @@ namespace msb
             {
               double sq8[8], xa[8], xb[8];
               tmem_ld8(tm + C::SOFF + 16 * c, sq8);
-              tmem_ld8(tm + C::XOFF + 32 * c, xa);      // rows 8c   .. 8c+3
-              tmem_ld8(tm + C::XOFF + 32 * c + 16, xb); // rows 8c+4 .. 8c+7
+              tmem_ld8x2(tm + C::XOFF + 32 * c, tm + C::XOFF + 32 * c + 16, xa, xb); // rows 8c.., 8c+4..
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj)
                 {

@@ -333,3 +333,49 @@ def test_tensor_memory_kernel_matches_default_kernel(msb, oracle):
         assert _rel(Mb, Ma) < 1e-10 and _rel(bb, ba) < 1e-10
         for x, y in zip(pa, pb):
             assert _rel(y, x) < 1e-10
+
+
+@pytest.mark.parametrize("l,tier", [(5, 1), (6, 1), (4, 2), (7, 2)])
+def test_general_quadrilateral_and_rectangular_cells(msb, oracle, l, tier):
+    """general_cell (basis.tpp:94) accepts any straight-sided quadrilateral: a skewed cell
+    exercises the full Q1 mapping path of the assembly, a 2:1 rectangle the axis-aligned path
+    with hx != hy; f = 3.5 instead of the reference's 2."""
+    cd, co = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    cor = np.array([
+        [[0.10, 0.20], [0.35, 0.22], [0.12, 0.41], [0.38, 0.47]],      # skewed quadrilateral
+        [[0.50, 0.25], [0.75, 0.25], [0.50, 0.375], [0.75, 0.375]],   # 2:1 rectangle
+        [[0.25, 0.50], [0.375, 0.50], [0.25, 0.625], [0.375, 0.625]],  # square
+    ])
+    ref = oracle.run_cells(l, cor, co, rhs_value=3.5, n_threads=3)
+    with msb.BasisShard(l, cor, cd, rhs_value=3.5, tier=tier) as sh:
+        sh.run(1e-12, 5000)
+        M, b = sh.element_matrices()
+        it, res = sh.iteration_counts()
+        assert np.all(res <= 1e-12)
+        for c in range(3):
+            for ib in range(4):
+                assert _rel(sh.basis(c, ib), ref["phi"][c][ib]) < TOL_PHI, (c, ib)
+            assert _rel(M[c], ref["M"][c]) < TOL_MB and _rel(b[c], ref["b"][c]) < TOL_MB
+        # load: sum_i b_i = f |K|
+        area = [0.5 * abs((cor[c, 3, 0] - cor[c, 0, 0]) * (cor[c, 2, 1] - cor[c, 1, 1]) -
+                          (cor[c, 2, 0] - cor[c, 1, 0]) * (cor[c, 3, 1] - cor[c, 0, 1])) for c in range(3)]
+        assert np.abs(b.sum(axis=1) - 3.5 * np.array(area)).max() < 1e-13
+
+
+def test_handle_reuse_with_set_cells(msb, oracle):
+    """msb_set_cells streams another batch of cells through the same device workspace."""
+    cd, co = _coeffs(msb, oracle, msb.COEFF_REFERENCE)   # k = 57: no two coarse cells are alike
+    a, b = msb.coarse_corners(6, 100, 104), msb.coarse_corners(6, 2000, 2004)
+    with msb.BasisShard(6, a, cd) as sh:
+        sh.run()
+        Ma, _ = sh.element_matrices()
+        sh.set_cells(b)
+        with pytest.raises(msb.MsbError):
+            sh.element_matrices()          # results of the previous batch are invalidated
+        sh.run()
+        Mb, bb = sh.element_matrices()
+        phib = sh.basis(3, 2)
+    ref = oracle.run_cells(6, b, co, n_threads=4)
+    assert _rel(Mb, ref["M"]) < TOL_MB and _rel(bb, ref["b"]) < TOL_MB
+    assert _rel(phib, ref["phi"][3][2]) < TOL_PHI
+    assert _rel(Ma, ref["M"]) > 1e-3       # and they really are different cells

@@ -62,8 +62,9 @@ namespace DiffusionProblem
   };
 
   // solver parameters of solve_iterative (basis.tpp:297: SolverControl(1000, 1e-12)).  The GPU
-  // iterates Jacobi-preconditioned CG (SSOR's sweeps are sequential), which needs ~3.5x the
-  // reference's SSOR iterations, so the cap is a parameter; the stopping rule is unchanged.
+  // iterates CG with a multilevel preconditioner instead of SSOR (whose sweeps are sequential);
+  // it needs fewer iterations than the reference, but the cap stays a parameter.  The stopping
+  // rule is unchanged: absolute l2 norm of the unpreconditioned residual, every iteration.
   struct BasisSolverControl
   {
     double   tolerance = 1e-12;
@@ -177,6 +178,20 @@ namespace DiffusionProblem
       run_all(cell_basis_map, default_coefficient());
     }
 
+    // The same for the objects [first, last) of the map only, on one device: with several GPUs
+    // every device gets a contiguous CellId (= Morton) range, the ownership rule the reference
+    // inherits from p4est (ms.tpp:52).  Safe to call concurrently from one host thread per device.
+    static void run_range(typename std::map<CellId, DiffusionProblemBasis<dim>>::iterator first,
+                          typename std::map<CellId, DiffusionProblemBasis<dim>>::iterator last,
+                          const Coefficients::TensorCoefficient<dim> &matrix_coeff,
+                          const BasisSolverControl &control, int device_id)
+    {
+      std::map<CellId, DiffusionProblemBasis<dim> *> ptrs;
+      for (auto it = first; it != last; ++it)
+        ptrs[it->first] = &it->second;
+      run_pointers(ptrs, matrix_coeff, control, device_id);
+    }
+
     void output_global_solution_in_cell() const
     {
       if (!is_set_global_weights)
@@ -228,12 +243,15 @@ namespace DiffusionProblem
     void set_verbose(bool v) { verbose = v; }
 
   private:
+  public:
     static const Coefficients::TensorCoefficient<dim> &default_coefficient()
     {
       // assemble_system hard-wires Coefficients::MatrixCoeff<dim> (basis.tpp:184)
       static const Coefficients::MatrixCoeff<dim> c;
       return c;
     }
+
+  private:
 
     void require_batch() const
     {

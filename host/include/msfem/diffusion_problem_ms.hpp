@@ -17,7 +17,9 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <exception>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "msfem/coefficients.hpp"
@@ -33,10 +35,12 @@ namespace DiffusionProblem
     static_assert(dim == 2, "only the 2D path is built");
 
   public:
-    DiffusionProblemMultiscale(unsigned int n_refine, unsigned int n_refine_local, int device_id = 0)
+    DiffusionProblemMultiscale(unsigned int n_refine, unsigned int n_refine_local, int device_id = 0,
+                               int n_devices = 1)
       : n_refine(n_refine)
       , n_refine_local(n_refine_local)
       , device_id(device_id)
+      , n_devices(n_devices < 1 ? 1 : n_devices)
     {}
 
     void set_coefficient(const Coefficients::TensorCoefficient<dim> *c) { matrix_coeff = c; }
@@ -48,7 +52,7 @@ namespace DiffusionProblem
       std::cout << std::endl
                 << "===========================================" << std::endl
                 << "Solving >> MULTISCALE << problem in " << dim << "D." << std::endl;
-      std::cout << "Running with the B200 basis stage on 1 rank(s)..." << std::endl;
+      std::cout << "Running with the B200 basis stage on " << n_devices << " GPU(s)..." << std::endl;
       make_grid();
       setup_system();
       timed("basis initialization and computation", [&] { initialize_and_compute_basis(); });
@@ -152,10 +156,43 @@ namespace DiffusionProblem
           DiffusionProblemBasis<dim> current_cell_problem(n_refine_local, cells[m], /*subdomain*/ 0, 0);
           cell_basis_map.insert(std::make_pair(cells[m].id(), current_cell_problem));
         }
-      if (matrix_coeff)
-        DiffusionProblemBasis<dim>::run_all(cell_basis_map, *matrix_coeff, BasisSolverControl(), device_id);
-      else
-        DiffusionProblemBasis<dim>::run_all(cell_basis_map);
+      const Coefficients::TensorCoefficient<dim> &coeff =
+        matrix_coeff ? *matrix_coeff : DiffusionProblemBasis<dim>::default_coefficient();
+      if (n_devices == 1)
+        {
+          DiffusionProblemBasis<dim>::run_all(cell_basis_map, coeff, BasisSolverControl(), device_id);
+          return;
+        }
+      // one host thread and one GPU batch per device, contiguous Morton ranges
+      // [C g / P, C (g+1) / P) -- what "mpirun -n P" does to the reference (ms.tpp:52)
+      const std::size_t               C = cell_basis_map.size();
+      std::vector<std::thread>        workers;
+      std::vector<std::exception_ptr> errors(n_devices);
+      auto                            it = cell_basis_map.begin();
+      std::size_t                     pos = 0;
+      for (int g = 0; g < n_devices; ++g)
+        {
+          const std::size_t hi    = C * (g + 1) / n_devices;
+          auto              first = it;
+          while (pos < hi)
+            ++it, ++pos;
+          auto last = it;
+          workers.emplace_back([=, &coeff, &errors]() {
+            try
+              {
+                DiffusionProblemBasis<dim>::run_range(first, last, coeff, BasisSolverControl(), device_id + g);
+              }
+            catch (...)
+              {
+                errors[g] = std::current_exception();
+              }
+          });
+        }
+      for (auto &w : workers)
+        w.join();
+      for (auto &e : errors)
+        if (e)
+          std::rethrow_exception(e);
     }
 
     void cell_dofs(std::size_t m, unsigned (&ld)[4]) const
@@ -343,7 +380,7 @@ namespace DiffusionProblem
     }
 
     unsigned int n_refine, n_refine_local;
-    int          device_id;
+    int          device_id, n_devices;
     unsigned     nc = 0, n_coarse_dofs = 0;
     double       H = 1.0;
     bool         write_output = false;

@@ -5,7 +5,7 @@
 // (main.cxx:29-35) are out of scope (component 4).
 //
 //   msfem_main [--n-refine R] [--n-refine-local L] [--coeff reference|periodic|inclusions]
-//              [--dump coarse_solution.txt] [--output] [--device D]
+//              [--dump coarse_solution.txt] [--output] [--device D] [--gpus P]
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -23,7 +23,7 @@ main(int argc, char *argv[])
       unsigned int n_refine = 3, n_refine_local = 7;
       std::string  coeff = "reference", dump;
       bool         output = false;
-      int          device = 0;
+      int          device = 0, gpus = 1;
       for (int i = 1; i < argc; ++i)
         {
           const std::string a = argv[i];
@@ -37,6 +37,8 @@ main(int argc, char *argv[])
             dump = argv[++i];
           else if (a == "--device" && i + 1 < argc)
             device = std::atoi(argv[++i]);
+          else if (a == "--gpus" && i + 1 < argc)
+            gpus = std::atoi(argv[++i]);
           else if (a == "--output")
             output = true;
           else
@@ -53,7 +55,7 @@ main(int argc, char *argv[])
       else
         throw std::runtime_error("unknown coefficient " + coeff);
 
-      DiffusionProblem::DiffusionProblemMultiscale<2> diffusion_ms_problem_2d(n_refine, n_refine_local, device);
+      DiffusionProblem::DiffusionProblemMultiscale<2> diffusion_ms_problem_2d(n_refine, n_refine_local, device, gpus);
       diffusion_ms_problem_2d.set_coefficient(c.get());
       diffusion_ms_problem_2d.set_output(output);
       diffusion_ms_problem_2d.run();

@@ -107,3 +107,23 @@ def test_cpp_driver_reports_no_convergence_like_the_reference(tmp_path):
     exe = os.path.join(ROOT, "host", "_build", "msfem_main")
     out = subprocess.run([exe, "--coeff", "nonsense"], cwd=str(tmp_path), capture_output=True, text=True)
     assert out.returncode == 1 and "Exception on processing" in out.stderr
+
+
+def test_cpp_driver_on_two_gpus_matches_one_gpu(tmp_path):
+    """One handle and one host thread per device over contiguous Morton ranges (the ownership
+    the reference gets from mpirun -n P): the coarse solution must not depend on P."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "mpi_parallel_multiscale_diffusion_fem_b200", "libmsfem_basis.so"))
+    if lib.msb_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    exe = os.path.join(ROOT, "host", "_build", "msfem_main")
+    sols = []
+    for gpus in (1, 2):
+        dump = str(tmp_path / ("coarse%d.txt" % gpus))
+        out = subprocess.run([exe, "--n-refine", "4", "--n-refine-local", "5", "--gpus", str(gpus),
+                              "--dump", dump], cwd=str(tmp_path), capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr + out.stdout
+        lines = open(dump).read().split("\n")
+        n = int(lines[0])
+        sols.append(np.array([float(v) for v in lines[1:1 + n]]))
+    assert np.array_equal(sols[0], sols[1])     # same kernels, same cells: bitwise identical

@@ -44,7 +44,7 @@ typedef enum
 {
   MSB_OK                 = 0,
   MSB_ERR_INVALID_ARG    = -1,
-  MSB_ERR_UNSUPPORTED    = -2, /* dim == 3, n_refine_local out of range          */
+  MSB_ERR_UNSUPPORTED    = -2, /* dim/tier/coefficient/n_refine_local not built   */
   MSB_ERR_NO_DEVICE      = -3, /* no CUDA device / wrong architecture            */
   MSB_ERR_CUDA           = -4, /* a CUDA call failed, see msb_last_error()       */
   MSB_ERR_NO_CONVERGENCE = -5, /* some local solve hit max_iter (basis.tpp:297)  */
@@ -85,7 +85,7 @@ typedef struct
 typedef struct
 {
   int32_t        abi_version;    /* MSB_ABI_VERSION                               */
-  int32_t        dim;            /* 2                                             */
+  int32_t        dim;            /* 2 or 3 (diffusion_problem_basis.inst.cc:15-16) */
   int32_t        n_refine_local; /* l: n = 2^l fine cells per direction, 1..9     */
   int32_t        n_cells;        /* coarse cells of this shard                    */
   int32_t        device_id;      /* CUDA device ordinal                           */
@@ -100,7 +100,9 @@ typedef struct msb_handle_s *msb_handle;
 
 /* Replaces the construction loop ms.tpp:50-73 (DiffusionProblemBasis ctor,
  * basis.tpp:18-50).  corners: [n_cells][2^dim][dim] doubles, deal.II vertex
- * order.  coeff_table: NULL unless coeff.kind == MSB_COEFF_TABLE, then
+ * order.  dim 3 (hexahedral cells, 8 bases, 1 <= n_refine_local <= 6) takes
+ * MSB_COEFF_REFERENCE (MatrixCoeff<3>, matrix_coeff.tpp:28-41) or MSB_COEFF_CONSTANT
+ * and always runs in the streamed tier.  coeff_table: NULL unless coeff.kind == MSB_COEFF_TABLE, then
  * [n_cells][n*n fine cells, iy*n+ix][4 q-points, x fastest][a00,a01,a10,a11]. */
 int msb_create(const msb_config *cfg, const double *corners, const double *coeff_table,
                msb_handle *out);
@@ -127,10 +129,10 @@ int msb_sync(msb_handle h);
 int msb_get_failure(msb_handle h, int32_t *cell, int32_t *index_basis, double *residual);
 
 /* get_global_element_matrix / get_global_element_rhs (basis.tpp:320-333) for
- * all cells: M [n_cells][4][4] row-major, b [n_cells][4]. */
+ * all cells: M [n_cells][2^dim][2^dim] row-major, b [n_cells][2^dim]. */
 int msb_get_element_matrices(msb_handle h, double *M, double *b);
 
-/* solver_control.last_step() of every solve (basis.tpp:310-316): [n_cells][4];
+/* solver_control.last_step() of every solve (basis.tpp:310-316): [n_cells][2^dim];
  * residuals: final ||r||_2 of every solve, may be NULL. */
 int msb_get_iteration_counts(msb_handle h, int32_t *iters, double *residuals);
 
@@ -138,11 +140,13 @@ int msb_get_iteration_counts(msb_handle h, int32_t *iters, double *residuals);
  * deal.II DoF order. */
 int msb_get_basis(msb_handle h, int32_t cell, int32_t index_basis, double *out);
 
-/* DoF map of the local mesh (basis.tpp:106): dof_of_vertex[jy*(n+1)+jx]. */
+/* DoF map of the local mesh (basis.tpp:106): dof_of_vertex[jy*(n+1)+jx]
+ * (dim 3: [(jz*(n+1)+jy)*(n+1)+jx]). */
 int msb_get_dof_map(msb_handle h, uint32_t *dof_of_vertex);
 
-/* Constraint set `index_basis` of one cell (basis.tpp:119-135): the 4n
- * constrained DoFs in ascending order and their inhomogeneities. */
+/* Constraint set `index_basis` of one cell (basis.tpp:119-135): the
+ * (n+1)^dim - (n-1)^dim constrained DoFs (4n for dim 2) in ascending order and
+ * their inhomogeneities. */
 int msb_get_constraints(msb_handle h, int32_t cell, int32_t index_basis, uint32_t *dofs,
                         double *values);
 
@@ -153,7 +157,7 @@ int msb_apply_operator(msb_handle h, int32_t cell, const double *x, double *y);
 int msb_get_load_vector(msb_handle h, int32_t cell, double *F);
 
 /* set_global_weights for all cells (basis.tpp:352-377; caller
- * send_global_weights_to_cell ms.tpp:299-325): w [n_cells][4]. */
+ * send_global_weights_to_cell ms.tpp:299-325): w [n_cells][2^dim]. */
 int msb_set_global_weights(msb_handle h, const double *w);
 
 /* global_solution of one cell (basis.hpp, basis.tpp:421-435), deal.II order. */

@@ -88,16 +88,19 @@ class BasisShard:
     of diffusion_problem_ms.hpp:230 together with the loop ms.tpp:81-87 that runs it."""
 
     def __init__(self, n_refine_local, corners, coeff, rhs_value=2.0, device_id=0,
-                 tier=TIER_AUTO, variant=0, table=None):
+                 tier=TIER_AUTO, variant=0, table=None, dim=2):
         self._lib = load_library()
         self._h = C.c_void_p()
-        corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(-1, 4, 2)
+        self.dim = int(dim)
+        self.nb = 1 << self.dim  # bases per coarse cell (GeometryInfo<dim>::vertices_per_cell)
+        corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(-1, self.nb, self.dim)
         self.n_cells = corners.shape[0]
         self.l = int(n_refine_local)
         self.n = 1 << self.l
-        self.N = (self.n + 1) ** 2
+        self.N = (self.n + 1) ** self.dim
+        self.n_boundary = self.N - (self.n - 1) ** self.dim
         cfg = Config()
-        cfg.abi_version, cfg.dim, cfg.n_refine_local = ABI_VERSION, 2, self.l
+        cfg.abi_version, cfg.dim, cfg.n_refine_local = ABI_VERSION, self.dim, self.l
         cfg.n_cells, cfg.device_id, cfg.tier, cfg.variant = self.n_cells, device_id, tier, variant
         cfg.rhs_value = rhs_value
         cfg.coeff = coeff
@@ -132,7 +135,7 @@ class BasisShard:
         self.close()
 
     def set_cells(self, corners, table=None):
-        corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(-1, 4, 2)
+        corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(-1, self.nb, self.dim)
         assert corners.shape[0] == self.n_cells
         tab = None if table is None else np.ascontiguousarray(table, dtype=np.float64)
         self._check(self._lib.msb_set_cells(self._h, _dp(corners), None if tab is None else _dp(tab)))
@@ -162,14 +165,14 @@ class BasisShard:
 
     # -- accessors -----------------------------------------------------------------------
     def element_matrices(self):
-        M = np.empty((self.n_cells, 4, 4), dtype=np.float64)
-        b = np.empty((self.n_cells, 4), dtype=np.float64)
+        M = np.empty((self.n_cells, self.nb, self.nb), dtype=np.float64)
+        b = np.empty((self.n_cells, self.nb), dtype=np.float64)
         self._check(self._lib.msb_get_element_matrices(self._h, _dp(M), _dp(b)))
         return M, b
 
     def iteration_counts(self):
-        it = np.empty((self.n_cells, 4), dtype=np.int32)
-        res = np.empty((self.n_cells, 4), dtype=np.float64)
+        it = np.empty((self.n_cells, self.nb), dtype=np.int32)
+        res = np.empty((self.n_cells, self.nb), dtype=np.float64)
         self._check(self._lib.msb_get_iteration_counts(
             self._h, it.ctypes.data_as(C.POINTER(C.c_int32)), _dp(res)))
         return it, res
@@ -187,11 +190,11 @@ class BasisShard:
     def dof_map(self):
         out = np.empty(self.N, dtype=np.uint32)
         self._check(self._lib.msb_get_dof_map(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32))))
-        return out.reshape(self.n + 1, self.n + 1)
+        return out.reshape((self.n + 1,) * self.dim)
 
     def constraints(self, cell, index_basis):
-        dofs = np.empty(4 * self.n, dtype=np.uint32)
-        vals = np.empty(4 * self.n, dtype=np.float64)
+        dofs = np.empty(self.n_boundary, dtype=np.uint32)
+        vals = np.empty(self.n_boundary, dtype=np.float64)
         self._check(self._lib.msb_get_constraints(
             self._h, C.c_int32(cell), C.c_int32(index_basis),
             dofs.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(vals)))
@@ -209,7 +212,7 @@ class BasisShard:
         return F
 
     def set_global_weights(self, w):
-        w = np.ascontiguousarray(w, dtype=np.float64).reshape(self.n_cells, 4)
+        w = np.ascontiguousarray(w, dtype=np.float64).reshape(self.n_cells, self.nb)
         self._check(self._lib.msb_set_global_weights(self._h, _dp(w)))
 
     def global_solution(self, cell):

@@ -68,49 +68,58 @@ msb_device_count(void)
   return n;
 }
 
-// BasisQ1<2> coefficient matrix (basis_q1.tpp:26-47): inverse of the point matrix
-// [1, x, y, xy] at the four vertices, by Gauss-Jordan with partial pivoting.
+// BasisQ1<dim> coefficient matrix (basis_q1.tpp:26-47 for dim 2, :50-75 for dim 3): inverse of
+// the point matrix [1, x, y, xy] resp. [1, x, y, z, xy, yz, xz, xyz] at the vertices, by
+// Gauss-Jordan with partial pivoting.
 static bool
-basis_q1_matrix(const double *corners, double *coef)
+basis_q1_matrix(int dim, const double *corners, double *coef)
 {
-  double a[4][8];
-  for (int i = 0; i < 4; ++i)
+  const int nb = 1 << dim;
+  double    a[8][16];
+  for (int i = 0; i < nb; ++i)
     {
-      const double x = corners[2 * i], y = corners[2 * i + 1];
-      a[i][0] = 1.0, a[i][1] = x, a[i][2] = y, a[i][3] = x * y;
-      for (int j = 0; j < 4; ++j)
-        a[i][4 + j] = i == j ? 1.0 : 0.0;
+      const double x = corners[dim * i], y = corners[dim * i + 1];
+      a[i][0] = 1.0, a[i][1] = x, a[i][2] = y;
+      if (dim == 2)
+        a[i][3] = x * y;
+      else
+        {
+          const double z = corners[dim * i + 2];
+          a[i][3] = z, a[i][4] = x * y, a[i][5] = y * z, a[i][6] = x * z, a[i][7] = x * y * z;
+        }
+      for (int j = 0; j < nb; ++j)
+        a[i][nb + j] = i == j ? 1.0 : 0.0;
     }
-  for (int c = 0; c < 4; ++c)
+  for (int c = 0; c < nb; ++c)
     {
       int piv = c;
-      for (int r = c + 1; r < 4; ++r)
+      for (int r = c + 1; r < nb; ++r)
         if (fabs(a[r][c]) > fabs(a[piv][c]))
           piv = r;
       if (a[piv][c] == 0.0)
         return false;
       if (piv != c)
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 2 * nb; ++j)
           {
             const double t = a[c][j];
             a[c][j]        = a[piv][j];
             a[piv][j]      = t;
           }
       const double inv = 1.0 / a[c][c];
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 2 * nb; ++j)
         a[c][j] *= inv;
-      for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < nb; ++r)
         if (r != c)
           {
             const double f = a[r][c];
             if (f != 0.0)
-              for (int j = 0; j < 8; ++j)
+              for (int j = 0; j < 2 * nb; ++j)
                 a[r][j] -= f * a[c][j];
           }
     }
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 4; ++j)
-      coef[4 * i + j] = a[i][4 + j];
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j < nb; ++j)
+      coef[nb * i + j] = a[i][nb + j];
   return true;
 }
 
@@ -141,10 +150,16 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
   if (cfg->abi_version != MSB_ABI_VERSION)
     return fail(MSB_ERR_INVALID_ARG, "msb_create: abi_version %d, library has %d", cfg->abi_version,
                 MSB_ABI_VERSION);
-  if (cfg->dim != 2)
-    return fail(MSB_ERR_UNSUPPORTED, "msb_create: dim=%d (only the 2D path is built)", cfg->dim);
-  if (cfg->n_refine_local < 1 || cfg->n_refine_local > 9)
-    return fail(MSB_ERR_UNSUPPORTED, "msb_create: n_refine_local=%d outside 1..9", cfg->n_refine_local);
+  if (cfg->dim != 2 && cfg->dim != 3)
+    return fail(MSB_ERR_UNSUPPORTED, "msb_create: dim=%d (the reference instantiates 2 and 3)", cfg->dim);
+  const int max_l = cfg->dim == 2 ? 9 : 6;
+  if (cfg->n_refine_local < 1 || cfg->n_refine_local > max_l)
+    return fail(MSB_ERR_UNSUPPORTED, "msb_create: n_refine_local=%d outside 1..%d for dim=%d",
+                cfg->n_refine_local, max_l, cfg->dim);
+  if (cfg->dim == 3 && cfg->coeff.kind != MSB_COEFF_REFERENCE && cfg->coeff.kind != MSB_COEFF_CONSTANT)
+    return fail(MSB_ERR_UNSUPPORTED, "msb_create: dim=3 supports MSB_COEFF_REFERENCE and MSB_COEFF_CONSTANT");
+  if (cfg->dim == 3 && cfg->tier == MSB_TIER_SMEM)
+    return fail(MSB_ERR_UNSUPPORTED, "msb_create: dim=3 runs in the streamed tier");
   if (cfg->n_cells < 1)
     return fail(MSB_ERR_INVALID_ARG, "msb_create: n_cells=%d", cfg->n_cells);
   if (cfg->coeff.kind < MSB_COEFF_REFERENCE || cfg->coeff.kind > MSB_COEFF_TABLE)
@@ -175,16 +190,21 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
   if (!h)
     return fail(MSB_ERR_INVALID_ARG, "msb_create: out of host memory");
   Shard &s    = h->s;
+  s.dim       = cfg->dim;
+  s.nb        = 1 << s.dim;
+  s.nst       = s.dim == 2 ? (int)ST_NARR : (int)ST3_NARR;
   s.l         = cfg->n_refine_local;
   s.n         = 1 << s.l;
   s.np        = s.n + 1;
-  s.N         = s.np * s.np;
+  s.N         = s.dim == 2 ? s.np * s.np : s.np * s.np * s.np;
   s.n_cells   = cfg->n_cells;
   s.device    = cfg->device_id;
   s.variant   = cfg->variant;
   s.coeff     = cfg->coeff;
   s.rhs_value = cfg->rhs_value;
   s.tier      = cfg->tier;
+  if (s.dim == 3)
+    s.tier = MSB_TIER_STREAMED;
   if (s.tier == MSB_TIER_AUTO)
     s.tier = smem_tier_supported(s.l) ? MSB_TIER_SMEM : MSB_TIER_STREAMED;
   if (s.tier == MSB_TIER_SMEM && !smem_tier_supported(s.l))
@@ -193,10 +213,10 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
       return fail(MSB_ERR_UNSUPPORTED, "msb_create: shared-memory tier needs 3 <= n_refine_local <= 6");
     }
 
-  const size_t C = (size_t)s.n_cells, N = (size_t)s.N;
-  std::vector<double> q1(16 * C);
+  const size_t C = (size_t)s.n_cells, N = (size_t)s.N, NB = (size_t)s.nb, NCORN = NB * s.dim;
+  std::vector<double> q1(NB * NB * C);
   for (size_t c = 0; c < C; ++c)
-    if (!basis_q1_matrix(corners + 8 * c, q1.data() + 16 * c))
+    if (!basis_q1_matrix(s.dim, corners + NCORN * c, q1.data() + NB * NB * c))
       {
         delete h;
         return fail(MSB_ERR_INVALID_ARG, "msb_create: coarse cell %zu is degenerate", c);
@@ -216,14 +236,14 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
     }                                                                                          \
   while (0)
 
-  ALLOC(s.d_corners, 8 * C);
-  ALLOC(s.d_q1coef, 16 * C);
-  ALLOC(s.d_sten, C * ST_NARR * N);
-  ALLOC(s.d_phi, C * 4 * N);
-  ALLOC(s.d_M, 16 * C);
-  ALLOC(s.d_b, 4 * C);
-  ALLOC(s.d_iters, 4 * C);
-  ALLOC(s.d_res, 4 * C);
+  ALLOC(s.d_corners, NCORN * C);
+  ALLOC(s.d_q1coef, NB * NB * C);
+  ALLOC(s.d_sten, C * s.nst * N);
+  ALLOC(s.d_phi, C * NB * N);
+  ALLOC(s.d_M, NB * NB * C);
+  ALLOC(s.d_b, NB * C);
+  ALLOC(s.d_iters, NB * C);
+  ALLOC(s.d_res, NB * C);
   ALLOC(s.d_fail, 2);
   ALLOC(s.d_dofmap, N);
   ALLOC(s.d_invmap, N);
@@ -233,15 +253,17 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
     ALLOC(s.d_table, C * (size_t)s.n * s.n * 16);
   if (s.tier == MSB_TIER_STREAMED)
     {
-      ALLOC(s.d_wr, C * 4 * N);
-      ALLOC(s.d_wp, C * 4 * N);
-      ALLOC(s.d_wq, C * 4 * N);
-      ALLOC(s.d_wz, C * 4 * N);
-      ALLOC(s.d_wv, C * 4 * streamed_coarse_nodes(s.l));
-      ALLOC(s.d_dinv, C * streamed_coarse_nodes(s.l));
-      ALLOC(s.d_gal, streamed_galerkin_scratch_doubles(s.l, s.n_cells));
-      ALLOC(s.d_scal, 4 * C);
-      ALLOC(s.d_part, 4 * C * 2 * 3 * 32);
+      const size_t cn = s.dim == 2 ? streamed_coarse_nodes(s.l) : dim3_coarse_nodes(s.l);
+      ALLOC(s.d_wr, C * NB * N);
+      ALLOC(s.d_wp, C * NB * N);
+      ALLOC(s.d_wq, C * NB * N);
+      ALLOC(s.d_wz, C * NB * N);
+      ALLOC(s.d_wv, C * NB * cn);
+      ALLOC(s.d_dinv, C * cn);
+      if (s.dim == 2)
+        ALLOC(s.d_gal, streamed_galerkin_scratch_doubles(s.l, s.n_cells));
+      ALLOC(s.d_scal, NB * C);
+      ALLOC(s.d_part, NB * C * (size_t)(s.dim == 2 ? 2 * 3 * 32 : dim3_part_stride()));
     }
 #undef ALLOC
 
@@ -249,16 +271,16 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
   for (int i = 0; i < 4 && e == cudaSuccess; ++i)
     e = cudaEventCreate(&s.ev[i]);
   if (e == cudaSuccess)
-    e = cudaMemcpyAsync(s.d_corners, corners, sizeof(double) * 8 * C, cudaMemcpyHostToDevice, s.stream);
+    e = cudaMemcpyAsync(s.d_corners, corners, sizeof(double) * NCORN * C, cudaMemcpyHostToDevice, s.stream);
   if (e == cudaSuccess)
-    e = cudaMemcpyAsync(s.d_q1coef, q1.data(), sizeof(double) * 16 * C, cudaMemcpyHostToDevice, s.stream);
+    e = cudaMemcpyAsync(s.d_q1coef, q1.data(), sizeof(double) * NB * NB * C, cudaMemcpyHostToDevice, s.stream);
   if (e == cudaSuccess && s.d_table)
     e = cudaMemcpyAsync(s.d_table, coeff_table, sizeof(double) * C * (size_t)s.n * s.n * 16,
                         cudaMemcpyHostToDevice, s.stream);
   if (e == cudaSuccess)
     e = cudaStreamSynchronize(s.stream);
   if (e == cudaSuccess)
-    e = launch_dofmap(s, s.stream);
+    e = s.dim == 2 ? launch_dofmap(s, s.stream) : launch_dofmap3(s, s.stream);
   if (e != cudaSuccess)
     {
       free_shard(s);
@@ -280,13 +302,14 @@ msb_set_cells(msb_handle h, const double *corners, const double *coeff_table)
   CUDA_TRY(cudaSetDevice(s.device));
   if (s.run_pending)
     CUDA_TRY(cudaStreamSynchronize(s.run_stream));
-  const size_t        C = (size_t)s.n_cells;
-  std::vector<double> q1(16 * C);
+  const size_t        C = (size_t)s.n_cells, NB = (size_t)s.nb, NCORN = NB * s.dim;
+  std::vector<double> q1(NB * NB * C);
   for (size_t c = 0; c < C; ++c)
-    if (!basis_q1_matrix(corners + 8 * c, q1.data() + 16 * c))
+    if (!basis_q1_matrix(s.dim, corners + NCORN * c, q1.data() + NB * NB * c))
       return fail(MSB_ERR_INVALID_ARG, "msb_set_cells: coarse cell %zu is degenerate", c);
-  CUDA_TRY(cudaMemcpyAsync(s.d_corners, corners, sizeof(double) * 8 * C, cudaMemcpyHostToDevice, s.stream));
-  CUDA_TRY(cudaMemcpyAsync(s.d_q1coef, q1.data(), sizeof(double) * 16 * C, cudaMemcpyHostToDevice, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(s.d_corners, corners, sizeof(double) * NCORN * C, cudaMemcpyHostToDevice, s.stream));
+  CUDA_TRY(cudaMemcpyAsync(s.d_q1coef, q1.data(), sizeof(double) * NB * NB * C, cudaMemcpyHostToDevice,
+                           s.stream));
   if (s.d_table)
     CUDA_TRY(cudaMemcpyAsync(s.d_table, coeff_table, sizeof(double) * C * (size_t)s.n * s.n * 16,
                              cudaMemcpyHostToDevice, s.stream));
@@ -324,10 +347,15 @@ msb_run_async(msb_handle h, double tol_abs, int32_t max_iter, void *cuda_stream)
   const int32_t init_fail[2] = {INT_MAX, 0};
   CUDA_TRY(cudaMemcpyAsync(s.d_fail, init_fail, sizeof init_fail, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaEventRecord(s.ev[0], st));
-  CUDA_TRY(launch_assemble(s, st, &s.n_launches));
+  if (s.dim == 3)
+    CUDA_TRY(launch_assemble3(s, st, &s.n_launches));
+  else
+    CUDA_TRY(launch_assemble(s, st, &s.n_launches));
   s.assembled = true;
   CUDA_TRY(cudaEventRecord(s.ev[1], st));
-  if (s.tier == MSB_TIER_SMEM && s.variant < 100)
+  if (s.dim == 3)
+    CUDA_TRY(launch_solve3(s, tol_abs, max_iter, st, &s.n_launches));
+  else if (s.tier == MSB_TIER_SMEM && s.variant < 100)
     CUDA_TRY(launch_solve_bpx(s, tol_abs, max_iter, st, &s.n_launches)); // multilevel PCG (default)
   else if (s.tier == MSB_TIER_SMEM)
     CUDA_TRY(launch_solve_smem(s, tol_abs, max_iter, st, &s.n_launches)); // Jacobi PCG (variant >= 100)
@@ -335,7 +363,10 @@ msb_run_async(msb_handle h, double tol_abs, int32_t max_iter, void *cuda_stream)
     CUDA_TRY(launch_solve_streamed(s, tol_abs, max_iter, st, &s.n_launches));
   s.tier_used = s.tier;
   CUDA_TRY(cudaEventRecord(s.ev[2], st));
-  CUDA_TRY(launch_element_matrices(s, st, &s.n_launches));
+  if (s.dim == 3)
+    CUDA_TRY(launch_element_matrices3(s, st, &s.n_launches));
+  else
+    CUDA_TRY(launch_element_matrices(s, st, &s.n_launches));
   CUDA_TRY(cudaEventRecord(s.ev[3], st));
   s.run_pending = true;
   s.weights_set = false;
@@ -361,7 +392,7 @@ msb_sync(msb_handle h)
     s.last_status = fail(MSB_ERR_NO_CONVERGENCE,
                          "local solve (cell %d, basis %d) did not reach the tolerance within max_iter "
                          "(the reference throws SolverControl::NoConvergence here)",
-                         f[0] / 4, f[0] % 4);
+                         f[0] / s.nb, f[0] % s.nb);
   return s.last_status;
 }
 
@@ -412,9 +443,9 @@ msb_get_failure(msb_handle h, int32_t *cell, int32_t *index_basis, double *resid
       return MSB_OK;
     }
   if (cell)
-    *cell = f[0] / 4;
+    *cell = f[0] / h->s.nb;
   if (index_basis)
-    *index_basis = f[0] % 4;
+    *index_basis = f[0] % h->s.nb;
   if (residual)
     CUDA_TRY(cudaMemcpy(residual, h->s.d_res + f[0], sizeof(double), cudaMemcpyDeviceToHost));
   return MSB_OK;
@@ -426,11 +457,11 @@ msb_get_element_matrices(msb_handle h, double *M, double *b)
   int rc = need_ran(h, "msb_get_element_matrices");
   if (rc != MSB_OK)
     return rc;
-  const size_t C = (size_t)h->s.n_cells;
+  const size_t C = (size_t)h->s.n_cells, NB = (size_t)h->s.nb;
   if (M)
-    CUDA_TRY(cudaMemcpy(M, h->s.d_M, sizeof(double) * 16 * C, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(M, h->s.d_M, sizeof(double) * NB * NB * C, cudaMemcpyDeviceToHost));
   if (b)
-    CUDA_TRY(cudaMemcpy(b, h->s.d_b, sizeof(double) * 4 * C, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(b, h->s.d_b, sizeof(double) * NB * C, cudaMemcpyDeviceToHost));
   return MSB_OK;
 }
 
@@ -440,18 +471,18 @@ msb_get_iteration_counts(msb_handle h, int32_t *iters, double *residuals)
   int rc = need_ran(h, "msb_get_iteration_counts");
   if (rc != MSB_OK)
     return rc;
-  const size_t C = (size_t)h->s.n_cells;
+  const size_t C = (size_t)h->s.n_cells, NB = (size_t)h->s.nb;
   if (iters)
-    CUDA_TRY(cudaMemcpy(iters, h->s.d_iters, sizeof(int32_t) * 4 * C, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(iters, h->s.d_iters, sizeof(int32_t) * NB * C, cudaMemcpyDeviceToHost));
   if (residuals)
-    CUDA_TRY(cudaMemcpy(residuals, h->s.d_res, sizeof(double) * 4 * C, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(residuals, h->s.d_res, sizeof(double) * NB * C, cudaMemcpyDeviceToHost));
   return MSB_OK;
 }
 
 static int
 check_cell(msb_handle h, int32_t cell, int32_t ib, const char *who)
 {
-  if (cell < 0 || cell >= h->s.n_cells || ib < 0 || ib > 3)
+  if (cell < 0 || cell >= h->s.n_cells || ib < 0 || ib >= h->s.nb)
     return fail(MSB_ERR_INVALID_ARG, "%s: cell %d / basis %d out of range", who, cell, ib);
   return MSB_OK;
 }
@@ -465,7 +496,7 @@ msb_get_basis(msb_handle h, int32_t cell, int32_t ib, double *out)
   if ((rc = check_cell(h, cell, ib, "msb_get_basis")) != MSB_OK || !out)
     return rc != MSB_OK ? rc : fail(MSB_ERR_INVALID_ARG, "msb_get_basis: null out");
   Shard &s = h->s;
-  CUDA_TRY(launch_permute(s, s.d_phi + ((size_t)cell * 4 + ib) * s.N, s.d_tmp, true, s.stream));
+  CUDA_TRY(launch_permute(s, s.d_phi + ((size_t)cell * s.nb + ib) * s.N, s.d_tmp, true, s.stream));
   CUDA_TRY(cudaMemcpyAsync(out, s.d_tmp, sizeof(double) * s.N, cudaMemcpyDeviceToHost, s.stream));
   CUDA_TRY(cudaStreamSynchronize(s.stream));
   return MSB_OK;
@@ -491,10 +522,13 @@ msb_get_constraints(msb_handle h, int32_t cell, int32_t ib, uint32_t *dofs, doub
     return rc;
   Shard &s = h->s;
   CUDA_TRY(cudaSetDevice(s.device));
-  const int nb    = 4 * s.n;
+  const int nb    = s.dim == 2 ? 4 * s.n : s.N - (s.n - 1) * (s.n - 1) * (s.n - 1);
   uint32_t *d_dof = reinterpret_cast<uint32_t *>(s.d_tmp);       // nb uint32 <= N doubles
   double   *d_val = s.d_tmp + s.N;
-  CUDA_TRY(launch_constraints(s, cell, ib, d_dof, d_val, s.stream));
+  if (s.dim == 3)
+    CUDA_TRY(launch_constraints3(s, cell, ib, d_dof, d_val, s.stream));
+  else
+    CUDA_TRY(launch_constraints(s, cell, ib, d_dof, d_val, s.stream));
   CUDA_TRY(cudaMemcpyAsync(dofs, d_dof, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, s.stream));
   CUDA_TRY(cudaMemcpyAsync(values, d_val, sizeof(double) * nb, cudaMemcpyDeviceToHost, s.stream));
   CUDA_TRY(cudaStreamSynchronize(s.stream));
@@ -514,7 +548,10 @@ ensure_assembled(msb_handle h)
   if (!s.assembled)
     {
       int nl = 0;
-      CUDA_TRY(launch_assemble(s, s.stream, &nl));
+      if (s.dim == 3)
+        CUDA_TRY(launch_assemble3(s, s.stream, &nl));
+      else
+        CUDA_TRY(launch_assemble(s, s.stream, &nl));
       CUDA_TRY(cudaStreamSynchronize(s.stream));
       s.assembled = true;
     }
@@ -536,7 +573,10 @@ msb_apply_operator(msb_handle h, int32_t cell, const double *x, double *y)
   double *d_in = s.d_tmp, *d_lex = s.d_tmp + s.N, *d_out = s.d_tmp + 2 * (size_t)s.N;
   CUDA_TRY(cudaMemcpyAsync(d_in, x, sizeof(double) * s.N, cudaMemcpyHostToDevice, s.stream));
   CUDA_TRY(launch_permute(s, d_in, d_lex, false, s.stream));      // dof order -> lex
-  CUDA_TRY(launch_apply_operator(s, cell, d_lex, d_out, s.stream));
+  if (s.dim == 3)
+    CUDA_TRY(launch_apply_operator3(s, cell, d_lex, d_out, s.stream));
+  else
+    CUDA_TRY(launch_apply_operator(s, cell, d_lex, d_out, s.stream));
   CUDA_TRY(launch_permute(s, d_out, d_in, true, s.stream));       // lex -> dof order
   CUDA_TRY(cudaMemcpyAsync(y, d_in, sizeof(double) * s.N, cudaMemcpyDeviceToHost, s.stream));
   CUDA_TRY(cudaStreamSynchronize(s.stream));
@@ -555,7 +595,7 @@ msb_get_load_vector(msb_handle h, int32_t cell, double *F)
   CUDA_TRY(cudaSetDevice(s.device));
   if ((rc = ensure_assembled(h)) != MSB_OK)
     return rc;
-  CUDA_TRY(launch_permute(s, s.d_sten + ((size_t)cell * ST_NARR + ST_F) * s.N, s.d_tmp, true, s.stream));
+  CUDA_TRY(launch_permute(s, s.d_sten + ((size_t)cell * s.nst + (s.dim == 2 ? (int)ST_F : (int)ST3_F)) * s.N, s.d_tmp, true, s.stream));
   CUDA_TRY(cudaMemcpyAsync(F, s.d_tmp, sizeof(double) * s.N, cudaMemcpyDeviceToHost, s.stream));
   CUDA_TRY(cudaStreamSynchronize(s.stream));
   return MSB_OK;
@@ -574,8 +614,8 @@ msb_set_global_weights(msb_handle h, const double *w)
   if (!s.d_gsol)
     CUDA_TRY(cudaMalloc((void **)&s.d_gsol, sizeof(double) * C * s.N));
   double *d_w = nullptr;
-  CUDA_TRY(cudaMalloc((void **)&d_w, sizeof(double) * 4 * C));
-  cudaError_t e = cudaMemcpyAsync(d_w, w, sizeof(double) * 4 * C, cudaMemcpyHostToDevice, s.stream);
+  CUDA_TRY(cudaMalloc((void **)&d_w, sizeof(double) * s.nb * C));
+  cudaError_t e = cudaMemcpyAsync(d_w, w, sizeof(double) * s.nb * C, cudaMemcpyHostToDevice, s.stream);
   if (e == cudaSuccess)
     e = launch_global_solution(s, d_w, s.stream);
   if (e == cudaSuccess)
@@ -632,7 +672,7 @@ msb_get_algorithmic_bytes(msb_handle h, double *bytes, double *mean_iterations)
   if (rc != MSB_OK)
     return rc;
   Shard               &s = h->s;
-  const size_t         n = 4 * (size_t)s.n_cells;
+  const size_t         n = (size_t)s.nb * s.n_cells;
   std::vector<int32_t> it(n);
   CUDA_TRY(cudaMemcpy(it.data(), s.d_iters, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
   // W = N (96 k + 16) bytes per solve

@@ -1,0 +1,1222 @@
+// msb_dim3.cu -- the dim = 3 instantiation of the local basis stage
+// (diffusion_problem_basis.inst.cc:15-16; BasisQ1<3> basis_q1.tpp:50-75,99-113; MatrixCoeff<3>
+// matrix_coeff.tpp:28-41,66-91): hexahedral coarse cells, (2^l+1)^3 fine Q1 nodes, 8 bases.
+//
+// Data layout in HBM, node index "lex" = (jz*np + jy)*np + jx:
+//   corners [C][8][3], q1coef [C][64]
+//   sten    [C][15][N]  symmetric 27-point stencil of the unconstrained fine stiffness matrix:
+//                       array 0 = diagonal, array k = 1..13 = coupling of node t with node
+//                       t + offset(13 + k) where offset(e) = (e%3-1, (e/3)%3-1, e/9-1) (the 13
+//                       "forward" neighbours), array 14 = load vector F
+//   phi     [C][8][N], M [C][64], b [C][8], iters/res [C][8]
+//
+// The solver is the batched multilevel-preconditioned CG of msb_solve_stream.cu in three
+// dimensions: all (cell, basis) solves advance together through K1 (p = z + beta p), K2
+// (q = K p, matrix-free 27-point), K3 (x, r update), restrict / prolong over the nested
+// trilinear hierarchy with exact Galerkin diagonals, and the fine-level z = r/D + P z_1.  Dot
+// products are deterministic two-level sums with parity double-buffered partials; the stopping
+// rule is the reference's ||r||_2 <= tol checked every iteration (basis.tpp:297).
+#include <limits.h>
+#include <math.h>
+
+#include "msb_internal.cuh"
+
+namespace msb
+{
+  namespace d3
+  {
+    constexpr int NB      = 8;
+    constexpr int NST     = ST3_NARR;
+    constexpr int THREADS = 256;
+    constexpr int MAXBLK  = 40;             // max CTAs per coarse cell in the fine kernels
+    constexpr int PSTRIDE = 2 * 3 * MAXBLK; // doubles per solve: [parity][rz|pq|rr][blk]
+    constexpr int MAXLEV  = 8;
+
+    // ------------------------------------------------------------------------- helpers
+    __host__ __device__ inline uint32_t
+    compact3(uint32_t m)
+    {
+      uint32_t x = m & 0x09249249u;
+      x          = (x | (x >> 2)) & 0x030c30c3u;
+      x          = (x | (x >> 4)) & 0x0300f00fu;
+      x          = (x | (x >> 8)) & 0x030000ffu;
+      x          = (x | (x >> 16)) & 0x000003ffu;
+      return x;
+    }
+
+    __host__ __device__ inline uint32_t
+    spread3(uint32_t x)
+    {
+      x &= 0x000003ffu;
+      x = (x | (x << 16)) & 0x030000ffu;
+      x = (x | (x << 8)) & 0x0300f00fu;
+      x = (x | (x << 4)) & 0x030c30c3u;
+      x = (x | (x << 2)) & 0x09249249u;
+      return x;
+    }
+
+    __host__ __device__ inline uint32_t
+    morton3(uint32_t ix, uint32_t iy, uint32_t iz)
+    {
+      return spread3(ix) | (spread3(iy) << 1) | (spread3(iz) << 2);
+    }
+
+    // trilinear image of the uniform grid (exact for axis-aligned dyadic bricks)
+    __device__ inline void
+    fine_vertex3(const double *__restrict__ c, int n, int jx, int jy, int jz, double p[3])
+    {
+      const double rn = 1.0 / (double)n, s = jx * rn, t = jy * rn, u = jz * rn;
+      const double w[8] = {(1 - s) * (1 - t) * (1 - u), s * (1 - t) * (1 - u), (1 - s) * t * (1 - u),
+                           s * t * (1 - u),             (1 - s) * (1 - t) * u, s * (1 - t) * u,
+                           (1 - s) * t * u,             s * t * u};
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        {
+          double v = 0.0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            v += c[3 * k + a] * w[k];
+          p[a] = v;
+        }
+    }
+
+    // BasisQ1<3>::value (basis_q1.tpp:99-113), coef[r*8+ib], monomials 1,x,y,z,xy,yz,xz,xyz
+    __device__ inline double
+    basis_q1_value3(const double *__restrict__ coef, int ib, const double p[3])
+    {
+      const double x = p[0], y = p[1], z = p[2];
+      return coef[ib] + coef[8 + ib] * x + coef[16 + ib] * y + coef[24 + ib] * z + coef[32 + ib] * x * y +
+             coef[40 + ib] * y * z + coef[48 + ib] * x * z + coef[56 + ib] * x * y * z;
+    }
+
+    __device__ __forceinline__ int
+    off_of(int e, int np)
+    {
+      return (e / 9 - 1) * np * np + ((e / 3) % 3 - 1) * np + (e % 3 - 1);
+    }
+
+    // coupling K(t, t + offset(e)); both nodes must exist
+    __device__ __forceinline__ double
+    sten3_get(const double *__restrict__ S, int N, int np, int t, int e)
+    {
+      if (e == 13)
+        return S[t];
+      if (e > 13)
+        return S[(size_t)(e - 13) * N + t];
+      return S[(size_t)(13 - e) * N + t + off_of(e, np)];
+    }
+
+    __device__ __forceinline__ void
+    decode3(int t, int np, int &jx, int &jy, int &jz)
+    {
+      jx          = t % np;
+      const int q = t / np;
+      jy          = q % np;
+      jz          = q / np;
+    }
+
+    __device__ __forceinline__ bool
+    on_boundary3(int jx, int jy, int jz, int n)
+    {
+      return jx == 0 || jy == 0 || jz == 0 || jx == n || jy == n || jz == n;
+    }
+
+    // block-wide deterministic sums of NV values -> valid on thread 0
+    template <int NV>
+    __device__ __forceinline__ void
+    block_sum_to(double (&v)[NV], double *sbuf /*[THREADS/32][NV]*/)
+    {
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1)
+            v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+          if (lane == 0)
+            sbuf[warp * NV + k] = v[k];
+        }
+      __syncthreads();
+      if (threadIdx.x == 0)
+        {
+#pragma unroll
+          for (int k = 0; k < NV; ++k)
+            {
+              double s = 0.0;
+              for (int w = 0; w < (int)blockDim.x / 32; ++w)
+                s += sbuf[w * NV + k];
+              v[k] = s;
+            }
+        }
+    }
+
+    // ========================================================================== DoF map
+    // deal.II first-touch numbering on the 3D Morton-ordered fine cells (closed form, as in 2D)
+    __device__ inline uint32_t
+    first_touch_cell3(int n, int jx, int jy, int jz, int &lv)
+    {
+      uint32_t best = 0xffffffffu;
+      lv            = 0;
+#pragma unroll
+      for (int v = 0; v < 8; ++v)
+        {
+          const int ix = jx - (v & 1), iy = jy - ((v >> 1) & 1), iz = jz - (v >> 2);
+          if (ix < 0 || iy < 0 || iz < 0 || ix >= n || iy >= n || iz >= n)
+            continue;
+          const uint32_t m = morton3((uint32_t)ix, (uint32_t)iy, (uint32_t)iz);
+          if (m < best)
+            {
+              best = m;
+              lv   = v;
+            }
+        }
+      return best;
+    }
+
+    __global__ void
+    dofmap3_count_kernel(int n, uint32_t *__restrict__ cnt, uint32_t *__restrict__ mask)
+    {
+      const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+      if (m >= (uint32_t)(n * n * n))
+        return;
+      const int ix = (int)compact3(m), iy = (int)compact3(m >> 1), iz = (int)compact3(m >> 2);
+      uint32_t  msk = 0;
+#pragma unroll
+      for (int v = 0; v < 8; ++v)
+        {
+          int lv;
+          if (first_touch_cell3(n, ix + (v & 1), iy + ((v >> 1) & 1), iz + (v >> 2), lv) == m)
+            msk |= 1u << v;
+        }
+      mask[m] = msk;
+      cnt[m]  = __popc(msk);
+    }
+
+    // single-block exclusive scan (n^3 <= 2^18 entries)
+    __global__ void
+    dofmap3_scan_kernel(int total, const uint32_t *__restrict__ cnt, uint32_t *__restrict__ base)
+    {
+      __shared__ uint32_t part[1024];
+      const int           T     = blockDim.x;
+      const int           chunk = (total + T - 1) / T;
+      const int           lo    = min(total, (int)threadIdx.x * chunk), hi = min(total, lo + chunk);
+      uint32_t            s = 0;
+      for (int i = lo; i < hi; ++i)
+        s += cnt[i];
+      part[threadIdx.x] = s;
+      __syncthreads();
+      if (threadIdx.x == 0)
+        {
+          uint32_t run = 0;
+          for (int t = 0; t < T; ++t)
+            {
+              const uint32_t v = part[t];
+              part[t]          = run;
+              run += v;
+            }
+        }
+      __syncthreads();
+      uint32_t run = part[threadIdx.x];
+      for (int i = lo; i < hi; ++i)
+        {
+          base[i] = run;
+          run += cnt[i];
+        }
+    }
+
+    __global__ void
+    dofmap3_assign_kernel(int n, const uint32_t *__restrict__ base, const uint32_t *__restrict__ mask,
+                          uint32_t *__restrict__ dofmap, uint32_t *__restrict__ invmap)
+    {
+      const int np  = n + 1;
+      const int lex = blockIdx.x * blockDim.x + threadIdx.x;
+      if (lex >= np * np * np)
+        return;
+      int jx, jy, jz, lv;
+      decode3(lex, np, jx, jy, jz);
+      const uint32_t m   = first_touch_cell3(n, jx, jy, jz, lv);
+      const uint32_t dof = base[m] + __popc(mask[m] & ((1u << lv) - 1u));
+      dofmap[lex]        = dof;
+      invmap[dof]        = (uint32_t)lex;
+    }
+
+    // ========================================================================== assembly
+    struct Coeff3
+    {
+      int    kind;
+      double a0;
+      double rot[9]; // MatrixCoeff<3> rotation (matrix_coeff.tpp:28-41), filled on the host
+    };
+
+    __device__ inline void
+    coeff3_eval(const Coeff3 &c, double x, double y, double A[9])
+    {
+      if (c.kind == MSB_COEFF_REFERENCE)
+        {
+          // matrix_coeff.tpp:66-91 with the header's PI_D (sic) -- depends on x and y only
+          const double PI_D = 3.14592653509793218403;
+          const double a =
+            1.0 * (1.0 - 0.9999 * (0.5 * sin(2 * PI_D * 57 * x) + 0.5 * sin(2 * PI_D * 57 * y)));
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              A[3 * i + j] = (c.rot[3 * i] * a) * c.rot[3 * j] + (c.rot[3 * i + 1] * a) * c.rot[3 * j + 1] +
+                             (c.rot[3 * i + 2] * a) * c.rot[3 * j + 2];
+          return;
+        }
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+        A[i] = 0.0;
+      A[0] = A[4] = A[8] = c.a0;
+    }
+
+    // assemble_system (basis.tpp:159-242) for dim = 3, node-centric: every thread gathers the row
+    // of its node from the <= 8 adjacent fine hexes (QGauss<3>(2), MappingQ1, FE_Q<3>(1)) and
+    // stores the diagonal, the 13 forward couplings and the load entry.  No atomics: the sum
+    // order is fixed (cells in local-vertex order, quadrature points in order).
+    __global__ void __launch_bounds__(128)
+    assemble3_kernel(int n, const double *__restrict__ corners, Coeff3 cf, double rhs_value,
+                     double *__restrict__ sten)
+    {
+      const int np = n + 1, N = np * np * np, cell = blockIdx.y;
+      const int t  = blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= N)
+        return;
+      const double *c = corners + 24 * (size_t)cell;
+      double       *S = sten + (size_t)cell * NST * N;
+      int           jx, jy, jz;
+      decode3(t, np, jx, jy, jz);
+      const double g0 = 0.5 - 0.5 / sqrt(3.0), g1 = 0.5 + 0.5 / sqrt(3.0);
+      double       acc[14], F = 0.0;
+#pragma unroll
+      for (int k = 0; k < 14; ++k)
+        acc[k] = 0.0;
+#pragma unroll 1
+      for (int cv = 0; cv < 8; ++cv)
+        {
+          // this node is local vertex cv of fine cell (ix, iy, iz)
+          const int cvx = cv & 1, cvy = (cv >> 1) & 1, cvz = cv >> 2;
+          const int ix = jx - cvx, iy = jy - cvy, iz = jz - cvz;
+          if (ix < 0 || iy < 0 || iz < 0 || ix >= n || iy >= n || iz >= n)
+            continue;
+          double P[8][3];
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            fine_vertex3(c, n, ix + (v & 1), iy + ((v >> 1) & 1), iz + (v >> 2), P[v]);
+          double row[8], fe = 0.0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            row[j] = 0.0;
+#pragma unroll 1
+          for (int q = 0; q < 8; ++q)
+            {
+              const double xi = (q & 1) ? g1 : g0, eta = ((q >> 1) & 1) ? g1 : g0, ze = (q >> 2) ? g1 : g0;
+              double       Nv[8], dN[8][3];
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                {
+                  const double fx = (v & 1) ? xi : 1 - xi, fy = ((v >> 1) & 1) ? eta : 1 - eta,
+                               fz = (v >> 2) ? ze : 1 - ze;
+                  const double sx = (v & 1) ? 1.0 : -1.0, sy = ((v >> 1) & 1) ? 1.0 : -1.0,
+                               sz = (v >> 2) ? 1.0 : -1.0;
+                  Nv[v]    = fx * fy * fz;
+                  dN[v][0] = sx * fy * fz;
+                  dN[v][1] = fx * sy * fz;
+                  dN[v][2] = fx * fy * sz;
+                }
+              double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, xq[3] = {0, 0, 0};
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                  {
+                    xq[a] += P[v][a] * Nv[v];
+#pragma unroll
+                    for (int b = 0; b < 3; ++b)
+                      J[a][b] += P[v][a] * dN[v][b];
+                  }
+              const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -
+                                 J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                                 J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+              double Ji[3][3];
+              Ji[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det;
+              Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+              Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+              Ji[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det;
+              Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+              Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+              Ji[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det;
+              Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+              Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+              const double JxW = det * 0.125;
+              double       A[9];
+              coeff3_eval(cf, xq[0], xq[1], A);
+              double G[8][3];
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                  G[v][a] = Ji[0][a] * dN[v][0] + Ji[1][a] * dN[v][1] + Ji[2][a] * dN[v][2];
+              // own gradient and shape value, selected without dynamic register indexing
+              double gi[3] = {0, 0, 0}, ni = 0.0;
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                if (v == cv)
+                  {
+                    gi[0] = G[v][0], gi[1] = G[v][1], gi[2] = G[v][2];
+                    ni = Nv[v];
+                  }
+              double tt[3];
+#pragma unroll
+              for (int b = 0; b < 3; ++b)
+                tt[b] = gi[0] * A[b] + gi[1] * A[3 + b] + gi[2] * A[6 + b];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                row[j] += (tt[0] * G[j][0] + tt[1] * G[j][1] + tt[2] * G[j][2]) * JxW;
+              fe += ni * rhs_value * JxW;
+            }
+          // scatter the row: neighbour offset of local vertex j relative to this node
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            {
+              const int e = 13 + ((j & 1) - cvx) + 3 * (((j >> 1) & 1) - cvy) + 9 * ((j >> 2) - cvz);
+#pragma unroll
+              for (int k = 0; k < 14; ++k)
+                if (e - 13 == k)
+                  acc[k] += row[j];
+            }
+          F += fe;
+        }
+#pragma unroll
+      for (int k = 0; k < 14; ++k)
+        S[(size_t)k * N + t] = acc[k];
+      S[(size_t)ST3_F * N + t] = F;
+    }
+
+    // ========================================================================== solver
+    struct Levels3
+    {
+      int npl[MAXLEV + 1]; // nodes per direction of level l (0 = fine)
+      int off[MAXLEV + 2]; // node offset of level l >= 1 in the packed coarse arrays
+      int levels, cn;
+    };
+
+    struct Params3
+    {
+      int           n, nblk, layers; // fine kernels: node layers (jz) per CTA
+      const double *corners, *q1coef, *sten;
+      double       *x, *r, *p, *q, *z; // [C][8][N]
+      double       *v;                 // [C][8][cn]
+      double       *dinv;              // [C][cn]
+      double       *part;              // [C][8][PSTRIDE]
+      double       *rzprev;            // [C][8]
+      int32_t      *iters;
+      double       *res;
+      double        tol2;
+      int           it;
+      Levels3       L;
+    };
+
+    __device__ __forceinline__ double *
+    part_ptr(double *part, int sidx, int parity, int which)
+    {
+      return part + (size_t)sidx * PSTRIDE + (parity * 3 + which) * MAXBLK;
+    }
+
+    __device__ __forceinline__ double
+    sum_part(const double *part, int nblk)
+    {
+      double s = 0.0;
+      for (int b = 0; b < nblk; ++b)
+        s += part[b];
+      return s;
+    }
+
+    __device__ __forceinline__ int
+    solve_done(const Params3 &P, int sidx, int parity, double *rr_out)
+    {
+      const double rr = sum_part(part_ptr(P.part, sidx, parity, 2), P.nblk);
+      if (rr_out)
+        *rr_out = rr;
+      return (P.iters[sidx] >= 0) || (rr <= P.tol2);
+    }
+
+    __device__ __forceinline__ bool
+    cell_done(const Params3 &P, int cell, int parity, int *sdone /*shared[8]*/)
+    {
+      if (threadIdx.x < NB)
+        sdone[threadIdx.x] = solve_done(P, cell * NB + threadIdx.x, parity, nullptr);
+      __syncthreads();
+      int all = 1;
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        all &= sdone[k];
+      return all != 0;
+    }
+
+    // exact Galerkin diagonal of level l at coarse node X: D = w^T K w with w the level-l
+    // trilinear hat function sampled on the fine grid.  One CTA per (coarse node, cell).
+    __global__ void __launch_bounds__(64)
+    galerkin_diag3_kernel(Params3 P, int l)
+    {
+      const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y;
+      const int npl = P.L.npl[l], nin = npl - 2;
+      const int X = 1 + blockIdx.x % nin, Y = 1 + (blockIdx.x / nin) % nin, Z = 1 + blockIdx.x / (nin * nin);
+      const double *S = P.sten + (size_t)cell * NST * N;
+      const int     h = 1 << l, side = 2 * h - 1;
+      const double  rh = 1.0 / (double)h;
+      double        acc[1] = {0.0};
+      for (int s = threadIdx.x; s < side * side * side; s += blockDim.x)
+        {
+          const int ax = s % side - (h - 1), ay = (s / side) % side - (h - 1), az = s / (side * side) - (h - 1);
+          const double wi = (1.0 - abs(ax) * rh) * (1.0 - abs(ay) * rh) * (1.0 - abs(az) * rh);
+          const int    t  = ((Z * h + az) * np + (Y * h + ay)) * np + (X * h + ax);
+          double       kw = 0.0;
+#pragma unroll 1
+          for (int e = 0; e < 27; ++e)
+            {
+              const int bx = ax + e % 3 - 1, by = ay + (e / 3) % 3 - 1, bz = az + e / 9 - 1;
+              if (abs(bx) >= h || abs(by) >= h || abs(bz) >= h)
+                continue;
+              const double wj = (1.0 - abs(bx) * rh) * (1.0 - abs(by) * rh) * (1.0 - abs(bz) * rh);
+              kw = fma(sten3_get(S, N, np, t, e), wj, kw);
+            }
+          acc[0] = fma(wi, kw, acc[0]);
+        }
+      __shared__ double sbuf[2];
+      block_sum_to<1>(acc, sbuf);
+      if (threadIdx.x == 0)
+        P.dinv[(size_t)cell * P.L.cn + P.L.off[l] + (Z * npl + Y) * npl + X] = 1.0 / acc[0];
+    }
+
+    // r = -K_IB g_B on interior rows (condense), x = g on the boundary, p = 0, partial r.r
+    __global__ void __launch_bounds__(THREADS)
+    init3_kernel(Params3 P)
+    {
+      const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y, blk = blockIdx.x;
+      const double *S = P.sten + (size_t)cell * NST * N;
+      const double *c = P.corners + 24 * (size_t)cell, *q1 = P.q1coef + 64 * (size_t)cell;
+      const int     z0 = blk * P.layers, z1 = min(np, z0 + P.layers);
+      double        acc[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        acc[k] = 0.0;
+      for (int t = z0 * np * np + threadIdx.x; t < z1 * np * np; t += THREADS)
+        {
+          int jx, jy, jz;
+          decode3(t, np, jx, jy, jz);
+          double rv[NB], xv[NB];
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            rv[k] = xv[k] = 0.0;
+          if (on_boundary3(jx, jy, jz, n))
+            {
+              double p[3];
+              fine_vertex3(c, n, jx, jy, jz, p);
+#pragma unroll
+              for (int k = 0; k < NB; ++k)
+                xv[k] = basis_q1_value3(q1, k, p);
+            }
+          else if (jx == 1 || jy == 1 || jz == 1 || jx == n - 1 || jy == n - 1 || jz == n - 1)
+            {
+#pragma unroll 1
+              for (int e = 0; e < 27; ++e)
+                {
+                  const int bx = jx + e % 3 - 1, by = jy + (e / 3) % 3 - 1, bz = jz + e / 9 - 1;
+                  if (!on_boundary3(bx, by, bz, n))
+                    continue;
+                  const double kij = sten3_get(S, N, np, t, e);
+                  double       p[3];
+                  fine_vertex3(c, n, bx, by, bz, p);
+#pragma unroll
+                  for (int k = 0; k < NB; ++k)
+                    rv[k] -= kij * basis_q1_value3(q1, k, p);
+                }
+#pragma unroll
+              for (int k = 0; k < NB; ++k)
+                acc[k] += rv[k] * rv[k];
+            }
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            {
+              const size_t o = ((size_t)cell * NB + k) * N + t;
+              P.x[o]         = xv[k];
+              P.r[o]         = rv[k];
+              P.p[o]         = 0.0;
+            }
+        }
+      __shared__ double sbuf[(THREADS / 32) * NB];
+      block_sum_to<NB>(acc, sbuf);
+      if (threadIdx.x == 0)
+        {
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            part_ptr(P.part, cell * NB + k, 0, 2)[blk] = acc[k];
+        }
+    }
+
+    // K1: bookkeeping of the previous iteration, then p = z + beta p
+    __global__ void __launch_bounds__(THREADS)
+    k1_kernel(Params3 P)
+    {
+      const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y, blk = blockIdx.x;
+      const int par = (P.it - 1) & 1;
+      __shared__ double sbeta[NB];
+      __shared__ int    sdone[NB];
+      if (threadIdx.x < NB)
+        {
+          const int    k = threadIdx.x, sidx = cell * NB + k;
+          double       rr;
+          const int    dn = solve_done(P, sidx, par, &rr);
+          const double rz = sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
+          sdone[k]        = dn;
+          sbeta[k]        = P.it == 1 ? 0.0 : rz / P.rzprev[sidx];
+          if (blk == 0 && dn && P.iters[sidx] < 0)
+            {
+              P.iters[sidx] = P.it - 1;
+              P.res[sidx]   = sqrt(rr);
+            }
+        }
+      __syncthreads();
+      int all = 1;
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        all &= sdone[k];
+      if (all)
+        return;
+      const int z0 = blk * P.layers, z1 = min(np, z0 + P.layers);
+      for (int t = z0 * np * np + threadIdx.x; t < z1 * np * np; t += THREADS)
+        {
+          int jx, jy, jz;
+          decode3(t, np, jx, jy, jz);
+          if (on_boundary3(jx, jy, jz, n))
+            continue;
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            {
+              if (sdone[k])
+                continue;
+              const size_t o = ((size_t)cell * NB + k) * N + t;
+              P.p[o]         = fma(sbeta[k], P.p[o], P.z[o]);
+            }
+        }
+    }
+
+    // K2: q = K p on interior rows (p vanishes on the boundary), partial p.q
+    __global__ void __launch_bounds__(THREADS)
+    k2_kernel(Params3 P)
+    {
+      const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y, blk = blockIdx.x;
+      const int par = (P.it - 1) & 1;
+      __shared__ int    sdone[NB];
+      __shared__ double sbuf[(THREADS / 32) * NB];
+      if (cell_done(P, cell, par, sdone))
+        return;
+      const double *S  = P.sten + (size_t)cell * NST * N;
+      const int     z0 = blk * P.layers, z1 = min(np, z0 + P.layers);
+      double        acc[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        acc[k] = 0.0;
+      for (int t = z0 * np * np + threadIdx.x; t < z1 * np * np; t += THREADS)
+        {
+          int jx, jy, jz;
+          decode3(t, np, jx, jy, jz);
+          if (on_boundary3(jx, jy, jz, n))
+            continue;
+          double y[NB];
+          {
+            const double kc = S[t];
+#pragma unroll
+            for (int k = 0; k < NB; ++k)
+              y[k] = sdone[k] ? 0.0 : kc * P.p[((size_t)cell * NB + k) * N + t];
+          }
+#pragma unroll
+          for (int f = 1; f <= 13; ++f)
+            {
+              // forward neighbour t + o (coefficient stored here) and backward neighbour t - o
+              // (coefficient stored there)
+              const int    e = 13 + f, o = (e / 9 - 1) * np * np + ((e / 3) % 3 - 1) * np + (e % 3 - 1);
+              const double kf = S[(size_t)f * N + t], kb = S[(size_t)f * N + t - o];
+#pragma unroll
+              for (int k = 0; k < NB; ++k)
+                {
+                  if (sdone[k])
+                    continue;
+                  const double *p = P.p + ((size_t)cell * NB + k) * N + t;
+                  y[k]            = fma(kf, p[o], y[k]);
+                  y[k]            = fma(kb, p[-o], y[k]);
+                }
+            }
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            {
+              if (sdone[k])
+                continue;
+              const size_t o = ((size_t)cell * NB + k) * N + t;
+              P.q[o]         = y[k];
+              acc[k]         = fma(P.p[o], y[k], acc[k]);
+            }
+        }
+      block_sum_to<NB>(acc, sbuf);
+      if (threadIdx.x == 0)
+        {
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            if (!sdone[k])
+              part_ptr(P.part, cell * NB + k, P.it & 1, 1)[blk] = acc[k];
+        }
+    }
+
+    // K3: alpha = rz/pq ; x += alpha p ; r -= alpha q ; partial r.r
+    __global__ void __launch_bounds__(THREADS)
+    k3_kernel(Params3 P)
+    {
+      const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y, blk = blockIdx.x;
+      const int par = (P.it - 1) & 1;
+      __shared__ int    sdone[NB];
+      __shared__ double salpha[NB];
+      __shared__ double sbuf[(THREADS / 32) * NB];
+      if (threadIdx.x < NB)
+        {
+          const int sidx      = cell * NB + threadIdx.x;
+          const int dn        = solve_done(P, sidx, par, nullptr);
+          sdone[threadIdx.x]  = dn;
+          const double rz     = sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
+          const double pq     = sum_part(part_ptr(P.part, sidx, P.it & 1, 1), P.nblk);
+          salpha[threadIdx.x] = dn ? 0.0 : rz / pq;
+        }
+      __syncthreads();
+      int all = 1;
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        all &= sdone[k];
+      if (all)
+        return;
+      const int z0 = blk * P.layers, z1 = min(np, z0 + P.layers);
+      double    acc[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        acc[k] = 0.0;
+      for (int t = z0 * np * np + threadIdx.x; t < z1 * np * np; t += THREADS)
+        {
+          int jx, jy, jz;
+          decode3(t, np, jx, jy, jz);
+          if (on_boundary3(jx, jy, jz, n))
+            continue;
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            {
+              if (sdone[k])
+                continue;
+              const size_t o  = ((size_t)cell * NB + k) * N + t;
+              const double a  = salpha[k];
+              P.x[o]          = fma(a, P.p[o], P.x[o]);
+              const double rn = fma(-a, P.q[o], P.r[o]);
+              P.r[o]          = rn;
+              acc[k]          = fma(rn, rn, acc[k]);
+            }
+        }
+      block_sum_to<NB>(acc, sbuf);
+      if (threadIdx.x == 0)
+        {
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            if (!sdone[k])
+              {
+                const int sidx = cell * NB + k;
+                part_ptr(P.part, sidx, P.it & 1, 2)[blk] = acc[k];
+                if (blk == 0)
+                  P.rzprev[sidx] = sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
+              }
+        }
+    }
+
+    // restriction r_l = P^T r_{l-1}: full weighting over the 27 fine neighbours
+    __global__ void __launch_bounds__(THREADS)
+    restrict3_kernel(Params3 P, int l, int rpar)
+    {
+      const int cell = blockIdx.y, npl = P.L.npl[l], nin = npl - 2, npf = P.L.npl[l - 1];
+      __shared__ int sdone[NB];
+      if (cell_done(P, cell, rpar, sdone))
+        return;
+      const int t = blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= nin * nin * nin)
+        return;
+      const int    cx = 1 + t % nin, cy = 1 + (t / nin) % nin, cz = 1 + t / (nin * nin);
+      const size_t Nf = (size_t)npf * npf * npf;
+#pragma unroll 1
+      for (int k = 0; k < NB; ++k)
+        {
+          if (sdone[k])
+            continue;
+          const double *src = l == 1 ? P.r + ((size_t)cell * NB + k) * Nf :
+                                       P.v + ((size_t)cell * NB + k) * P.L.cn + P.L.off[l - 1];
+          double pl[3];
+#pragma unroll
+          for (int az = -1; az <= 1; ++az)
+            {
+              double row[3];
+#pragma unroll
+              for (int ay = -1; ay <= 1; ++ay)
+                {
+                  const double *s = src + ((size_t)(2 * cz + az) * npf + (2 * cy + ay)) * npf + 2 * cx;
+                  row[ay + 1]     = fma(0.5, s[-1] + s[1], s[0]);
+                }
+              pl[az + 1] = fma(0.5, row[0] + row[2], row[1]);
+            }
+          P.v[((size_t)cell * NB + k) * P.L.cn + P.L.off[l] + (cz * npl + cy) * npl + cx] =
+            fma(0.5, pl[0] + pl[2], pl[1]);
+        }
+    }
+
+    // trilinear interpolation of the next-coarser level at node (fx, fy, fz) of this level
+    __device__ __forceinline__ double
+    interp3(const double *__restrict__ vc, int npc, int fx, int fy, int fz)
+    {
+      const int xl = fx >> 1, xh = (fx + 1) >> 1, yl = fy >> 1, yh = (fy + 1) >> 1, zl = fz >> 1,
+                zh = (fz + 1) >> 1;
+      const double *a = vc + ((size_t)zl * npc + yl) * npc, *b = vc + ((size_t)zl * npc + yh) * npc;
+      const double *c = vc + ((size_t)zh * npc + yl) * npc, *d = vc + ((size_t)zh * npc + yh) * npc;
+      return 0.125 * (((a[xl] + a[xh]) + (b[xl] + b[xh])) + ((c[xl] + c[xh]) + (d[xl] + d[xh])));
+    }
+
+    // prolongation z_l = r_l / D_l + P z_{l+1}, in place (coarsest level: z = r / D)
+    __global__ void __launch_bounds__(THREADS)
+    prolong3_kernel(Params3 P, int l, int rpar)
+    {
+      const int cell = blockIdx.y, npl = P.L.npl[l], nin = npl - 2;
+      __shared__ int sdone[NB];
+      if (cell_done(P, cell, rpar, sdone))
+        return;
+      const int t = blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= nin * nin * nin)
+        return;
+      const int    fx = 1 + t % nin, fy = 1 + (t / nin) % nin, fz = 1 + t / (nin * nin);
+      const int    i  = (fz * npl + fy) * npl + fx;
+      const double di = P.dinv[(size_t)cell * P.L.cn + P.L.off[l] + i];
+#pragma unroll 1
+      for (int k = 0; k < NB; ++k)
+        {
+          if (sdone[k])
+            continue;
+          double *vl = P.v + ((size_t)cell * NB + k) * P.L.cn + P.L.off[l];
+          double  v  = vl[i] * di;
+          if (l < P.L.levels)
+            v += interp3(P.v + ((size_t)cell * NB + k) * P.L.cn + P.L.off[l + 1], P.L.npl[l + 1], fx, fy, fz);
+          vl[i] = v;
+        }
+    }
+
+    // fine level: z = r / D + P z_1 on interior rows; partial r.z into parity rpar
+    __global__ void __launch_bounds__(THREADS)
+    fine3_kernel(Params3 P, int rpar)
+    {
+      const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y, blk = blockIdx.x;
+      __shared__ int    sdone[NB];
+      __shared__ double sbuf[(THREADS / 32) * NB];
+      if (cell_done(P, cell, rpar, sdone))
+        return;
+      const double *KC  = P.sten + (size_t)cell * NST * N;
+      const int     np1 = P.L.npl[1];
+      const int     z0 = blk * P.layers, z1 = min(np, z0 + P.layers);
+      double        acc[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        acc[k] = 0.0;
+      for (int t = z0 * np * np + threadIdx.x; t < z1 * np * np; t += THREADS)
+        {
+          int jx, jy, jz;
+          decode3(t, np, jx, jy, jz);
+          if (on_boundary3(jx, jy, jz, n))
+            continue;
+          const double dinv = 1.0 / KC[t];
+#pragma unroll 1
+          for (int k = 0; k < NB; ++k)
+            {
+              if (sdone[k])
+                continue;
+              const size_t o = ((size_t)cell * NB + k) * N + t;
+              const double c = P.L.levels < 1 ? 0.0 :
+                                 interp3(P.v + ((size_t)cell * NB + k) * P.L.cn + P.L.off[1], np1, jx, jy, jz);
+              const double rv = P.r[o], zv = fma(rv, dinv, c);
+              P.z[o]          = zv;
+              acc[k]          = fma(rv, zv, acc[k]);
+            }
+        }
+      block_sum_to<NB>(acc, sbuf);
+      if (threadIdx.x == 0)
+        {
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            if (!sdone[k])
+              part_ptr(P.part, cell * NB + k, rpar, 0)[blk] = acc[k];
+        }
+    }
+
+    __global__ void
+    finalize3_kernel(Params3 P, int n_solves, int32_t *fail)
+    {
+      const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+      if (sidx >= n_solves || P.iters[sidx] >= 0)
+        return;
+      const double rr = sum_part(part_ptr(P.part, sidx, P.it & 1, 2), P.nblk);
+      P.iters[sidx]   = P.it;
+      P.res[sidx]     = sqrt(rr);
+      if (!(rr <= P.tol2))
+        atomicMin(fail, sidx);
+    }
+
+    __global__ void
+    count3_kernel(Params3 P, int n_solves, int32_t *remaining)
+    {
+      const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+      if (sidx >= n_solves || P.iters[sidx] >= 0)
+        return;
+      if (!(sum_part(part_ptr(P.part, sidx, P.it & 1, 2), P.nblk) <= P.tol2))
+        atomicAdd(remaining, 1);
+    }
+
+    static Levels3
+    make_levels(int l)
+    {
+      Levels3   L = {};
+      const int n = 1 << l;
+      L.levels    = l - 1;
+      L.npl[0]    = n + 1;
+      int off     = 0;
+      for (int k = 1; k <= L.levels; ++k)
+        {
+          L.npl[k] = (n >> k) + 1;
+          L.off[k] = off;
+          off += L.npl[k] * L.npl[k] * L.npl[k];
+        }
+      L.off[L.levels + 1] = off;
+      L.cn                = off;
+      return L;
+    }
+
+    static Params3
+    shifted(const Params3 &P, const Shard &s, int c0)
+    {
+      Params3      Q = P;
+      const size_t N = (size_t)s.N;
+      Q.corners += 24 * (size_t)c0, Q.q1coef += 64 * (size_t)c0, Q.sten += (size_t)c0 * NST * N;
+      Q.x += (size_t)c0 * NB * N, Q.r += (size_t)c0 * NB * N, Q.p += (size_t)c0 * NB * N;
+      Q.q += (size_t)c0 * NB * N, Q.z += (size_t)c0 * NB * N, Q.v += (size_t)c0 * NB * P.L.cn;
+      Q.dinv += (size_t)c0 * P.L.cn, Q.part += (size_t)c0 * NB * PSTRIDE;
+      Q.rzprev += NB * (size_t)c0, Q.iters += NB * (size_t)c0, Q.res += NB * (size_t)c0;
+      return Q;
+    }
+
+    // ===================================================================== element matrices
+    // assemble_global_element_matrix (basis.tpp:245-285) with dofs_per_cell = 8: M_ij =
+    // phi_i . (K phi_j) over all N DoFs with the unconstrained K, b_i = phi_i . F.
+    // One CTA per coarse cell, fixed summation order.
+    __global__ void __launch_bounds__(THREADS)
+    element_matrix3_kernel(int n, const double *__restrict__ sten, const double *__restrict__ phi,
+                           double *__restrict__ M, double *__restrict__ b)
+    {
+      const int     np = n + 1, N = np * np * np, cell = blockIdx.x;
+      const double *S = sten + (size_t)cell * NST * N;
+      const double *Ph = phi + (size_t)cell * NB * N;
+      double        acc[72];
+#pragma unroll
+      for (int k = 0; k < 72; ++k)
+        acc[k] = 0.0;
+      for (int t = threadIdx.x; t < N; t += THREADS)
+        {
+          int jx, jy, jz;
+          decode3(t, np, jx, jy, jz);
+          double kp[NB], pc[NB];
+          {
+            const double kc = S[t];
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+              {
+                pc[j] = Ph[(size_t)j * N + t];
+                kp[j] = kc * pc[j];
+              }
+          }
+#pragma unroll 1
+          for (int e = 0; e < 27; ++e)
+            {
+              if (e == 13)
+                continue;
+              const int bx = jx + e % 3 - 1, by = jy + (e / 3) % 3 - 1, bz = jz + e / 9 - 1;
+              if (bx < 0 || by < 0 || bz < 0 || bx > n || by > n || bz > n)
+                continue;
+              const double kij = sten3_get(S, N, np, t, e);
+              const int    o   = off_of(e, np);
+#pragma unroll
+              for (int j = 0; j < NB; ++j)
+                kp[j] = fma(kij, Ph[(size_t)j * N + t + o], kp[j]);
+            }
+          const double f = S[(size_t)ST3_F * N + t];
+#pragma unroll
+          for (int i = 0; i < NB; ++i)
+            {
+#pragma unroll
+              for (int j = 0; j < NB; ++j)
+                acc[NB * i + j] = fma(pc[i], kp[j], acc[NB * i + j]);
+              acc[64 + i] = fma(pc[i], f, acc[64 + i]);
+            }
+        }
+      __shared__ double sbuf[(THREADS / 32) * 72];
+      block_sum_to<72>(acc, sbuf);
+      if (threadIdx.x == 0)
+        {
+#pragma unroll
+          for (int k = 0; k < 64; ++k)
+            M[64 * (size_t)cell + k] = acc[k];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            b[8 * (size_t)cell + k] = acc[64 + k];
+        }
+    }
+
+    __global__ void
+    apply_operator3_kernel(int n, const double *__restrict__ S, const double *__restrict__ x,
+                           double *__restrict__ y)
+    {
+      const int np = n + 1, N = np * np * np, t = blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= N)
+        return;
+      int jx, jy, jz;
+      decode3(t, np, jx, jy, jz);
+      double v = 0.0;
+      for (int e = 0; e < 27; ++e)
+        {
+          const int bx = jx + e % 3 - 1, by = jy + (e / 3) % 3 - 1, bz = jz + e / 9 - 1;
+          if (bx < 0 || by < 0 || bz < 0 || bx > n || by > n || bz > n)
+            continue;
+          v = fma(sten3_get(S, N, np, t, e), x[t + off_of(e, np)], v);
+        }
+      y[t] = v;
+    }
+
+    // constraint set of one (cell, basis): boundary DoFs ascending + BasisQ1<3> values
+    // (basis.tpp:119-135); position = number of boundary DoFs with a smaller index
+    __global__ void
+    constraints3_kernel(int n, const uint32_t *__restrict__ dofmap, const double *__restrict__ corners,
+                        const double *__restrict__ q1coef, int ib, uint32_t *__restrict__ dofs,
+                        double *__restrict__ vals)
+    {
+      const int np = n + 1, N = np * np * np, t = blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= N)
+        return;
+      int jx, jy, jz;
+      decode3(t, np, jx, jy, jz);
+      if (!on_boundary3(jx, jy, jz, n))
+        return;
+      const uint32_t d    = dofmap[t];
+      int            rank = 0;
+      for (int k = 0; k < N; ++k)
+        {
+          int kx, ky, kz;
+          decode3(k, np, kx, ky, kz);
+          if (on_boundary3(kx, ky, kz, n))
+            rank += dofmap[k] < d;
+        }
+      double p[3];
+      fine_vertex3(corners, n, jx, jy, jz, p);
+      dofs[rank] = d;
+      vals[rank] = basis_q1_value3(q1coef, ib, p);
+    }
+  } // namespace d3
+
+  // ============================================================================ launchers
+  size_t
+  dim3_coarse_nodes(int l)
+  {
+    const size_t cn = (size_t)d3::make_levels(l).cn;
+    return cn ? cn : 1;
+  }
+
+  int
+  dim3_part_stride()
+  {
+    return d3::PSTRIDE;
+  }
+
+  cudaError_t
+  launch_dofmap3(const Shard &s, cudaStream_t st)
+  {
+    const int   ncell = s.n * s.n * s.n;
+    uint32_t   *tmp   = nullptr;
+    cudaError_t e     = cudaMalloc(&tmp, sizeof(uint32_t) * 3 * (size_t)ncell);
+    if (e != cudaSuccess)
+      return e;
+    uint32_t *cnt = tmp, *mask = tmp + ncell, *base = tmp + 2 * (size_t)ncell;
+    d3::dofmap3_count_kernel<<<(ncell + 255) / 256, 256, 0, st>>>(s.n, cnt, mask);
+    d3::dofmap3_scan_kernel<<<1, 1024, 0, st>>>(ncell, cnt, base);
+    d3::dofmap3_assign_kernel<<<(s.N + 255) / 256, 256, 0, st>>>(s.n, base, mask, s.d_dofmap, s.d_invmap);
+    e = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    return e != cudaSuccess ? e : cudaGetLastError();
+  }
+
+  cudaError_t
+  launch_assemble3(const Shard &s, cudaStream_t st, int *n_launches)
+  {
+    d3::Coeff3 cf;
+    cf.kind = s.coeff.kind;
+    cf.a0   = s.coeff.par[0];
+    // MatrixCoeff<3> rotation (matrix_coeff.tpp:28-41) with alpha = PI_D/3, beta = PI_D/6,
+    // gamma = PI_D/4 (matrix_coeff.hpp:45-48)
+    const double PI_D = 3.14592653509793218403;
+    const double al = PI_D / 3, be = PI_D / 6, ga = PI_D / 4;
+    cf.rot[0] = cos(al) * cos(ga) - sin(al) * cos(be) * sin(ga);
+    cf.rot[1] = -cos(al) * sin(ga) - sin(al) * cos(be) * cos(ga);
+    cf.rot[2] = sin(al) * sin(be);
+    cf.rot[3] = sin(al) * cos(ga) + cos(al) * cos(be) * sin(ga);
+    cf.rot[4] = -sin(al) * sin(ga) + cos(al) * cos(be) * cos(ga);
+    cf.rot[5] = -cos(al) * sin(be);
+    cf.rot[6] = sin(be) * sin(ga);
+    cf.rot[7] = sin(be) * cos(ga);
+    cf.rot[8] = cos(be);
+    for (int c0 = 0; c0 < s.n_cells; c0 += 65535)
+      {
+        const int nc = s.n_cells - c0 < 65535 ? s.n_cells - c0 : 65535;
+        d3::assemble3_kernel<<<dim3((s.N + 127) / 128, nc), 128, 0, st>>>(
+          s.n, s.d_corners + 24 * (size_t)c0, cf, s.rhs_value, s.d_sten + (size_t)c0 * ST3_NARR * s.N);
+        ++*n_launches;
+      }
+    return cudaGetLastError();
+  }
+
+  cudaError_t
+  launch_solve3(Shard &s, double tol, int max_iter, cudaStream_t st, int *n_launches)
+  {
+    using namespace d3;
+    Params3 P;
+    P.n        = s.n;
+    int layers = 1;
+    while ((s.np + layers - 1) / layers > MAXBLK)
+      layers *= 2;
+    P.layers  = layers;
+    P.nblk    = (s.np + layers - 1) / layers;
+    P.corners = s.d_corners;
+    P.q1coef  = s.d_q1coef;
+    P.sten    = s.d_sten;
+    P.x       = s.d_phi;
+    P.r       = s.d_wr;
+    P.p       = s.d_wp;
+    P.q       = s.d_wq;
+    P.z       = s.d_wz;
+    P.v       = s.d_wv;
+    P.dinv    = s.d_dinv;
+    P.part    = s.d_part;
+    P.rzprev  = s.d_scal;
+    P.iters   = s.d_iters;
+    P.res     = s.d_res;
+    P.tol2    = tol * tol;
+    P.it      = 0;
+    P.L       = make_levels(s.l);
+    const Levels3 &L        = P.L;
+    const int      n_solves = NB * s.n_cells;
+    const int      C        = s.n_cells;
+    cudaError_t    e;
+
+#define TRY(call)                  \
+  if ((e = (call)) != cudaSuccess) \
+  return e
+
+    TRY(cudaMemsetAsync(s.d_iters, 0xff, sizeof(int32_t) * n_solves, st));
+    TRY(cudaMemsetAsync(s.d_part, 0, sizeof(double) * (size_t)n_solves * PSTRIDE, st));
+    TRY(cudaMemsetAsync(s.d_wv, 0, sizeof(double) * (size_t)n_solves * dim3_coarse_nodes(s.l), st));
+    TRY(cudaMemsetAsync(s.d_dinv, 0, sizeof(double) * (size_t)C * dim3_coarse_nodes(s.l), st));
+
+    auto for_slices = [&](auto &&launch) {
+      for (int c0 = 0; c0 < C; c0 += 65535)
+        {
+          const int nc = C - c0 < 65535 ? C - c0 : 65535;
+          launch(shifted(P, s, c0), nc);
+          ++*n_launches;
+        }
+    };
+    for (int l = 1; l <= L.levels; ++l)
+      {
+        const int nin = L.npl[l] - 2;
+        for_slices([&](const Params3 &Q, int nc) {
+          galerkin_diag3_kernel<<<dim3(nin * nin * nin, nc), 64, 0, st>>>(Q, l);
+        });
+      }
+    auto precondition = [&](int rpar) {
+      for (int l = 1; l <= L.levels; ++l)
+        {
+          const int nin = L.npl[l] - 2, tot = nin * nin * nin;
+          for_slices([&](const Params3 &Q, int nc) {
+            restrict3_kernel<<<dim3((tot + THREADS - 1) / THREADS, nc), THREADS, 0, st>>>(Q, l, rpar);
+          });
+        }
+      for (int l = L.levels; l >= 1; --l)
+        {
+          const int nin = L.npl[l] - 2, tot = nin * nin * nin;
+          for_slices([&](const Params3 &Q, int nc) {
+            prolong3_kernel<<<dim3((tot + THREADS - 1) / THREADS, nc), THREADS, 0, st>>>(Q, l, rpar);
+          });
+        }
+      for_slices([&](const Params3 &Q, int nc) {
+        fine3_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q, rpar);
+      });
+    };
+
+    for_slices([&](const Params3 &Q, int nc) { init3_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
+    precondition(0);
+
+    int32_t   h_remaining = 1;
+    int       it          = 0;
+    const int check_every = 4;
+    while (it < max_iter)
+      {
+        if (it % check_every == 0)
+          {
+            P.it = it;
+            TRY(cudaMemsetAsync(s.d_flags, 0, sizeof(int32_t), st));
+            count3_kernel<<<(n_solves + 255) / 256, 256, 0, st>>>(P, n_solves, s.d_flags);
+            ++*n_launches;
+            TRY(cudaMemcpyAsync(&h_remaining, s.d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            TRY(cudaStreamSynchronize(st));
+            if (h_remaining == 0)
+              break;
+          }
+        ++it;
+        P.it = it;
+        for_slices([&](const Params3 &Q, int nc) { k1_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
+        for_slices([&](const Params3 &Q, int nc) { k2_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
+        for_slices([&](const Params3 &Q, int nc) { k3_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
+        precondition(it & 1);
+      }
+    P.it = it;
+    finalize3_kernel<<<(n_solves + 255) / 256, 256, 0, st>>>(P, n_solves, s.d_fail);
+    ++*n_launches;
+#undef TRY
+    return cudaGetLastError();
+  }
+
+  cudaError_t
+  launch_element_matrices3(const Shard &s, cudaStream_t st, int *n_launches)
+  {
+    d3::element_matrix3_kernel<<<s.n_cells, d3::THREADS, 0, st>>>(s.n, s.d_sten, s.d_phi, s.d_M, s.d_b);
+    ++*n_launches;
+    return cudaGetLastError();
+  }
+
+  cudaError_t
+  launch_apply_operator3(const Shard &s, int cell, const double *d_x, double *d_y, cudaStream_t st)
+  {
+    d3::apply_operator3_kernel<<<(s.N + 255) / 256, 256, 0, st>>>(
+      s.n, s.d_sten + (size_t)cell * ST3_NARR * s.N, d_x, d_y);
+    return cudaGetLastError();
+  }
+
+  cudaError_t
+  launch_constraints3(const Shard &s, int cell, int ib, uint32_t *d_dofs, double *d_vals, cudaStream_t st)
+  {
+    d3::constraints3_kernel<<<(s.N + 127) / 128, 128, 0, st>>>(
+      s.n, s.d_dofmap, s.d_corners + 24 * (size_t)cell, s.d_q1coef + 64 * (size_t)cell, ib, d_dofs, d_vals);
+    return cudaGetLastError();
+  }
+} // namespace msb

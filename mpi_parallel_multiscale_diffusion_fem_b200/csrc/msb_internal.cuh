@@ -29,10 +29,17 @@ namespace msb
     ST_F   = 5,
     ST_NARR = 6
   };
+  // dim = 3 (msb_dim3.cu): diagonal, 13 forward couplings, load vector
+  enum
+  {
+    ST3_F    = 14,
+    ST3_NARR = 15
+  };
 
   struct Shard
   {
-    int     l, n, np, N; // n = 2^l, np = n+1, N = np*np
+    int     dim = 2, nb = 4, nst = ST_NARR; // bases per cell 2^dim, stencil arrays per cell
+    int     l, n, np, N; // n = 2^l, np = n+1, N = np^dim
     int     n_cells;
     int     device;
     int     tier, variant;
@@ -88,6 +95,17 @@ namespace msb
   cudaError_t launch_global_solution(const Shard &s, const double *d_w, cudaStream_t st);
   cudaError_t launch_constraints(const Shard &s, int cell, int ib, uint32_t *d_dofs, double *d_vals,
                                  cudaStream_t st);
+  // dim = 3 (msb_dim3.cu)
+  cudaError_t launch_dofmap3(const Shard &s, cudaStream_t st);
+  cudaError_t launch_assemble3(const Shard &s, cudaStream_t st, int *n_launches);
+  cudaError_t launch_solve3(Shard &s, double tol, int max_iter, cudaStream_t st, int *n_launches);
+  cudaError_t launch_element_matrices3(const Shard &s, cudaStream_t st, int *n_launches);
+  cudaError_t launch_apply_operator3(const Shard &s, int cell, const double *d_x_lex, double *d_y_lex,
+                                     cudaStream_t st);
+  cudaError_t launch_constraints3(const Shard &s, int cell, int ib, uint32_t *d_dofs, double *d_vals,
+                                  cudaStream_t st);
+  size_t      dim3_coarse_nodes(int l);
+  int         dim3_part_stride();
   bool        smem_tier_supported(int l);
   size_t      streamed_coarse_nodes(int l);
   size_t      streamed_galerkin_scratch_doubles(int l, int n_cells);

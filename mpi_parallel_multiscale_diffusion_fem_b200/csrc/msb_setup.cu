@@ -689,20 +689,18 @@ namespace msb
   // Purely bandwidth bound: reads 4N, writes N doubles per cell.
   // ======================================================================================
   __global__ void __launch_bounds__(256)
-  global_solution_kernel(int N, const double *__restrict__ phi, const double *__restrict__ w,
+  global_solution_kernel(int N, int nb, const double *__restrict__ phi, const double *__restrict__ w,
                          double *__restrict__ out)
   {
     const int     cell = blockIdx.y;
-    const double *P    = phi + (size_t)cell * 4 * N;
-    const double  w0 = w[4 * cell], w1 = w[4 * cell + 1], w2 = w[4 * cell + 2], w3 = w[4 * cell + 3];
+    const double *P    = phi + (size_t)cell * nb * N;
+    const double *wc   = w + (size_t)nb * cell;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
       {
-        // same accumulation order as Vector::sadd(1, w_i, phi_i) for i = 0..3
+        // same accumulation order as Vector::sadd(1, w_i, phi_i) for i = 0..2^dim-1
         double v = 0.0;
-        v        = v + w0 * P[i];
-        v        = v + w1 * P[(size_t)N + i];
-        v        = v + w2 * P[2 * (size_t)N + i];
-        v        = v + w3 * P[3 * (size_t)N + i];
+        for (int k = 0; k < nb; ++k)
+          v = v + wc[k] * P[(size_t)k * N + i];
         out[(size_t)cell * N + i] = v;
       }
   }
@@ -715,7 +713,7 @@ namespace msb
       {
         const int nc = s.n_cells - c0 < 65535 ? s.n_cells - c0 : 65535;
         global_solution_kernel<<<dim3(bx, nc), 256, 0, st>>>(
-          s.N, s.d_phi + (size_t)c0 * 4 * s.N, d_w + 4 * (size_t)c0, s.d_gsol + (size_t)c0 * s.N);
+          s.N, s.nb, s.d_phi + (size_t)c0 * s.nb * s.N, d_w + (size_t)s.nb * c0, s.d_gsol + (size_t)c0 * s.N);
       }
     return cudaGetLastError();
   }

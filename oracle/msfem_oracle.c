@@ -717,3 +717,445 @@ orc_global_solution(int N, const double *phi, const double w[4], double *out)
     for (int d = 0; d < N; ++d)
       out[d] = 1 * out[d] + w[i] * phi[(size_t)i * N + d];
 }
+
+/* ========================================================================== 3D
+ * DiffusionProblemBasis<3>: same run() (basis.tpp:438-474), dim-templated code paths.
+ * condense / ssor / pcg / orc_vmult above are dimension-agnostic (they see a CSR). */
+
+static inline uint32_t
+morton3_compact(uint32_t m)
+{
+  /* keep every third bit of m, compacted */
+  uint32_t x = m & 0x09249249u;
+  x          = (x | (x >> 2)) & 0x030c30c3u;
+  x          = (x | (x >> 4)) & 0x0300f00fu;
+  x          = (x | (x >> 8)) & 0x030000ffu;
+  x          = (x | (x >> 16)) & 0x000003ffu;
+  return x;
+}
+
+int
+orc3_n_dofs(int l)
+{
+  const int n = 1 << l;
+  return (n + 1) * (n + 1) * (n + 1);
+}
+
+/* refine_global + distribute_dofs(FE_Q<3>(1)): active cells in 3D Morton order (child =
+ * ix_bit + 2 iy_bit + 4 iz_bit), the 8 vertices of each cell numbered at first touch */
+void
+orc3_dof_map(int l, uint32_t *dof)
+{
+  const uint32_t n = 1u << l, np = n + 1;
+  for (uint32_t i = 0; i < np * np * np; ++i)
+    dof[i] = 0xffffffffu;
+  uint32_t next = 0;
+  for (uint32_t m = 0; m < n * n * n; ++m)
+    {
+      const uint32_t ix = morton3_compact(m), iy = morton3_compact(m >> 1), iz = morton3_compact(m >> 2);
+      for (uint32_t v = 0; v < 8; ++v)
+        {
+          const uint32_t jx = ix + (v & 1u), jy = iy + ((v >> 1) & 1u), jz = iz + (v >> 2);
+          uint32_t      *d  = dof + (jz * np + jy) * np + jx;
+          if (*d == 0xffffffffu)
+            *d = next++;
+        }
+    }
+}
+
+int
+orc3_boundary_dofs(int l, uint32_t *out)
+{
+  const uint32_t n = 1u << l, np = n + 1;
+  uint32_t *dof = (uint32_t *)malloc(sizeof(uint32_t) * np * np * np);
+  orc3_dof_map(l, dof);
+  int cnt = 0;
+  for (uint32_t jz = 0; jz < np; ++jz)
+    for (uint32_t jy = 0; jy < np; ++jy)
+      for (uint32_t jx = 0; jx < np; ++jx)
+        if (jx == 0 || jy == 0 || jz == 0 || jx == n || jy == n || jz == n)
+          out[cnt++] = dof[(jz * np + jy) * np + jx];
+  qsort(out, (size_t)cnt, sizeof(uint32_t), cmp_u32);
+  free(dof);
+  return cnt;
+}
+
+/* trilinear image of the uniform grid (exact for axis-aligned dyadic bricks) */
+static inline void
+fine_vertex3(const double c[24], uint32_t n, uint32_t jx, uint32_t jy, uint32_t jz, double p[3])
+{
+  const double s = (double)jx / (double)n, t = (double)jy / (double)n, u = (double)jz / (double)n;
+  const double w[8] = {(1 - s) * (1 - t) * (1 - u), s * (1 - t) * (1 - u), (1 - s) * t * (1 - u),
+                       s * t * (1 - u),             (1 - s) * (1 - t) * u, s * (1 - t) * u,
+                       (1 - s) * t * u,             s * t * u};
+  for (int a = 0; a < 3; ++a)
+    {
+      double v = 0.0;
+      for (int k = 0; k < 8; ++k)
+        v += c[3 * k + a] * w[k];
+      p[a] = v;
+    }
+}
+
+/* dense inverse by Gauss-Jordan with partial pivoting (stands in for FullMatrix::invert) */
+static void
+invert_dense(int n, const double *m, double *inv)
+{
+  double *a = (double *)malloc(sizeof(double) * n * 2 * n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      {
+        a[i * 2 * n + j]     = m[i * n + j];
+        a[i * 2 * n + n + j] = i == j ? 1.0 : 0.0;
+      }
+  for (int c = 0; c < n; ++c)
+    {
+      int piv = c;
+      for (int r = c + 1; r < n; ++r)
+        if (fabs(a[r * 2 * n + c]) > fabs(a[piv * 2 * n + c]))
+          piv = r;
+      if (piv != c)
+        for (int j = 0; j < 2 * n; ++j)
+          {
+            const double t     = a[c * 2 * n + j];
+            a[c * 2 * n + j]   = a[piv * 2 * n + j];
+            a[piv * 2 * n + j] = t;
+          }
+      const double ip = 1.0 / a[c * 2 * n + c];
+      for (int j = 0; j < 2 * n; ++j)
+        a[c * 2 * n + j] *= ip;
+      for (int r = 0; r < n; ++r)
+        if (r != c)
+          {
+            const double f = a[r * 2 * n + c];
+            if (f != 0.0)
+              for (int j = 0; j < 2 * n; ++j)
+                a[r * 2 * n + j] -= f * a[c * 2 * n + j];
+          }
+    }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      inv[i * n + j] = a[i * 2 * n + n + j];
+  free(a);
+}
+
+/* basis_q1.tpp:50-75: rows (1, x, y, z, xy, yz, xz, xyz) at the 8 vertices, inverted */
+void
+orc3_basis_q1_coeffs(const double corners[24], double coef[64])
+{
+  double pm[64];
+  for (int i = 0; i < 8; ++i)
+    {
+      const double x = corners[3 * i], y = corners[3 * i + 1], z = corners[3 * i + 2];
+      double      *r = pm + 8 * i;
+      r[0] = 1, r[1] = x, r[2] = y, r[3] = z, r[4] = x * y, r[5] = y * z, r[6] = x * z, r[7] = x * y * z;
+    }
+  invert_dense(8, pm, coef);
+}
+
+/* basis_q1.tpp:99-113 */
+double
+orc3_basis_q1_value(const double coef[64], int ib, double x, double y, double z)
+{
+  return coef[0 * 8 + ib] + coef[1 * 8 + ib] * x + coef[2 * 8 + ib] * y + coef[3 * 8 + ib] * z +
+         coef[4 * 8 + ib] * x * y + coef[5 * 8 + ib] * y * z + coef[6 * 8 + ib] * x * z +
+         coef[7 * 8 + ib] * x * y * z;
+}
+
+void
+orc3_coeff_eval(const orc_coeff *c, double x, double y, double z, double A[9])
+{
+  (void)z; /* the reference coefficient depends on x and y only, also in 3D (matrix_coeff.tpp:84-86) */
+  if (c->kind == ORC_COEFF_REFERENCE)
+    {
+      /* matrix_coeff.hpp:45-48, matrix_coeff.tpp:28-41, :66-91 */
+      const int    k     = 57;
+      const double scale = 0.9999;
+      const double al = PI_D / 3, be = PI_D / 6, ga = PI_D / 4;
+      const double rot[3][3] = {
+        {cos(al) * cos(ga) - sin(al) * cos(be) * sin(ga), -cos(al) * sin(ga) - sin(al) * cos(be) * cos(ga),
+         sin(al) * sin(be)},
+        {sin(al) * cos(ga) + cos(al) * cos(be) * sin(ga), -sin(al) * sin(ga) + cos(al) * cos(be) * cos(ga),
+         -cos(al) * sin(be)},
+        {sin(be) * sin(ga), sin(be) * cos(ga), cos(be)}};
+      const double a =
+        1.0 * (1.0 - scale * (0.5 * sin(2 * PI_D * k * x) + 0.5 * sin(2 * PI_D * k * y)));
+      double t[3][3];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+          t[i][j] = rot[i][j] * a; /* rot * (a I) */
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+          A[3 * i + j] = t[i][0] * rot[j][0] + t[i][1] * rot[j][1] + t[i][2] * rot[j][2];
+      return;
+    }
+  for (int i = 0; i < 9; ++i)
+    A[i] = 0.0;
+  A[0] = A[4] = A[8] = c->par[0];
+}
+
+void
+orc3_constraint_values(int l, const double corners[24], int ib, double *vals)
+{
+  const uint32_t n = 1u << l, np = n + 1, N = np * np * np;
+  uint32_t *dof = (uint32_t *)malloc(sizeof(uint32_t) * N);
+  uint32_t *bd  = (uint32_t *)malloc(sizeof(uint32_t) * N);
+  double   *g   = (double *)malloc(sizeof(double) * N);
+  double    coef[64];
+  orc3_dof_map(l, dof);
+  orc3_basis_q1_coeffs(corners, coef);
+  for (uint32_t jz = 0; jz < np; ++jz)
+    for (uint32_t jy = 0; jy < np; ++jy)
+      for (uint32_t jx = 0; jx < np; ++jx)
+        {
+          double p[3];
+          fine_vertex3(corners, n, jx, jy, jz, p);
+          g[dof[(jz * np + jy) * np + jx]] = orc3_basis_q1_value(coef, ib, p[0], p[1], p[2]);
+        }
+  const int nb = orc3_boundary_dofs(l, bd);
+  for (int i = 0; i < nb; ++i)
+    vals[i] = g[bd[i]];
+  free(dof), free(bd), free(g);
+}
+
+/* 27-point sparsity, diagonal first then ascending columns */
+static uint64_t
+build_sparsity3(int l, const uint32_t *dof, uint64_t *rowptr, uint32_t *col)
+{
+  const uint32_t n = 1u << l, np = n + 1, N = np * np * np;
+  uint32_t *cnt = (uint32_t *)calloc(N, sizeof(uint32_t));
+  for (uint32_t jz = 0; jz < np; ++jz)
+    for (uint32_t jy = 0; jy < np; ++jy)
+      for (uint32_t jx = 0; jx < np; ++jx)
+        {
+          const uint32_t wx = 1 + (jx > 0) + (jx < n), wy = 1 + (jy > 0) + (jy < n),
+                         wz = 1 + (jz > 0) + (jz < n);
+          cnt[dof[(jz * np + jy) * np + jx]] = wx * wy * wz;
+        }
+  rowptr[0] = 0;
+  for (uint32_t r = 0; r < N; ++r)
+    rowptr[r + 1] = rowptr[r] + cnt[r];
+  for (uint32_t jz = 0; jz < np; ++jz)
+    for (uint32_t jy = 0; jy < np; ++jy)
+      for (uint32_t jx = 0; jx < np; ++jx)
+        {
+          const uint32_t r = dof[(jz * np + jy) * np + jx];
+          uint32_t      *c = col + rowptr[r];
+          uint32_t       k = 0;
+          c[k++]           = r;
+          for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+              for (int dx = -1; dx <= 1; ++dx)
+                {
+                  if (dx == 0 && dy == 0 && dz == 0)
+                    continue;
+                  const int x = (int)jx + dx, y = (int)jy + dy, z = (int)jz + dz;
+                  if (x < 0 || y < 0 || z < 0 || x > (int)n || y > (int)n || z > (int)n)
+                    continue;
+                  c[k++] = dof[((uint32_t)z * np + (uint32_t)y) * np + (uint32_t)x];
+                }
+          qsort(c + 1, k - 1, sizeof(uint32_t), cmp_u32);
+        }
+  free(cnt);
+  return rowptr[N];
+}
+
+/* assemble_system for dim = 3: QGauss<3>(2), FE_Q<3>(1), MappingQ1 */
+static void
+assemble3(int l, const double corners[24], const orc_coeff *c, double rhs_value, const uint32_t *dof,
+          const uint64_t *rowptr, const uint32_t *col, double *val, double *F)
+{
+  const uint32_t n = 1u << l, np = n + 1, N = np * np * np;
+  memset(val, 0, sizeof(double) * rowptr[N]);
+  memset(F, 0, sizeof(double) * N);
+  const double gp[2] = {0.5 - 0.5 / sqrt(3.0), 0.5 + 0.5 / sqrt(3.0)};
+  for (uint32_t m = 0; m < n * n * n; ++m)
+    {
+      const uint32_t ix = morton3_compact(m), iy = morton3_compact(m >> 1), iz = morton3_compact(m >> 2);
+      double         P[8][3];
+      uint32_t       ld[8];
+      for (uint32_t v = 0; v < 8; ++v)
+        {
+          const uint32_t jx = ix + (v & 1u), jy = iy + ((v >> 1) & 1u), jz = iz + (v >> 2);
+          fine_vertex3(corners, n, jx, jy, jz, P[v]);
+          ld[v] = dof[(jz * np + jy) * np + jx];
+        }
+      double Ke[8][8] = {{0}}, Fe[8] = {0};
+      for (int q = 0; q < 8; ++q)
+        {
+          const double xi = gp[q & 1], eta = gp[(q >> 1) & 1], ze = gp[q >> 2];
+          double       Nv[8], dN[8][3];
+          for (int v = 0; v < 8; ++v)
+            {
+              const double fx = (v & 1) ? xi : 1 - xi, fy = ((v >> 1) & 1) ? eta : 1 - eta,
+                           fz = (v >> 2) ? ze : 1 - ze;
+              const double sx = (v & 1) ? 1.0 : -1.0, sy = ((v >> 1) & 1) ? 1.0 : -1.0,
+                           sz = (v >> 2) ? 1.0 : -1.0;
+              Nv[v]    = fx * fy * fz;
+              dN[v][0] = sx * fy * fz;
+              dN[v][1] = fx * sy * fz;
+              dN[v][2] = fx * fy * sz;
+            }
+          double J[3][3] = {{0}}, xq[3] = {0, 0, 0};
+          for (int v = 0; v < 8; ++v)
+            for (int a = 0; a < 3; ++a)
+              {
+                xq[a] += P[v][a] * Nv[v];
+                for (int b = 0; b < 3; ++b)
+                  J[a][b] += P[v][a] * dN[v][b];
+              }
+          const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -
+                             J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                             J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+          double Ji[3][3]; /* inverse Jacobian */
+          Ji[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det;
+          Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+          Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+          Ji[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det;
+          Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+          Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+          Ji[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det;
+          Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+          Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+          const double JxW = det * 0.125;
+          double       G[8][3];
+          for (int v = 0; v < 8; ++v)
+            for (int a = 0; a < 3; ++a)
+              G[v][a] = Ji[0][a] * dN[v][0] + Ji[1][a] * dN[v][1] + Ji[2][a] * dN[v][2];
+          double A[9];
+          orc3_coeff_eval(c, xq[0], xq[1], xq[2], A);
+          for (int i = 0; i < 8; ++i)
+            {
+              double t[3];
+              for (int b = 0; b < 3; ++b)
+                t[b] = G[i][0] * A[b] + G[i][1] * A[3 + b] + G[i][2] * A[6 + b];
+              for (int j = 0; j < 8; ++j)
+                Ke[i][j] += (t[0] * G[j][0] + t[1] * G[j][1] + t[2] * G[j][2]) * JxW;
+              Fe[i] += Nv[i] * rhs_value * JxW;
+            }
+        }
+      for (int i = 0; i < 8; ++i)
+        {
+          for (int j = 0; j < 8; ++j)
+            *csr_entry(rowptr, col, val, ld[i], ld[j]) += Ke[i][j];
+          F[ld[i]] += Fe[i];
+        }
+    }
+}
+
+uint64_t
+orc3_assemble(int l, const double corners[24], const orc_coeff *c, double rhs_value, uint64_t *rowptr,
+              uint32_t *col, double *val, double *F)
+{
+  const uint32_t n = 1u << l, np = n + 1;
+  uint32_t *dof = (uint32_t *)malloc(sizeof(uint32_t) * np * np * np);
+  orc3_dof_map(l, dof);
+  const uint64_t nnz = build_sparsity3(l, dof, rowptr, col);
+  assemble3(l, corners, c, rhs_value, dof, rowptr, col, val, F);
+  free(dof);
+  return nnz;
+}
+
+static int
+run_cell3(int l, const double corners[24], const orc_coeff *c, double rhs_value, double tol,
+          int max_iter, int precond, double omega, double *phi_out, double *M, double *b, int32_t *iters,
+          double *res)
+{
+  const uint32_t n = 1u << l, np = n + 1, N = np * np * np;
+  uint32_t      *dof    = (uint32_t *)malloc(sizeof(uint32_t) * N);
+  uint64_t      *rowptr = (uint64_t *)malloc(sizeof(uint64_t) * (N + 1));
+  uint32_t      *col    = (uint32_t *)malloc(sizeof(uint32_t) * 27 * (size_t)N);
+  double        *K      = (double *)malloc(sizeof(double) * 27 * (size_t)N);
+  double        *S      = (double *)malloc(sizeof(double) * 27 * (size_t)N);
+  uint64_t      *rod    = (uint64_t *)malloc(sizeof(uint64_t) * N);
+  double        *F = (double *)malloc(sizeof(double) * N), *rhs = (double *)malloc(sizeof(double) * N);
+  double        *g = (double *)malloc(sizeof(double) * N), *w0 = (double *)malloc(sizeof(double) * N);
+  double        *w1 = (double *)malloc(sizeof(double) * N), *w2 = (double *)malloc(sizeof(double) * N);
+  double        *phi   = (double *)malloc(sizeof(double) * 8 * (size_t)N);
+  unsigned char *is_bd = (unsigned char *)calloc(N, 1);
+  int            fail  = 0;
+  double         coef[64];
+
+  orc3_dof_map(l, dof);
+  const uint64_t nnz = build_sparsity3(l, dof, rowptr, col);
+  for (uint32_t r = 0; r < N; ++r)
+    {
+      uint64_t k = rowptr[r] + 1;
+      while (k < rowptr[r + 1] && col[k] < r)
+        ++k;
+      rod[r] = k;
+    }
+  assemble3(l, corners, c, rhs_value, dof, rowptr, col, K, F);
+  orc3_basis_q1_coeffs(corners, coef);
+  for (uint32_t jz = 0; jz < np; ++jz)
+    for (uint32_t jy = 0; jy < np; ++jy)
+      for (uint32_t jx = 0; jx < np; ++jx)
+        if (jx == 0 || jy == 0 || jz == 0 || jx == n || jy == n || jz == n)
+          is_bd[dof[(jz * np + jy) * np + jx]] = 1;
+
+  for (int ib = 0; ib < 8; ++ib)
+    {
+      for (uint32_t jz = 0; jz < np; ++jz)
+        for (uint32_t jy = 0; jy < np; ++jy)
+          for (uint32_t jx = 0; jx < np; ++jx)
+            {
+              const uint32_t d = dof[(jz * np + jy) * np + jx];
+              if (is_bd[d])
+                {
+                  double p[3];
+                  fine_vertex3(corners, n, jx, jy, jz, p);
+                  g[d] = orc3_basis_q1_value(coef, ib, p[0], p[1], p[2]);
+                }
+              else
+                g[d] = 0.0;
+            }
+      memset(rhs, 0, sizeof(double) * N);
+      memcpy(S, K, sizeof(double) * nnz);
+      condense(N, rowptr, col, S, rhs, is_bd, g);
+      double *x = phi + (size_t)ib * N;
+      memset(x, 0, sizeof(double) * N);
+      const int it =
+        pcg(N, rowptr, col, S, rod, precond, omega, rhs, x, tol, max_iter, w0, w1, w2, &res[ib]);
+      iters[ib] = it < 0 ? -it : it;
+      if (it < 0 && !fail)
+        fail = 1 + ib;
+      for (uint32_t d = 0; d < N; ++d)
+        if (is_bd[d])
+          x[d] = g[d];
+    }
+  /* assemble_global_element_matrix: basis.tpp:245-285 with dofs_per_cell = 8 */
+  for (int i = 0; i < 8; ++i)
+    {
+      for (int j = 0; j < 8; ++j)
+        {
+          orc_vmult((int)N, rowptr, col, K, phi + (size_t)j * N, w0);
+          M[8 * i + j] = dot(N, phi + (size_t)i * N, w0);
+        }
+      b[i] = dot(N, phi + (size_t)i * N, F);
+    }
+  if (phi_out)
+    memcpy(phi_out, phi, sizeof(double) * 8 * (size_t)N);
+  free(dof), free(rowptr), free(col), free(K), free(S), free(rod), free(F), free(rhs), free(g);
+  free(w0), free(w1), free(w2), free(phi), free(is_bd);
+  return fail;
+}
+
+int
+orc3_run_cells(int l, int n_cells, const double *corners, const orc_coeff *c, double rhs_value,
+               double tol, int max_iter, int precond, double omega, int n_threads, double *phi, double *M,
+               double *b, int32_t *iters, double *res)
+{
+  const size_t n = (size_t)1 << l, N = (n + 1) * (n + 1) * (n + 1);
+  int          failed = 0;
+  if (n_threads < 1)
+    n_threads = 1;
+#pragma omp parallel for num_threads(n_threads) schedule(static) reduction(+ : failed)
+  for (int k = 0; k < n_cells; ++k)
+    {
+      const int f = run_cell3(l, corners + 24 * (size_t)k, c, rhs_value, tol, max_iter, precond, omega,
+                              phi ? phi + (size_t)k * 8 * N : NULL, M + 64 * (size_t)k, b + 8 * (size_t)k,
+                              iters + 8 * (size_t)k, res + 8 * (size_t)k);
+      failed += (f != 0);
+    }
+  return failed;
+}

@@ -97,6 +97,28 @@ int orc_run_cells(int l, int n_cells, const double *corners, const orc_coeff *c,
 /* set_global_weights (basis.tpp:352-377): out = sum_i w[i] * phi[i]. */
 void orc_global_solution(int N, const double *phi, const double w[4], double *out);
 
+/* ------------------------------------------------------------------- 3D ----
+ * The dim = 3 instantiation of the same class (diffusion_problem_basis.inst.cc:15-16;
+ * BasisQ1<3> basis_q1.tpp:50-75,99-113; MatrixCoeff<3> matrix_coeff.tpp:28-41).
+ * Vertices and children in deal.II's lexicographic hex order (x fastest), fine cells in
+ * 3D Morton order, 2x2x2 Gauss, trilinear mapping, 2^3 = 8 bases per coarse cell.
+ * Arrays are indexed [jz][jy][jx]; corners are [8][3]; coefficient tensors are 3x3 row-major.
+ * Coefficient kinds: ORC_COEFF_REFERENCE, ORC_COEFF_CONSTANT. */
+int    orc3_n_dofs(int l);
+void   orc3_dof_map(int l, uint32_t *dof_of_vertex);
+int    orc3_boundary_dofs(int l, uint32_t *out);
+void   orc3_basis_q1_coeffs(const double corners[24], double coef[64]);
+double orc3_basis_q1_value(const double coef[64], int index_basis, double x, double y, double z);
+void   orc3_coeff_eval(const orc_coeff *c, double x, double y, double z, double A[9]);
+void   orc3_constraint_values(int l, const double corners[24], int index_basis, double *vals);
+/* nnz is returned; col/val must hold 27 * (n+1)^3 entries */
+uint64_t orc3_assemble(int l, const double corners[24], const orc_coeff *c, double rhs_value,
+                       uint64_t *rowptr, uint32_t *col, double *val, double *F);
+/* phi [n_cells][8][N] or NULL, M [n_cells][64], b [n_cells][8], iters/res [n_cells][8] */
+int orc3_run_cells(int l, int n_cells, const double *corners, const orc_coeff *c, double rhs_value,
+                   double tol, int max_iter, int precond, double omega, int n_threads, double *phi,
+                   double *M, double *b, int32_t *iters, double *res);
+
 #ifdef __cplusplus
 }
 #endif

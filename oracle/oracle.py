@@ -161,3 +161,97 @@ def coarse_corners(r, cells=None):
         out[:, v, 0] = (ix + (v & 1)) * H
         out[:, v, 1] = (iy + (v >> 1)) * H
     return out
+
+
+# ------------------------------------------------------------------------ 3D --
+
+def n_dofs3(l):
+    return ((1 << l) + 1) ** 3
+
+
+def n_boundary3(l):
+    n = 1 << l
+    return (n + 1) ** 3 - (n - 1) ** 3
+
+
+def dof_map3(l):
+    np_ = (1 << l) + 1
+    out = np.empty(n_dofs3(l), dtype=np.uint32)
+    lib().orc3_dof_map(C.c_int(l), _p(out, C.c_uint32))
+    return out.reshape(np_, np_, np_)
+
+
+def boundary_dofs3(l):
+    out = np.empty(n_boundary3(l), dtype=np.uint32)
+    k = lib().orc3_boundary_dofs(C.c_int(l), _p(out, C.c_uint32))
+    return out[:k]
+
+
+def basis_q1_coeffs3(corners):
+    corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(24)
+    out = np.empty(64, dtype=np.float64)
+    lib().orc3_basis_q1_coeffs(_p(corners, C.c_double), _p(out, C.c_double))
+    return out.reshape(8, 8)
+
+
+def coeff_eval3(c, x, y, z):
+    out = np.empty(9, dtype=np.float64)
+    lib().orc3_coeff_eval(C.byref(c), C.c_double(x), C.c_double(y), C.c_double(z), _p(out, C.c_double))
+    return out.reshape(3, 3)
+
+
+def constraint_values3(l, corners, ib):
+    corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(24)
+    out = np.empty(n_boundary3(l), dtype=np.float64)
+    lib().orc3_constraint_values(C.c_int(l), _p(corners, C.c_double), C.c_int(ib), _p(out, C.c_double))
+    return out
+
+
+def assemble3(l, corners, c, rhs_value=2.0):
+    N = n_dofs3(l)
+    corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(24)
+    rowptr = np.empty(N + 1, dtype=np.uint64)
+    col = np.empty(27 * N, dtype=np.uint32)
+    val = np.empty(27 * N, dtype=np.float64)
+    F = np.empty(N, dtype=np.float64)
+    f = lib().orc3_assemble
+    f.restype = C.c_uint64
+    nnz = f(C.c_int(l), _p(corners, C.c_double), C.byref(c), C.c_double(rhs_value),
+            _p(rowptr, C.c_uint64), _p(col, C.c_uint32), _p(val, C.c_double), _p(F, C.c_double))
+    return rowptr, col[:nnz], val[:nnz], F
+
+
+def run_cells3(l, corners, c, rhs_value=2.0, tol=1e-12, max_iter=1000, precond=PRECOND_SSOR,
+               omega=1.6, n_threads=1, keep_phi=True):
+    """DiffusionProblemBasis<3>::run() over the given coarse hexes.  corners: [C,8,3]."""
+    corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(-1, 8, 3)
+    nc = corners.shape[0]
+    N = n_dofs3(l)
+    phi = np.empty((nc, 8, N), dtype=np.float64) if keep_phi else None
+    M = np.empty((nc, 8, 8), dtype=np.float64)
+    b = np.empty((nc, 8), dtype=np.float64)
+    iters = np.empty((nc, 8), dtype=np.int32)
+    res = np.empty((nc, 8), dtype=np.float64)
+    failed = lib().orc3_run_cells(
+        C.c_int(l), C.c_int(nc), _p(corners, C.c_double), C.byref(c), C.c_double(rhs_value),
+        C.c_double(tol), C.c_int(max_iter), C.c_int(precond), C.c_double(omega), C.c_int(n_threads),
+        None if phi is None else _p(phi, C.c_double), _p(M, C.c_double), _p(b, C.c_double),
+        _p(iters, C.c_int32), _p(res, C.c_double))
+    return dict(phi=phi, M=M, b=b, iters=iters, res=res, failed=failed)
+
+
+def coarse_corners3(r, cells=None):
+    """Corner points [C,8,3] of the (2^r)^3 coarse mesh on [0,1]^3 in 3D Morton order."""
+    nc = 1 << r
+    H = 1.0 / nc
+    m = np.arange(nc ** 3, dtype=np.uint64) if cells is None else np.asarray(cells, dtype=np.uint64)
+    idx = np.zeros((3, m.size), dtype=np.uint64)
+    for bit in range(r):
+        for a in range(3):
+            idx[a] |= ((m >> np.uint64(3 * bit + a)) & np.uint64(1)) << np.uint64(bit)
+    out = np.empty((m.size, 8, 3), dtype=np.float64)
+    for v in range(8):
+        out[:, v, 0] = (idx[0] + (v & 1)) * H
+        out[:, v, 1] = (idx[1] + ((v >> 1) & 1)) * H
+        out[:, v, 2] = (idx[2] + (v >> 2)) * H
+    return out

@@ -48,7 +48,8 @@ def test_argument_validation_happens_before_any_device_work(msb):
 
     ptr = corners.ctypes.data_as(C.POINTER(C.c_double))
     assert lib.msb_create(C.byref(make(abi_version=99)), ptr, None, C.byref(h)) == -1
-    assert lib.msb_create(C.byref(make(dim=3)), ptr, None, C.byref(h)) == -2      # 3D not built
+    assert lib.msb_create(C.byref(make(dim=4)), ptr, None, C.byref(h)) == -2      # only dim 2 and 3
+    assert lib.msb_create(C.byref(make(dim=3, n_refine_local=7)), ptr, None, C.byref(h)) == -2
     assert b"dim=3" in lib.msb_last_error()
     assert lib.msb_create(C.byref(make(n_refine_local=12)), ptr, None, C.byref(h)) == -2
     assert lib.msb_create(C.byref(make(n_cells=0)), ptr, None, C.byref(h)) == -1

@@ -1,0 +1,152 @@
+"""dim = 3 parity of the sm_100a basis stage (through the C ABI) with the CPU oracle's
+restatement of DiffusionProblemBasis<3> (diffusion_problem_basis.inst.cc:15-16).
+
+Same bars as in 2D: DoF maps and constraint index sets bit-exact; bases within 1e-8 relative
+L2; M (8x8), b (8) within 1e-8 relative; both sides converged to ||r||_2 <= 1e-12 absolute.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_PHI = 1e-8
+TOL_MB = 1e-8
+
+
+def _coeffs(msb, oracle, kind, par=()):
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
+    return coeff_desc(kind, par, 0), oracle.coeff(kind, par, 0)
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b))
+
+
+def _skewed_hex():
+    # a general straight-edged hexahedron (trilinear, non-affine mapping)
+    c = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0],
+                  [0, 0, 1], [1, 0, 1], [0, 1, 1], [1, 1, 1]], dtype=np.float64)
+    d = np.array([[0, 0, 0], [.1, -.05, .02], [-.04, .08, 0], [.12, .1, -.06],
+                  [.03, .02, .07], [-.05, .04, .1], [.02, -.06, -.03], [.2, .15, .1]])
+    return ((c + d) * 0.25 + 0.3)[None]
+
+
+@pytest.mark.parametrize("l", [1, 2, 3, 4, 5])
+def test_dof_map_bit_exact_3d(msb, oracle, l):
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_CONSTANT, (1.0,))
+    with msb.BasisShard(l, oracle.coarse_corners3(0), cd, dim=3) as sh:
+        assert np.array_equal(sh.dof_map(), oracle.dof_map3(l))
+
+
+@pytest.mark.parametrize("l", [2, 4])
+def test_constraint_sets_3d(msb, oracle, l):
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    cor = oracle.coarse_corners3(2, [13, 62])
+    with msb.BasisShard(l, cor, cd, dim=3) as sh:
+        for cell in range(2):
+            for ib in (0, 3, 5, 7):
+                dofs, vals = sh.constraints(cell, ib)
+                assert np.array_equal(dofs, oracle.boundary_dofs3(l))
+                assert np.abs(vals - oracle.constraint_values3(l, cor[cell], ib)).max() < 1e-9
+
+
+@pytest.mark.parametrize("l,kind,par,skew", [(3, 0, (), False), (4, 0, (), False), (3, 3, (2.5,), False),
+                                             (3, 0, (), True)])
+def test_matrix_free_operator_matches_csr_vmult_3d(msb, oracle, l, kind, par, skew):
+    import scipy.sparse as sp
+    cd, co = _coeffs(msb, oracle, kind, par)
+    cor = _skewed_hex() if skew else oracle.coarse_corners3(2, [37])
+    rowptr, col, val, F = oracle.assemble3(l, cor[0], co)
+    N = oracle.n_dofs3(l)
+    K = sp.csr_matrix((val, col.astype(np.int64), rowptr.astype(np.int64)), shape=(N, N))
+    rng = np.random.default_rng(l)
+    with msb.BasisShard(l, cor, cd, dim=3) as sh:
+        for _ in range(2):
+            x = rng.standard_normal(N)
+            assert _rel(sh.apply_operator(0, x), K @ x) < 5e-14
+        assert np.abs(sh.load_vector(0) - F).max() < 1e-15 * max(1.0, np.abs(F).max() / 1e-6)
+
+
+@pytest.mark.parametrize("l,r,cells,kind,par", [
+    (2, 1, [0, 7], 0, ()), (3, 2, [5, 21, 63], 0, ()), (4, 2, [9, 40], 0, ()), (3, 1, [3], 3, (1.0,)),
+    (5, 3, [100], 0, ())])
+def test_bases_and_element_matrices_match_oracle_3d(msb, oracle, l, r, cells, kind, par):
+    cd, co = _coeffs(msb, oracle, kind, par)
+    cor = oracle.coarse_corners3(r, cells)
+    ref = oracle.run_cells3(l, cor, co, n_threads=4)
+    assert ref["failed"] == 0
+    with msb.BasisShard(l, cor, cd, dim=3) as sh:
+        sh.run(1e-12, 1000)
+        M, b = sh.element_matrices()
+        it, res = sh.iteration_counts()
+        assert M.shape == (len(cells), 8, 8) and it.shape == (len(cells), 8)
+        assert (res <= 1e-12).all() and (it > 0).all()
+        for c in range(len(cells)):
+            for ib in range(8):
+                assert _rel(sh.basis(c, ib), ref["phi"][c, ib]) < TOL_PHI
+            assert _rel(M[c], ref["M"][c]) < TOL_MB
+            assert _rel(b[c], ref["b"][c]) < TOL_MB
+
+
+def test_skewed_hex_matches_oracle(msb, oracle):
+    cd, co = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    cor = _skewed_hex()
+    ref = oracle.run_cells3(3, cor, co)
+    with msb.BasisShard(3, cor, cd, dim=3) as sh:
+        sh.run(1e-12, 1000)
+        M, b = sh.element_matrices()
+        for ib in range(8):
+            assert _rel(sh.basis(0, ib), ref["phi"][0, ib]) < TOL_PHI
+        assert _rel(M[0], ref["M"][0]) < TOL_MB and _rel(b[0], ref["b"][0]) < TOL_MB
+
+
+def test_invariants_3d(msb, oracle):
+    """SURVEY Appendix B in 3D: partition of unity, zero row sums, sum b = f |K|, symmetry."""
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    r, l = 2, 4
+    cor = oracle.coarse_corners3(r)
+    with msb.BasisShard(l, cor, cd, dim=3) as sh:
+        sh.run(1e-12, 1000)
+        M, b = sh.element_matrices()
+        assert np.abs(M.sum(axis=2)).max() < 1e-9
+        assert np.abs(M - M.transpose(0, 2, 1)).max() < 1e-9
+        assert np.abs(b.sum(axis=1) - 2.0 * (0.25 ** 3)).max() < 1e-11
+        s = sum(sh.basis(17, ib) for ib in range(8))
+        assert np.abs(s - 1.0).max() < 1e-9
+        # multilevel preconditioner keeps the iteration count small
+        it, _ = sh.iteration_counts()
+        assert it.max() < 60
+        w = np.random.default_rng(0).standard_normal((sh.n_cells, 8))
+        sh.set_global_weights(w)
+        ref = sum(w[17, ib] * sh.basis(17, ib) for ib in range(8))
+        assert np.abs(sh.global_solution(17) - ref).max() < 1e-13
+
+
+def test_constant_coefficient_reproduces_trilinear_basis(msb, oracle):
+    """a = const on a brick: the multiscale bases are the trilinear Q1 functions themselves."""
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_CONSTANT, (1.0,))
+    cor = oracle.coarse_corners3(1, [6])
+    l = 3
+    with msb.BasisShard(l, cor, cd, dim=3) as sh:
+        sh.run(1e-12, 1000)
+        M, _ = sh.element_matrices()
+        h = 0.5
+        assert np.allclose(np.diag(M[0]), h / 3, atol=1e-10)
+        dm = sh.dof_map()
+        n = 1 << l
+        g = np.arange(n + 1) / n
+        Z, Y, X = np.meshgrid(g, g, g, indexing="ij")
+        phi7 = np.empty(sh.N)
+        phi7[dm.ravel()] = (X * Y * Z).ravel()
+        assert np.abs(sh.basis(0, 7) - phi7).max() < 1e-10
+
+
+def test_unsupported_3d_requests_fail_loudly(msb, oracle):
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import MsbError, coeff_desc
+    cor = oracle.coarse_corners3(0)
+    with pytest.raises(MsbError):
+        msb.BasisShard(3, cor, coeff_desc(msb.COEFF_PERIODIC, (0.1, 0.9)), dim=3)
+    with pytest.raises(MsbError):
+        msb.BasisShard(7, cor, coeff_desc(msb.COEFF_CONSTANT, (1.0,)), dim=3)
+    with pytest.raises(MsbError):
+        msb.BasisShard(3, cor, coeff_desc(msb.COEFF_CONSTANT, (1.0,)), dim=3, tier=msb.TIER_SMEM)

@@ -235,3 +235,57 @@ def test_openmp_batch_equals_serial(oracle):
     b = oracle.run_cells(4, cor, c, n_threads=4)
     assert np.array_equal(a["M"], b["M"]) and np.array_equal(a["iters"], b["iters"])
     assert np.array_equal(a["phi"], b["phi"])
+
+
+# ------------------------------------------------------------------------------ dim = 3
+def test_dof_map3_is_first_touch_permutation(oracle):
+    for l in (1, 2, 3):
+        d = oracle.dof_map3(l)
+        N = oracle.n_dofs3(l)
+        assert sorted(d.ravel().tolist()) == list(range(N))
+        # the first fine cell holds DoFs 0..7 in deal.II's lexicographic vertex order
+        assert d[0:2, 0:2, 0:2].ravel().tolist() == list(range(8))
+    # l = 1: second cell (child 1, +x) adds its four new vertices in vertex order
+    d = oracle.dof_map3(1)
+    assert [d[0, 0, 2], d[0, 1, 2], d[1, 0, 2], d[1, 1, 2]] == [8, 9, 10, 11]
+    assert oracle.boundary_dofs3(2).size == 5 ** 3 - 3 ** 3
+
+
+def test_matrix_coeff3_is_rotated_isotropic(oracle):
+    """MatrixCoeff<3> (matrix_coeff.tpp:28-41, :66-91): R (a I) R^T = a I up to rounding."""
+    c = oracle.coeff(oracle.COEFF_REFERENCE)
+    A = oracle.coeff_eval3(c, 0.3, 0.2, 0.9)
+    a2 = oracle.coeff_eval(c, 0.3, 0.2)[0, 0]
+    assert np.allclose(A, a2 * np.eye(3), atol=1e-15)
+
+
+def test_basis_q1_3d_is_nodal(oracle):
+    cor = oracle.coarse_corners3(1, [5])[0]
+    coef = oracle.basis_q1_coeffs3(cor)
+    pm = np.array([[1, x, y, z, x * y, y * z, x * z, x * y * z] for x, y, z in cor])
+    assert np.allclose(pm @ coef, np.eye(8), atol=1e-12)
+
+
+def test_run_cells3_invariants(oracle):
+    """SURVEY Appendix B carried to dim 3; a = const reproduces the trilinear element matrix."""
+    import scipy.sparse as sp
+    l = 3
+    cor = oracle.coarse_corners3(1, [5])
+    N = oracle.n_dofs3(l)
+    for kind, par in ((oracle.COEFF_CONSTANT, (1.0,)), (oracle.COEFF_REFERENCE, ())):
+        c = oracle.coeff(kind, par)
+        rp, col, val, F = oracle.assemble3(l, cor[0], c)
+        K = sp.csr_matrix((val, col.astype(np.int64), rp.astype(np.int64)), shape=(N, N))
+        assert abs(K - K.T).max() < 1e-15
+        assert np.abs(K @ np.ones(N)).max() < 1e-14
+        assert abs(F.sum() - 2.0 * 0.125) < 1e-14
+        r = oracle.run_cells3(l, cor, c)
+        assert r["failed"] == 0 and (r["res"] <= 1e-12).all()
+        assert np.abs(r["phi"][0].sum(axis=0) - 1).max() < 1e-10
+        assert np.abs(r["M"][0].sum(axis=1)).max() < 1e-12
+        assert abs(r["b"][0].sum() - 0.25) < 1e-12
+        if kind == oracle.COEFF_CONSTANT:
+            h = 0.5
+            assert np.allclose(np.diag(r["M"][0]), h / 3, atol=1e-12)
+            assert np.isclose(r["M"][0][0, 7], -h / 12, atol=1e-12)
+            assert np.isclose(r["M"][0][0, 1], 0.0, atol=1e-12)

@@ -35,17 +35,28 @@ WORKLOADS = {
     "cfg5": (6, 8, 1, (1.0 / 64, 0.9999), 0),         # 64x64 x 256x256 (streamed tier)
     "cfg1": (3, 7, 0, (), 0),                         # the reference's default run
     "target-refcoef": (8, 6, 0, (), 0),
+    # dim = 3: (r, l, kind, par, seed, dim)
+    "3d-16x16": (4, 4, 0, (), 0, 3),                  # 16^3 coarse x 16^3 fine hexes, 32768 solves
+    "3d-8x32": (3, 5, 0, (), 0, 3),                   # 8^3 coarse x 32^3 fine hexes, 4096 solves
 }
+
+
+def workload(name):
+    w = WORKLOADS[name]
+    return w if len(w) == 6 else w + (2,)
+
+
 METRIC = "multiscale basis solves/sec"
 UNIT = "solves/s"
 
 
 def describe(name, n_cells):
-    r, l, kind, par, seed = WORKLOADS[name]
+    r, l, kind, par, seed, dim = workload(name)
     kinds = ["reference MatrixCoeff (k=57, PI_D typo)", "periodic eps=1/64", "random inclusions 1e4",
              "constant", "table"]
-    return "%s: %dx%d coarse x %dx%d fine Q1, %s, f=2, tol 1e-12 abs, %d cells = %d solves" % (
-        name, 1 << r, 1 << r, 1 << l, 1 << l, kinds[kind], n_cells, 4 * n_cells)
+    return "%s: %s coarse x %s fine Q1, %s, f=2, tol 1e-12 abs, %d cells = %d solves" % (
+        name, "x".join([str(1 << r)] * dim), "x".join([str(1 << l)] * dim), kinds[kind], n_cells,
+        (1 << dim) * n_cells)
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -108,14 +119,16 @@ def cpu_baseline(name, cells_per_core=None, budget_s=12.0):
     built).  All host cores, contiguous Morton ranges per core, bounded sample."""
     from oracle import oracle as O
     O.build()
-    r, l, kind, par, seed = WORKLOADS[name]
+    r, l, kind, par, seed, dim = workload(name)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-    total = (1 << r) ** 2
+    total = (1 << r) ** dim
     c = O.coeff(kind, par, seed)
+    run_cells = O.run_cells if dim == 2 else O.run_cells3
+    corners_of = O.coarse_corners if dim == 2 else O.coarse_corners3
     # calibrate on 1 cell per core, then size the sample to ~budget_s of wall time
     probe = min(total, cores)
     t0 = time.perf_counter()
-    O.run_cells(l, O.coarse_corners(r, list(range(probe))), c, n_threads=cores, keep_phi=False)
+    run_cells(l, corners_of(r, list(range(probe))), c, n_threads=cores, keep_phi=False)
     per_cell = max(1e-4, (time.perf_counter() - t0))
     if cells_per_core is None:
         cells_per_core = int(max(1, min(256, budget_s / per_cell)))
@@ -123,16 +136,16 @@ def cpu_baseline(name, cells_per_core=None, budget_s=12.0):
     # spread the sample over the Morton curve so that it sees the whole coefficient range
     stride = max(1, total // ncell)
     cells = list(range(0, stride * ncell, stride))[:ncell]
-    cor = O.coarse_corners(r, cells)
+    cor = corners_of(r, cells)
     t0 = time.perf_counter()
-    res = O.run_cells(l, cor, c, n_threads=cores, keep_phi=False)
+    res = run_cells(l, cor, c, n_threads=cores, keep_phi=False)
     dt = time.perf_counter() - t0
     assert res["failed"] == 0
-    return {"value": 4 * ncell / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": (1 << dim) * ncell / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d of %d coarse cells (every %d-th along the Morton curve), %d per core, "
                       "%.2f s wall, mean SSOR-PCG iterations %.1f"
                       % (ncell, total, stride, cells_per_core, dt, float(res["iters"].mean())),
-            "seconds": dt, "solves": 4 * ncell}
+            "seconds": dt, "solves": (1 << dim) * ncell}
 
 
 def run_reference_arm(args):
@@ -147,13 +160,13 @@ def run_reference_arm(args):
     tot_s = sum(v["seconds"] for v in vals)
     tot_n = sum(v["solves"] for v in vals)
     value = tot_n / tot_s
-    r, l, kind, par, seed = WORKLOADS[args.workload]
+    r, l, kind, par, seed, dim = workload(args.workload)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / len(vals),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": describe(args.workload, (1 << r) ** 2),
+        "config": {"workload": describe(args.workload, (1 << r) ** dim),
                    "note": "reference binary unbuildable here (needs deal.II/MPI/Trilinos): timed the "
                            "oracle port of its SSOR-PCG local solver on all host cores; each step is a "
                            "bounded sample of the workload's coarse cells"},
@@ -201,23 +214,24 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    r, l, kind, par, seed = WORKLOADS[args.workload]
-    total_cells = (1 << r) ** 2
+    r, l, kind, par, seed, dim = workload(args.workload)
+    nb = 1 << dim
+    total_cells = (1 << r) ** dim
     if args.cells:
         total_cells = min(total_cells, args.cells)
     lo, hi = pkg.morton_partition(total_cells, rank, world)
     n_local = hi - lo
-    N = ((1 << l) + 1) ** 2
+    N = ((1 << l) + 1) ** dim
 
     # host inputs/outputs in pinned memory (the e2e leg copies them every step)
-    corners_np = pkg.coarse_corners(r, lo, hi)
+    corners_np = pkg.coarse_corners(r, lo, hi) if dim == 2 else pkg.coarse_corners3(r, lo, hi)
     h_corners = torch.from_numpy(corners_np).pin_memory()
-    h_M = torch.empty((n_local, 4, 4), dtype=torch.float64).pin_memory()
-    h_b = torch.empty((n_local, 4), dtype=torch.float64).pin_memory()
-    h_it = torch.empty((n_local, 4), dtype=torch.int32).pin_memory()
+    h_M = torch.empty((n_local, nb, nb), dtype=torch.float64).pin_memory()
+    h_b = torch.empty((n_local, nb), dtype=torch.float64).pin_memory()
+    h_it = torch.empty((n_local, nb), dtype=torch.int32).pin_memory()
 
     sh = pkg.BasisShard(l, corners_np, coeff_desc(kind, par, seed), device_id=local_rank,
-                        variant=args.variant)
+                        variant=args.variant, dim=dim)
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
 
@@ -267,7 +281,7 @@ def main():
     else:
         solve_ms_max = float(stats[3].item())
     alg_bytes_all, iters_all, launches_all = float(stats[0]), float(stats[1]), int(stats[2])
-    n_solves = 4 * total_cells
+    n_solves = nb * total_cells
     value = n_solves / (ms_step * 1e-3)
 
     # ---- end-to-end leg: host buffers in, host buffers out, through the C ABI -------------
@@ -303,7 +317,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item()) / args.steps
         e2e = {"value": n_solves / (e2e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h_corners.numel() * 8 + n_local * 16 * 8),
+               "h2d_bytes_per_step": int(h_corners.numel() * 8 + n_local * nb * nb * 8),
                "d2h_bytes_per_step": int(h_M.numel() * 8 + h_b.numel() * 8 + h_it.numel() * 4),
                "ms_per_step": e2e_ms,
                "api": "msb_set_cells + msb_run_async + msb_sync + msb_get_element_matrices + "
@@ -314,7 +328,7 @@ def main():
     M, b = sh.element_matrices()
     H = 1.0 / (1 << r)
     ok = bool(np.all(res_np <= 1e-12) and np.abs(M.sum(axis=2)).max() < 1e-8 * np.abs(M).max()
-              and np.abs(b.sum(axis=1) - 2 * H * H).max() < 1e-9 * H * H)
+              and np.abs(b.sum(axis=1) - 2 * H ** dim).max() < 1e-9 * H ** dim)
     if not ok:
         raise SystemExit("bench.py: results failed the invariants (zero row sums / load / residual)")
 
@@ -340,7 +354,7 @@ def main():
             "config": {"workload": describe(args.workload, total_cells),
                        "partition": "contiguous Morton ranges over %d rank(s) (p4est rule)" % world,
                        "l2": "working set (stencil + bases = %.1f GB per GPU) far larger than L2; "
-                             "no flush needed" % (n_local * 10 * N * 8 / 1e9),
+                             "no flush needed" % (n_local * (10 if dim == 2 else 23) * N * 8 / 1e9),
                        "mean_pcg_iterations": iters_all / n_solves,
                        "preconditioner": ("multilevel diagonal scaling (BPX), exact Galerkin diagonals" if args.variant < 100 else "Jacobi (symmetric diagonal scaling)"),
                        "variant": args.variant},
@@ -349,7 +363,7 @@ def main():
             "gpu_launches": launches_all,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": (("solve_bpx_tm_kernel" if (l == 6 and args.variant in (0, 5)) else "solve_bpx_kernel") if args.variant < 100 else "solve_smem_kernel") if sh.run_stats()["tier"] == 1 else "stream_k*",
+                         "kernel": (("solve_bpx_tm_kernel" if (l == 6 and args.variant in (0, 5)) else "solve_bpx_kernel") if args.variant < 100 else "solve_smem_kernel") if sh.run_stats()["tier"] == 1 else ("stream_k*" if dim == 2 else "d3::k2_kernel + siblings"),
                          "kernel_ms_per_launch": solve_ms_max,
                          "peak_source": peak_src,
                          "note": "achieved = ALGORITHMIC streaming bytes N(96k+16)/solve (SURVEY 8d) / "

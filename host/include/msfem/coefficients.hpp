@@ -58,9 +58,8 @@ namespace Coefficients
   public:
     MatrixCoeff()
     {
-      static_assert(dim == 2, "only the 2D path is built");
-      rot[0][0] = std::cos(alpha), rot[0][1] = std::sin(alpha);
-      rot[1][0] = -std::sin(alpha), rot[1][1] = std::cos(alpha);
+      static_assert(dim == 2 || dim == 3, "the reference instantiates dim 2 and 3");
+      set_rotation(rot);
     }
     Tensor<2, dim> value(const Point<dim> &p) const override
     {
@@ -79,9 +78,26 @@ namespace Coefficients
     }
 
   private:
+    // matrix_coeff.tpp:17-25 (dim 2) and :28-41 (dim 3, Euler angles alpha, beta, gamma)
+    void set_rotation(Tensor<2, 2> &r) const
+    {
+      r[0][0] = std::cos(alpha), r[0][1] = std::sin(alpha);
+      r[1][0] = -std::sin(alpha), r[1][1] = std::cos(alpha);
+    }
+    void set_rotation(Tensor<2, 3> &r) const
+    {
+      const double ca = std::cos(alpha), sa = std::sin(alpha), cb = std::cos(beta), sb = std::sin(beta),
+                   cg = std::cos(gamma), sg = std::sin(gamma);
+      r[0][0] = ca * cg - sa * cb * sg, r[0][1] = -ca * sg - sa * cb * cg, r[0][2] = sa * sb;
+      r[1][0] = sa * cg + ca * cb * sg, r[1][1] = -sa * sg + ca * cb * cg, r[1][2] = -ca * sb;
+      r[2][0] = sb * sg, r[2][1] = sb * cg, r[2][2] = cb;
+    }
+
     const int      k            = 57;
     const double   scale_factor = 0.9999;
     const double   alpha        = PI_D / 3;
+    const double   beta         = PI_D / 6;
+    const double   gamma        = PI_D / 4;
     Tensor<2, dim> rot;
   };
 
@@ -180,47 +196,54 @@ namespace Coefficients
     BasisQ1() = delete;
     explicit BasisQ1(const CoarseCell<dim> &cell)
       : index_basis(0)
-      , coeff_matrix(4, 4)
+      , coeff_matrix(1 << dim, 1 << dim)
     {
-      static_assert(dim == 2, "only the 2D path is built");
-      // rows (1, x, y, xy) at the four vertices, inverted by Gauss-Jordan elimination;
-      // column i then holds the monomial coefficients of the basis of vertex i
-      double a[4][8];
-      for (int i = 0; i < 4; ++i)
+      static_assert(dim == 2 || dim == 3, "the reference instantiates dim 2 and 3");
+      // rows (1, x, y, xy) resp. (1, x, y, z, xy, yz, xz, xyz) at the vertices
+      // (basis_q1.tpp:26-47, :50-75), inverted by Gauss-Jordan elimination; column i then
+      // holds the monomial coefficients of the basis of vertex i
+      constexpr int nb = 1 << dim;
+      double        a[nb][2 * nb];
+      for (int i = 0; i < nb; ++i)
         {
-          const Point<dim> &p = cell.vertex(i);
-          a[i][0] = 1, a[i][1] = p(0), a[i][2] = p(1), a[i][3] = p(0) * p(1);
-          for (int j = 0; j < 4; ++j)
-            a[i][4 + j] = (i == j);
+          double m[8];
+          monomials(cell.vertex(i), m);
+          for (int j = 0; j < nb; ++j)
+            a[i][j] = m[j], a[i][nb + j] = (i == j);
         }
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < nb; ++c)
         {
           int piv = c;
-          for (int r = c + 1; r < 4; ++r)
+          for (int r = c + 1; r < nb; ++r)
             if (std::fabs(a[r][c]) > std::fabs(a[piv][c]))
               piv = r;
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < 2 * nb; ++j)
             std::swap(a[c][j], a[piv][j]);
           const double inv = 1.0 / a[c][c];
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < 2 * nb; ++j)
             a[c][j] *= inv;
-          for (int r = 0; r < 4; ++r)
+          for (int r = 0; r < nb; ++r)
             if (r != c)
               {
                 const double f = a[r][c];
-                for (int j = 0; j < 8; ++j)
+                for (int j = 0; j < 2 * nb; ++j)
                   a[r][j] -= f * a[c][j];
               }
         }
-      for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j)
-          coeff_matrix(i, j) = a[i][4 + j];
+      for (int i = 0; i < nb; ++i)
+        for (int j = 0; j < nb; ++j)
+          coeff_matrix(i, j) = a[i][nb + j];
     }
     void   set_index(unsigned int index) { index_basis = index; }
+    // basis_q1.tpp:86-96 (dim 2), :99-113 (dim 3)
     double value(const Point<dim> &p, const unsigned int /*component*/ = 0) const
     {
-      return coeff_matrix(0, index_basis) + coeff_matrix(1, index_basis) * p(0) +
-             coeff_matrix(2, index_basis) * p(1) + coeff_matrix(3, index_basis) * p(0) * p(1);
+      double m[8];
+      monomials(p, m);
+      double v = 0.0;
+      for (int k = 0; k < (1 << dim); ++k)
+        v += coeff_matrix(k, index_basis) * m[k];
+      return v;
     }
     void value_list(const std::vector<Point<dim>> &points, std::vector<double> &values,
                     const unsigned int = 0) const
@@ -231,6 +254,16 @@ namespace Coefficients
     }
 
   private:
+    static void monomials(const Point<2> &p, double m[8])
+    {
+      m[0] = 1, m[1] = p(0), m[2] = p(1), m[3] = p(0) * p(1);
+    }
+    static void monomials(const Point<3> &p, double m[8])
+    {
+      m[0] = 1, m[1] = p(0), m[2] = p(1), m[3] = p(2), m[4] = p(0) * p(1), m[5] = p(1) * p(2);
+      m[6] = p(0) * p(2), m[7] = p(0) * p(1) * p(2);
+    }
+
     unsigned int       index_basis;
     FullMatrix<double> coeff_matrix;
   };

@@ -89,7 +89,7 @@ namespace DiffusionProblem
             const std::vector<double> &table, double rhs_value, int device_id)
         : n_cells(corners.size() / (dim * (1 << dim)))
         , n_refine_local(n_refine_local)
-        , weights(4 * n_cells, 0.0)
+        , weights((std::size_t(1) << dim) * n_cells, 0.0)
       {
         msb_config cfg{};
         cfg.abi_version    = MSB_ABI_VERSION;
@@ -128,6 +128,7 @@ namespace DiffusionProblem
   {
   public:
     DiffusionProblemBasis() = delete;
+    static constexpr unsigned NB = 1u << dim; // GeometryInfo<dim>::vertices_per_cell
 
     DiffusionProblemBasis(unsigned int n_refine_local, const CoarseCell<dim> &global_cell,
                           unsigned int local_subdomain, MPI_Comm_shim mpi_communicator = 0)
@@ -146,7 +147,7 @@ namespace DiffusionProblem
       , verbose(false)
       , last_steps(1 << dim, 0)
     {
-      static_assert(dim == 2, "only the 2D path is built (3D is a 'next' row)");
+      static_assert(dim == 2 || dim == 3, "the reference instantiates dim 2 and 3");
       for (unsigned int v = 0; v < (1u << dim); ++v)
         corner_points[v] = global_cell.vertex(v);
     }
@@ -212,7 +213,7 @@ namespace DiffusionProblem
       if (batch)
         {
           for (unsigned i = 0; i < (1u << dim); ++i)
-            batch->weights[4 * index_in_batch + i] = weights[i];
+            batch->weights[NB * index_in_batch + i] = weights[i];
           batch->weights_dirty = true;
         }
       is_set_global_weights = true;
@@ -238,7 +239,7 @@ namespace DiffusionProblem
     std::size_t n_dofs() const
     {
       const std::size_t np = (std::size_t(1) << n_refine_local) + 1;
-      return np * np;
+      return dim == 2 ? np * np : np * np * np;
     }
     void set_verbose(bool v) { verbose = v; }
 
@@ -277,7 +278,7 @@ namespace DiffusionProblem
       const unsigned l = objs.begin()->second->n_refine_local;
       const unsigned n = 1u << l;
       std::vector<double> corners;
-      corners.reserve(objs.size() * 8);
+      corners.reserve(objs.size() * NB * dim);
       for (auto &kv : objs)
         for (unsigned v = 0; v < (1u << dim); ++v)
           for (int d = 0; d < dim; ++d)
@@ -285,6 +286,8 @@ namespace DiffusionProblem
 
       const msb_coeff_desc desc = coeff.device_descriptor();
       std::vector<double>  table;
+      if (desc.kind == MSB_COEFF_TABLE && dim != 2)
+        throw BasisStageError(MSB_ERR_UNSUPPORTED, "tabulated coefficients are built for dim 2 only");
       if (desc.kind == MSB_COEFF_TABLE)
         {
           // a coefficient class the device has no formula for: evaluate its value_list at the
@@ -323,8 +326,8 @@ namespace DiffusionProblem
         throw BasisStageError(rc, msb_last_error());
 
       const std::size_t    C = objs.size();
-      std::vector<double>  M(16 * C), b(4 * C), res(4 * C);
-      std::vector<int32_t> its(4 * C);
+      std::vector<double>  M(NB * NB * C), b(NB * C), res(NB * C);
+      std::vector<int32_t> its(NB * C);
       internal::check(msb_get_element_matrices(batch->handle, M.data(), b.data()));
       internal::check(msb_get_iteration_counts(batch->handle, its.data(), res.data()));
 
@@ -334,19 +337,19 @@ namespace DiffusionProblem
           DiffusionProblemBasis<dim> &o = *kv.second;
           o.batch          = batch;
           o.index_in_batch = k;
-          for (unsigned i = 0; i < 4; ++i)
+          for (unsigned i = 0; i < NB; ++i)
             {
-              for (unsigned j = 0; j < 4; ++j)
-                o.global_element_matrix(i, j) = M[16 * k + 4 * i + j];
+              for (unsigned j = 0; j < NB; ++j)
+                o.global_element_matrix(i, j) = M[NB * NB * k + NB * i + j];
               // the reference accumulates b with += and never resets it (basis.tpp:280)
-              o.global_element_rhs(i) += b[4 * k + i];
-              o.last_steps[i] = (unsigned)its[4 * k + i];
+              o.global_element_rhs(i) += b[NB * k + i];
+              o.last_steps[i] = (unsigned)its[NB * k + i];
             }
           o.is_built_global_element_matrix = true;
           if (o.filename_global.empty())
             o.set_filename_global();
           if (o.verbose)
-            for (unsigned i = 0; i < 4; ++i)
+            for (unsigned i = 0; i < NB; ++i)
               std::cout << "   (cell   " << o.global_cell_id.to_string() << ") (basis   " << i << ")   "
                         << o.last_steps[i] << " fine CG iterations needed to obtain convergence."
                         << std::endl;
@@ -372,8 +375,8 @@ namespace DiffusionProblem
       std::ostringstream name;
       name << (dim == 2 ? "2d-" : "3d-") << "basis." << std::setw(5) << std::setfill('0') << 0
            << ".cell-" << global_cell_id.to_string() << ".vtu";
-      std::vector<std::vector<double>> phi(4);
-      for (unsigned i = 0; i < 4; ++i)
+      std::vector<std::vector<double>> phi(NB);
+      for (unsigned i = 0; i < NB; ++i)
         get_basis(i, phi[i]);
       write_vtu_multi(name.str(), phi, "basis_");
     }
@@ -386,38 +389,52 @@ namespace DiffusionProblem
     void write_vtu_multi(const std::string &fn, const std::vector<std::vector<double>> &fields,
                          const std::string &prefix, bool numbered = true) const
     {
-      const unsigned        n = 1u << n_refine_local, np = n + 1;
-      std::vector<uint32_t> dof(np * np);
+      const unsigned        n = 1u << n_refine_local, np = n + 1, npz = dim == 3 ? np : 1, nz = dim == 3 ? n : 1;
+      const std::size_t     n_pts = n_dofs(), n_cells = std::size_t(n) * n * nz;
+      std::vector<uint32_t> dof(n_pts);
       internal::check(msb_get_dof_map(batch->handle, dof.data()));
       std::ofstream out(fn.c_str());
       out << std::setprecision(17);
       out << "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" "
              "byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n<Piece NumberOfPoints=\""
-          << np * np << "\" NumberOfCells=\"" << n * n << "\">\n<Points>\n<DataArray type=\"Float64\" "
+          << n_pts << "\" NumberOfCells=\"" << n_cells << "\">\n<Points>\n<DataArray type=\"Float64\" "
              "NumberOfComponents=\"3\" format=\"ascii\">\n";
       const auto &c = corner_points;
-      for (unsigned jy = 0; jy < np; ++jy)
-        for (unsigned jx = 0; jx < np; ++jx)
-          {
-            const double s = double(jx) / n, t = double(jy) / n;
-            for (int d = 0; d < dim; ++d)
-              out << c[0](d) + s * (c[1](d) - c[0](d)) + t * (c[2](d) - c[0](d)) +
-                       s * t * ((c[3](d) - c[2](d)) - (c[1](d) - c[0](d)))
-                  << " ";
-            out << "0\n";
-          }
+      for (unsigned jz = 0; jz < npz; ++jz)
+        for (unsigned jy = 0; jy < np; ++jy)
+          for (unsigned jx = 0; jx < np; ++jx)
+            {
+              // multilinear image of the uniform grid: sum_v c_v N_v(s, t, u)
+              const double s = double(jx) / n, t = double(jy) / n, u = dim == 3 ? double(jz) / n : 0.0;
+              for (int d = 0; d < 3; ++d)
+                {
+                  double x = 0.0;
+                  if (d < dim)
+                    for (unsigned v = 0; v < NB; ++v)
+                      x += c[v](d) * ((v & 1) ? s : 1 - s) * (((v >> 1) & 1) ? t : 1 - t) *
+                           (dim == 3 ? ((v >> 2) ? u : 1 - u) : 1.0);
+                  out << x << (d < 2 ? " " : "\n");
+                }
+            }
       out << "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int32\" Name=\"connectivity\" "
              "format=\"ascii\">\n";
-      for (unsigned iy = 0; iy < n; ++iy)
-        for (unsigned ix = 0; ix < n; ++ix)
-          out << iy * np + ix << " " << iy * np + ix + 1 << " " << (iy + 1) * np + ix + 1 << " "
-              << (iy + 1) * np + ix << "\n";
+      for (unsigned iz = 0; iz < nz; ++iz)
+        for (unsigned iy = 0; iy < n; ++iy)
+          for (unsigned ix = 0; ix < n; ++ix)
+            {
+              // VTK_QUAD / VTK_HEXAHEDRON vertex order (counter-clockwise, bottom then top)
+              const std::size_t b = (std::size_t(iz) * np + iy) * np + ix, up = std::size_t(np) * np;
+              out << b << " " << b + 1 << " " << b + np + 1 << " " << b + np;
+              if (dim == 3)
+                out << " " << b + up << " " << b + up + 1 << " " << b + up + np + 1 << " " << b + up + np;
+              out << "\n";
+            }
       out << "</DataArray>\n<DataArray type=\"Int32\" Name=\"offsets\" format=\"ascii\">\n";
-      for (unsigned k = 1; k <= n * n; ++k)
-        out << 4 * k << "\n";
+      for (std::size_t k = 1; k <= n_cells; ++k)
+        out << NB * k << "\n";
       out << "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n";
-      for (unsigned k = 0; k < n * n; ++k)
-        out << "9\n";
+      for (std::size_t k = 0; k < n_cells; ++k)
+        out << (dim == 2 ? "9\n" : "12\n");
       out << "</DataArray>\n</Cells>\n<PointData Scalars=\"scalars\">\n";
       for (std::size_t f = 0; f < fields.size(); ++f)
         {
@@ -425,7 +442,7 @@ namespace DiffusionProblem
           if (numbered)
             out << f;
           out << "\" format=\"ascii\">\n";
-          for (unsigned lex = 0; lex < np * np; ++lex)
+          for (std::size_t lex = 0; lex < n_pts; ++lex)
             out << fields[f][dof[lex]] << "\n";
           out << "</DataArray>\n";
         }

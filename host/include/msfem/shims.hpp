@@ -159,15 +159,16 @@ namespace msfem
   {
   public:
     CellId() = default;
-    CellId(unsigned depth, std::uint64_t morton)
+    CellId(unsigned depth, std::uint64_t morton, unsigned dim = 2)
       : depth_(depth)
+      , dim_(dim)
       , morton_(morton)
     {}
     std::string to_string() const
     {
       std::string s = "0_" + std::to_string(depth_) + ":";
       for (unsigned k = 0; k < depth_; ++k)
-        s += char('0' + ((morton_ >> (2 * (depth_ - 1 - k))) & 3u));
+        s += char('0' + ((morton_ >> (dim_ * (depth_ - 1 - k))) & ((1u << dim_) - 1u)));
       return s;
     }
     bool          operator<(const CellId &o) const { return morton_ < o.morton_; }
@@ -177,6 +178,7 @@ namespace msfem
 
   private:
     unsigned      depth_  = 0;
+    unsigned      dim_    = 2;
     std::uint64_t morton_ = 0;
   };
 } // namespace msfem

@@ -8,9 +8,9 @@ plumbing only: a ctypes binding of the C ABI used by tests/ and bench.py, the co
 from .binding import (BasisShard, MsbError, CoeffDesc, lib_path, load_library,
                       COEFF_REFERENCE, COEFF_PERIODIC, COEFF_INCLUSIONS, COEFF_CONSTANT,
                       COEFF_TABLE, TIER_AUTO, TIER_SMEM, TIER_STREAMED, EXPORTED_SYMBOLS)
-from .coarse import coarse_corners, morton_partition, cell_id_string
+from .coarse import coarse_corners, coarse_corners3, morton_partition, cell_id_string
 
 __all__ = ["BasisShard", "MsbError", "CoeffDesc", "lib_path", "load_library",
            "COEFF_REFERENCE", "COEFF_PERIODIC", "COEFF_INCLUSIONS", "COEFF_CONSTANT",
            "COEFF_TABLE", "TIER_AUTO", "TIER_SMEM", "TIER_STREAMED", "EXPORTED_SYMBOLS",
-           "coarse_corners", "morton_partition", "cell_id_string"]
+           "coarse_corners", "coarse_corners3", "morton_partition", "cell_id_string"]

@@ -30,6 +30,25 @@ def coarse_corners(r, lo=0, hi=None):
     return out
 
 
+def coarse_corners3(r, lo=0, hi=None):
+    """Corner points [hi-lo, 8, 3] (deal.II hex vertex order, x fastest) of the coarse cells with
+    3D Morton index in [lo, hi) of the (2^r)^3 mesh on the unit cube."""
+    nc = 1 << r
+    hi = nc ** 3 if hi is None else hi
+    m = np.arange(lo, hi, dtype=np.uint64)
+    idx = np.zeros((3, m.size), dtype=np.uint64)
+    for bit in range(r):
+        for a in range(3):
+            idx[a] |= ((m >> np.uint64(3 * bit + a)) & np.uint64(1)) << np.uint64(bit)
+    H = 1.0 / nc
+    out = np.empty((m.size, 8, 3), dtype=np.float64)
+    for v in range(8):
+        out[:, v, 0] = (idx[0] + (v & 1)) * H
+        out[:, v, 1] = (idx[1] + ((v >> 1) & 1)) * H
+        out[:, v, 2] = (idx[2] + (v >> 2)) * H
+    return out
+
+
 def morton_partition(n_cells, rank, world):
     """Contiguous Z-curve range of rank `rank` of `world` (uniform weights): the p4est rule the
     reference inherits for cell ownership (ms.tpp:52)."""

@@ -292,6 +292,14 @@ namespace msb
 #pragma unroll
       for (int k = 0; k < 14; ++k)
         acc[k] = 0.0;
+      // axis-aligned brick (the coarse meshes the drivers build): constant diagonal Jacobian
+      bool aligned = true;
+#pragma unroll
+      for (int v = 0; v < 8; ++v)
+        aligned = aligned && c[3 * v] == ((v & 1) ? c[3] : c[0]) && c[3 * v + 1] == (((v >> 1) & 1) ? c[7] : c[1]) &&
+                  c[3 * v + 2] == ((v >> 2) ? c[14] : c[2]);
+      const double rn = 1.0 / (double)n;
+      const double hx = (c[3] - c[0]) * rn, hy = (c[7] - c[1]) * rn, hz = (c[14] - c[2]) * rn;
 #pragma unroll 1
       for (int cv = 0; cv < 8; ++cv)
         {
@@ -301,9 +309,12 @@ namespace msb
           if (ix < 0 || iy < 0 || iz < 0 || ix >= n || iy >= n || iz >= n)
             continue;
           double P[8][3];
+          if (!aligned)
+            {
 #pragma unroll
-          for (int v = 0; v < 8; ++v)
-            fine_vertex3(c, n, ix + (v & 1), iy + ((v >> 1) & 1), iz + (v >> 2), P[v]);
+              for (int v = 0; v < 8; ++v)
+                fine_vertex3(c, n, ix + (v & 1), iy + ((v >> 1) & 1), iz + (v >> 2), P[v]);
+            }
           double row[8], fe = 0.0;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -325,39 +336,52 @@ namespace msb
                   dN[v][1] = fx * sy * fz;
                   dN[v][2] = fx * fy * sz;
                 }
-              double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, xq[3] = {0, 0, 0};
+              double G[8][3], xq[3], JxW;
+              if (aligned)
+                {
+                  xq[0] = c[0] + (ix + xi) * hx, xq[1] = c[1] + (iy + eta) * hy, xq[2] = c[2] + (iz + ze) * hz;
+                  JxW   = hx * hy * hz * 0.125;
+                  const double ihx = 1.0 / hx, ihy = 1.0 / hy, ihz = 1.0 / hz;
 #pragma unroll
-              for (int v = 0; v < 8; ++v)
+                  for (int v = 0; v < 8; ++v)
+                    G[v][0] = dN[v][0] * ihx, G[v][1] = dN[v][1] * ihy, G[v][2] = dN[v][2] * ihz;
+                }
+              else
+                {
+                  double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+                  xq[0] = xq[1] = xq[2] = 0.0;
 #pragma unroll
-                for (int a = 0; a < 3; ++a)
-                  {
-                    xq[a] += P[v][a] * Nv[v];
+                  for (int v = 0; v < 8; ++v)
 #pragma unroll
-                    for (int b = 0; b < 3; ++b)
-                      J[a][b] += P[v][a] * dN[v][b];
-                  }
-              const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -
-                                 J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
-                                 J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
-              double Ji[3][3];
-              Ji[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det;
-              Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
-              Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
-              Ji[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det;
-              Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
-              Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
-              Ji[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det;
-              Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
-              Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
-              const double JxW = det * 0.125;
-              double       A[9];
+                    for (int a = 0; a < 3; ++a)
+                      {
+                        xq[a] += P[v][a] * Nv[v];
+#pragma unroll
+                        for (int b = 0; b < 3; ++b)
+                          J[a][b] += P[v][a] * dN[v][b];
+                      }
+                  const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -
+                                     J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                                     J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+                  double Ji[3][3];
+                  Ji[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det;
+                  Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+                  Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+                  Ji[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det;
+                  Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+                  Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+                  Ji[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det;
+                  Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+                  Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+                  JxW      = det * 0.125;
+#pragma unroll
+                  for (int v = 0; v < 8; ++v)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+                      G[v][a] = Ji[0][a] * dN[v][0] + Ji[1][a] * dN[v][1] + Ji[2][a] * dN[v][2];
+                }
+              double A[9];
               coeff3_eval(cf, xq[0], xq[1], A);
-              double G[8][3];
-#pragma unroll
-              for (int v = 0; v < 8; ++v)
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-                  G[v][a] = Ji[0][a] * dN[v][0] + Ji[1][a] * dN[v][1] + Ji[2][a] * dN[v][2];
               // own gradient and shape value, selected without dynamic register indexing
               double gi[3] = {0, 0, 0}, ni = 0.0;
 #pragma unroll
@@ -404,7 +428,8 @@ namespace msb
 
     struct Params3
     {
-      int           n, nblk, layers; // fine kernels: node layers (jz) per CTA
+      int           n, nblk, chunk; // fine kernels: contiguous nodes per CTA (multiple of THREADS)
+      int           by, zc, nys, nblk2; // K2 tiling: rows per y-slab, planes per z-chunk, slabs, CTAs
       const double *corners, *q1coef, *sten;
       double       *x, *r, *p, *q, *z; // [C][8][N]
       double       *v;                 // [C][8][cn]
@@ -497,12 +522,12 @@ namespace msb
       const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y, blk = blockIdx.x;
       const double *S = P.sten + (size_t)cell * NST * N;
       const double *c = P.corners + 24 * (size_t)cell, *q1 = P.q1coef + 64 * (size_t)cell;
-      const int     z0 = blk * P.layers, z1 = min(np, z0 + P.layers);
+      const int     t0 = blk * P.chunk, t1 = min(N, t0 + P.chunk);
       double        acc[NB];
 #pragma unroll
       for (int k = 0; k < NB; ++k)
         acc[k] = 0.0;
-      for (int t = z0 * np * np + threadIdx.x; t < z1 * np * np; t += THREADS)
+      for (int t = t0 + threadIdx.x; t < t1; t += THREADS)
         {
           int jx, jy, jz;
           decode3(t, np, jx, jy, jz);
@@ -585,8 +610,8 @@ namespace msb
         all &= sdone[k];
       if (all)
         return;
-      const int z0 = blk * P.layers, z1 = min(np, z0 + P.layers);
-      for (int t = z0 * np * np + threadIdx.x; t < z1 * np * np; t += THREADS)
+      const int t0 = blk * P.chunk, t1 = min(N, t0 + P.chunk);
+      for (int t = t0 + threadIdx.x; t < t1; t += THREADS)
         {
           int jx, jy, jz;
           decode3(t, np, jx, jy, jz);
@@ -614,12 +639,12 @@ namespace msb
       if (cell_done(P, cell, par, sdone))
         return;
       const double *S  = P.sten + (size_t)cell * NST * N;
-      const int     z0 = blk * P.layers, z1 = min(np, z0 + P.layers);
+      const int     t0 = blk * P.chunk, t1 = min(N, t0 + P.chunk);
       double        acc[NB];
 #pragma unroll
       for (int k = 0; k < NB; ++k)
         acc[k] = 0.0;
-      for (int t = z0 * np * np + threadIdx.x; t < z1 * np * np; t += THREADS)
+      for (int t = t0 + threadIdx.x; t < t1; t += THREADS)
         {
           int jx, jy, jz;
           decode3(t, np, jx, jy, jz);
@@ -669,6 +694,106 @@ namespace msb
         }
     }
 
+    // K2 (tiled): the same q = K p, with p staged through shared memory.  A CTA owns a slab of
+    // `by` interior rows (all x) and marches over `zc` z-planes; four plane slots hold the 8
+    // bases of planes z-1, z, z+1 and the one being prefetched, so every p value is read from
+    // HBM/L2 (zc+2)/zc times instead of 27 and the 216 neighbour reads per node are conflict-free
+    // LDS.  Coefficients (27 per node, shared by the 8 bases) stay in global memory / L1.
+    __global__ void __launch_bounds__(THREADS)
+    k2m_kernel(Params3 P)
+    {
+      extern __shared__ double sp[]; // [4][NB][(by+2)*np]
+      const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y, blk = blockIdx.x;
+      const int par = (P.it - 1) & 1;
+      __shared__ int    sdone[NB];
+      __shared__ double sbuf[(THREADS / 32) * NB];
+      if (cell_done(P, cell, par, sdone))
+        return;
+      const int     ys = blk % P.nys, zi = blk / P.nys;
+      const int     y0 = 1 + ys * P.by, y1 = min(n, y0 + P.by);
+      const int     z0 = 1 + zi * P.zc, z1 = min(n, z0 + P.zc);
+      const int     psz = (P.by + 2) * np, cnt = (y1 - y0 + 2) * np;
+      const double *S  = P.sten + (size_t)cell * NST * N;
+      const double *pg = P.p + (size_t)cell * NB * N;
+      double       *qg = P.q + (size_t)cell * NB * N;
+
+      auto load_plane = [&](int z) {
+        const int src = (z * np + (y0 - 1)) * np;
+#pragma unroll 1
+        for (int k = 0; k < NB; ++k)
+          {
+            if (sdone[k])
+              continue;
+            double       *dst = sp + (size_t)((z & 3) * NB + k) * psz;
+            const double *sg  = pg + (size_t)k * N + src;
+            for (int i = threadIdx.x; i < cnt; i += THREADS)
+              dst[i] = sg[i];
+          }
+      };
+
+      const int  nx = n - 1, yy = threadIdx.x / nx, x = 1 + threadIdx.x % nx, y = y0 + yy;
+      const bool active = y < y1 && threadIdx.x < nx * P.by;
+      const int  sb = (yy + 1) * np + x; // index inside a plane slot
+      double     acc[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        acc[k] = 0.0;
+
+      load_plane(z0 - 1);
+      load_plane(z0);
+      for (int z = z0; z < z1; ++z)
+        {
+          load_plane(z + 1);
+          __syncthreads();
+          if (!active)
+            continue;
+          const int     t  = (z * np + y) * np + x;
+          const double *s0 = sp + (size_t)(z & 3) * NB * psz + sb;
+          double        yv[NB], pc[NB];
+          {
+            const double kc = S[t];
+#pragma unroll
+            for (int k = 0; k < NB; ++k)
+              {
+                pc[k] = s0[k * psz];
+                yv[k] = kc * pc[k];
+              }
+          }
+#pragma unroll
+          for (int f = 1; f <= 13; ++f)
+            {
+              const int     e = 13 + f, dz = e / 9 - 1, dy = (e / 3) % 3 - 1, dx = e % 3 - 1;
+              const int     o = (dz * np + dy) * np + dx, so = dy * np + dx;
+              const double  kf = S[(size_t)f * N + t], kb = S[(size_t)f * N + t - o];
+              const double *sf = sp + (size_t)((z + dz) & 3) * NB * psz + sb + so;
+              const double *sr = sp + (size_t)((z - dz) & 3) * NB * psz + sb - so;
+#pragma unroll
+              for (int k = 0; k < NB; ++k)
+                {
+                  yv[k] = fma(kf, sf[k * psz], yv[k]);
+                  yv[k] = fma(kb, sr[k * psz], yv[k]);
+                }
+            }
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            {
+              if (sdone[k])
+                continue;
+              qg[(size_t)k * N + t] = yv[k];
+              acc[k]                = fma(pc[k], yv[k], acc[k]);
+            }
+        }
+      __syncthreads();
+      block_sum_to<NB>(acc, sbuf);
+      if (threadIdx.x == 0)
+        {
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            if (!sdone[k])
+              part_ptr(P.part, cell * NB + k, P.it & 1, 1)[blk] = acc[k];
+        }
+    }
+
     // K3: alpha = rz/pq ; x += alpha p ; r -= alpha q ; partial r.r
     __global__ void __launch_bounds__(THREADS)
     k3_kernel(Params3 P)
@@ -684,7 +809,7 @@ namespace msb
           const int dn        = solve_done(P, sidx, par, nullptr);
           sdone[threadIdx.x]  = dn;
           const double rz     = sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
-          const double pq     = sum_part(part_ptr(P.part, sidx, P.it & 1, 1), P.nblk);
+          const double pq     = sum_part(part_ptr(P.part, sidx, P.it & 1, 1), P.nblk2);
           salpha[threadIdx.x] = dn ? 0.0 : rz / pq;
         }
       __syncthreads();
@@ -694,12 +819,12 @@ namespace msb
         all &= sdone[k];
       if (all)
         return;
-      const int z0 = blk * P.layers, z1 = min(np, z0 + P.layers);
+      const int t0 = blk * P.chunk, t1 = min(N, t0 + P.chunk);
       double    acc[NB];
 #pragma unroll
       for (int k = 0; k < NB; ++k)
         acc[k] = 0.0;
-      for (int t = z0 * np * np + threadIdx.x; t < z1 * np * np; t += THREADS)
+      for (int t = t0 + threadIdx.x; t < t1; t += THREADS)
         {
           int jx, jy, jz;
           decode3(t, np, jx, jy, jz);
@@ -820,12 +945,12 @@ namespace msb
         return;
       const double *KC  = P.sten + (size_t)cell * NST * N;
       const int     np1 = P.L.npl[1];
-      const int     z0 = blk * P.layers, z1 = min(np, z0 + P.layers);
+      const int     t0 = blk * P.chunk, t1 = min(N, t0 + P.chunk);
       double        acc[NB];
 #pragma unroll
       for (int k = 0; k < NB; ++k)
         acc[k] = 0.0;
-      for (int t = z0 * np * np + threadIdx.x; t < z1 * np * np; t += THREADS)
+      for (int t = t0 + threadIdx.x; t < t1; t += THREADS)
         {
           int jx, jy, jz;
           decode3(t, np, jx, jy, jz);
@@ -1092,11 +1217,31 @@ namespace msb
     using namespace d3;
     Params3 P;
     P.n        = s.n;
-    int layers = 1;
-    while ((s.np + layers - 1) / layers > MAXBLK)
-      layers *= 2;
-    P.layers  = layers;
-    P.nblk    = (s.np + layers - 1) / layers;
+    // contiguous node ranges, a multiple of the CTA size so that no pass runs half empty
+    P.chunk   = THREADS * ((s.N + THREADS * MAXBLK - 1) / (THREADS * MAXBLK));
+    P.nblk    = (s.N + P.chunk - 1) / P.chunk;
+    // K2 tiling: slabs of `by` interior rows x all columns (about one node per thread), z-chunks
+    // of `zc` planes; nys * nzc <= MAXBLK partial-sum slots
+    const int nin = s.n - 1;
+    P.by          = nin < THREADS / nin ? nin : (THREADS / nin > 0 ? THREADS / nin : 1);
+    P.nys         = (nin + P.by - 1) / P.by;
+    {
+      const int max_zc = MAXBLK / P.nys > 0 ? MAXBLK / P.nys : 1;
+      P.zc             = (nin + max_zc - 1) / max_zc;
+      if (P.zc < 8)
+        P.zc = 8;
+    }
+    P.nblk2 = P.nys * ((nin + P.zc - 1) / P.zc);
+    const size_t k2_smem = sizeof(double) * 4 * NB * (size_t)(P.by + 2) * s.np;
+    const bool   k2_tiled = s.variant != 1 && nin * P.by <= THREADS && P.nblk2 <= MAXBLK && k2_smem <= 200 * 1024;
+    if (k2_tiled)
+      {
+        cudaError_t ea = cudaFuncSetAttribute(k2m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem);
+        if (ea != cudaSuccess)
+          return ea;
+      }
+    else
+      P.nblk2 = P.nblk;
     P.corners = s.d_corners;
     P.q1coef  = s.d_q1coef;
     P.sten    = s.d_sten;
@@ -1185,7 +1330,12 @@ namespace msb
         ++it;
         P.it = it;
         for_slices([&](const Params3 &Q, int nc) { k1_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
-        for_slices([&](const Params3 &Q, int nc) { k2_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
+        if (k2_tiled)
+          for_slices([&](const Params3 &Q, int nc) {
+            k2m_kernel<<<dim3(P.nblk2, nc), THREADS, k2_smem, st>>>(Q);
+          });
+        else
+          for_slices([&](const Params3 &Q, int nc) { k2_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
         for_slices([&](const Params3 &Q, int nc) { k3_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
         precondition(it & 1);
       }

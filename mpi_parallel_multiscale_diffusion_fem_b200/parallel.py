@@ -17,25 +17,25 @@ def shard_range(n_cells, rank=None, world=None):
 
 
 def gather_coarse_contributions(M_local, b_local, n_cells_total, device=None):
-    """all_gather of the [n_local, 20] packed (M | b) blocks of every rank; returns
-    (M [C,4,4], b [C,4]) in Morton order on every rank.  NCCL with CUDA tensors on the GPU
-    box, gloo with CPU tensors in the CPU tests."""
+    """all_gather of the [n_local, nb*nb + nb] packed (M | b) blocks of every rank (nb = 2^dim
+    bases per cell); returns (M [C,nb,nb], b [C,nb]) in Morton order on every rank.  NCCL with
+    CUDA tensors on the GPU box, gloo with CPU tensors in the CPU tests."""
     world, rank = dist.get_world_size(), dist.get_rank()
     M_local = torch.as_tensor(M_local, dtype=torch.float64)
     b_local = torch.as_tensor(b_local, dtype=torch.float64)
-    n_local = M_local.shape[0]
+    n_local, nb = M_local.shape[0], b_local.shape[-1]
     lo, hi = morton_partition(n_cells_total, rank, world)
     assert hi - lo == n_local, "shard does not match the Morton partition"
-    pack = torch.cat([M_local.reshape(n_local, 16), b_local.reshape(n_local, 4)], dim=1).contiguous()
+    pack = torch.cat([M_local.reshape(n_local, nb * nb), b_local.reshape(n_local, nb)], dim=1).contiguous()
     if device is not None:
         pack = pack.to(device)
     outs = []
     for q in range(world):
         a, b = morton_partition(n_cells_total, q, world)
-        outs.append(torch.empty((b - a, 20), dtype=torch.float64, device=pack.device))
+        outs.append(torch.empty((b - a, nb * nb + nb), dtype=torch.float64, device=pack.device))
     dist.all_gather(outs, pack)
     full = torch.cat(outs, dim=0)
-    return full[:, :16].reshape(-1, 4, 4), full[:, 16:].reshape(-1, 4)
+    return full[:, :nb * nb].reshape(-1, nb, nb), full[:, nb * nb:].reshape(-1, nb)
 
 
 def max_over_ranks(value, device=None):

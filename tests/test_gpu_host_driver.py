@@ -127,3 +127,25 @@ def test_cpp_driver_on_two_gpus_matches_one_gpu(tmp_path):
         n = int(lines[0])
         sols.append(np.array([float(v) for v in lines[1:1 + n]]))
     assert np.array_equal(sols[0], sols[1])     # same kernels, same cells: bitwise identical
+
+
+def test_cpp_basis3d_matches_oracle(oracle, tmp_path):
+    """The dim = 3 basis stage through the C++ mirror (DiffusionProblemBasis<3>::run_all):
+    element matrices and right-hand sides of all 8 coarse hexes against the oracle."""
+    exe = os.path.join(ROOT, "host", "_build", "msfem_basis3d")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host")])
+    dump = tmp_path / "mb3d.txt"
+    out = subprocess.run([exe, "--n-refine", "1", "--n-refine-local", "3", "--dump", str(dump)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    assert "8 coarse cells, 64 local solves" in out.stdout
+    ref = oracle.run_cells3(3, oracle.coarse_corners3(1), oracle.coeff(oracle.COEFF_REFERENCE), n_threads=4,
+                            keep_phi=False)
+    rows = [ln.split() for ln in open(dump)]
+    assert [r[0] for r in rows] == ["0_1:%d" % k for k in range(8)]      # CellId order = Morton
+    for k, r in enumerate(rows):
+        v = np.array(r[1:], dtype=np.float64)
+        M, b = v[:64].reshape(8, 8), v[64:]
+        assert np.linalg.norm(M - ref["M"][k]) / np.linalg.norm(ref["M"][k]) < 1e-8
+        assert np.linalg.norm(b - ref["b"][k]) / np.linalg.norm(ref["b"][k]) < 1e-8

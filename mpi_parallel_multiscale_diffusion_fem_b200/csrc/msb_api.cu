@@ -123,6 +123,23 @@ basis_q1_matrix(int dim, const double *corners, double *coef)
   return true;
 }
 
+// dim 3: are all coarse cells axis-aligned bricks (vertex v = v0 + (bit0 hx, bit1 hy, bit2 hz))?
+static bool
+all_bricks(const double *corners, size_t n_cells)
+{
+  for (size_t k = 0; k < n_cells; ++k)
+    {
+      const double *c = corners + 24 * k;
+      for (int v = 0; v < 8; ++v)
+        if (c[3 * v] != ((v & 1) ? c[3] : c[0]) || c[3 * v + 1] != (((v >> 1) & 1) ? c[7] : c[1]) ||
+            c[3 * v + 2] != ((v >> 2) ? c[14] : c[2]))
+          return false;
+      if (!(c[3] > c[0] && c[7] > c[1] && c[14] > c[2]))
+        return false;
+    }
+  return true;
+}
+
 static void
 free_shard(Shard &s)
 {
@@ -205,6 +222,7 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
   s.tier      = cfg->tier;
   if (s.dim == 3)
     s.tier = MSB_TIER_STREAMED;
+  s.bricks = s.dim == 3 && all_bricks(corners, (size_t)s.n_cells);
   if (s.tier == MSB_TIER_AUTO)
     s.tier = smem_tier_supported(s.l) ? MSB_TIER_SMEM : MSB_TIER_STREAMED;
   if (s.tier == MSB_TIER_SMEM && !smem_tier_supported(s.l))
@@ -314,6 +332,7 @@ msb_set_cells(msb_handle h, const double *corners, const double *coeff_table)
     CUDA_TRY(cudaMemcpyAsync(s.d_table, coeff_table, sizeof(double) * C * (size_t)s.n * s.n * 16,
                              cudaMemcpyHostToDevice, s.stream));
   CUDA_TRY(cudaStreamSynchronize(s.stream));
+  s.bricks    = s.dim == 3 && all_bricks(corners, C);
   s.assembled = s.ran = s.weights_set = s.run_pending = false;
   return MSB_OK;
 }

@@ -418,6 +418,115 @@ namespace msb
       S[(size_t)ST3_F * N + t] = F;
     }
 
+    // The same assembly when every coarse cell is an axis-aligned brick and A(x) = a(x, y) B with
+    // a constant matrix B (MatrixCoeff<3>: B = R R^T; constant coefficient: B = I) -- what the
+    // drivers build.  Then K_e(i, j) = sum_q a_q T[q][i][j] with geometry factors
+    // T[q][i][j] = JxW grad N_i(q) . B grad N_j(q) that are the same for every fine cell, and the
+    // separable sines of a(x, y) come from two 2n-entry tables: 64 FMAs per adjacent cell instead
+    // of a trilinear Jacobian, its inverse and two sines per quadrature point.
+    __global__ void __launch_bounds__(128)
+    assemble3_brick_kernel(int n, const double *__restrict__ corners, Coeff3 cf, double rhs_value,
+                           double *__restrict__ sten)
+    {
+      __shared__ double sT[512];            // [q][i][j]
+      __shared__ double sax[128], say[128]; // 0.5 sin(2 PI_D 57 x_q) at 2*ix+qx, same in y
+      const int     np = n + 1, N = np * np * np, cell = blockIdx.y;
+      const int     t  = blockIdx.x * blockDim.x + threadIdx.x;
+      const double *c  = corners + 24 * (size_t)cell;
+      double       *S  = sten + (size_t)cell * NST * N;
+      const double  rn = 1.0 / (double)n;
+      const double  hx = (c[3] - c[0]) * rn, hy = (c[7] - c[1]) * rn, hz = (c[14] - c[2]) * rn;
+      const double  g0 = 0.5 - 0.5 / sqrt(3.0), g1 = 0.5 + 0.5 / sqrt(3.0);
+      const double  JxW = hx * hy * hz * 0.125;
+      const bool    ref = cf.kind == MSB_COEFF_REFERENCE;
+      for (int idx = threadIdx.x; idx < 512; idx += blockDim.x)
+        {
+          const int    q = idx >> 6, i = (idx >> 3) & 7, j = idx & 7;
+          const double xi = (q & 1) ? g1 : g0, eta = ((q >> 1) & 1) ? g1 : g0, ze = (q >> 2) ? g1 : g0;
+          double       gi[3], gj[3];
+          {
+            const double fx = (i & 1) ? xi : 1 - xi, fy = ((i >> 1) & 1) ? eta : 1 - eta, fz = (i >> 2) ? ze : 1 - ze;
+            gi[0] = ((i & 1) ? 1.0 : -1.0) * fy * fz / hx;
+            gi[1] = fx * (((i >> 1) & 1) ? 1.0 : -1.0) * fz / hy;
+            gi[2] = fx * fy * ((i >> 2) ? 1.0 : -1.0) / hz;
+          }
+          {
+            const double fx = (j & 1) ? xi : 1 - xi, fy = ((j >> 1) & 1) ? eta : 1 - eta, fz = (j >> 2) ? ze : 1 - ze;
+            gj[0] = ((j & 1) ? 1.0 : -1.0) * fy * fz / hx;
+            gj[1] = fx * (((j >> 1) & 1) ? 1.0 : -1.0) * fz / hy;
+            gj[2] = fx * fy * ((j >> 2) ? 1.0 : -1.0) / hz;
+          }
+          double v = 0.0;
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+            {
+              double tb = 0.0; // (gi . B)_a with B = rot rot^T or I
+#pragma unroll
+              for (int b = 0; b < 3; ++b)
+                {
+                  const double Bba = ref ? cf.rot[3 * b] * cf.rot[3 * a] + cf.rot[3 * b + 1] * cf.rot[3 * a + 1] +
+                                             cf.rot[3 * b + 2] * cf.rot[3 * a + 2] :
+                                           (a == b ? 1.0 : 0.0);
+                  tb += gi[b] * Bba;
+                }
+              v += tb * gj[a];
+            }
+          sT[idx] = v * JxW;
+        }
+      if (ref)
+        {
+          const double PI_D = 3.14592653509793218403;
+          for (int idx = threadIdx.x; idx < 2 * n; idx += blockDim.x)
+            {
+              const double g = (idx & 1) ? g1 : g0;
+              sax[idx]       = 0.5 * sin(2 * PI_D * 57 * (c[0] + ((idx >> 1) + g) * hx));
+              say[idx]       = 0.5 * sin(2 * PI_D * 57 * (c[1] + ((idx >> 1) + g) * hy));
+            }
+        }
+      __syncthreads();
+      if (t >= N)
+        return;
+      int jx, jy, jz;
+      decode3(t, np, jx, jy, jz);
+      double acc[14], F = 0.0;
+#pragma unroll
+      for (int k = 0; k < 14; ++k)
+        acc[k] = 0.0;
+#pragma unroll
+      for (int cv = 0; cv < 8; ++cv)
+        {
+          const int cvx = cv & 1, cvy = (cv >> 1) & 1, cvz = cv >> 2;
+          const int ix = jx - cvx, iy = jy - cvy, iz = jz - cvz;
+          if (ix < 0 || iy < 0 || iz < 0 || ix >= n || iy >= n || iz >= n)
+            continue;
+          double aq[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            aq[q] = ref ? 1.0 * (1.0 - 0.9999 * (sax[2 * ix + (q & 1)] + say[2 * iy + (q >> 1)])) : cf.a0;
+          double row[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            row[j] = 0.0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              row[j] += aq[q & 3] * sT[q * 64 + cv * 8 + j];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            {
+              const int e = ((j & 1) - cvx) + 3 * (((j >> 1) & 1) - cvy) + 9 * ((j >> 2) - cvz);
+              if (e >= 0)
+                acc[e] += row[j];
+            }
+          F += rhs_value * JxW;
+        }
+#pragma unroll
+      for (int k = 0; k < 14; ++k)
+        S[(size_t)k * N + t] = acc[k];
+      S[(size_t)ST3_F * N + t] = F;
+    }
+
     // ========================================================================== solver
     struct Levels3
     {
@@ -449,29 +558,34 @@ namespace msb
       return part + (size_t)sidx * PSTRIDE + (parity * 3 + which) * MAXBLK;
     }
 
+    // deterministic sum of the nblk (<= 64) partials of one quantity by ONE WARP: a fixed
+    // butterfly, so every lane of every CTA of the cell obtains the same bits
     __device__ __forceinline__ double
-    sum_part(const double *part, int nblk)
+    warp_sum_part(const double *part, int nblk)
     {
-      double s = 0.0;
-      for (int b = 0; b < nblk; ++b)
-        s += part[b];
-      return s;
+      const int lane = threadIdx.x & 31;
+      double    v    = lane < nblk ? part[lane] : 0.0;
+      if (lane + 32 < nblk)
+        v += part[lane + 32];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, off);
+      return v;
     }
 
-    __device__ __forceinline__ int
-    solve_done(const Params3 &P, int sidx, int parity, double *rr_out)
-    {
-      const double rr = sum_part(part_ptr(P.part, sidx, parity, 2), P.nblk);
-      if (rr_out)
-        *rr_out = rr;
-      return (P.iters[sidx] >= 0) || (rr <= P.tol2);
-    }
-
+    // done(solve) as seen by every CTA of a cell: recorded in an earlier launch (iters >= 0) or
+    // implied by the r.r partials of parity `parity`.  Warp k of the CTA evaluates basis k.
     __device__ __forceinline__ bool
     cell_done(const Params3 &P, int cell, int parity, int *sdone /*shared[8]*/)
     {
-      if (threadIdx.x < NB)
-        sdone[threadIdx.x] = solve_done(P, cell * NB + threadIdx.x, parity, nullptr);
+      const int warp = threadIdx.x >> 5;
+      if (warp < NB)
+        {
+          const int    sidx = cell * NB + warp;
+          const double rr   = warp_sum_part(part_ptr(P.part, sidx, parity, 2), P.nblk);
+          if ((threadIdx.x & 31) == 0)
+            sdone[warp] = (P.iters[sidx] >= 0) || (rr <= P.tol2);
+        }
       __syncthreads();
       int all = 1;
 #pragma unroll
@@ -482,7 +596,7 @@ namespace msb
 
     // exact Galerkin diagonal of level l at coarse node X: D = w^T K w with w the level-l
     // trilinear hat function sampled on the fine grid.  One CTA per (coarse node, cell).
-    __global__ void __launch_bounds__(64)
+    __global__ void __launch_bounds__(256)
     galerkin_diag3_kernel(Params3 P, int l)
     {
       const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y;
@@ -497,19 +611,20 @@ namespace msb
           const int ax = s % side - (h - 1), ay = (s / side) % side - (h - 1), az = s / (side * side) - (h - 1);
           const double wi = (1.0 - abs(ax) * rh) * (1.0 - abs(ay) * rh) * (1.0 - abs(az) * rh);
           const int    t  = ((Z * h + az) * np + (Y * h + ay)) * np + (X * h + ax);
-          double       kw = 0.0;
-#pragma unroll 1
-          for (int e = 0; e < 27; ++e)
+          // w^T K w = sum_i w_i (K_ii w_i + 2 sum_{forward j} K_ij w_j): only the stored couplings
+          double kw = S[t] * wi;
+#pragma unroll
+          for (int f = 1; f <= 13; ++f)
             {
-              const int bx = ax + e % 3 - 1, by = ay + (e / 3) % 3 - 1, bz = az + e / 9 - 1;
+              const int e = 13 + f, bx = ax + e % 3 - 1, by = ay + (e / 3) % 3 - 1, bz = az + e / 9 - 1;
               if (abs(bx) >= h || abs(by) >= h || abs(bz) >= h)
                 continue;
               const double wj = (1.0 - abs(bx) * rh) * (1.0 - abs(by) * rh) * (1.0 - abs(bz) * rh);
-              kw = fma(sten3_get(S, N, np, t, e), wj, kw);
+              kw = fma(2.0 * S[(size_t)f * N + t], wj, kw);
             }
           acc[0] = fma(wi, kw, acc[0]);
         }
-      __shared__ double sbuf[2];
+      __shared__ double sbuf[8];
       block_sum_to<1>(acc, sbuf);
       if (threadIdx.x == 0)
         P.dinv[(size_t)cell * P.L.cn + P.L.off[l] + (Z * npl + Y) * npl + X] = 1.0 / acc[0];
@@ -589,18 +704,21 @@ namespace msb
       const int par = (P.it - 1) & 1;
       __shared__ double sbeta[NB];
       __shared__ int    sdone[NB];
-      if (threadIdx.x < NB)
+      if ((threadIdx.x >> 5) < NB)
         {
-          const int    k = threadIdx.x, sidx = cell * NB + k;
-          double       rr;
-          const int    dn = solve_done(P, sidx, par, &rr);
-          const double rz = sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
-          sdone[k]        = dn;
-          sbeta[k]        = P.it == 1 ? 0.0 : rz / P.rzprev[sidx];
-          if (blk == 0 && dn && P.iters[sidx] < 0)
+          const int    k = threadIdx.x >> 5, sidx = cell * NB + k;
+          const double rr = warp_sum_part(part_ptr(P.part, sidx, par, 2), P.nblk);
+          const double rz = warp_sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
+          if ((threadIdx.x & 31) == 0)
             {
-              P.iters[sidx] = P.it - 1;
-              P.res[sidx]   = sqrt(rr);
+              const int dn = (P.iters[sidx] >= 0) || (rr <= P.tol2);
+              sdone[k]     = dn;
+              sbeta[k]     = P.it == 1 ? 0.0 : rz / P.rzprev[sidx];
+              if (blk == 0 && dn && P.iters[sidx] < 0)
+                {
+                  P.iters[sidx] = P.it - 1;
+                  P.res[sidx]   = sqrt(rr);
+                }
             }
         }
       __syncthreads();
@@ -699,7 +817,8 @@ namespace msb
     // bases of planes z-1, z, z+1 and the one being prefetched, so every p value is read from
     // HBM/L2 (zc+2)/zc times instead of 27 and the 216 neighbour reads per node are conflict-free
     // LDS.  Coefficients (27 per node, shared by the 8 bases) stay in global memory / L1.
-    __global__ void __launch_bounds__(THREADS)
+    template <int MINB>
+    __global__ void __launch_bounds__(THREADS, MINB)
     k2m_kernel(Params3 P)
     {
       extern __shared__ double sp[]; // [4][NB][(by+2)*np]
@@ -717,17 +836,19 @@ namespace msb
       const double *pg = P.p + (size_t)cell * NB * N;
       double       *qg = P.q + (size_t)cell * NB * N;
 
+      // asynchronous global -> shared copies (cp.async, no register staging): the plane z+2 is in
+      // flight while plane z is being computed
       auto load_plane = [&](int z) {
         const int src = (z * np + (y0 - 1)) * np;
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k < NB; ++k)
           {
             if (sdone[k])
               continue;
-            double       *dst = sp + (size_t)((z & 3) * NB + k) * psz;
-            const double *sg  = pg + (size_t)k * N + src;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(sp + (size_t)((z & 3) * NB + k) * psz);
+            const double  *sg  = pg + (size_t)k * N + src;
             for (int i = threadIdx.x; i < cnt; i += THREADS)
-              dst[i] = sg[i];
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * i), "l"(sg + i) : "memory");
           }
       };
 
@@ -741,10 +862,15 @@ namespace msb
 
       load_plane(z0 - 1);
       load_plane(z0);
+      load_plane(z0 + 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
       for (int z = z0; z < z1; ++z)
         {
-          load_plane(z + 1);
-          __syncthreads();
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncthreads(); // planes z-1, z, z+1 have landed; everyone is done with plane z-2
+          if (z + 1 < z1)
+            load_plane(z + 2);
+          asm volatile("cp.async.commit_group;" ::: "memory");
           if (!active)
             continue;
           const int     t  = (z * np + y) * np + x;
@@ -803,14 +929,20 @@ namespace msb
       __shared__ int    sdone[NB];
       __shared__ double salpha[NB];
       __shared__ double sbuf[(THREADS / 32) * NB];
-      if (threadIdx.x < NB)
+      __shared__ double srz[NB];
+      if ((threadIdx.x >> 5) < NB)
         {
-          const int sidx      = cell * NB + threadIdx.x;
-          const int dn        = solve_done(P, sidx, par, nullptr);
-          sdone[threadIdx.x]  = dn;
-          const double rz     = sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
-          const double pq     = sum_part(part_ptr(P.part, sidx, P.it & 1, 1), P.nblk2);
-          salpha[threadIdx.x] = dn ? 0.0 : rz / pq;
+          const int    k = threadIdx.x >> 5, sidx = cell * NB + k;
+          const double rr = warp_sum_part(part_ptr(P.part, sidx, par, 2), P.nblk);
+          const double rz = warp_sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
+          const double pq = warp_sum_part(part_ptr(P.part, sidx, P.it & 1, 1), P.nblk2);
+          if ((threadIdx.x & 31) == 0)
+            {
+              const int dn = (P.iters[sidx] >= 0) || (rr <= P.tol2);
+              sdone[k]     = dn;
+              srz[k]       = rz;
+              salpha[k]    = dn ? 0.0 : rz / pq;
+            }
         }
       __syncthreads();
       int all = 1;
@@ -853,7 +985,7 @@ namespace msb
                 const int sidx = cell * NB + k;
                 part_ptr(P.part, sidx, P.it & 1, 2)[blk] = acc[k];
                 if (blk == 0)
-                  P.rzprev[sidx] = sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
+                  P.rzprev[sidx] = srz[k];
               }
         }
     }
@@ -980,26 +1112,32 @@ namespace msb
         }
     }
 
+    // after the loop (P.it = last executed iteration): record every solve not yet recorded
+    // (one warp per solve)
     __global__ void
     finalize3_kernel(Params3 P, int n_solves, int32_t *fail)
     {
-      const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+      const int sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
       if (sidx >= n_solves || P.iters[sidx] >= 0)
         return;
-      const double rr = sum_part(part_ptr(P.part, sidx, P.it & 1, 2), P.nblk);
-      P.iters[sidx]   = P.it;
-      P.res[sidx]     = sqrt(rr);
+      const double rr = warp_sum_part(part_ptr(P.part, sidx, P.it & 1, 2), P.nblk);
+      if ((threadIdx.x & 31) != 0)
+        return;
+      P.iters[sidx] = P.it;
+      P.res[sidx]   = sqrt(rr);
       if (!(rr <= P.tol2))
         atomicMin(fail, sidx);
     }
 
+    // number of solves still running after iteration P.it (one warp per solve)
     __global__ void
     count3_kernel(Params3 P, int n_solves, int32_t *remaining)
     {
-      const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+      const int sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
       if (sidx >= n_solves || P.iters[sidx] >= 0)
         return;
-      if (!(sum_part(part_ptr(P.part, sidx, P.it & 1, 2), P.nblk) <= P.tol2))
+      const double rr = warp_sum_part(part_ptr(P.part, sidx, P.it & 1, 2), P.nblk);
+      if ((threadIdx.x & 31) == 0 && !(rr <= P.tol2))
         atomicAdd(remaining, 1);
     }
 
@@ -1204,8 +1342,12 @@ namespace msb
     for (int c0 = 0; c0 < s.n_cells; c0 += 65535)
       {
         const int nc = s.n_cells - c0 < 65535 ? s.n_cells - c0 : 65535;
-        d3::assemble3_kernel<<<dim3((s.N + 127) / 128, nc), 128, 0, st>>>(
-          s.n, s.d_corners + 24 * (size_t)c0, cf, s.rhs_value, s.d_sten + (size_t)c0 * ST3_NARR * s.N);
+        if (s.bricks && s.variant != 3)
+          d3::assemble3_brick_kernel<<<dim3((s.N + 127) / 128, nc), 128, 0, st>>>(
+            s.n, s.d_corners + 24 * (size_t)c0, cf, s.rhs_value, s.d_sten + (size_t)c0 * ST3_NARR * s.N);
+        else
+          d3::assemble3_kernel<<<dim3((s.N + 127) / 128, nc), 128, 0, st>>>(
+            s.n, s.d_corners + 24 * (size_t)c0, cf, s.rhs_value, s.d_sten + (size_t)c0 * ST3_NARR * s.N);
         ++*n_launches;
       }
     return cudaGetLastError();
@@ -1218,8 +1360,11 @@ namespace msb
     Params3 P;
     P.n        = s.n;
     // contiguous node ranges, a multiple of the CTA size so that no pass runs half empty
-    P.chunk   = THREADS * ((s.N + THREADS * MAXBLK - 1) / (THREADS * MAXBLK));
-    P.nblk    = (s.N + P.chunk - 1) / P.chunk;
+    // and sized so that a shard fills the GPU a few times over without making the CTAs tiny
+    int want = (6000 + s.n_cells - 1) / s.n_cells;
+    want     = want < 1 ? 1 : (want > MAXBLK ? MAXBLK : want);
+    P.chunk  = THREADS * ((s.N + THREADS * want - 1) / (THREADS * want));
+    P.nblk   = (s.N + P.chunk - 1) / P.chunk;
     // K2 tiling: slabs of `by` interior rows x all columns (about one node per thread), z-chunks
     // of `zc` planes; nys * nzc <= MAXBLK partial-sum slots
     const int nin = s.n - 1;
@@ -1236,7 +1381,9 @@ namespace msb
     const bool   k2_tiled = s.variant != 1 && nin * P.by <= THREADS && P.nblk2 <= MAXBLK && k2_smem <= 200 * 1024;
     if (k2_tiled)
       {
-        cudaError_t ea = cudaFuncSetAttribute(k2m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem);
+        cudaError_t ea = cudaFuncSetAttribute(k2m_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem);
+        if (ea == cudaSuccess)
+          ea = cudaFuncSetAttribute(k2m_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem);
         if (ea != cudaSuccess)
           return ea;
       }
@@ -1285,7 +1432,8 @@ namespace msb
       {
         const int nin = L.npl[l] - 2;
         for_slices([&](const Params3 &Q, int nc) {
-          galerkin_diag3_kernel<<<dim3(nin * nin * nin, nc), 64, 0, st>>>(Q, l);
+          const int side = (2 << l) - 1;
+          galerkin_diag3_kernel<<<dim3(nin * nin * nin, nc), side * side * side >= 256 ? 256 : 64, 0, st>>>(Q, l);
         });
       }
     auto precondition = [&](int rpar) {
@@ -1320,7 +1468,7 @@ namespace msb
           {
             P.it = it;
             TRY(cudaMemsetAsync(s.d_flags, 0, sizeof(int32_t), st));
-            count3_kernel<<<(n_solves + 255) / 256, 256, 0, st>>>(P, n_solves, s.d_flags);
+            count3_kernel<<<(n_solves + 7) / 8, 256, 0, st>>>(P, n_solves, s.d_flags);
             ++*n_launches;
             TRY(cudaMemcpyAsync(&h_remaining, s.d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             TRY(cudaStreamSynchronize(st));
@@ -1332,7 +1480,10 @@ namespace msb
         for_slices([&](const Params3 &Q, int nc) { k1_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
         if (k2_tiled)
           for_slices([&](const Params3 &Q, int nc) {
-            k2m_kernel<<<dim3(P.nblk2, nc), THREADS, k2_smem, st>>>(Q);
+            if (s.variant == 2)
+              k2m_kernel<3><<<dim3(P.nblk2, nc), THREADS, k2_smem, st>>>(Q);
+            else
+              k2m_kernel<2><<<dim3(P.nblk2, nc), THREADS, k2_smem, st>>>(Q);
           });
         else
           for_slices([&](const Params3 &Q, int nc) { k2_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
@@ -1340,7 +1491,7 @@ namespace msb
         precondition(it & 1);
       }
     P.it = it;
-    finalize3_kernel<<<(n_solves + 255) / 256, 256, 0, st>>>(P, n_solves, s.d_fail);
+    finalize3_kernel<<<(n_solves + 7) / 8, 256, 0, st>>>(P, n_solves, s.d_fail);
     ++*n_launches;
 #undef TRY
     return cudaGetLastError();

@@ -73,6 +73,7 @@ namespace msb
     cudaStream_t run_stream = nullptr;
     cudaEvent_t  ev[4]  = {nullptr, nullptr, nullptr, nullptr};
     bool         assembled = false, ran = false, weights_set = false, run_pending = false;
+    bool         bricks = false;      // dim 3: every coarse cell is an axis-aligned brick
     int          n_launches = 0;
     int          tier_used  = 0;
     int          last_status = 0;

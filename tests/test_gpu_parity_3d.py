@@ -68,7 +68,7 @@ def test_matrix_free_operator_matches_csr_vmult_3d(msb, oracle, l, kind, par, sk
 
 
 @pytest.mark.parametrize("l,r,cells,kind,par", [
-    (2, 1, [0, 7], 0, ()), (3, 2, [5, 21, 63], 0, ()), (4, 2, [9, 40], 0, ()), (3, 1, [3], 3, (1.0,)),
+    (1, 1, [2, 4], 0, ()), (2, 1, [0, 7], 0, ()), (3, 2, [5, 21, 63], 0, ()), (4, 2, [9, 40], 0, ()), (3, 1, [3], 3, (1.0,)),
     (5, 3, [100], 0, ())])
 def test_bases_and_element_matrices_match_oracle_3d(msb, oracle, l, r, cells, kind, par):
     cd, co = _coeffs(msb, oracle, kind, par)
@@ -150,3 +150,36 @@ def test_unsupported_3d_requests_fail_loudly(msb, oracle):
         msb.BasisShard(7, cor, coeff_desc(msb.COEFF_CONSTANT, (1.0,)), dim=3)
     with pytest.raises(MsbError):
         msb.BasisShard(3, cor, coeff_desc(msb.COEFF_CONSTANT, (1.0,)), dim=3, tier=msb.TIER_SMEM)
+
+
+def test_no_convergence_is_reported_3d(msb, oracle):
+    """max_iter too small: MSB_ERR_NO_CONVERGENCE + the failing (cell, basis), as the reference's
+    SolverControl::NoConvergence (basis.tpp:303)."""
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import MsbError, coeff_desc
+    cor = oracle.coarse_corners3(1, [0, 1])
+    with msb.BasisShard(4, cor, coeff_desc(msb.COEFF_REFERENCE), dim=3) as sh:
+        with pytest.raises(MsbError) as ei:
+            sh.run(1e-12, 3)
+        assert ei.value.code == -5
+        cell, ib, res = sh.failure()
+        assert (cell, ib) == (0, 0) and res > 1e-12
+        it, _ = sh.iteration_counts()
+        assert (it == 3).all()
+        sh.run(1e-12, 1000)          # the handle stays usable
+        assert sh.failure()[0] == -1
+
+
+def test_handle_reuse_with_set_cells_3d(msb, oracle):
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
+    a, b = oracle.coarse_corners3(2, [3, 9]), oracle.coarse_corners3(2, [40, 41])
+    cd = coeff_desc(msb.COEFF_REFERENCE)
+    with msb.BasisShard(3, a, cd, dim=3) as sh, msb.BasisShard(3, b, cd, dim=3) as sh2:
+        sh.run()
+        Ma, _ = sh.element_matrices()
+        sh.set_cells(b)
+        sh.run()
+        Mb, _ = sh.element_matrices()
+        sh2.run()
+        Mb2, _ = sh2.element_matrices()
+        assert np.array_equal(Mb, Mb2)           # deterministic, independent of handle history
+        assert not np.array_equal(Ma, Mb)

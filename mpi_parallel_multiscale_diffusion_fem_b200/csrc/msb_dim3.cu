@@ -735,14 +735,18 @@ namespace msb
           decode3(t, np, jx, jy, jz);
           if (on_boundary3(jx, jy, jz, n))
             continue;
+          // all loads first (unconditional: memory-level parallelism), predicated stores after
+          double pv[NB], zv[NB];
 #pragma unroll
           for (int k = 0; k < NB; ++k)
             {
-              if (sdone[k])
-                continue;
               const size_t o = ((size_t)cell * NB + k) * N + t;
-              P.p[o]         = fma(sbeta[k], P.p[o], P.z[o]);
+              pv[k] = P.p[o], zv[k] = P.z[o];
             }
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            if (!sdone[k])
+              P.p[((size_t)cell * NB + k) * N + t] = fma(sbeta[k], pv[k], zv[k]);
         }
     }
 
@@ -962,6 +966,13 @@ namespace msb
           decode3(t, np, jx, jy, jz);
           if (on_boundary3(jx, jy, jz, n))
             continue;
+          double pv[NB], qv[NB], rv[NB], xv[NB];
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            {
+              const size_t o = ((size_t)cell * NB + k) * N + t;
+              pv[k] = P.p[o], qv[k] = P.q[o], rv[k] = P.r[o], xv[k] = P.x[o];
+            }
 #pragma unroll
           for (int k = 0; k < NB; ++k)
             {
@@ -969,8 +980,8 @@ namespace msb
                 continue;
               const size_t o  = ((size_t)cell * NB + k) * N + t;
               const double a  = salpha[k];
-              P.x[o]          = fma(a, P.p[o], P.x[o]);
-              const double rn = fma(-a, P.q[o], P.r[o]);
+              P.x[o]          = fma(a, pv[k], xv[k]);
+              const double rn = fma(-a, qv[k], rv[k]);
               P.r[o]          = rn;
               acc[k]          = fma(rn, rn, acc[k]);
             }
@@ -1088,18 +1099,24 @@ namespace msb
           decode3(t, np, jx, jy, jz);
           if (on_boundary3(jx, jy, jz, n))
             continue;
-          const double dinv = 1.0 / KC[t];
-#pragma unroll 1
+          const double kc = KC[t];
+          double       rv[NB], cv[NB];
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            rv[k] = P.r[((size_t)cell * NB + k) * N + t];
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            cv[k] = P.L.levels < 1 ? 0.0 :
+                      interp3(P.v + ((size_t)cell * NB + k) * P.L.cn + P.L.off[1], np1, jx, jy, jz);
+          const double dinv = 1.0 / kc;
+#pragma unroll
           for (int k = 0; k < NB; ++k)
             {
               if (sdone[k])
                 continue;
-              const size_t o = ((size_t)cell * NB + k) * N + t;
-              const double c = P.L.levels < 1 ? 0.0 :
-                                 interp3(P.v + ((size_t)cell * NB + k) * P.L.cn + P.L.off[1], np1, jx, jy, jz);
-              const double rv = P.r[o], zv = fma(rv, dinv, c);
-              P.z[o]          = zv;
-              acc[k]          = fma(rv, zv, acc[k]);
+              const double zv = fma(rv[k], dinv, cv[k]);
+              P.z[((size_t)cell * NB + k) * N + t] = zv;
+              acc[k]                               = fma(rv[k], zv, acc[k]);
             }
         }
       block_sum_to<NB>(acc, sbuf);

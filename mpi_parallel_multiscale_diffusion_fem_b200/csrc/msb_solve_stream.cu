@@ -67,33 +67,34 @@ namespace msb
     return part + (size_t)sidx * PART_STRIDE + (parity * 3 + which) * STREAM_MAXBLK;
   }
 
+  // deterministic sum of the nblk (<= 32) partials of one quantity by ONE WARP: a fixed
+  // butterfly, so every lane of every CTA of the cell obtains the same bits
   __device__ __forceinline__ double
-  sum_part(const double *part, int nblk)
+  warp_sum_part(const double *part, int nblk)
   {
-    double s = 0.0;
-    for (int b = 0; b < nblk; ++b)
-      s += part[b];
-    return s;
+    const int lane = threadIdx.x & 31;
+    double    v    = lane < nblk ? part[lane] : 0.0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+      v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
   }
 
-  // done(solve) as seen by every CTA of a cell: either recorded in an earlier launch
-  // (iters >= 0) or implied by the r.r partials of parity `parity`.  A CTA that races with the
-  // recording CTA re-derives the same answer from the partials.
-  __device__ __forceinline__ int
-  solve_done(const StreamParams &P, int sidx, int parity, double *rr_out)
-  {
-    const double rr = sum_part(part_ptr(P.part, sidx, parity, 2), P.nblk);
-    if (rr_out)
-      *rr_out = rr;
-    return (P.iters[sidx] >= 0) || (rr <= P.tol2);
-  }
-
-  // all four solves of a cell done?  (four threads evaluate, the block shares the answer)
+  // all four solves of a cell done?  done(solve) as seen by every CTA of a cell: either recorded
+  // in an earlier launch (iters >= 0) or implied by the r.r partials of parity `parity`; a CTA
+  // that races with the recording CTA re-derives the same answer from the partials.  Warp k
+  // evaluates basis k, the block shares the answer.
   __device__ __forceinline__ bool
   cell_done(const StreamParams &P, int cell, int parity, int *sdone /*shared[4]*/)
   {
-    if (threadIdx.x < 4)
-      sdone[threadIdx.x] = solve_done(P, cell * 4 + threadIdx.x, parity, nullptr);
+    const int warp = threadIdx.x >> 5;
+    if (warp < 4)
+      {
+        const int    sidx = cell * 4 + warp;
+        const double rr   = warp_sum_part(part_ptr(P.part, sidx, parity, 2), P.nblk);
+        if ((threadIdx.x & 31) == 0)
+          sdone[warp] = (P.iters[sidx] >= 0) || (rr <= P.tol2);
+      }
     __syncthreads();
     return sdone[0] && sdone[1] && sdone[2] && sdone[3];
   }
@@ -227,18 +228,21 @@ namespace msb
     const int par = (P.it - 1) & 1;
     __shared__ double sbeta[4];
     __shared__ int    sdone[4];
-    if (threadIdx.x < 4)
+    if ((threadIdx.x >> 5) < 4)
       {
-        const int    k = threadIdx.x, sidx = cell * 4 + k;
-        double       rr;
-        const int    dn = solve_done(P, sidx, par, &rr);
-        const double rz = sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
-        sdone[k]        = dn;
-        sbeta[k]        = P.it == 1 ? 0.0 : rz / P.rzprev[sidx];
-        if (blk == 0 && dn && P.iters[sidx] < 0)
+        const int    k = threadIdx.x >> 5, sidx = cell * 4 + k;
+        const double rr = warp_sum_part(part_ptr(P.part, sidx, par, 2), P.nblk);
+        const double rz = warp_sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
+        if ((threadIdx.x & 31) == 0)
           {
-            P.iters[sidx] = P.it - 1;
-            P.res[sidx]   = sqrt(rr);
+            const int dn = (P.iters[sidx] >= 0) || (rr <= P.tol2);
+            sdone[k]     = dn;
+            sbeta[k]     = P.it == 1 ? 0.0 : rz / P.rzprev[sidx];
+            if (blk == 0 && dn && P.iters[sidx] < 0)
+              {
+                P.iters[sidx] = P.it - 1;
+                P.res[sidx]   = sqrt(rr);
+              }
           }
       }
     __syncthreads();
@@ -250,14 +254,18 @@ namespace msb
         const int jx = t % np, jy = t / np;
         if (jx == 0 || jy == 0 || jx == n || jy == n)
           continue;
+        // all loads first (unconditional: memory-level parallelism), predicated stores after
+        double pv[4], zv[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           {
-            if (sdone[k])
-              continue;
             const size_t o = ((size_t)cell * 4 + k) * N + t;
-            P.p[o]         = fma(sbeta[k], P.p[o], P.z[o]);
+            pv[k] = P.p[o], zv[k] = P.z[o];
           }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (!sdone[k])
+            P.p[((size_t)cell * 4 + k) * N + t] = fma(sbeta[k], pv[k], zv[k]);
       }
   }
 
@@ -283,24 +291,30 @@ namespace msb
         const double kN = S[ST_KN * N + t], kS = S[ST_KN * N + t - np];
         const double kNE = S[ST_KD1 * N + t], kSW = S[ST_KD1 * N + t - np - 1];
         const double kNW = S[ST_KD2 * N + t - 1], kSE = S[ST_KD2 * N + t - np];
+        double pw[4][9];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          {
+            const double *p = P.p + ((size_t)cell * 4 + k) * N + t;
+            pw[k][0] = p[0], pw[k][1] = p[1], pw[k][2] = p[-1], pw[k][3] = p[np], pw[k][4] = p[-np];
+            pw[k][5] = p[np + 1], pw[k][6] = p[-np - 1], pw[k][7] = p[np - 1], pw[k][8] = p[-np + 1];
+          }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           {
             if (sdone[k])
               continue;
-            const double *p  = P.p + ((size_t)cell * 4 + k) * N + t;
-            const double  pc = p[0];
-            double        y  = kc * pc;
-            y = fma(kE, p[1], y);
-            y = fma(kW, p[-1], y);
-            y = fma(kN, p[np], y);
-            y = fma(kS, p[-np], y);
-            y = fma(kNE, p[np + 1], y);
-            y = fma(kSW, p[-np - 1], y);
-            y = fma(kNW, p[np - 1], y);
-            y = fma(kSE, p[-np + 1], y);
+            double y = kc * pw[k][0];
+            y = fma(kE, pw[k][1], y);
+            y = fma(kW, pw[k][2], y);
+            y = fma(kN, pw[k][3], y);
+            y = fma(kS, pw[k][4], y);
+            y = fma(kNE, pw[k][5], y);
+            y = fma(kSW, pw[k][6], y);
+            y = fma(kNW, pw[k][7], y);
+            y = fma(kSE, pw[k][8], y);
             P.q[((size_t)cell * 4 + k) * N + t] = y;
-            acc[k] = fma(pc, y, acc[k]);
+            acc[k] = fma(pw[k][0], y, acc[k]);
           }
       }
     block_sum_to<4>(acc, sbuf);
@@ -323,14 +337,20 @@ namespace msb
     __shared__ int    sdone[4];
     __shared__ double salpha[4];
     __shared__ double sbuf[8 * 4];
-    if (threadIdx.x < 4)
+    __shared__ double srz[4];
+    if ((threadIdx.x >> 5) < 4)
       {
-        const int sidx      = cell * 4 + threadIdx.x;
-        const int dn        = solve_done(P, sidx, par, nullptr);
-        sdone[threadIdx.x]  = dn;
-        const double rz     = sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
-        const double pq     = sum_part(part_ptr(P.part, sidx, P.it & 1, 1), P.nblk);
-        salpha[threadIdx.x] = dn ? 0.0 : rz / pq;
+        const int    k = threadIdx.x >> 5, sidx = cell * 4 + k;
+        const double rr = warp_sum_part(part_ptr(P.part, sidx, par, 2), P.nblk);
+        const double rz = warp_sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
+        const double pq = warp_sum_part(part_ptr(P.part, sidx, P.it & 1, 1), P.nblk);
+        if ((threadIdx.x & 31) == 0)
+          {
+            const int dn = (P.iters[sidx] >= 0) || (rr <= P.tol2);
+            sdone[k]     = dn;
+            srz[k]       = rz;
+            salpha[k]    = dn ? 0.0 : rz / pq;
+          }
       }
     __syncthreads();
     if (sdone[0] && sdone[1] && sdone[2] && sdone[3])
@@ -342,6 +362,13 @@ namespace msb
         const int jx = t % np, jy = t / np;
         if (jx == 0 || jy == 0 || jx == n || jy == n)
           continue;
+        double pv[4], qv[4], rv[4], xv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          {
+            const size_t o = ((size_t)cell * 4 + k) * N + t;
+            pv[k] = P.p[o], qv[k] = P.q[o], rv[k] = P.r[o], xv[k] = P.x[o];
+          }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           {
@@ -349,8 +376,8 @@ namespace msb
               continue;
             const size_t o  = ((size_t)cell * 4 + k) * N + t;
             const double a  = salpha[k];
-            P.x[o]          = fma(a, P.p[o], P.x[o]);
-            const double rn = fma(-a, P.q[o], P.r[o]);
+            P.x[o]          = fma(a, pv[k], xv[k]);
+            const double rn = fma(-a, qv[k], rv[k]);
             P.r[o]          = rn;
             acc[k]          = fma(rn, rn, acc[k]);
           }
@@ -366,7 +393,7 @@ namespace msb
               part_ptr(P.part, sidx, P.it & 1, 2)[blk] = acc[k];
               // r.z of the iteration just consumed becomes "previous" for the next K1
               if (blk == 0)
-                P.rzprev[sidx] = sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
+                P.rzprev[sidx] = srz[k];
             }
       }
   }
@@ -448,20 +475,28 @@ namespace msb
         const int jx = t % np, jy = t / np;
         if (jx == 0 || jy == 0 || jx == n || jy == n)
           continue;
-        const double dinv = 1.0 / KC[t];
+        const double kc = KC[t];
         const int    xl = jx >> 1, xh = (jx + 1) >> 1, yl = jy >> 1, yh = (jy + 1) >> 1;
+        double       rv[4], cv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          rv[k] = P.r[((size_t)cell * 4 + k) * N + t];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          {
+            const double *v1 = P.v + ((size_t)cell * 4 + k) * P.L.cn + P.L.off[1];
+            cv[k] = P.L.levels < 1 ? 0.0 : // n = 2 has no coarse level: plain Jacobi
+              0.25 * ((v1[yl * np1 + xl] + v1[yl * np1 + xh]) + (v1[yh * np1 + xl] + v1[yh * np1 + xh]));
+          }
+        const double dinv = 1.0 / kc;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           {
             if (sdone[k])
               continue;
-            const size_t  o  = ((size_t)cell * 4 + k) * N + t;
-            const double *v1 = P.v + ((size_t)cell * 4 + k) * P.L.cn + P.L.off[1];
-            const double  c = P.L.levels < 1 ? 0.0 : // n = 2 has no coarse level: plain Jacobi
-              0.25 * ((v1[yl * np1 + xl] + v1[yl * np1 + xh]) + (v1[yh * np1 + xl] + v1[yh * np1 + xh]));
-            const double rv = P.r[o], zv = fma(rv, dinv, c);
-            P.z[o]          = zv;
-            acc[k]          = fma(rv, zv, acc[k]);
+            const double zv = fma(rv[k], dinv, cv[k]);
+            P.z[((size_t)cell * 4 + k) * N + t] = zv;
+            acc[k]                              = fma(rv[k], zv, acc[k]);
           }
       }
     block_sum_to<4>(acc, sbuf);
@@ -475,27 +510,31 @@ namespace msb
   }
 
   // after the loop (P.it = last executed iteration): record every solve not yet recorded
+  // (one warp per solve)
   __global__ void
   stream_finalize_kernel(StreamParams P, int n_solves, int32_t *fail)
   {
-    const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (sidx >= n_solves || P.iters[sidx] >= 0)
       return;
-    const double rr = sum_part(part_ptr(P.part, sidx, P.it & 1, 2), P.nblk);
-    P.iters[sidx]   = P.it;
-    P.res[sidx]     = sqrt(rr);
+    const double rr = warp_sum_part(part_ptr(P.part, sidx, P.it & 1, 2), P.nblk);
+    if ((threadIdx.x & 31) != 0)
+      return;
+    P.iters[sidx] = P.it;
+    P.res[sidx]   = sqrt(rr);
     if (!(rr <= P.tol2))
       atomicMin(fail, sidx);
   }
 
-  // number of solves still running after iteration P.it
+  // number of solves still running after iteration P.it (one warp per solve)
   __global__ void
   stream_count_kernel(StreamParams P, int n_solves, int32_t *remaining)
   {
-    const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (sidx >= n_solves || P.iters[sidx] >= 0)
       return;
-    if (!(sum_part(part_ptr(P.part, sidx, P.it & 1, 2), P.nblk) <= P.tol2))
+    const double rr = warp_sum_part(part_ptr(P.part, sidx, P.it & 1, 2), P.nblk);
+    if ((threadIdx.x & 31) == 0 && !(rr <= P.tol2))
       atomicAdd(remaining, 1);
   }
 
@@ -664,7 +703,7 @@ namespace msb
           {
             P.it = it;
             TRY(cudaMemsetAsync(s.d_flags, 0, sizeof(int32_t), st));
-            stream_count_kernel<<<(n_solves + 255) / 256, 256, 0, st>>>(P, n_solves, s.d_flags);
+            stream_count_kernel<<<(n_solves + 7) / 8, 256, 0, st>>>(P, n_solves, s.d_flags);
             ++*n_launches;
             TRY(cudaMemcpyAsync(&h_remaining, s.d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             TRY(cudaStreamSynchronize(st));
@@ -685,7 +724,7 @@ namespace msb
         precondition(it & 1);
       }
     P.it = it;
-    stream_finalize_kernel<<<(n_solves + 255) / 256, 256, 0, st>>>(P, n_solves, s.d_fail);
+    stream_finalize_kernel<<<(n_solves + 7) / 8, 256, 0, st>>>(P, n_solves, s.d_fail);
     ++*n_launches;
 #undef TRY
     return cudaGetLastError();

@@ -15,3 +15,11 @@ for n in 2 4 8; do
 done
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29520 bench.py --impl reference --gpus $N --steps 1 --warmup 0 > gpurun_out/scale_ref.json 2> gpurun_out/scale_ref.err
 cut -c1-200 gpurun_out/scale_ref.json; tail -2 gpurun_out/scale_ref.err
+# other BASELINE configurations and the 3D workload on all N GPUs
+if [ "${EXTRA:-1}" = "1" ]; then
+  for w in cfg3 cfg4 cfg5 3d-16x16; do
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29530 bench.py --gpus $N --steps 3 --warmup 3 --workload $w > gpurun_out/scale_${w}_n$N.json 2> gpurun_out/scale_${w}_n$N.err
+    grep '"metric"' gpurun_out/scale_${w}_n$N.json | cut -c1-200; tail -1 gpurun_out/scale_${w}_n$N.err
+  done
+  python -m pytest tests/test_gpu_host_driver.py -q -k "two_gpus" 2>&1 | tail -2
+fi

@@ -242,6 +242,13 @@ namespace DiffusionProblem
       return dim == 2 ? np * np : np * np * np;
     }
     void set_verbose(bool v) { verbose = v; }
+    // vertex (lexicographic) -> deal.II DoF index of the local mesh (same for every cell)
+    void get_dof_map(std::vector<uint32_t> &out) const
+    {
+      require_batch();
+      out.resize(n_dofs());
+      internal::check(msb_get_dof_map(batch->handle, out.data()));
+    }
 
   private:
   public:

@@ -1,11 +1,12 @@
 // main.cxx -- driver with the shape of the reference's source/main.cxx:16-84: the same
 // hard-wired default problem (n_refine = 3, n_refine_local = 7, 2D; main.cxx:23-25), the
 // same top-level exception handling (return 1), running the MsFEM problem whose basis
-// stage executes on the B200.  The two standard-FEM "truth" runs of the reference
-// (main.cxx:29-35) are out of scope (component 4).
+// stage executes on the B200.  With --truth the two standard-FEM runs of the reference
+// (main.cxx:29-35: DiffusionProblem<2> at n_refine and at n_refine + n_refine_local) are run as
+// well and the MsFEM-vs-fine-FEM difference is reported.
 //
 //   msfem_main [--n-refine R] [--n-refine-local L] [--coeff reference|periodic|inclusions]
-//              [--dump coarse_solution.txt] [--output] [--device D] [--gpus P]
+//              [--dump coarse_solution.txt] [--output] [--device D] [--gpus P] [--truth]
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -13,6 +14,7 @@
 #include <iostream>
 #include <memory>
 
+#include "msfem/diffusion_problem.hpp"
 #include "msfem/diffusion_problem_ms.hpp"
 
 int
@@ -22,7 +24,7 @@ main(int argc, char *argv[])
     {
       unsigned int n_refine = 3, n_refine_local = 7;
       std::string  coeff = "reference", dump;
-      bool         output = false;
+      bool         output = false, truth = false;
       int          device = 0, gpus = 1;
       for (int i = 1; i < argc; ++i)
         {
@@ -41,6 +43,8 @@ main(int argc, char *argv[])
             gpus = std::atoi(argv[++i]);
           else if (a == "--output")
             output = true;
+          else if (a == "--truth")
+            truth = true;
           else
             throw std::runtime_error("unknown argument " + a);
         }
@@ -55,10 +59,76 @@ main(int argc, char *argv[])
       else
         throw std::runtime_error("unknown coefficient " + coeff);
 
+      // create the CUDA contexts and load the kernels before any timed section (a one-off
+      // process start-up cost of ~1 s per device that has no counterpart in the reference)
+      for (int g = 0; g < gpus; ++g)
+        {
+          msb_config warm{};
+          warm.abi_version = MSB_ABI_VERSION, warm.dim = 2, warm.n_refine_local = 1, warm.n_cells = 1;
+          warm.device_id = device + g, warm.rhs_value = 2.0, warm.coeff.kind = MSB_COEFF_CONSTANT;
+          warm.coeff.par[0]           = 1.0;
+          const double unit_square[8] = {0, 0, 1, 0, 0, 1, 1, 1};
+          msb_handle   h              = nullptr;
+          if (msb_create(&warm, unit_square, nullptr, &h) != MSB_OK)
+            throw std::runtime_error(std::string("device start-up failed: ") + msb_last_error());
+          msb_destroy(h);
+        }
+
       DiffusionProblem::DiffusionProblemMultiscale<2> diffusion_ms_problem_2d(n_refine, n_refine_local, device, gpus);
       diffusion_ms_problem_2d.set_coefficient(c.get());
       diffusion_ms_problem_2d.set_output(output);
       diffusion_ms_problem_2d.run();
+
+      double ms_vs_fine = -1.0, coarse_vs_fine = -1.0;
+      if (truth)
+        {
+          // main.cxx:29-35: the standard problem on the coarse and on the fine mesh
+          DiffusionProblem::DiffusionProblem<2> diffusion_problem_2d_coarse(n_refine, device);
+          diffusion_problem_2d_coarse.set_coefficient(c.get());
+          diffusion_problem_2d_coarse.set_output(output);
+          diffusion_problem_2d_coarse.run();
+          DiffusionProblem::DiffusionProblem<2> diffusion_problem_2d_fine(n_refine + n_refine_local, device);
+          diffusion_problem_2d_fine.set_coefficient(c.get());
+          diffusion_problem_2d_fine.set_output(output);
+          diffusion_problem_2d_fine.run();
+
+          // MsFEM reconstruction u_ms = sum_i w_i phi_i on every coarse cell against the fine FEM
+          // solution at the same vertices (relative l2 over all (cell, vertex) pairs)
+          const unsigned        nl = 1u << n_refine_local, npl = nl + 1, nc = 1u << n_refine;
+          std::vector<uint32_t> ldof;
+          std::vector<double>   ums;
+          double                num = 0.0, den = 0.0, num_c = 0.0, den_c = 0.0;
+          for (auto &kv : diffusion_ms_problem_2d.get_cell_basis_map())
+            {
+              const std::uint64_t m = kv.first.morton();
+              unsigned            ix = 0, iy = 0;
+              for (unsigned b = 0; b < n_refine; ++b)
+                ix |= unsigned((m >> (2 * b)) & 1u) << b, iy |= unsigned((m >> (2 * b + 1)) & 1u) << b;
+              if (ldof.empty())
+                kv.second.get_dof_map(ldof);
+              kv.second.get_global_solution(ums);
+              for (unsigned jy = 0; jy < npl; ++jy)
+                for (unsigned jx = 0; jx < npl; ++jx)
+                  {
+                    const double uf = diffusion_problem_2d_fine.value_at_vertex(ix * nl + jx, iy * nl + jy);
+                    const double d  = ums[ldof[jy * npl + jx]] - uf;
+                    num += d * d, den += uf * uf;
+                  }
+            }
+          for (unsigned jy = 0; jy <= nc; ++jy)
+            for (unsigned jx = 0; jx <= nc; ++jx)
+              {
+                const double uf = diffusion_problem_2d_fine.value_at_vertex(jx * nl, jy * nl);
+                const double d  = diffusion_problem_2d_coarse.value_at_vertex(jx, jy) - uf;
+                num_c += d * d, den_c += uf * uf;
+              }
+          ms_vs_fine     = std::sqrt(num / den);
+          coarse_vs_fine = std::sqrt(num_c / den_c);
+          std::cout << "   MsFEM reconstruction vs fine standard FEM (" << (nc * nl) << " x " << (nc * nl)
+                    << " cells), relative l2 over all fine vertices: " << ms_vs_fine << std::endl
+                    << "   coarse standard FEM vs fine standard FEM, relative l2 over the coarse vertices: "
+                    << coarse_vs_fine << std::endl;
+        }
 
       if (!dump.empty())
         {
@@ -69,6 +139,8 @@ main(int argc, char *argv[])
           for (double v : u)
             f << v << "\n";
           f << "basis_seconds " << diffusion_ms_problem_2d.basis_seconds() << "\n";
+          if (truth)
+            f << "ms_vs_fine_rel_l2 " << ms_vs_fine << "\ncoarse_vs_fine_rel_l2 " << coarse_vs_fine << "\n";
         }
     }
   catch (std::exception &exc)

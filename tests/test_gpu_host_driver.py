@@ -149,3 +149,61 @@ def test_cpp_basis3d_matches_oracle(oracle, tmp_path):
         M, b = v[:64].reshape(8, 8), v[64:]
         assert np.linalg.norm(M - ref["M"][k]) / np.linalg.norm(ref["M"][k]) < 1e-8
         assert np.linalg.norm(b - ref["b"][k]) / np.linalg.norm(ref["b"][k]) < 1e-8
+
+
+def test_cpp_truth_run_and_msfem_error(oracle, tmp_path):
+    """the standard-FEM "truth" run (DiffusionProblem<2>, main.cxx:29-35) through the
+    C++ mirror.  Checked against an independent direct solve of the oracle's CSR of the same fine
+    problem, and the MsFEM reconstruction must be far closer to the fine solution than the coarse
+    standard FEM is (the point of the method)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    exe = os.path.join(ROOT, "host", "_build", "msfem_main")
+    r, l = 2, 4                                   # 4x4 coarse cells x 16x16 fine cells = 64x64 mesh
+    dump = str(tmp_path / "truth.txt")
+    out = subprocess.run([exe, "--n-refine", str(r), "--n-refine-local", str(l), "--truth", "--output",
+                          "--dump", dump], cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr + out.stdout
+    vals = dict(ln.split() for ln in open(dump).read().split("\n") if ln and ln[0].isalpha())
+    ms_err, coarse_err = float(vals["ms_vs_fine_rel_l2"]), float(vals["coarse_vs_fine_rel_l2"])
+    assert ms_err < 0.05, ms_err
+    assert ms_err < 0.5 * coarse_err, (ms_err, coarse_err)
+    assert os.path.exists(tmp_path / ("solution-std_2d_refinements-%d.0000.vtu" % (r + l)))
+    assert os.path.exists(tmp_path / ("solution-std_2d_refinements-%d.pvtu" % r))
+
+    # independent fine solve: the oracle's CSR of the unit square refined r+l times
+    L = r + l
+    n = 1 << L
+    np_, h = n + 1, 1.0 / n
+    co = oracle.coeff(oracle.COEFF_REFERENCE)
+    unit = np.array([[0, 0], [1, 0], [0, 1], [1, 1]], dtype=np.float64)
+    rowptr, col, val, F = oracle.assemble(L, unit, co)
+    N = np_ * np_
+    K = sp.csr_matrix((val, col.astype(np.int64), rowptr.astype(np.int64)), shape=(N, N))
+    dof = oracle.dof_map(L)
+    g = [0.5 - 0.5 / np.sqrt(3.0), 0.5 + 0.5 / np.sqrt(3.0)]
+    b = F.copy()
+    for k in range(n):
+        for q in range(2):
+            s = (k + g[q]) * h
+            vx = np.cos(2 * PI_D * 1.0) * np.cos(2 * PI_D * s) * 0.5 * h
+            b[dof[k, n]] += vx * (1 - g[q])
+            b[dof[k + 1, n]] += vx * g[q]
+            vy = np.cos(2 * PI_D * s) * np.cos(2 * PI_D * 1.0) * 0.5 * h
+            b[dof[n, k]] += vy * (1 - g[q])
+            b[dof[n, k + 1]] += vy * g[q]
+    u = np.zeros(N)
+    fixed = np.zeros(N, dtype=bool)
+    for j in range(np_):
+        for (jx, jy) in ((0, j), (j, 0)):
+            d = dof[jy, jx]
+            fixed[d] = True
+            u[d] = (jx * h - 0.5) ** 2 + (jy * h - 0.5) ** 2
+    free = ~fixed
+    u[free] = spla.spsolve(K[free][:, free].tocsc(), b[free] - K[free][:, fixed] @ u[fixed])
+    # the driver's fine solution, from its VTU (lexicographic point data)
+    txt = open(tmp_path / ("solution-std_2d_refinements-%d.0000.vtu" % L)).read()
+    data = txt.split('Name="u" format="ascii">')[1].split("</DataArray>")[0].split()
+    u_cpp = np.array(data, dtype=np.float64).reshape(np_, np_)
+    u_ref = u[dof.ravel()].reshape(np_, np_)
+    assert np.linalg.norm(u_cpp - u_ref) / np.linalg.norm(u_ref) < 1e-8

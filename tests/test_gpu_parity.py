@@ -379,3 +379,21 @@ def test_handle_reuse_with_set_cells(msb, oracle):
     assert _rel(Mb, ref["M"]) < TOL_MB and _rel(bb, ref["b"]) < TOL_MB
     assert _rel(phib, ref["phi"][3][2]) < TOL_PHI
     assert _rel(Ma, ref["M"]) > 1e-3       # and they really are different cells
+
+
+def test_more_than_65535_cells_streamed_tier(msb, oracle):
+    """gridDim.y slices of the streamed tier: 70 000 coarse cells at 4x4 fine cells."""
+    cd, co = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    lo, hi = 150000, 220000                 # of the 512x512 coarse mesh
+    cor = msb.coarse_corners(9, lo, hi)
+    with msb.BasisShard(2, cor, cd, tier=msb.TIER_STREAMED) as sh:
+        sh.run(1e-12, 200)
+        M, b = sh.element_matrices()
+        it, res = sh.iteration_counts()
+        assert (res <= 1e-12).all() and (it >= 1).all()
+        assert np.abs(M.sum(axis=2)).max() < 1e-12
+        pick = [0, 65534, 65535, 65536, 69999]
+        ref = oracle.run_cells(2, cor[pick], co, keep_phi=False)
+        for k, c in enumerate(pick):
+            assert _rel(M[c], ref["M"][k]) < TOL_MB
+            assert _rel(b[c], ref["b"][k]) < TOL_MB

@@ -183,3 +183,22 @@ def test_handle_reuse_with_set_cells_3d(msb, oracle):
         Mb2, _ = sh2.element_matrices()
         assert np.array_equal(Mb, Mb2)           # deterministic, independent of handle history
         assert not np.array_equal(Ma, Mb)
+
+
+def test_more_than_65535_cells_3d(msb, oracle):
+    """gridDim.y slices: a shard larger than 65 535 coarse cells runs in several launches."""
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
+    r = 6                                   # 64^3 = 262 144 coarse hexes; take 70 000 of them
+    lo, hi = 100000, 170000
+    cor = msb.coarse_corners3(r, lo, hi)
+    with msb.BasisShard(1, cor, coeff_desc(msb.COEFF_REFERENCE), dim=3) as sh:
+        sh.run(1e-12, 100)
+        M, b = sh.element_matrices()
+        it, res = sh.iteration_counts()
+        assert (res <= 1e-12).all() and (it >= 1).all()
+        assert np.abs(M.sum(axis=2)).max() < 1e-12
+        assert np.abs(b.sum(axis=1) - 2.0 / 64 ** 3).max() < 1e-17
+        pick = [0, 65534, 65535, 65536, 69999]
+        ref = oracle.run_cells3(1, cor[pick], oracle.coeff(oracle.COEFF_REFERENCE), keep_phi=False)
+        for k, c in enumerate(pick):
+            assert _rel(M[c], ref["M"][k]) < TOL_MB

@@ -4,7 +4,7 @@
 // p4est and Trilinos.  Method names and the order of run() follow ms.tpp:445-491.
 //
 // What is NOT the reference here (and is out of the accelerated path):
-// the coarse mesh is the structured 2^r x 2^r refinement of hyper_cube(0,1,colorize) held
+// the coarse mesh is the structured (2^r)^dim refinement of hyper_cube(0,1,colorize) held
 // as plain arrays in Morton / CellId order (ms.tpp:97-99), the coarse matrix is a host CSR,
 // and the coarse system is solved by a host Jacobi-PCG to the reference's tolerance
 // (SolverControl(n_dofs, 1e-12), ms.tpp:264) instead of Trilinos AMG-CG.  One process
@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdint>
 #include <fstream>
 #include <iostream>
 #include <map>
@@ -32,7 +33,8 @@ namespace DiffusionProblem
   template <int dim>
   class DiffusionProblemMultiscale
   {
-    static_assert(dim == 2, "only the 2D path is built");
+    static_assert(dim == 2 || dim == 3, "the reference instantiates dim 2 and 3");
+    static constexpr unsigned NB = 1u << dim; // vertices (= multiscale bases) per coarse cell
 
   public:
     DiffusionProblemMultiscale(unsigned int n_refine, unsigned int n_refine_local, int device_id = 0,
@@ -84,14 +86,38 @@ namespace DiffusionProblem
       timings[name] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
 
-    static unsigned compact(unsigned m)
+    // coordinate index `axis` of the coarse cell with Morton index m (bits interleaved x, y[, z])
+    unsigned cell_index(std::uint64_t m, unsigned axis) const
     {
-      unsigned x = m & 0x55555555u;
-      x          = (x | (x >> 1)) & 0x33333333u;
-      x          = (x | (x >> 2)) & 0x0f0f0f0fu;
-      x          = (x | (x >> 4)) & 0x00ff00ffu;
-      x          = (x | (x >> 8)) & 0x0000ffffu;
-      return x;
+      unsigned v = 0;
+      for (unsigned b = 0; b < n_refine; ++b)
+        v |= unsigned((m >> (dim * b + axis)) & 1u) << b;
+      return v;
+    }
+    std::size_t n_cells_total() const
+    {
+      std::size_t t = 1;
+      for (int a = 0; a < dim; ++a)
+        t *= nc;
+      return t;
+    }
+    std::size_t n_vertices_total() const
+    {
+      std::size_t t = 1;
+      for (int a = 0; a < dim; ++a)
+        t *= nc + 1;
+      return t;
+    }
+    // lexicographic index of vertex v of cell m in the (nc+1)^dim vertex grid
+    std::size_t vertex_lex(std::uint64_t m, unsigned v) const
+    {
+      std::size_t lex = 0, stride = 1;
+      for (unsigned a = 0; a < (unsigned)dim; ++a)
+        {
+          lex += (cell_index(m, a) + ((v >> a) & 1u)) * stride;
+          stride *= nc + 1;
+        }
+      return lex;
     }
 
     // ms.tpp:91-103: hyper_cube(0,1,colorize=true), refine_global(n_refine); active cells in
@@ -100,50 +126,60 @@ namespace DiffusionProblem
     {
       nc = 1u << n_refine;
       H  = 1.0 / nc;
-      cells.resize((std::size_t)nc * nc);
-      for (unsigned m = 0; m < nc * nc; ++m)
+      cells.resize(n_cells_total());
+      for (std::uint64_t m = 0; m < cells.size(); ++m)
         {
-          const unsigned   ix = compact(m), iy = compact(m >> 1);
           CoarseCell<dim> &c = cells[m];
-          for (unsigned v = 0; v < 4; ++v)
-            c.vertices[v] = Point<dim>((ix + (v & 1)) * H, (iy + (v >> 1)) * H);
-          c.cell_id        = CellId(n_refine, m);
-          c.boundary_id[0] = ix == 0 ? 0 : 255;      // x = 0
-          c.boundary_id[1] = ix == nc - 1 ? 1 : 255; // x = 1
-          c.boundary_id[2] = iy == 0 ? 2 : 255;      // y = 0
-          c.boundary_id[3] = iy == nc - 1 ? 3 : 255; // y = 1
+          for (unsigned v = 0; v < NB; ++v)
+            for (unsigned a = 0; a < (unsigned)dim; ++a)
+              c.vertices[v](a) = (cell_index(m, a) + ((v >> a) & 1u)) * H;
+          c.cell_id = CellId(n_refine, m, dim);
+          for (unsigned a = 0; a < (unsigned)dim; ++a)
+            {
+              c.boundary_id[2 * a]     = cell_index(m, a) == 0 ? 2 * a : 255;          // x_a = 0
+              c.boundary_id[2 * a + 1] = cell_index(m, a) == nc - 1 ? 2 * a + 1 : 255; // x_a = 1
+            }
         }
       std::cout << "Number of active global cells: " << cells.size() << std::endl;
     }
 
-    // ms.tpp:106-156: first-touch DoF numbering, Dirichlet values on boundary ids 0 and 2
+    // ms.tpp:106-156: first-touch DoF numbering, Dirichlet values on the even boundary ids
+    // (x_a = 0 for every axis a, ms.tpp:129-139)
     void setup_system()
     {
       const unsigned np = nc + 1;
-      dof_of_vertex.assign((std::size_t)np * np, ~0u);
+      dof_of_vertex.assign(n_vertices_total(), ~0u);
       unsigned next = 0;
-      for (unsigned m = 0; m < nc * nc; ++m)
-        {
-          const unsigned ix = compact(m), iy = compact(m >> 1);
-          for (unsigned v = 0; v < 4; ++v)
-            {
-              unsigned &d = dof_of_vertex[(iy + (v >> 1)) * np + ix + (v & 1)];
-              if (d == ~0u)
-                d = next++;
-            }
-        }
+      for (std::uint64_t m = 0; m < cells.size(); ++m)
+        for (unsigned v = 0; v < NB; ++v)
+          {
+            unsigned &d = dof_of_vertex[vertex_lex(m, v)];
+            if (d == ~0u)
+              d = next++;
+          }
       n_coarse_dofs = next;
       is_constrained.assign(n_coarse_dofs, 0);
       constraint_value.assign(n_coarse_dofs, 0.0);
       const Coefficients::DirichletBC<dim> dirichlet_bc;
-      for (unsigned jy = 0; jy < np; ++jy)
-        for (unsigned jx = 0; jx < np; ++jx)
-          if (jx == 0 || jy == 0) // boundary ids 0 (x=0) and 2 (y=0), ms.tpp:130-137
+      for (std::size_t lex = 0; lex < dof_of_vertex.size(); ++lex)
+        {
+          Point<dim>  p;
+          bool        on_dirichlet = false;
+          std::size_t rest         = lex;
+          for (unsigned a = 0; a < (unsigned)dim; ++a)
             {
-              const unsigned d    = dof_of_vertex[jy * np + jx];
-              is_constrained[d]   = 1;
-              constraint_value[d] = dirichlet_bc.value(Point<dim>(jx * H, jy * H));
+              const unsigned j = rest % np;
+              rest /= np;
+              p(a) = j * H;
+              on_dirichlet |= j == 0;
             }
+          if (on_dirichlet)
+            {
+              const unsigned d    = dof_of_vertex[lex];
+              is_constrained[d]   = 1;
+              constraint_value[d] = dirichlet_bc.value(p);
+            }
+        }
       solution.assign(n_coarse_dofs, 0.0);
     }
 
@@ -195,43 +231,64 @@ namespace DiffusionProblem
           std::rethrow_exception(e);
     }
 
-    void cell_dofs(std::size_t m, unsigned (&ld)[4]) const
+    void cell_dofs(std::size_t m, unsigned (&ld)[NB]) const
     {
-      const unsigned np = nc + 1, ix = compact((unsigned)m), iy = compact((unsigned)m >> 1);
-      for (unsigned v = 0; v < 4; ++v)
-        ld[v] = dof_of_vertex[(iy + (v >> 1)) * np + ix + (v & 1)];
+      for (unsigned v = 0; v < NB; ++v)
+        ld[v] = dof_of_vertex[vertex_lex(m, v)];
     }
 
-    // ms.tpp:159-255: element matrices from the basis objects, Neumann face terms on boundary
-    // ids 1 and 3 (QGauss<1>(2), standard Q1 face shape values), scatter into the coarse system
+    // ms.tpp:159-255: element matrices from the basis objects, Neumann face terms on the odd
+    // boundary ids (QGauss<dim-1>(2), standard Q1 face shape values), scatter into the coarse system
     void assemble_system()
     {
       rows.assign(n_coarse_dofs, {});
       system_rhs.assign(n_coarse_dofs, 0.0);
       const Coefficients::NeumannBC<dim> neumann_bc;
       const double g[2] = {0.5 - 0.5 / std::sqrt(3.0), 0.5 + 0.5 / std::sqrt(3.0)};
-      std::size_t  m    = 0;
+      const unsigned n_face_q = 1u << (dim - 1);
+      double         JxW      = 1.0;
+      for (int a = 1; a < dim; ++a)
+        JxW *= 0.5 * H;
+      std::size_t m = 0;
       for (auto &kv : cell_basis_map)
         {
           const FullMatrix<double> &cell_matrix = kv.second.get_global_element_matrix();
           Vector<double>            cell_rhs    = kv.second.get_global_element_rhs();
           const CoarseCell<dim>    &c           = cells[m];
-          // face 1: x = x1 (vertices 1,3); face 3: y = y1 (vertices 2,3)
-          for (int face = 1; face <= 3; face += 2)
-            if (c.boundary_id[face] == (unsigned)face)
-              for (int q = 0; q < 2; ++q)
-                {
-                  const Point<dim> &a  = c.vertex(face == 1 ? 1 : 2), &b = c.vertex(3);
-                  const Point<dim>  xq(a(0) + g[q] * (b(0) - a(0)), a(1) + g[q] * (b(1) - a(1)));
-                  const double      JxW = 0.5 * H, val = neumann_bc.value(xq);
-                  cell_rhs(face == 1 ? 1 : 2) += val * (1.0 - g[q]) * JxW;
-                  cell_rhs(3) += val * g[q] * JxW;
-                }
-          unsigned ld[4];
-          cell_dofs(m, ld);
-          for (int i = 0; i < 4; ++i)
+          for (unsigned axis = 0; axis < (unsigned)dim; ++axis)
             {
-              for (int j = 0; j < 4; ++j)
+              const unsigned face = 2 * axis + 1; // x_axis = 1 side of the cell
+              if (c.boundary_id[face] != face)
+                continue;
+              for (unsigned q = 0; q < n_face_q; ++q)
+                {
+                  // quadrature point: tensor Gauss point in the tangential axes
+                  double     t[3] = {0, 0, 0};
+                  Point<dim> xq;
+                  unsigned   bit = 0;
+                  for (unsigned b = 0; b < (unsigned)dim; ++b)
+                    {
+                      t[b]  = b == axis ? 1.0 : g[(q >> bit++) & 1u];
+                      xq(b) = c.vertex(0)(b) + t[b] * H;
+                    }
+                  const double val = neumann_bc.value(xq);
+                  for (unsigned v = 0; v < NB; ++v)
+                    {
+                      if (!((v >> axis) & 1u))
+                        continue; // only the vertices of this face carry a face shape function
+                      double shape = 1.0;
+                      for (unsigned b = 0; b < (unsigned)dim; ++b)
+                        if (b != axis)
+                          shape *= ((v >> b) & 1u) ? t[b] : 1.0 - t[b];
+                      cell_rhs(v) += val * shape * JxW;
+                    }
+                }
+            }
+          unsigned ld[NB];
+          cell_dofs(m, ld);
+          for (unsigned i = 0; i < NB; ++i)
+            {
+              for (unsigned j = 0; j < NB; ++j)
                 rows[ld[i]][ld[j]] += cell_matrix(i, j);
               system_rhs[ld[i]] += cell_rhs(i);
             }
@@ -304,10 +361,10 @@ namespace DiffusionProblem
       std::size_t m = 0;
       for (auto &kv : cell_basis_map)
         {
-          unsigned ld[4];
+          unsigned ld[NB];
           cell_dofs(m++, ld);
-          std::vector<double> extracted_weights(4);
-          for (int i = 0; i < 4; ++i)
+          std::vector<double> extracted_weights(NB);
+          for (unsigned i = 0; i < NB; ++i)
             extracted_weights[i] = solution[ld[i]];
           kv.second.set_global_weights(extracted_weights);
         }
@@ -316,31 +373,39 @@ namespace DiffusionProblem
     // ms.tpp:328-379 (one rank: a single VTU)
     void output_global_coarse() const
     {
-      const unsigned np = nc + 1;
-      std::ofstream  out("solution-ms_coarse-2d_refinements-" + std::to_string(n_refine) + ".0000.vtu");
+      const unsigned    np = nc + 1, npz = dim == 3 ? np : 1, ncz = dim == 3 ? nc : 1;
+      const std::string d  = dim == 2 ? "2d" : "3d";
+      std::ofstream     out("solution-ms_coarse-" + d + "_refinements-" + std::to_string(n_refine) + ".0000.vtu");
       out.precision(17);
       out << "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" "
              "byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n<Piece NumberOfPoints=\""
-          << np * np << "\" NumberOfCells=\"" << nc * nc << "\">\n<Points>\n<DataArray type=\"Float64\" "
-             "NumberOfComponents=\"3\" format=\"ascii\">\n";
-      for (unsigned jy = 0; jy < np; ++jy)
-        for (unsigned jx = 0; jx < np; ++jx)
-          out << jx * H << " " << jy * H << " 0\n";
+          << n_vertices_total() << "\" NumberOfCells=\"" << n_cells_total()
+          << "\">\n<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
+      for (unsigned jz = 0; jz < npz; ++jz)
+        for (unsigned jy = 0; jy < np; ++jy)
+          for (unsigned jx = 0; jx < np; ++jx)
+            out << jx * H << " " << jy * H << " " << jz * H << "\n";
       out << "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int32\" Name=\"connectivity\" "
              "format=\"ascii\">\n";
-      for (unsigned iy = 0; iy < nc; ++iy)
-        for (unsigned ix = 0; ix < nc; ++ix)
-          out << iy * np + ix << " " << iy * np + ix + 1 << " " << (iy + 1) * np + ix + 1 << " "
-              << (iy + 1) * np + ix << "\n";
+      for (unsigned iz = 0; iz < ncz; ++iz)
+        for (unsigned iy = 0; iy < nc; ++iy)
+          for (unsigned ix = 0; ix < nc; ++ix)
+            {
+              const std::size_t b = (std::size_t(iz) * np + iy) * np + ix, up = std::size_t(np) * np;
+              out << b << " " << b + 1 << " " << b + np + 1 << " " << b + np;
+              if (dim == 3)
+                out << " " << b + up << " " << b + up + 1 << " " << b + up + np + 1 << " " << b + up + np;
+              out << "\n";
+            }
       out << "</DataArray>\n<DataArray type=\"Int32\" Name=\"offsets\" format=\"ascii\">\n";
-      for (unsigned k = 1; k <= nc * nc; ++k)
-        out << 4 * k << "\n";
+      for (std::size_t k = 1; k <= n_cells_total(); ++k)
+        out << NB * k << "\n";
       out << "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n";
-      for (unsigned k = 0; k < nc * nc; ++k)
-        out << "9\n";
+      for (std::size_t k = 0; k < n_cells_total(); ++k)
+        out << (dim == 2 ? "9\n" : "12\n");
       out << "</DataArray>\n</Cells>\n<PointData Scalars=\"scalars\">\n<DataArray type=\"Float64\" "
              "Name=\"u\" format=\"ascii\">\n";
-      for (unsigned i = 0; i < np * np; ++i)
+      for (std::size_t i = 0; i < n_vertices_total(); ++i)
         out << solution[dof_of_vertex[i]] << "\n";
       out << "</DataArray>\n</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n";
     }
@@ -354,7 +419,7 @@ namespace DiffusionProblem
           kv.second.output_global_solution_in_cell();
           filenames.push_back(kv.second.get_filename_global());
         }
-      std::ofstream out("solution-ms_fine-2d.pvtu");
+      std::ofstream out(dim == 2 ? "solution-ms_fine-2d.pvtu" : "solution-ms_fine-3d.pvtu");
       out << "<?xml version=\"1.0\"?>\n<VTKFile type=\"PUnstructuredGrid\" version=\"0.1\" "
              "byte_order=\"LittleEndian\">\n<PUnstructuredGrid GhostLevel=\"0\">\n<PPointData "
              "Scalars=\"scalars\">\n<PDataArray type=\"Float64\" Name=\"solution\" format=\"ascii\"/>\n"

@@ -7,6 +7,8 @@
 //
 //   msfem_main [--n-refine R] [--n-refine-local L] [--coeff reference|periodic|inclusions]
 //              [--dump coarse_solution.txt] [--output] [--device D] [--gpus P] [--truth]
+//              [--dim 3]   the 3D block of the reference's main (main.cxx:42-55, disabled there by
+//                          is_2d = true): the multiscale problem on the unit cube
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -25,7 +27,7 @@ main(int argc, char *argv[])
       unsigned int n_refine = 3, n_refine_local = 7;
       std::string  coeff = "reference", dump;
       bool         output = false, truth = false;
-      int          device = 0, gpus = 1;
+      int          device = 0, gpus = 1, dim = 2;
       for (int i = 1; i < argc; ++i)
         {
           const std::string a = argv[i];
@@ -45,9 +47,13 @@ main(int argc, char *argv[])
             output = true;
           else if (a == "--truth")
             truth = true;
+          else if (a == "--dim" && i + 1 < argc)
+            dim = std::atoi(argv[++i]);
           else
             throw std::runtime_error("unknown argument " + a);
         }
+      if (dim != 2 && dim != 3)
+        throw std::runtime_error("--dim must be 2 or 3");
 
       std::unique_ptr<Coefficients::TensorCoefficient<2>> c;
       if (coeff == "reference")
@@ -72,6 +78,28 @@ main(int argc, char *argv[])
           if (msb_create(&warm, unit_square, nullptr, &h) != MSB_OK)
             throw std::runtime_error(std::string("device start-up failed: ") + msb_last_error());
           msb_destroy(h);
+        }
+
+      if (dim == 3)
+        {
+          // main.cxx:52-54 (MatrixCoeff<3> is the only coefficient the reference has in 3D)
+          if (coeff != "reference" || truth)
+            throw std::runtime_error("--dim 3 supports --coeff reference only, and no --truth run");
+          DiffusionProblem::DiffusionProblemMultiscale<3> diffusion_ms_problem_3d(n_refine, n_refine_local, device,
+                                                                                  gpus);
+          diffusion_ms_problem_3d.set_output(output);
+          diffusion_ms_problem_3d.run();
+          if (!dump.empty())
+            {
+              std::ofstream f(dump.c_str());
+              f << std::setprecision(17);
+              const auto &u = diffusion_ms_problem_3d.get_solution();
+              f << u.size() << "\n";
+              for (double v : u)
+                f << v << "\n";
+              f << "basis_seconds " << diffusion_ms_problem_3d.basis_seconds() << "\n";
+            }
+          return 0;
         }
 
       DiffusionProblem::DiffusionProblemMultiscale<2> diffusion_ms_problem_2d(n_refine, n_refine_local, device, gpus);

@@ -207,3 +207,89 @@ def test_cpp_truth_run_and_msfem_error(oracle, tmp_path):
     u_cpp = np.array(data, dtype=np.float64).reshape(np_, np_)
     u_ref = u[dof.ravel()].reshape(np_, np_)
     assert np.linalg.norm(u_cpp - u_ref) / np.linalg.norm(u_ref) < 1e-8
+
+
+def _coarse_reference_3d(oracle, r, l, co):
+    """The dim = 3 coarse problem (ms.tpp:106-296 with dim = 3) fed with the ORACLE's 8x8 element
+    matrices: first-touch coarse DoFs on the 3D Morton-ordered hexes, Dirichlet data on x=0 / y=0 / z=0,
+    Neumann data on x=1 / y=1 / z=1 with 2x2 Gauss points and bilinear face shape values, direct solve."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    nc = 1 << r
+    H = 1.0 / nc
+    res = oracle.run_cells3(l, oracle.coarse_corners3(r), co, n_threads=os.cpu_count() or 1, keep_phi=False)
+    assert res["failed"] == 0
+    np_ = nc + 1
+    dof = -np.ones((np_, np_, np_), dtype=np.int64)
+    nxt, cells = 0, []
+    for m in range(nc ** 3):
+        idx = [sum(((m >> (3 * b + a)) & 1) << b for b in range(r)) for a in range(3)]
+        ld = []
+        for v in range(8):
+            j = [idx[a] + ((v >> a) & 1) for a in range(3)]
+            if dof[j[2], j[1], j[0]] < 0:
+                dof[j[2], j[1], j[0]] = nxt
+                nxt += 1
+            ld.append(dof[j[2], j[1], j[0]])
+        cells.append((idx, ld))
+    n = nxt
+    K = sp.lil_matrix((n, n))
+    f = np.zeros(n)
+    g = [0.5 - 0.5 / np.sqrt(3.0), 0.5 + 0.5 / np.sqrt(3.0)]
+    neu = lambda x, y: np.cos(2 * PI_D * x) * np.cos(2 * PI_D * y)
+    for m, (idx, ld) in enumerate(cells):
+        be = res["b"][m].copy()
+        for axis in range(3):
+            if idx[axis] != nc - 1:
+                continue
+            others = [b for b in range(3) if b != axis]
+            for q0 in range(2):
+                for q1 in range(2):
+                    t = [0.0, 0.0, 0.0]
+                    t[axis] = 1.0
+                    t[others[0]], t[others[1]] = g[q0], g[q1]
+                    x = [(idx[b] + t[b]) * H for b in range(3)]
+                    val = neu(x[0], x[1]) * (0.5 * H) ** 2
+                    for v in range(8):
+                        if not (v >> axis) & 1:
+                            continue
+                        shape = 1.0
+                        for b in others:
+                            shape *= t[b] if (v >> b) & 1 else 1.0 - t[b]
+                        be[v] += val * shape
+        for i in range(8):
+            f[ld[i]] += be[i]
+            for j in range(8):
+                K[ld[i], ld[j]] += res["M"][m][i, j]
+    u = np.zeros(n)
+    fixed = np.zeros(n, dtype=bool)
+    for jz in range(np_):
+        for jy in range(np_):
+            for jx in range(np_):
+                if jx == 0 or jy == 0 or jz == 0:
+                    d = dof[jz, jy, jx]
+                    fixed[d] = True
+                    u[d] = (jx * H - 0.5) ** 2 + (jy * H - 0.5) ** 2
+    K = K.tocsr()
+    free = ~fixed
+    u[free] = spla.spsolve(K[free][:, free].tocsc(), f[free] - K[free][:, fixed] @ u[fixed])
+    return u
+
+
+@pytest.mark.parametrize("r,l", [(1, 3), (2, 2)])
+def test_cpp_driver_3d_coarse_solution(oracle, tmp_path, r, l):
+    """main.cxx:42-55 (the 3D block) through the C++ mirror: final coarse solution within 1e-8."""
+    exe = os.path.join(ROOT, "host", "_build", "msfem_main")
+    dump = str(tmp_path / "coarse3d.txt")
+    out = subprocess.run([exe, "--dim", "3", "--n-refine", str(r), "--n-refine-local", str(l), "--dump", dump,
+                          "--output"], cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr + out.stdout
+    lines = open(dump).read().split("\n")
+    n = int(lines[0])
+    u = np.array([float(x) for x in lines[1:1 + n]])
+    ref = _coarse_reference_3d(oracle, r, l, oracle.coeff(oracle.COEFF_REFERENCE))
+    assert n == ref.size == ((1 << r) + 1) ** 3
+    assert np.linalg.norm(u - ref) / np.linalg.norm(ref) < 1e-8
+    assert os.path.exists(tmp_path / ("solution-ms_coarse-3d_refinements-%d.0000.vtu" % r))
+    assert os.path.exists(tmp_path / "solution-ms_fine-3d.pvtu")
+    assert len([f for f in os.listdir(tmp_path) if f.startswith("solution-ms_fine-3d.")]) == 8 ** r + 1

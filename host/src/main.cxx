@@ -19,6 +19,63 @@
 #include "msfem/diffusion_problem.hpp"
 #include "msfem/diffusion_problem_ms.hpp"
 
+// main.cxx:29-35 / :44-50: the standard problem on the coarse and on the fine mesh, then the MsFEM
+// reconstruction u_ms = sum_i w_i phi_i on every coarse cell against the fine FEM solution at the same
+// vertices (relative l2 over all (cell, vertex) pairs) and the coarse standard FEM at the coarse vertices
+template <int dim>
+static void
+truth_runs(DiffusionProblem::DiffusionProblemMultiscale<dim> &ms, unsigned n_refine, unsigned n_refine_local,
+           const Coefficients::TensorCoefficient<dim> *c, int device, bool output, double &ms_vs_fine,
+           double &coarse_vs_fine)
+{
+  DiffusionProblem::DiffusionProblem<dim> coarse(n_refine, device);
+  coarse.set_coefficient(c);
+  coarse.set_output(output);
+  coarse.run();
+  DiffusionProblem::DiffusionProblem<dim> fine(n_refine + n_refine_local, device);
+  fine.set_coefficient(c);
+  fine.set_output(output);
+  fine.run();
+
+  const unsigned        nl = 1u << n_refine_local, npl = nl + 1, nc = 1u << n_refine, npz = dim == 3 ? npl : 1;
+  std::vector<uint32_t> ldof;
+  std::vector<double>   ums;
+  double                num = 0.0, den = 0.0, num_c = 0.0, den_c = 0.0;
+  for (auto &kv : ms.get_cell_basis_map())
+    {
+      const std::uint64_t m      = kv.first.morton();
+      unsigned            idx[3] = {0, 0, 0};
+      for (unsigned b = 0; b < n_refine; ++b)
+        for (unsigned a = 0; a < (unsigned)dim; ++a)
+          idx[a] |= unsigned((m >> (dim * b + a)) & 1u) << b;
+      if (ldof.empty())
+        kv.second.get_dof_map(ldof);
+      kv.second.get_global_solution(ums);
+      for (unsigned jz = 0; jz < npz; ++jz)
+        for (unsigned jy = 0; jy < npl; ++jy)
+          for (unsigned jx = 0; jx < npl; ++jx)
+            {
+              const double uf = fine.value_at_vertex(idx[0] * nl + jx, idx[1] * nl + jy, idx[2] * nl + jz);
+              const double d  = ums[ldof[(std::size_t(jz) * npl + jy) * npl + jx]] - uf;
+              num += d * d, den += uf * uf;
+            }
+    }
+  for (unsigned jz = 0; jz <= (dim == 3 ? nc : 0); ++jz)
+    for (unsigned jy = 0; jy <= nc; ++jy)
+      for (unsigned jx = 0; jx <= nc; ++jx)
+        {
+          const double uf = fine.value_at_vertex(jx * nl, jy * nl, jz * nl);
+          const double d  = coarse.value_at_vertex(jx, jy, jz) - uf;
+          num_c += d * d, den_c += uf * uf;
+        }
+  ms_vs_fine     = std::sqrt(num / den);
+  coarse_vs_fine = std::sqrt(num_c / den_c);
+  std::cout << "   MsFEM reconstruction vs fine standard FEM (" << (nc * nl) << "^" << dim
+            << " cells), relative l2 over all fine vertices: " << ms_vs_fine << std::endl
+            << "   coarse standard FEM vs fine standard FEM, relative l2 over the coarse vertices: "
+            << coarse_vs_fine << std::endl;
+}
+
 int
 main(int argc, char *argv[])
 {
@@ -83,12 +140,16 @@ main(int argc, char *argv[])
       if (dim == 3)
         {
           // main.cxx:52-54 (MatrixCoeff<3> is the only coefficient the reference has in 3D)
-          if (coeff != "reference" || truth)
-            throw std::runtime_error("--dim 3 supports --coeff reference only, and no --truth run");
+          if (coeff != "reference")
+            throw std::runtime_error("--dim 3 supports --coeff reference only");
           DiffusionProblem::DiffusionProblemMultiscale<3> diffusion_ms_problem_3d(n_refine, n_refine_local, device,
                                                                                   gpus);
           diffusion_ms_problem_3d.set_output(output);
           diffusion_ms_problem_3d.run();
+          double ms_vs_fine = -1.0, coarse_vs_fine = -1.0;
+          if (truth) // main.cxx:44-50
+            truth_runs<3>(diffusion_ms_problem_3d, n_refine, n_refine_local, nullptr, device, output, ms_vs_fine,
+                          coarse_vs_fine);
           if (!dump.empty())
             {
               std::ofstream f(dump.c_str());
@@ -98,6 +159,8 @@ main(int argc, char *argv[])
               for (double v : u)
                 f << v << "\n";
               f << "basis_seconds " << diffusion_ms_problem_3d.basis_seconds() << "\n";
+              if (truth)
+                f << "ms_vs_fine_rel_l2 " << ms_vs_fine << "\ncoarse_vs_fine_rel_l2 " << coarse_vs_fine << "\n";
             }
           return 0;
         }
@@ -110,52 +173,8 @@ main(int argc, char *argv[])
       double ms_vs_fine = -1.0, coarse_vs_fine = -1.0;
       if (truth)
         {
-          // main.cxx:29-35: the standard problem on the coarse and on the fine mesh
-          DiffusionProblem::DiffusionProblem<2> diffusion_problem_2d_coarse(n_refine, device);
-          diffusion_problem_2d_coarse.set_coefficient(c.get());
-          diffusion_problem_2d_coarse.set_output(output);
-          diffusion_problem_2d_coarse.run();
-          DiffusionProblem::DiffusionProblem<2> diffusion_problem_2d_fine(n_refine + n_refine_local, device);
-          diffusion_problem_2d_fine.set_coefficient(c.get());
-          diffusion_problem_2d_fine.set_output(output);
-          diffusion_problem_2d_fine.run();
-
-          // MsFEM reconstruction u_ms = sum_i w_i phi_i on every coarse cell against the fine FEM
-          // solution at the same vertices (relative l2 over all (cell, vertex) pairs)
-          const unsigned        nl = 1u << n_refine_local, npl = nl + 1, nc = 1u << n_refine;
-          std::vector<uint32_t> ldof;
-          std::vector<double>   ums;
-          double                num = 0.0, den = 0.0, num_c = 0.0, den_c = 0.0;
-          for (auto &kv : diffusion_ms_problem_2d.get_cell_basis_map())
-            {
-              const std::uint64_t m = kv.first.morton();
-              unsigned            ix = 0, iy = 0;
-              for (unsigned b = 0; b < n_refine; ++b)
-                ix |= unsigned((m >> (2 * b)) & 1u) << b, iy |= unsigned((m >> (2 * b + 1)) & 1u) << b;
-              if (ldof.empty())
-                kv.second.get_dof_map(ldof);
-              kv.second.get_global_solution(ums);
-              for (unsigned jy = 0; jy < npl; ++jy)
-                for (unsigned jx = 0; jx < npl; ++jx)
-                  {
-                    const double uf = diffusion_problem_2d_fine.value_at_vertex(ix * nl + jx, iy * nl + jy);
-                    const double d  = ums[ldof[jy * npl + jx]] - uf;
-                    num += d * d, den += uf * uf;
-                  }
-            }
-          for (unsigned jy = 0; jy <= nc; ++jy)
-            for (unsigned jx = 0; jx <= nc; ++jx)
-              {
-                const double uf = diffusion_problem_2d_fine.value_at_vertex(jx * nl, jy * nl);
-                const double d  = diffusion_problem_2d_coarse.value_at_vertex(jx, jy) - uf;
-                num_c += d * d, den_c += uf * uf;
-              }
-          ms_vs_fine     = std::sqrt(num / den);
-          coarse_vs_fine = std::sqrt(num_c / den_c);
-          std::cout << "   MsFEM reconstruction vs fine standard FEM (" << (nc * nl) << " x " << (nc * nl)
-                    << " cells), relative l2 over all fine vertices: " << ms_vs_fine << std::endl
-                    << "   coarse standard FEM vs fine standard FEM, relative l2 over the coarse vertices: "
-                    << coarse_vs_fine << std::endl;
+          truth_runs<2>(diffusion_ms_problem_2d, n_refine, n_refine_local, c.get(), device, output, ms_vs_fine,
+                        coarse_vs_fine);
         }
 
       if (!dump.empty())

@@ -293,3 +293,18 @@ def test_cpp_driver_3d_coarse_solution(oracle, tmp_path, r, l):
     assert os.path.exists(tmp_path / ("solution-ms_coarse-3d_refinements-%d.0000.vtu" % r))
     assert os.path.exists(tmp_path / "solution-ms_fine-3d.pvtu")
     assert len([f for f in os.listdir(tmp_path) if f.startswith("solution-ms_fine-3d.")]) == 8 ** r + 1
+
+
+def test_cpp_truth_run_3d(tmp_path):
+    """main.cxx:44-50: the 3D standard problems (DiffusionProblem<3>, 27-point operator through the C ABI)
+    next to the 3D multiscale problem; MsFEM must beat the coarse standard FEM against the fine one."""
+    exe = os.path.join(ROOT, "host", "_build", "msfem_main")
+    dump = str(tmp_path / "truth3d.txt")
+    out = subprocess.run([exe, "--dim", "3", "--n-refine", "2", "--n-refine-local", "3", "--truth", "--dump", dump],
+                         cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert "Solving >> STANDARD << problem in 3D." in out.stdout
+    vals = dict(ln.split() for ln in open(dump).read().split("\n") if ln and ln[0].isalpha())
+    ms_err, coarse_err = float(vals["ms_vs_fine_rel_l2"]), float(vals["coarse_vs_fine_rel_l2"])
+    assert ms_err < 0.05, ms_err
+    assert ms_err < coarse_err, (ms_err, coarse_err)

@@ -1077,6 +1077,98 @@ namespace msb
         }
     }
 
+    // All coarse levels l >= l0 in ONE kernel, one CTA per cell, the level vectors of the eight
+    // bases in shared memory: restrict level l0 from level l0-1 (global), down to the coarsest
+    // level, z_l = r_l / D_l + P z_{l+1} back up, write level l0 for the finer prolongations.
+    __global__ void __launch_bounds__(THREADS)
+    coarse_fused3_kernel(Params3 P, int l0, int rpar)
+    {
+      extern __shared__ double sv[]; // [(level l0..L)][8][npl^3], level offset 8 * (off[l] - off[l0])
+      const int cell = blockIdx.x;
+      __shared__ int sdone[NB];
+      if (cell_done(P, cell, rpar, sdone))
+        return;
+      const int L = P.L.levels, tot = NB * (P.L.off[L + 1] - P.L.off[l0]);
+      for (int i = threadIdx.x; i < tot; i += THREADS)
+        sv[i] = 0.0;
+      __syncthreads();
+      // full weighting of one coarse node from a finer level
+      auto fw = [](const double *src, int npf, int cx, int cy, int cz) {
+        double pl[3];
+#pragma unroll
+        for (int az = -1; az <= 1; ++az)
+          {
+            double row[3];
+#pragma unroll
+            for (int ay = -1; ay <= 1; ++ay)
+              {
+                const double *q = src + ((size_t)(2 * cz + az) * npf + (2 * cy + ay)) * npf + 2 * cx;
+                row[ay + 1]     = fma(0.5, q[-1] + q[1], q[0]);
+              }
+            pl[az + 1] = fma(0.5, row[0] + row[2], row[1]);
+          }
+        return fma(0.5, pl[0] + pl[2], pl[1]);
+      };
+      {
+        const int    npl = P.L.npl[l0], nin = npl - 2, npf = P.L.npl[l0 - 1], n3 = npl * npl * npl;
+        const size_t Nf  = (size_t)npf * npf * npf;
+        for (int t = threadIdx.x; t < NB * nin * nin * nin; t += THREADS)
+          {
+            const int k = t / (nin * nin * nin), u = t % (nin * nin * nin);
+            if (sdone[k])
+              continue;
+            const int     cx = 1 + u % nin, cy = 1 + (u / nin) % nin, cz = 1 + u / (nin * nin);
+            const double *src = l0 == 1 ? P.r + ((size_t)cell * NB + k) * Nf :
+                                          P.v + ((size_t)cell * NB + k) * P.L.cn + P.L.off[l0 - 1];
+            sv[k * n3 + (cz * npl + cy) * npl + cx] = fw(src, npf, cx, cy, cz);
+          }
+      }
+      __syncthreads();
+      for (int l = l0 + 1; l <= L; ++l)
+        {
+          const int     npl = P.L.npl[l], nin = npl - 2, npf = P.L.npl[l - 1], n3 = npl * npl * npl;
+          double       *dst = sv + NB * (P.L.off[l] - P.L.off[l0]);
+          const double *srl = sv + NB * (P.L.off[l - 1] - P.L.off[l0]);
+          for (int t = threadIdx.x; t < NB * nin * nin * nin; t += THREADS)
+            {
+              const int k = t / (nin * nin * nin), u = t % (nin * nin * nin);
+              const int cx = 1 + u % nin, cy = 1 + (u / nin) % nin, cz = 1 + u / (nin * nin);
+              dst[k * n3 + (cz * npl + cy) * npl + cx] = fw(srl + (size_t)k * npf * npf * npf, npf, cx, cy, cz);
+            }
+          __syncthreads();
+        }
+      for (int l = L; l >= l0; --l)
+        {
+          const int     npl = P.L.npl[l], nin = npl - 2, n3 = npl * npl * npl;
+          double       *vl  = sv + NB * (P.L.off[l] - P.L.off[l0]);
+          const double *di  = P.dinv + (size_t)cell * P.L.cn + P.L.off[l];
+          for (int t = threadIdx.x; t < NB * nin * nin * nin; t += THREADS)
+            {
+              const int k = t / (nin * nin * nin), u = t % (nin * nin * nin);
+              const int fx = 1 + u % nin, fy = 1 + (u / nin) % nin, fz = 1 + u / (nin * nin);
+              const int i  = (fz * npl + fy) * npl + fx;
+              double    v  = vl[k * n3 + i] * di[i];
+              if (l < L)
+                {
+                  const int npc = P.L.npl[l + 1];
+                  v += interp3(sv + NB * (P.L.off[l + 1] - P.L.off[l0]) + (size_t)k * npc * npc * npc, npc, fx, fy, fz);
+                }
+              vl[k * n3 + i] = v;
+            }
+          __syncthreads();
+        }
+      {
+        const int npl = P.L.npl[l0], nin = npl - 2, n3 = npl * npl * npl;
+        for (int t = threadIdx.x; t < NB * nin * nin * nin; t += THREADS)
+          {
+            const int k = t / (nin * nin * nin), u = t % (nin * nin * nin);
+            const int i = ((1 + u / (nin * nin)) * npl + 1 + (u / nin) % nin) * npl + 1 + u % nin;
+            if (!sdone[k])
+              P.v[((size_t)cell * NB + k) * P.L.cn + P.L.off[l0] + i] = sv[k * n3 + i];
+          }
+      }
+    }
+
     // fine level: z = r / D + P z_1 on interior rows; partial r.z into parity rpar
     __global__ void __launch_bounds__(THREADS)
     fine3_kernel(Params3 P, int rpar)
@@ -1453,15 +1545,31 @@ namespace msb
           galerkin_diag3_kernel<<<dim3(nin * nin * nin, nc), side * side * side >= 256 ? 256 : 64, 0, st>>>(Q, l);
         });
       }
+    // coarse levels l >= l0 run fused in one kernel when their vectors fit 64 KB of shared memory
+    int l0 = L.levels + 1;
+    while (l0 > 1 && sizeof(double) * NB * (size_t)(L.off[L.levels + 1] - L.off[l0 - 1]) <= 64 * 1024)
+      --l0;
+    if (s.variant == 4)
+      l0 = L.levels + 1; // unfused (comparison)
+    const size_t fused_smem = l0 <= L.levels ? sizeof(double) * NB * (size_t)(L.off[L.levels + 1] - L.off[l0]) : 0;
+    if (fused_smem)
+      TRY(cudaFuncSetAttribute(coarse_fused3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
     auto precondition = [&](int rpar) {
-      for (int l = 1; l <= L.levels; ++l)
+      for (int l = 1; l < l0 && l <= L.levels; ++l)
         {
           const int nin = L.npl[l] - 2, tot = nin * nin * nin;
           for_slices([&](const Params3 &Q, int nc) {
             restrict3_kernel<<<dim3((tot + THREADS - 1) / THREADS, nc), THREADS, 0, st>>>(Q, l, rpar);
           });
         }
-      for (int l = L.levels; l >= 1; --l)
+      if (fused_smem)
+        for (int c0 = 0; c0 < C; c0 += 65535)
+          {
+            const int nc = C - c0 < 65535 ? C - c0 : 65535;
+            coarse_fused3_kernel<<<nc, THREADS, fused_smem, st>>>(shifted(P, s, c0), l0, rpar);
+            ++*n_launches;
+          }
+      for (int l = (l0 <= L.levels ? l0 - 1 : L.levels); l >= 1; --l)
         {
           const int nin = L.npl[l] - 2, tot = nin * nin * nin;
           for_slices([&](const Params3 &Q, int nc) {

@@ -457,6 +457,102 @@ namespace msb
       }
   }
 
+  // All coarse levels l >= l0 in ONE kernel, one CTA per cell, the level vectors of the four bases
+  // in shared memory: restrict level l0 from level l0-1 (global), restrict down to the coarsest
+  // level, z_l = r_l / D_l + P z_{l+1} back up, write level l0 for the prolongation kernels of the
+  // finer levels.  Replaces 2 (L - l0 + 1) - 1 tiny launches per iteration, which dominate when a
+  // shard has few cells (the reference's default run: 64 cells).
+  __global__ void __launch_bounds__(STREAM_THREADS)
+  stream_coarse_fused_kernel(StreamParams P, int l0, int rpar)
+  {
+    extern __shared__ double sv[]; // [(level l0..L)][4][npl^2], level offset 4 * (off[l] - off[l0])
+    const int cell = blockIdx.x;
+    __shared__ int sdone[4];
+    if (cell_done(P, cell, rpar, sdone))
+      return;
+    const int L = P.L.levels, tot = 4 * (P.L.off[L + 1] - P.L.off[l0]);
+    for (int i = threadIdx.x; i < tot; i += STREAM_THREADS)
+      sv[i] = 0.0;
+    __syncthreads();
+    // level l0 from global memory
+    {
+      const int    npl = P.L.npl[l0], nin = npl - 2, npf = P.L.npl[l0 - 1];
+      const size_t Nf  = (size_t)npf * npf;
+      for (int t = threadIdx.x; t < nin * nin; t += STREAM_THREADS)
+        {
+          const int cx = 1 + t % nin, cy = 1 + t / nin;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            {
+              const double *src = l0 == 1 ? P.r + ((size_t)cell * 4 + k) * Nf :
+                                            P.v + ((size_t)cell * 4 + k) * P.L.cn + P.L.off[l0 - 1];
+              double row[3];
+#pragma unroll
+              for (int ay = -1; ay <= 1; ++ay)
+                {
+                  const double *q = src + (size_t)(2 * cy + ay) * npf + 2 * cx;
+                  row[ay + 1]     = fma(0.5, q[-1] + q[1], q[0]);
+                }
+              sv[k * npl * npl + cy * npl + cx] = fma(0.5, row[0] + row[2], row[1]);
+            }
+        }
+    }
+    __syncthreads();
+    // down: the same full weighting between shared-memory levels
+    for (int l = l0 + 1; l <= L; ++l)
+      {
+        const int     npl = P.L.npl[l], nin = npl - 2, npf = P.L.npl[l - 1];
+        double       *dst = sv + 4 * (P.L.off[l] - P.L.off[l0]);
+        const double *srl = sv + 4 * (P.L.off[l - 1] - P.L.off[l0]);
+        for (int t = threadIdx.x; t < 4 * nin * nin; t += STREAM_THREADS)
+          {
+            const int     k = t / (nin * nin), u = t % (nin * nin), cx = 1 + u % nin, cy = 1 + u / nin;
+            const double *src = srl + k * npf * npf;
+            double        row[3];
+#pragma unroll
+            for (int ay = -1; ay <= 1; ++ay)
+              {
+                const double *q = src + (2 * cy + ay) * npf + 2 * cx;
+                row[ay + 1]     = fma(0.5, q[-1] + q[1], q[0]);
+              }
+            dst[k * npl * npl + cy * npl + cx] = fma(0.5, row[0] + row[2], row[1]);
+          }
+        __syncthreads();
+      }
+    // up: z_l = r_l / D_l + P z_{l+1}, in place
+    for (int l = L; l >= l0; --l)
+      {
+        const int     npl = P.L.npl[l], nin = npl - 2;
+        double       *vl  = sv + 4 * (P.L.off[l] - P.L.off[l0]);
+        const double *di  = P.dinv + (size_t)cell * P.L.cn + P.L.off[l];
+        for (int t = threadIdx.x; t < 4 * nin * nin; t += STREAM_THREADS)
+          {
+            const int k = t / (nin * nin), u = t % (nin * nin), fx = 1 + u % nin, fy = 1 + u / nin;
+            const int i = fy * npl + fx;
+            double    v = vl[k * npl * npl + i] * di[i];
+            if (l < L)
+              {
+                const int     npc = P.L.npl[l + 1];
+                const double *vc  = sv + 4 * (P.L.off[l + 1] - P.L.off[l0]) + k * npc * npc;
+                const int     xl = fx >> 1, xh = (fx + 1) >> 1, yl = fy >> 1, yh = (fy + 1) >> 1;
+                v += 0.25 * ((vc[yl * npc + xl] + vc[yl * npc + xh]) + (vc[yh * npc + xl] + vc[yh * npc + xh]));
+              }
+            vl[k * npl * npl + i] = v;
+          }
+        __syncthreads();
+      }
+    // level l0 back to global memory (boundary entries stay zero)
+    {
+      const int npl = P.L.npl[l0], nin = npl - 2;
+      for (int t = threadIdx.x; t < 4 * nin * nin; t += STREAM_THREADS)
+        {
+          const int k = t / (nin * nin), u = t % (nin * nin), i = (1 + u / nin) * npl + 1 + u % nin;
+          if (!sdone[k])
+            P.v[((size_t)cell * 4 + k) * P.L.cn + P.L.off[l0] + i] = sv[k * npl * npl + i];
+        }
+    }
+  }
+
   // fine level: z = r / D + P z_1 on interior rows; partial r.z into parity `rpar`
   __global__ void __launch_bounds__(STREAM_THREADS)
   stream_fine_kernel(StreamParams P, int rpar)
@@ -665,9 +761,19 @@ namespace msb
           ++*n_launches;
         }
     };
+    // coarse levels l >= l0 run fused in one kernel when their vectors fit 64 KB of shared memory
+    int l0 = L.levels + 1;
+    while (l0 > 1 && sizeof(double) * 4 * (size_t)(L.off[L.levels + 1] - L.off[l0 - 1]) <= 64 * 1024)
+      --l0;
+    if (s.variant == 1)
+      l0 = L.levels + 1; // unfused (comparison)
+    const size_t fused_smem = l0 <= L.levels ? sizeof(double) * 4 * (size_t)(L.off[L.levels + 1] - L.off[l0]) : 0;
+    if (fused_smem)
+      TRY(cudaFuncSetAttribute(stream_coarse_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)fused_smem));
     // z = M^-1 r and r.z for the residual whose r.r partials sit in parity `rpar`
     auto precondition = [&](int rpar) {
-      for (int l = 1; l <= L.levels; ++l)
+      for (int l = 1; l < l0 && l <= L.levels; ++l)
         {
           const int nin = L.npl[l] - 2;
           for_slices([&](const StreamParams &Q, int nc) {
@@ -675,7 +781,14 @@ namespace msb
                                      STREAM_THREADS, 0, st>>>(Q, l, rpar);
           });
         }
-      for (int l = L.levels; l >= 1; --l)
+      if (fused_smem)
+        for (int c0 = 0; c0 < C; c0 += 65535)
+          {
+            const int nc = C - c0 < 65535 ? C - c0 : 65535;
+            stream_coarse_fused_kernel<<<nc, STREAM_THREADS, fused_smem, st>>>(shifted(P, s, c0), l0, rpar);
+            ++*n_launches;
+          }
+      for (int l = (l0 <= L.levels ? l0 - 1 : L.levels); l >= 1; --l)
         {
           const int nin = L.npl[l] - 2;
           for_slices([&](const StreamParams &Q, int nc) {

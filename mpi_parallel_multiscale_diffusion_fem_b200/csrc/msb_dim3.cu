@@ -1080,6 +1080,10 @@ namespace msb
     // All coarse levels l >= l0 in ONE kernel, one CTA per cell, the level vectors of the eight
     // bases in shared memory: restrict level l0 from level l0-1 (global), down to the coarsest
     // level, z_l = r_l / D_l + P z_{l+1} back up, write level l0 for the finer prolongations.
+    // FINE (only with l0 = 1): the CTA also applies the fine level z = r / D + P z_1 to its whole
+    // cell straight from the shared-memory level-1 vector (the residual it restricted a moment ago
+    // is still in L2) and produces the r.z partial, replacing fine3_kernel.
+    template <bool FINE>
     __global__ void __launch_bounds__(THREADS)
     coarse_fused3_kernel(Params3 P, int l0, int rpar)
     {
@@ -1157,16 +1161,63 @@ namespace msb
             }
           __syncthreads();
         }
-      {
-        const int npl = P.L.npl[l0], nin = npl - 2, n3 = npl * npl * npl;
-        for (int t = threadIdx.x; t < NB * nin * nin * nin; t += THREADS)
-          {
-            const int k = t / (nin * nin * nin), u = t % (nin * nin * nin);
-            const int i = ((1 + u / (nin * nin)) * npl + 1 + (u / nin) % nin) * npl + 1 + u % nin;
+      if (!FINE)
+        {
+          const int npl = P.L.npl[l0], nin = npl - 2, n3 = npl * npl * npl;
+          for (int t = threadIdx.x; t < NB * nin * nin * nin; t += THREADS)
+            {
+              const int k = t / (nin * nin * nin), u = t % (nin * nin * nin);
+              const int i = ((1 + u / (nin * nin)) * npl + 1 + (u / nin) % nin) * npl + 1 + u % nin;
+              if (!sdone[k])
+                P.v[((size_t)cell * NB + k) * P.L.cn + P.L.off[l0] + i] = sv[k * n3 + i];
+            }
+          return;
+        }
+      // fine level for the whole cell
+      const int     n = P.n, np = n + 1, N = np * np * np, np1 = P.L.npl[1], n13 = np1 * np1 * np1;
+      const double *KC = P.sten + (size_t)cell * NST * N;
+      double        acc[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        acc[k] = 0.0;
+      for (int t = threadIdx.x; t < N; t += THREADS)
+        {
+          int jx, jy, jz;
+          decode3(t, np, jx, jy, jz);
+          if (on_boundary3(jx, jy, jz, n))
+            continue;
+          const double kc = KC[t];
+          double       rv[NB];
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            rv[k] = P.r[((size_t)cell * NB + k) * N + t];
+          const double dinv = 1.0 / kc;
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            {
+              if (sdone[k])
+                continue;
+              const double zv = fma(rv[k], dinv, interp3(sv + (size_t)k * n13, np1, jx, jy, jz));
+              P.z[((size_t)cell * NB + k) * N + t] = zv;
+              acc[k]                               = fma(rv[k], zv, acc[k]);
+            }
+        }
+      __shared__ double sbuf[(THREADS / 32) * NB];
+      block_sum_to<NB>(acc, sbuf);
+      if (threadIdx.x < NB && !sdone[threadIdx.x])
+        {
+          // the single r.z partial of this solve; the other slots of the parity are cleared
+          double *pp = part_ptr(P.part, cell * NB + threadIdx.x, rpar, 0);
+          for (int b = 1; b < P.nblk; ++b)
+            pp[b] = 0.0;
+        }
+      if (threadIdx.x == 0)
+        {
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
             if (!sdone[k])
-              P.v[((size_t)cell * NB + k) * P.L.cn + P.L.off[l0] + i] = sv[k * n3 + i];
-          }
-      }
+              part_ptr(P.part, cell * NB + k, rpar, 0)[0] = acc[k];
+        }
     }
 
     // fine level: z = r / D + P z_1 on interior rows; partial r.z into parity rpar
@@ -1552,8 +1603,16 @@ namespace msb
     if (s.variant == 4)
       l0 = L.levels + 1; // unfused (comparison)
     const size_t fused_smem = l0 <= L.levels ? sizeof(double) * NB * (size_t)(L.off[L.levels + 1] - L.off[l0]) : 0;
+    // with every coarse level fused and enough cells to fill the GPU, the fused CTA also does the
+    // fine level of its cell
+    const bool fused_fine = fused_smem && l0 == 1 && C >= 296 && s.variant != 5;
     if (fused_smem)
-      TRY(cudaFuncSetAttribute(coarse_fused3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+      {
+        TRY(cudaFuncSetAttribute(coarse_fused3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)fused_smem));
+        TRY(cudaFuncSetAttribute(coarse_fused3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)fused_smem));
+      }
     auto precondition = [&](int rpar) {
       for (int l = 1; l < l0 && l <= L.levels; ++l)
         {
@@ -1566,9 +1625,14 @@ namespace msb
         for (int c0 = 0; c0 < C; c0 += 65535)
           {
             const int nc = C - c0 < 65535 ? C - c0 : 65535;
-            coarse_fused3_kernel<<<nc, THREADS, fused_smem, st>>>(shifted(P, s, c0), l0, rpar);
+            if (fused_fine)
+              coarse_fused3_kernel<true><<<nc, THREADS, fused_smem, st>>>(shifted(P, s, c0), l0, rpar);
+            else
+              coarse_fused3_kernel<false><<<nc, THREADS, fused_smem, st>>>(shifted(P, s, c0), l0, rpar);
             ++*n_launches;
           }
+      if (fused_fine)
+        return;
       for (int l = (l0 <= L.levels ? l0 - 1 : L.levels); l >= 1; --l)
         {
           const int nin = L.npl[l] - 2, tot = nin * nin * nin;

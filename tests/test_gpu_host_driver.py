@@ -13,6 +13,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PI_D = 3.14592653509793218403
 
 
+def _exe(name):
+    """Path of a host program; built on demand (the C++ mirror links the CUDA library's C ABI only)."""
+    exe = os.path.join(ROOT, "host", "_build", name)
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host")])
+    return exe
+
+
 def _coarse_reference(oracle, r, l, co):
     """Coarse system from oracle (M, b): first-touch coarse DoFs, Dirichlet on x=0 / y=0
     ((x-.5)^2+(y-.5)^2, dirichlet_bc.tpp:22), Neumann cos(2 PI_D x) cos(2 PI_D y) on x=1 / y=1
@@ -80,9 +88,7 @@ def _coarse_reference(oracle, r, l, co):
     (4, 6, "inclusions", 2, (2.0 ** -11, 0.2, 1e4, 1.0), 1234),
 ])
 def test_cpp_driver_coarse_solution(oracle, tmp_path, r, l, coeff, kind, par, seed):
-    exe = os.path.join(ROOT, "host", "_build", "msfem_main")
-    if not os.path.exists(exe):
-        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host")])
+    exe = _exe("msfem_main")
     dump = str(tmp_path / "coarse.txt")
     out = subprocess.run([exe, "--n-refine", str(r), "--n-refine-local", str(l), "--coeff", coeff,
                           "--dump", dump, "--output"], cwd=str(tmp_path), capture_output=True, text=True)
@@ -104,7 +110,7 @@ def test_cpp_driver_coarse_solution(oracle, tmp_path, r, l, coeff, kind, par, se
 def test_cpp_driver_reports_no_convergence_like_the_reference(tmp_path):
     """A failed local solve surfaces as an exception caught in main -> exit code 1
     (main.cxx:57-81)."""
-    exe = os.path.join(ROOT, "host", "_build", "msfem_main")
+    exe = _exe("msfem_main")
     out = subprocess.run([exe, "--coeff", "nonsense"], cwd=str(tmp_path), capture_output=True, text=True)
     assert out.returncode == 1 and "Exception on processing" in out.stderr
 
@@ -116,7 +122,7 @@ def test_cpp_driver_on_two_gpus_matches_one_gpu(tmp_path):
     lib = ctypes.CDLL(os.path.join(ROOT, "mpi_parallel_multiscale_diffusion_fem_b200", "libmsfem_basis.so"))
     if lib.msb_device_count() < 2:
         pytest.skip("needs two GPUs")
-    exe = os.path.join(ROOT, "host", "_build", "msfem_main")
+    exe = _exe("msfem_main")
     sols = []
     for gpus in (1, 2):
         dump = str(tmp_path / ("coarse%d.txt" % gpus))
@@ -132,9 +138,7 @@ def test_cpp_driver_on_two_gpus_matches_one_gpu(tmp_path):
 def test_cpp_basis3d_matches_oracle(oracle, tmp_path):
     """The dim = 3 basis stage through the C++ mirror (DiffusionProblemBasis<3>::run_all):
     element matrices and right-hand sides of all 8 coarse hexes against the oracle."""
-    exe = os.path.join(ROOT, "host", "_build", "msfem_basis3d")
-    if not os.path.exists(exe):
-        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host")])
+    exe = _exe("msfem_basis3d")
     dump = tmp_path / "mb3d.txt"
     out = subprocess.run([exe, "--n-refine", "1", "--n-refine-local", "3", "--dump", str(dump)],
                          capture_output=True, text=True, timeout=600)
@@ -158,7 +162,7 @@ def test_cpp_truth_run_and_msfem_error(oracle, tmp_path):
     standard FEM is (the point of the method)."""
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
-    exe = os.path.join(ROOT, "host", "_build", "msfem_main")
+    exe = _exe("msfem_main")
     r, l = 2, 4                                   # 4x4 coarse cells x 16x16 fine cells = 64x64 mesh
     dump = str(tmp_path / "truth.txt")
     out = subprocess.run([exe, "--n-refine", str(r), "--n-refine-local", str(l), "--truth", "--output",
@@ -279,7 +283,7 @@ def _coarse_reference_3d(oracle, r, l, co):
 @pytest.mark.parametrize("r,l", [(1, 3), (2, 2)])
 def test_cpp_driver_3d_coarse_solution(oracle, tmp_path, r, l):
     """main.cxx:42-55 (the 3D block) through the C++ mirror: final coarse solution within 1e-8."""
-    exe = os.path.join(ROOT, "host", "_build", "msfem_main")
+    exe = _exe("msfem_main")
     dump = str(tmp_path / "coarse3d.txt")
     out = subprocess.run([exe, "--dim", "3", "--n-refine", str(r), "--n-refine-local", str(l), "--dump", dump,
                           "--output"], cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
@@ -298,7 +302,7 @@ def test_cpp_driver_3d_coarse_solution(oracle, tmp_path, r, l):
 def test_cpp_truth_run_3d(tmp_path):
     """main.cxx:44-50: the 3D standard problems (DiffusionProblem<3>, 27-point operator through the C ABI)
     next to the 3D multiscale problem; MsFEM must beat the coarse standard FEM against the fine one."""
-    exe = os.path.join(ROOT, "host", "_build", "msfem_main")
+    exe = _exe("msfem_main")
     dump = str(tmp_path / "truth3d.txt")
     out = subprocess.run([exe, "--dim", "3", "--n-refine", "2", "--n-refine-local", "3", "--truth", "--dump", dump],
                          cwd=str(tmp_path), capture_output=True, text=True, timeout=900)

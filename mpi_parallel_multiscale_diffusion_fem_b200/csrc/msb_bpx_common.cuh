@@ -323,10 +323,85 @@ namespace msb
     };
 
     // mark(i): optional stage-timer hook (a no-op lambda in production builds).
-    // RPT > 0: sU holds the pre-summed strips of Presum<NL,NRHS,RPT>; RPT == 0: sU holds u itself.
-    template <int NL, int NRHS, int THREADS, int RPT, class DiT, class Mark>
+    // How the 49 x 49 inverse is spread over threads for the matvec: row r = tid / PARTS, the
+    // columns of a row in PARTS contiguous pieces of CH entries, fetched in NCHK chunks of 8.
+    template <int THREADS>
+    struct Exact7
+    {
+      // measured: one thread per row (PARTS = 1, warps 0-1) beats splitting rows over 2 or 4 lanes
+      // (more warps executing the chain costs more than the shorter chain saves)
+      static constexpr int PARTS = 1;
+      static constexpr int CH    = (49 + PARTS - 1) / PARTS; // entries per piece
+      static constexpr int NCHK  = (CH + 7) / 8;             // chunks of 8
+      static constexpr int WARPS = (49 * PARTS + 31) / 32;   // participating warps
+      // entry (chunk c, slot i) of thread tid: element [row][col] of the (symmetric) inverse
+      __device__ static __forceinline__ double
+      fetch(const double *Gi, int tid, int c, int i)
+      {
+        const int r = tid / PARTS, jl = 8 * c + i, j = (tid % PARTS) * CH + jl;
+        return (r < 49 && jl < CH && j < 49) ? Gi[j * 49 + r] : 0.0;
+      }
+    };
+
+    // Dense inverse of the Galerkin operator of the 7x7-unknown level (9-point stencil Gl on 9x9
+    // nodes, layout of Shard::d_sten), built in place in sGi[49][49] by a Gauss-Jordan sweep without
+    // pivoting (the operator is SPD).  With it the levels below 15x15 are solved EXACTLY instead of
+    // being diagonally scaled: the preconditioner becomes D^-1 + ... + P_7 A_7^-1 P_7^T, which
+    // removes the contrast dependence of the coarse part (cfg4: 67 -> 38 iterations).
+    template <int THREADS>
     __device__ __forceinline__ void
-    coarse_correction(const double *sU, double *sV, const DiT *sDi, int tid, int warp, int lane, Mark &&mark)
+    exact7_build(const double *Gl, double *sGi, int tid)
+    {
+      for (int t = tid; t < 49 * 49; t += THREADS)
+        sGi[t] = 0.0;
+      __syncthreads();
+      if (tid < 49)
+        {
+          const int X = 1 + tid % 7, Y = 1 + tid / 7;
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx)
+              {
+                const int bx = X + dx, by = Y + dy;
+                if (bx >= 1 && bx <= 7 && by >= 1 && by <= 7)
+                  sGi[tid * 49 + (by - 1) * 7 + bx - 1] = sten_get(Gl, 9, 81, X, Y, dx, dy);
+              }
+        }
+      __syncthreads();
+#pragma unroll 1
+      for (int k = 0; k < 49; ++k)
+        {
+          const double piv = 1.0 / sGi[k * 49 + k];
+          for (int t = tid; t < 49 * 49; t += THREADS)
+            {
+              const int i = t / 49, j = t - 49 * i;
+              if (i != k && j != k)
+                sGi[t] = fma(-sGi[i * 49 + k] * piv, sGi[k * 49 + j], sGi[t]);
+            }
+          __syncthreads();
+          if (tid < 49)
+            {
+              if (tid != k)
+                {
+                  sGi[k * 49 + tid] *= piv;
+                  sGi[tid * 49 + k] *= -piv;
+                }
+              else
+                sGi[k * 49 + k] = piv;
+            }
+          __syncthreads();
+        }
+    }
+
+    // RPT > 0: sU holds the pre-summed strips of Presum<NL,NRHS,RPT>; RPT == 0: sU holds u itself.
+    // EXACT7: gi(c, g) delivers rows 8c..8c+7 of column tid of the inverse built by exact7_build
+    // (from shared memory or from tensor memory; called by all lanes of warps 0-1); the 3x3 and
+    // 1x1 levels are not used.
+    template <int NL, int NRHS, int THREADS, int RPT, bool EXACT7 = false, class DiT, class Mark, class GiChunk = int>
+    __device__ __forceinline__ void
+    coarse_correction(const double *sU, double *sV, const DiT *sDi, int tid, int warp, int lane, Mark &&mark,
+                      GiChunk &&gi = 0)
     {
       using L             = Levels<NL>;
       constexpr int NWARP = THREADS / 32;
@@ -466,6 +541,78 @@ namespace msb
           double       *V3  = sV + (size_t)NRHS * L::lvl_off(B + 3); // 3x3 nodes
           const DiT *DB  = sDi + L::lvl_off(B), *D1 = sDi + L::lvl_off(B + 1);
           const DiT *D2  = sDi + L::lvl_off(B + 2), *D3 = sDi + L::lvl_off(B + 3);
+          if constexpr (EXACT7)
+            {
+              // r_7 = P^T r_15 by 49 threads, then t_7 = A_7^-1 r_7 with every row of the dense
+              // inverse split over X7::PARTS neighbouring lanes (row = tid / PARTS); the phases are
+              // fenced by a named barrier over the X7::WARPS participating warps only
+              using X = Exact7<THREADS>;
+              static_assert(32 * X::WARPS <= THREADS, "not enough threads for the exact coarse solve");
+              if (warp < X::WARPS)
+                {
+                  if (tid < 49)
+                    {
+                      const int cx = 1 + tid % 7, cy = 1 + tid / 7;
+                      double    row[3][NRHS], o[NRHS];
+#pragma unroll
+                      for (int ay = -1; ay <= 1; ++ay)
+                        {
+                          double a[NRHS], b[NRHS], c[NRHS];
+                          ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx - 1, a);
+                          ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx, b);
+                          ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx + 1, c);
+#pragma unroll
+                          for (int k = 0; k < NRHS; ++k)
+                            row[ay + 1][k] = fma(0.5, a[k] + c[k], b[k]);
+                        }
+#pragma unroll
+                      for (int k = 0; k < NRHS; ++k)
+                        o[k] = fma(0.5, row[0][k] + row[2][k], row[1][k]);
+                      stv<NRHS>(V1, cy * 9 + cx, o);
+                    }
+                  asm volatile("bar.sync 1, %0;" ::"n"(32 * X::WARPS) : "memory");
+                  const int r7 = tid / X::PARTS, q7 = tid % X::PARTS;
+                  double    acc0[NRHS], acc1[NRHS];
+#pragma unroll
+                  for (int k = 0; k < NRHS; ++k)
+                    acc0[k] = acc1[k] = 0.0;
+#pragma unroll
+                  for (int c = 0; c < X::NCHK; ++c)
+                    {
+                      double g[8];
+                      gi(c, g); // entries q7 * CH + 8c .. +7 of row r7 (zero where there is none)
+#pragma unroll
+                      for (int jj = 0; jj < 8; ++jj)
+                        {
+                          if (8 * c + jj >= X::CH)
+                            continue;
+                          const int j = min(48, q7 * X::CH + 8 * c + jj);
+                          double    u[NRHS];
+                          ldv<NRHS>(V1, (1 + j / 7) * 9 + 1 + j % 7, u);
+#pragma unroll
+                          for (int k = 0; k < NRHS; ++k)
+                            {
+                              if (jj & 1)
+                                acc1[k] = fma(g[jj], u[k], acc1[k]);
+                              else
+                                acc0[k] = fma(g[jj], u[k], acc0[k]);
+                            }
+                        }
+                    }
+#pragma unroll
+                  for (int k = 0; k < NRHS; ++k)
+                    {
+                      acc0[k] += acc1[k];
+#pragma unroll
+                      for (int off = 1; off < X::PARTS; off <<= 1)
+                        acc0[k] += __shfl_xor_sync(0xffffffffu, acc0[k], off);
+                    }
+                  asm volatile("bar.sync 1, %0;" ::"n"(32 * X::WARPS) : "memory");
+                  if (r7 < 49 && q7 == 0)
+                    stv<NRHS>(V1, (1 + r7 / 7) * 9 + 1 + r7 % 7, acc0);
+                }
+            }
+          else
           for (int task = warp; task < 12; task += NWARP)
             {
               if (task >= 10)
@@ -583,7 +730,7 @@ namespace msb
               for (int k = 0; k < NRHS; ++k)
                 v[k] *= di;
 #pragma unroll
-              for (int m = 1; m <= 3; ++m)
+              for (int m = 1; m <= (EXACT7 ? 1 : 3); ++m)
                 {
                   const int     R = 1 << m, npm = (16 >> m) + 1;
                   const double *Vm = m == 1 ? V1 : (m == 2 ? V2 : V3);

@@ -68,8 +68,11 @@ namespace msb
       }
       static constexpr int    CN  = lvl_off(NL); // total coarse nodes
       static constexpr int    RED = 3 * NRHS * NWARP;
+      // n = 32: the 7x7-unknown level is solved exactly with a dense inverse in shared memory
+      // (bpx::exact7_build); at n = 64 shared memory is full and n <= 16 has no such level
+      static constexpr bool   EXACT7 = NL == 5;
       static constexpr size_t smem_doubles =
-        4 * (size_t)n * n + 2 * (size_t)NRHS * N + (size_t)(NRHS + 1) * CN + 2 * RED + 8;
+        4 * (size_t)n * n + 2 * (size_t)NRHS * N + (size_t)(NRHS + 1) * CN + 2 * RED + 8 + (EXACT7 ? 49 * 49 : 0);
       static_assert(NWARP % WX == 0, "warp grid");
       static_assert(5 * CN <= 2 * NRHS * N, "Galerkin scratch must fit the p/u buffers");
     };
@@ -95,6 +98,7 @@ namespace msb
       double *sV   = sU + (size_t)NRHS * N;   // [CN][NRHS] coarse residuals / corrections
       double *sDi  = sV + (size_t)NRHS * CN;  // [CN] 1 / Galerkin diagonal
       double *sRed = sDi + CN;                // 2 reduction buffers
+      double *sGi  = sRed + 2 * C::RED + 8;   // [49][49] inverse of the 7x7-level operator (EXACT7)
 
       const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
       const int cell = blockIdx.x; // one CTA per coarse cell; its 4/NRHS groups of bases run in turn
@@ -147,6 +151,8 @@ namespace msb
             goff += 5 * Nl;
           }
       }
+      if constexpr (C::EXACT7)
+        exact7_build<THREADS>(sP + 5 * C::lvl_off(C::LW + 1), sGi, tid);
       // (b) s = d^-1/2 on every node into the u buffer (p buffer still holds the hierarchy,
       //     which is dead from here on)
       double *sS = sU;
@@ -256,10 +262,17 @@ namespace msb
         __syncthreads();
         ST_MARK(4)
         ST_MARK(5)
-        coarse_correction<NL, NRHS, THREADS, PRESUM_RPT>(sU, sV, sDi, tid, warp, lane, [&](int st_k) {
-          (void)st_k;
-          ST_MARK(st_k)
-        });
+        coarse_correction<NL, NRHS, THREADS, PRESUM_RPT, C::EXACT7>(
+          sU, sV, sDi, tid, warp, lane,
+          [&](int st_k) {
+            (void)st_k;
+            ST_MARK(st_k)
+          },
+          [&](int c, double(&g)[8]) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              g[i] = Exact7<THREADS>::fetch(sGi, tid, c, i);
+          });
         ST_MARK(11)
         // level 0: zhat = rhat + D^1/2 (P z_1).  The strip of RPT fine rows (first row odd, RPT
         // even) lies under RPT/2+1 coarse rows: their horizontal averages are loaded once and kept

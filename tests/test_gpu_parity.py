@@ -401,3 +401,19 @@ def test_more_than_65535_cells_streamed_tier(msb, oracle):
         for k, c in enumerate(pick):
             assert _rel(M[c], ref["M"][k]) < TOL_MB
             assert _rel(b[c], ref["b"][k]) < TOL_MB
+
+
+def test_streamed_tier_fused_and_unfused_coarse_levels_agree(msb, oracle):
+    """variant 1 of the streamed tier runs one launch per coarse level instead of the fused kernel."""
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    cor = msb.coarse_corners(3, 10, 14)
+    with msb.BasisShard(7, cor, cd) as a, msb.BasisShard(7, cor, cd, variant=1) as b:
+        a.run(1e-12, 5000)
+        b.run(1e-12, 5000)
+        ia, _ = a.iteration_counts()
+        ib, _ = b.iteration_counts()
+        assert np.abs(ia - ib).max() <= 1
+        Ma, _ = a.element_matrices()
+        Mb, _ = b.element_matrices()
+        assert _rel(Ma, Mb) < 1e-10
+        assert a.run_stats()["launches"] < b.run_stats()["launches"]

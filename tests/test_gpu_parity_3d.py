@@ -202,3 +202,24 @@ def test_more_than_65535_cells_3d(msb, oracle):
         ref = oracle.run_cells3(1, cor[pick], oracle.coeff(oracle.COEFF_REFERENCE), keep_phi=False)
         for k, c in enumerate(pick):
             assert _rel(M[c], ref["M"][k]) < TOL_MB
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+def test_alternative_3d_kernels_agree_with_the_default(msb, oracle, variant):
+    """variant 1: untiled K2, 2: K2 at 3 CTAs/SM, 3: general trilinear assembly instead of the brick
+    tables, 4: one launch per coarse level instead of the fused kernel, 5: separate fine-level
+    kernel.  Same algorithm, so the same iteration counts and bases to rounding."""
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
+    cor = msb.coarse_corners3(3, 0, 320)          # >= 296 cells: the fused fine step is active
+    cd = coeff_desc(msb.COEFF_REFERENCE)
+    with msb.BasisShard(3, cor, cd, dim=3) as a, msb.BasisShard(3, cor, cd, dim=3, variant=variant) as b:
+        a.run()
+        b.run()
+        ia, _ = a.iteration_counts()
+        ib, _ = b.iteration_counts()
+        assert np.abs(ia - ib).max() <= 1
+        Ma, ba = a.element_matrices()
+        Mb, bb = b.element_matrices()
+        assert _rel(Ma, Mb) < 1e-10 and _rel(ba, bb) < 1e-10
+        for c in (0, 319):
+            assert _rel(a.basis(c, 5), b.basis(c, 5)) < 1e-10

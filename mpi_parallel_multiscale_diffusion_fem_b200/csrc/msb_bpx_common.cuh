@@ -47,7 +47,7 @@ namespace msb
   };
 
   // two right-hand sides per pass with tensor memory as spill space (msb_solve_bpx_tm.cu)
-  cudaError_t launch_solve_bpx_tm(const BpxParams &P, int threads, cudaStream_t st);
+  cudaError_t launch_solve_bpx_tm(const BpxParams &P, int threads, bool exact7, cudaStream_t st);
 
   namespace bpx
   {
@@ -328,9 +328,9 @@ namespace msb
     template <int THREADS>
     struct Exact7
     {
-      // measured: one thread per row (PARTS = 1, warps 0-1) beats splitting rows over 2 or 4 lanes
-      // (more warps executing the chain costs more than the shorter chain saves)
-      static constexpr int PARTS = 1;
+      // 128-thread kernels: one thread per row (measured: better than 2 lanes per row); 512 threads:
+      // 8 lanes per row, one chunk of 7 entries each, so the whole CTA shares the chain
+      static constexpr int PARTS = THREADS >= 512 ? 8 : (THREADS >= 256 ? 4 : 1);
       static constexpr int CH    = (49 + PARTS - 1) / PARTS; // entries per piece
       static constexpr int NCHK  = (CH + 7) / 8;             // chunks of 8
       static constexpr int WARPS = (49 * PARTS + 31) / 32;   // participating warps

@@ -591,12 +591,14 @@ namespace msb
           // default: two bases in flight per CTA, tensor memory as spill space (1.07M vs 0.89M
           // solves/s on the target configuration against one basis per pass)
           if (s.variant == 5)
-            return launch_solve_bpx_tm(P, 256, st);
+            return launch_solve_bpx_tm(P, 256, false, st);
+          if (s.variant == 7)
+            return launch_solve_bpx_tm(P, 512, true, st); // + exact 7x7 coarse solve (A/B)
           if (s.variant == 6)
             return bpx::launch_one<6, 1, 512>(P, st);
           if (s.variant == 1)
             return bpx::launch_one<6, 1, 256>(P, st);
-          return launch_solve_bpx_tm(P, 512, st);
+          return launch_solve_bpx_tm(P, 512, false, st);
         default:
           return cudaErrorInvalidValue;
       }

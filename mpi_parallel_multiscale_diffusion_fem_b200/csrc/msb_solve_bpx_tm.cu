@@ -161,17 +161,22 @@ namespace msb
       static constexpr int XOFF = 0, POFF = 2 * RPT * NRHS, SOFF = 4 * RPT * NRHS;
       static constexpr int TCOLS = SOFF + 2 * RPT;
       static constexpr int TMEM_COLS = 512;
+      // behind the per-warp column blocks: the dense inverse of the 7x7-level Galerkin operator,
+      // the Exact7<THREADS> pieces of its rows in the tensor-memory lanes of warps 0..WARPS-1
+      using X7 = Exact7<THREADS>;
+      static constexpr int MOFF = (NWARP / 4) * TCOLS, MCOLS = ((X7::WARPS + 3) / 4) * 16 * X7::NCHK;
       static constexpr int RED   = 4 * NWARP;
       static constexpr size_t smem_bytes =
         sizeof(double) * (4 * (size_t)n * n + (size_t)NRHS * N + (size_t)NRHS * CN + 2 * RED + 8) +
         sizeof(float) * (size_t)CN;
       static_assert(RPT % 4 == 0 && NWARP % WX == 0, "strip shape");
-      static_assert((NWARP / 4) * TCOLS <= TMEM_COLS, "tensor memory columns");
+      static_assert(MOFF + MCOLS <= TMEM_COLS, "tensor memory columns");
       static_assert(5 * CN <= NRHS * N, "Galerkin scratch must fit the vector buffer");
       static_assert(smem_bytes <= 232448, "shared memory");
     };
 
-    template <int THREADS>
+    // EXACT: the 7x7 coarse level is solved exactly (bpx::exact7_build, inverse in tensor memory)
+    template <int THREADS, bool EXACT>
     __global__ void __launch_bounds__(THREADS, 1)
     solve_bpx_tm_kernel(BpxParams P)
     {
@@ -254,6 +259,29 @@ namespace msb
             goff += 5 * Nl;
           }
       }
+      // (a') exact coarse solve: invert the 49 x 49 operator of the 7x7 level in the (still unused)
+      //      coefficient area and park it in tensor memory
+      using X7            = typename C::X7;
+      const uint32_t tmat = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
+                            (uint32_t)(C::MOFF + (warp >> 2) * 16 * X7::NCHK);
+      if constexpr (EXACT)
+        {
+          exact7_build<THREADS>(sP + 5 * L::lvl_off(L::LW + 1), sE, tid);
+          if (warp < X7::WARPS)
+            {
+#pragma unroll
+              for (int c = 0; c < X7::NCHK; ++c)
+                {
+                  double g[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    g[i] = X7::fetch(sE, tid, c, i);
+                  tmem_st8(tmat + 16 * c, g);
+                }
+              tmem_wait_st();
+            }
+          __syncthreads();
+        }
       // (b) s = d^-1/2 on every node (the hierarchy scratch is dead from here on)
       double *sS = sP;
       for (int i = tid; i < N; i += THREADS)
@@ -393,10 +421,19 @@ namespace msb
             }
             __syncthreads();
             ST_MARK(4)
-            coarse_correction<NL, NRHS, THREADS, RPT>(sP, sV, sDi, tid, warp, lane, [&](int st_k) {
-              (void)st_k;
-              ST_MARK(st_k)
-            });
+            if constexpr (EXACT)
+              coarse_correction<NL, NRHS, THREADS, RPT, true>(
+                sP, sV, sDi, tid, warp, lane,
+                [&](int st_k) {
+                  (void)st_k;
+                  ST_MARK(st_k)
+                },
+                [&](int c, double(&g)[8]) { tmem_ld8(tmat + 16 * c, g); });
+            else
+              coarse_correction<NL, NRHS, THREADS, RPT>(sP, sV, sDi, tid, warp, lane, [&](int st_k) {
+                (void)st_k;
+                ST_MARK(st_k)
+              });
             ST_MARK(11)
             // level 0: zhat = rhat + D^1/2 (P z_1), coarse-row averages cached in registers
             {
@@ -676,12 +713,12 @@ namespace msb
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS));
     }
 
-    template <int THREADS>
+    template <int THREADS, bool EXACT>
     static cudaError_t
     launch_tm(const BpxParams &P, cudaStream_t st)
     {
       using C           = TmCfg<THREADS>;
-      auto        kern  = solve_bpx_tm_kernel<THREADS>;
+      auto        kern  = solve_bpx_tm_kernel<THREADS, EXACT>;
       cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
       if (e != cudaSuccess)
@@ -693,8 +730,10 @@ namespace msb
 
   // variant 4: 512 threads (8 DoFs x 2 bases per thread); variant 5: 256 threads (16 x 2)
   cudaError_t
-  launch_solve_bpx_tm(const BpxParams &P, int threads, cudaStream_t st)
+  launch_solve_bpx_tm(const BpxParams &P, int threads, bool exact7, cudaStream_t st)
   {
-    return threads == 256 ? bpx::launch_tm<256>(P, st) : bpx::launch_tm<512>(P, st);
+    if (threads == 256)
+      return bpx::launch_tm<256, false>(P, st);
+    return exact7 ? bpx::launch_tm<512, true>(P, st) : bpx::launch_tm<512, false>(P, st);
   }
 } // namespace msb

@@ -326,14 +326,17 @@ def test_tensor_memory_kernel_matches_default_kernel(msb, oracle):
         Ma, ba = a.element_matrices()
         ita, _ = a.iteration_counts()
         pa = [a.basis(c, ib) for c in (0, 150, 299) for ib in range(4)]
-    for variant in (0, 5):
+    for variant in (0, 5, 7):
         with msb.BasisShard(6, cor, cd, variant=variant) as b:
             b.run(1e-12, 5000)
             Mb, bb = b.element_matrices()
             itb, resb = b.iteration_counts()
             pb = [b.basis(c, ib) for c in (0, 150, 299) for ib in range(4)]
         assert np.all(resb <= 1e-12)
-        assert np.abs(ita - itb).max() <= 1
+        if variant == 7:   # + exact solve of the 7x7 coarse level: a stronger preconditioner
+            assert (itb <= ita).all() and itb.mean() < ita.mean()
+        else:
+            assert np.abs(ita - itb).max() <= 1
         assert _rel(Mb, Ma) < 1e-10 and _rel(bb, ba) < 1e-10
         for x, y in zip(pa, pb):
             assert _rel(y, x) < 1e-10

@@ -68,61 +68,6 @@ msb_device_count(void)
   return n;
 }
 
-// BasisQ1<dim> coefficient matrix (basis_q1.tpp:26-47 for dim 2, :50-75 for dim 3): inverse of
-// the point matrix [1, x, y, xy] resp. [1, x, y, z, xy, yz, xz, xyz] at the vertices, by
-// Gauss-Jordan with partial pivoting.
-static bool
-basis_q1_matrix(int dim, const double *corners, double *coef)
-{
-  const int nb = 1 << dim;
-  double    a[8][16];
-  for (int i = 0; i < nb; ++i)
-    {
-      const double x = corners[dim * i], y = corners[dim * i + 1];
-      a[i][0] = 1.0, a[i][1] = x, a[i][2] = y;
-      if (dim == 2)
-        a[i][3] = x * y;
-      else
-        {
-          const double z = corners[dim * i + 2];
-          a[i][3] = z, a[i][4] = x * y, a[i][5] = y * z, a[i][6] = x * z, a[i][7] = x * y * z;
-        }
-      for (int j = 0; j < nb; ++j)
-        a[i][nb + j] = i == j ? 1.0 : 0.0;
-    }
-  for (int c = 0; c < nb; ++c)
-    {
-      int piv = c;
-      for (int r = c + 1; r < nb; ++r)
-        if (fabs(a[r][c]) > fabs(a[piv][c]))
-          piv = r;
-      if (a[piv][c] == 0.0)
-        return false;
-      if (piv != c)
-        for (int j = 0; j < 2 * nb; ++j)
-          {
-            const double t = a[c][j];
-            a[c][j]        = a[piv][j];
-            a[piv][j]      = t;
-          }
-      const double inv = 1.0 / a[c][c];
-      for (int j = 0; j < 2 * nb; ++j)
-        a[c][j] *= inv;
-      for (int r = 0; r < nb; ++r)
-        if (r != c)
-          {
-            const double f = a[r][c];
-            if (f != 0.0)
-              for (int j = 0; j < 2 * nb; ++j)
-                a[r][j] -= f * a[c][j];
-          }
-    }
-  for (int i = 0; i < nb; ++i)
-    for (int j = 0; j < nb; ++j)
-      coef[nb * i + j] = a[i][nb + j];
-  return true;
-}
-
 // dim 3: are all coarse cells axis-aligned bricks (vertex v = v0 + (bit0 hx, bit1 hy, bit2 hz))?
 static bool
 all_bricks(const double *corners, size_t n_cells)
@@ -232,13 +177,6 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
     }
 
   const size_t C = (size_t)s.n_cells, N = (size_t)s.N, NB = (size_t)s.nb, NCORN = NB * s.dim;
-  std::vector<double> q1(NB * NB * C);
-  for (size_t c = 0; c < C; ++c)
-    if (!basis_q1_matrix(s.dim, corners + NCORN * c, q1.data() + NB * NB * c))
-      {
-        delete h;
-        return fail(MSB_ERR_INVALID_ARG, "msb_create: coarse cell %zu is degenerate", c);
-      }
 
 #define ALLOC(ptr, count)                                                                      \
   do                                                                                           \
@@ -290,8 +228,9 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
     e = cudaEventCreate(&s.ev[i]);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(s.d_corners, corners, sizeof(double) * NCORN * C, cudaMemcpyHostToDevice, s.stream);
+  int32_t bad_cell = INT_MAX;
   if (e == cudaSuccess)
-    e = cudaMemcpyAsync(s.d_q1coef, q1.data(), sizeof(double) * NB * NB * C, cudaMemcpyHostToDevice, s.stream);
+    e = launch_basis_q1(s, s.stream, &bad_cell); // BasisQ1 coefficient matrices, on the device
   if (e == cudaSuccess && s.d_table)
     e = cudaMemcpyAsync(s.d_table, coeff_table, sizeof(double) * C * (size_t)s.n * s.n * 16,
                         cudaMemcpyHostToDevice, s.stream);
@@ -304,6 +243,12 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
       free_shard(s);
       delete h;
       return fail(MSB_ERR_CUDA, "msb_create: device setup failed: %s", cudaGetErrorString(e));
+    }
+  if (bad_cell != INT_MAX)
+    {
+      free_shard(s);
+      delete h;
+      return fail(MSB_ERR_INVALID_ARG, "msb_create: coarse cell %d is degenerate", bad_cell);
     }
   *out = h;
   return MSB_OK;
@@ -320,14 +265,12 @@ msb_set_cells(msb_handle h, const double *corners, const double *coeff_table)
   CUDA_TRY(cudaSetDevice(s.device));
   if (s.run_pending)
     CUDA_TRY(cudaStreamSynchronize(s.run_stream));
-  const size_t        C = (size_t)s.n_cells, NB = (size_t)s.nb, NCORN = NB * s.dim;
-  std::vector<double> q1(NB * NB * C);
-  for (size_t c = 0; c < C; ++c)
-    if (!basis_q1_matrix(s.dim, corners + NCORN * c, q1.data() + NB * NB * c))
-      return fail(MSB_ERR_INVALID_ARG, "msb_set_cells: coarse cell %zu is degenerate", c);
+  const size_t C = (size_t)s.n_cells, NB = (size_t)s.nb, NCORN = NB * s.dim;
   CUDA_TRY(cudaMemcpyAsync(s.d_corners, corners, sizeof(double) * NCORN * C, cudaMemcpyHostToDevice, s.stream));
-  CUDA_TRY(cudaMemcpyAsync(s.d_q1coef, q1.data(), sizeof(double) * NB * NB * C, cudaMemcpyHostToDevice,
-                           s.stream));
+  int32_t bad_cell = INT_MAX;
+  CUDA_TRY(launch_basis_q1(s, s.stream, &bad_cell));
+  if (bad_cell != INT_MAX)
+    return fail(MSB_ERR_INVALID_ARG, "msb_set_cells: coarse cell %d is degenerate", bad_cell);
   if (s.d_table)
     CUDA_TRY(cudaMemcpyAsync(s.d_table, coeff_table, sizeof(double) * C * (size_t)s.n * s.n * 16,
                              cudaMemcpyHostToDevice, s.stream));

@@ -81,6 +81,7 @@ namespace msb
 
   // ---- launchers implemented in the .cu files -------------------------------------------
   cudaError_t launch_dofmap(const Shard &s, cudaStream_t st);
+  cudaError_t launch_basis_q1(const Shard &s, cudaStream_t st, int32_t *h_bad);
   cudaError_t launch_assemble(const Shard &s, cudaStream_t st, int *n_launches);
   cudaError_t launch_solve_smem(const Shard &s, double tol, int max_iter, cudaStream_t st,
                                 int *n_launches);

@@ -127,6 +127,96 @@ namespace msb
   }
 
   // ======================================================================================
+  // BasisQ1<dim> coefficient matrices (basis_q1.tpp:26-47 for dim 2, :50-75 for dim 3) of all
+  // cells: inverse of the point matrix [1, x, y, xy] resp. [1, x, y, z, xy, yz, xz, xyz] at the
+  // vertices, by Gauss-Jordan with partial pivoting, one thread per coarse cell.  A singular
+  // point matrix (degenerate cell) is reported through `bad` (smallest cell index).
+  // ======================================================================================
+  template <int DIM>
+  __global__ void __launch_bounds__(128)
+  basis_q1_kernel(int n_cells, const double *__restrict__ corners, double *__restrict__ q1coef,
+                  int32_t *__restrict__ bad)
+  {
+    constexpr int NB   = 1 << DIM;
+    const int     cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells)
+      return;
+    const double *c = corners + (size_t)cell * NB * DIM;
+    double        a[NB][2 * NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      {
+        const double x = c[DIM * i], y = c[DIM * i + 1];
+        a[i][0] = 1.0, a[i][1] = x, a[i][2] = y;
+        if constexpr (DIM == 2)
+          a[i][3] = x * y;
+        else
+          {
+            const double z = c[DIM * i + 2];
+            a[i][3] = z, a[i][4] = x * y, a[i][5] = y * z, a[i][6] = x * z, a[i][7] = x * y * z;
+          }
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          a[i][NB + j] = i == j ? 1.0 : 0.0;
+      }
+    for (int col = 0; col < NB; ++col)
+      {
+        int piv = col;
+        for (int r = col + 1; r < NB; ++r)
+          if (fabs(a[r][col]) > fabs(a[piv][col]))
+            piv = r;
+        if (a[piv][col] == 0.0)
+          {
+            atomicMin(bad, cell);
+            return;
+          }
+        if (piv != col)
+          for (int j = 0; j < 2 * NB; ++j)
+            {
+              const double t = a[col][j];
+              a[col][j]      = a[piv][j];
+              a[piv][j]      = t;
+            }
+        const double inv = 1.0 / a[col][col];
+        for (int j = 0; j < 2 * NB; ++j)
+          a[col][j] *= inv;
+        for (int r = 0; r < NB; ++r)
+          if (r != col)
+            {
+              const double f = a[r][col];
+              if (f != 0.0)
+                for (int j = 0; j < 2 * NB; ++j)
+                  a[r][j] -= f * a[col][j];
+            }
+      }
+    double *o = q1coef + (size_t)cell * NB * NB;
+    for (int i = 0; i < NB; ++i)
+      for (int j = 0; j < NB; ++j)
+        o[NB * i + j] = a[i][NB + j];
+  }
+
+  // d_fail[1] is used as the "degenerate cell" flag; *h_bad receives INT_MAX or the cell index
+  cudaError_t
+  launch_basis_q1(const Shard &s, cudaStream_t st, int32_t *h_bad)
+  {
+    const int32_t init = 0x7fffffff;
+    cudaError_t   e    = cudaMemcpyAsync(s.d_fail + 1, &init, sizeof init, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess)
+      return e;
+    const int grid = (s.n_cells + 127) / 128;
+    if (s.dim == 2)
+      basis_q1_kernel<2><<<grid, 128, 0, st>>>(s.n_cells, s.d_corners, s.d_q1coef, s.d_fail + 1);
+    else
+      basis_q1_kernel<3><<<grid, 128, 0, st>>>(s.n_cells, s.d_corners, s.d_q1coef, s.d_fail + 1);
+    if ((e = cudaGetLastError()) != cudaSuccess)
+      return e;
+    e = cudaMemcpyAsync(h_bad, s.d_fail + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess)
+      return e;
+    return cudaStreamSynchronize(st);
+  }
+
+  // ======================================================================================
   // Coefficient evaluation (device twins of include/coefficients/matrix_coeff.tpp and of
   // the BASELINE.md synthetic coefficients).
   // ======================================================================================

@@ -420,3 +420,23 @@ def test_streamed_tier_fused_and_unfused_coarse_levels_agree(msb, oracle):
         Mb, _ = b.element_matrices()
         assert _rel(Ma, Mb) < 1e-10
         assert a.run_stats()["launches"] < b.run_stats()["launches"]
+
+
+def test_degenerate_coarse_cell_is_rejected(msb, oracle):
+    """BasisQ1's point matrix (basis_q1.tpp:26-47) is singular for a cell with coincident vertices:
+    msb_create / msb_set_cells report the cell instead of producing NaNs."""
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import MsbError
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_CONSTANT, (1.0,))
+    good = msb.coarse_corners(2, 0, 3)
+    bad = good.copy()
+    bad[1, 3] = bad[1, 2]                      # two coincident vertices in cell 1
+    with pytest.raises(MsbError) as ei:
+        msb.BasisShard(3, bad, cd)
+    assert ei.value.code == -1 and "cell 1" in str(ei.value)
+    with msb.BasisShard(3, good, cd) as sh:
+        with pytest.raises(MsbError) as ei:
+            sh.set_cells(bad)
+        assert ei.value.code == -1
+        sh.set_cells(good)
+        sh.run()
+        assert np.abs(sh.element_matrices()[0].sum(axis=2)).max() < 1e-12

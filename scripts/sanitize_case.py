@@ -15,3 +15,14 @@ for l, variant, cells in cases:
         M, b = sh.element_matrices()
         it, res = sh.iteration_counts()
         print("l=%d variant=%d cells=%d iters=%s max|rowsum M|=%.2e" % (l, variant, cells, it[0].tolist(), np.abs(M.sum(axis=2)).max()), flush=True)
+# dim = 3: (l, variant, cells); 300 cells switch the fused coarse+fine kernel on
+cases3 = [(3, 0, 300), (3, 1, 2), (4, 0, 2), (2, 3, 2)]
+if len(sys.argv) > 1:
+    cases3 = [c for c in cases3 if "3d" in sys.argv[1:]]
+for l, variant, cells in cases3:
+    with pkg.BasisShard(l, pkg.coarse_corners3(3, 5, 5 + cells), coeff_desc(pkg.COEFF_REFERENCE), variant=variant,
+                        dim=3) as sh:
+        sh.run(1e-12, 6, allow_no_convergence=True)
+        M, b = sh.element_matrices()
+        it, res = sh.iteration_counts()
+        print("3d l=%d variant=%d cells=%d iters=%s" % (l, variant, cells, it[0].tolist()), flush=True)

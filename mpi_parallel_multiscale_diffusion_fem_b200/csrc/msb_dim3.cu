@@ -630,13 +630,48 @@ namespace msb
         P.dinv[(size_t)cell * P.L.cn + P.L.off[l] + (Z * npl + Y) * npl + X] = 1.0 / acc[0];
     }
 
-    // r = -K_IB g_B on interior rows (condense), x = g on the boundary, p = 0, partial r.r
+    // Initialisation in two passes.  (a) x = g (BasisQ1 values) on the boundary, 0 inside; r = p = 0.
     __global__ void __launch_bounds__(THREADS)
-    init3_kernel(Params3 P)
+    init3a_kernel(Params3 P)
+    {
+      const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y, blk = blockIdx.x;
+      const double *c = P.corners + 24 * (size_t)cell, *q1 = P.q1coef + 64 * (size_t)cell;
+      const int     t0 = blk * P.chunk, t1 = min(N, t0 + P.chunk);
+      for (int t = t0 + threadIdx.x; t < t1; t += THREADS)
+        {
+          int jx, jy, jz;
+          decode3(t, np, jx, jy, jz);
+          double xv[NB];
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            xv[k] = 0.0;
+          if (on_boundary3(jx, jy, jz, n))
+            {
+              double p[3];
+              fine_vertex3(c, n, jx, jy, jz, p);
+#pragma unroll
+              for (int k = 0; k < NB; ++k)
+                xv[k] = basis_q1_value3(q1, k, p);
+            }
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            {
+              const size_t o = ((size_t)cell * NB + k) * N + t;
+              P.x[o]         = xv[k];
+              P.r[o]         = 0.0;
+              P.p[o]         = 0.0;
+            }
+        }
+    }
+
+    // (b) r = -K_IB g_B on the interior rows next to the boundary (condense), reading g from x;
+    //     partial r.r into parity 0
+    __global__ void __launch_bounds__(THREADS)
+    init3b_kernel(Params3 P)
     {
       const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y, blk = blockIdx.x;
       const double *S = P.sten + (size_t)cell * NST * N;
-      const double *c = P.corners + 24 * (size_t)cell, *q1 = P.q1coef + 64 * (size_t)cell;
+      const double *X = P.x + (size_t)cell * NB * N;
       const int     t0 = blk * P.chunk, t1 = min(N, t0 + P.chunk);
       double        acc[NB];
 #pragma unroll
@@ -646,44 +681,38 @@ namespace msb
         {
           int jx, jy, jz;
           decode3(t, np, jx, jy, jz);
-          double rv[NB], xv[NB];
+          if (on_boundary3(jx, jy, jz, n) ||
+              !(jx == 1 || jy == 1 || jz == 1 || jx == n - 1 || jy == n - 1 || jz == n - 1))
+            continue;
+          double rv[NB];
 #pragma unroll
           for (int k = 0; k < NB; ++k)
-            rv[k] = xv[k] = 0.0;
-          if (on_boundary3(jx, jy, jz, n))
-            {
-              double p[3];
-              fine_vertex3(c, n, jx, jy, jz, p);
+            rv[k] = 0.0;
 #pragma unroll
-              for (int k = 0; k < NB; ++k)
-                xv[k] = basis_q1_value3(q1, k, p);
-            }
-          else if (jx == 1 || jy == 1 || jz == 1 || jx == n - 1 || jy == n - 1 || jz == n - 1)
+          for (int f = 1; f <= 13; ++f)
             {
-#pragma unroll 1
-              for (int e = 0; e < 27; ++e)
+              const int e = 13 + f, dz = e / 9 - 1, dy = (e / 3) % 3 - 1, dx = e % 3 - 1;
+              const int o = (dz * np + dy) * np + dx;
+              if (on_boundary3(jx + dx, jy + dy, jz + dz, n))
                 {
-                  const int bx = jx + e % 3 - 1, by = jy + (e / 3) % 3 - 1, bz = jz + e / 9 - 1;
-                  if (!on_boundary3(bx, by, bz, n))
-                    continue;
-                  const double kij = sten3_get(S, N, np, t, e);
-                  double       p[3];
-                  fine_vertex3(c, n, bx, by, bz, p);
+                  const double kf = S[(size_t)f * N + t];
 #pragma unroll
                   for (int k = 0; k < NB; ++k)
-                    rv[k] -= kij * basis_q1_value3(q1, k, p);
+                    rv[k] = fma(-kf, X[(size_t)k * N + t + o], rv[k]);
                 }
+              if (on_boundary3(jx - dx, jy - dy, jz - dz, n))
+                {
+                  const double kb = S[(size_t)f * N + t - o];
 #pragma unroll
-              for (int k = 0; k < NB; ++k)
-                acc[k] += rv[k] * rv[k];
+                  for (int k = 0; k < NB; ++k)
+                    rv[k] = fma(-kb, X[(size_t)k * N + t - o], rv[k]);
+                }
             }
 #pragma unroll
           for (int k = 0; k < NB; ++k)
             {
-              const size_t o = ((size_t)cell * NB + k) * N + t;
-              P.x[o]         = xv[k];
-              P.r[o]         = rv[k];
-              P.p[o]         = 0.0;
+              P.r[((size_t)cell * NB + k) * N + t] = rv[k];
+              acc[k]                               = fma(rv[k], rv[k], acc[k]);
             }
         }
       __shared__ double sbuf[(THREADS / 32) * NB];
@@ -1362,19 +1391,31 @@ namespace msb
                 kp[j] = kc * pc[j];
               }
           }
-#pragma unroll 1
-          for (int e = 0; e < 27; ++e)
-            {
-              if (e == 13)
-                continue;
-              const int bx = jx + e % 3 - 1, by = jy + (e / 3) % 3 - 1, bz = jz + e / 9 - 1;
-              if (bx < 0 || by < 0 || bz < 0 || bx > n || by > n || bz > n)
-                continue;
-              const double kij = sten3_get(S, N, np, t, e);
-              const int    o   = off_of(e, np);
+          // forward neighbour t + o (coupling stored here) and backward neighbour t - o (stored
+          // there), each only where that node exists
 #pragma unroll
-              for (int j = 0; j < NB; ++j)
-                kp[j] = fma(kij, Ph[(size_t)j * N + t + o], kp[j]);
+          for (int fw = 1; fw <= 13; ++fw)
+            {
+              const int  e = 13 + fw, dz = e / 9 - 1, dy = (e / 3) % 3 - 1, dx = e % 3 - 1;
+              const int  o = (dz * np + dy) * np + dx;
+              const bool hasf = (unsigned)(jx + dx) <= (unsigned)n && (unsigned)(jy + dy) <= (unsigned)n &&
+                                (unsigned)(jz + dz) <= (unsigned)n;
+              const bool hasb = (unsigned)(jx - dx) <= (unsigned)n && (unsigned)(jy - dy) <= (unsigned)n &&
+                                (unsigned)(jz - dz) <= (unsigned)n;
+              if (hasf)
+                {
+                  const double kf = S[(size_t)fw * N + t];
+#pragma unroll
+                  for (int j = 0; j < NB; ++j)
+                    kp[j] = fma(kf, Ph[(size_t)j * N + t + o], kp[j]);
+                }
+              if (hasb)
+                {
+                  const double kb = S[(size_t)fw * N + t - o];
+#pragma unroll
+                  for (int j = 0; j < NB; ++j)
+                    kp[j] = fma(kb, Ph[(size_t)j * N + t - o], kp[j]);
+                }
             }
           const double f = S[(size_t)ST3_F * N + t];
 #pragma unroll
@@ -1645,7 +1686,8 @@ namespace msb
       });
     };
 
-    for_slices([&](const Params3 &Q, int nc) { init3_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
+    for_slices([&](const Params3 &Q, int nc) { init3a_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
+    for_slices([&](const Params3 &Q, int nc) { init3b_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
     precondition(0);
 
     int32_t   h_remaining = 1;

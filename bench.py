@@ -38,6 +38,7 @@ WORKLOADS = {
     # dim = 3: (r, l, kind, par, seed, dim)
     "3d-16x16": (4, 4, 0, (), 0, 3),                  # 16^3 coarse x 16^3 fine hexes, 32768 solves
     "3d-8x32": (3, 5, 0, (), 0, 3),                   # 8^3 coarse x 32^3 fine hexes, 4096 solves
+    "3d-32x8": (5, 3, 0, (), 0, 3),                   # 32^3 coarse x 8^3 fine hexes, 262144 solves
 }
 
 

@@ -953,6 +953,75 @@ namespace msb
         }
     }
 
+    // K2 for small local meshes (n <= 8): one CTA per cell stages the whole p of the 8 bases in
+    // shared memory (same [basis][node] layout as in HBM) and sweeps all interior nodes, instead
+    // of marching planes that would occupy only (n-1)^2 of the 256 threads.
+    __global__ void __launch_bounds__(THREADS)
+    k2w_kernel(Params3 P)
+    {
+      extern __shared__ double sp[]; // [NB][N]
+      const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y, nin = n - 1;
+      const int par = (P.it - 1) & 1;
+      __shared__ int    sdone[NB];
+      __shared__ double sbuf[(THREADS / 32) * NB];
+      if (cell_done(P, cell, par, sdone))
+        return;
+      const double *S  = P.sten + (size_t)cell * NST * N;
+      const double *pg = P.p + (size_t)cell * NB * N;
+      double       *qg = P.q + (size_t)cell * NB * N;
+      for (int i = threadIdx.x; i < NB * N; i += THREADS)
+        sp[i] = pg[i];
+      __syncthreads();
+      double acc[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        acc[k] = 0.0;
+      for (int u = threadIdx.x; u < nin * nin * nin; u += THREADS)
+        {
+          const int     x = 1 + u % nin, y = 1 + (u / nin) % nin, z = 1 + u / (nin * nin);
+          const int     t = (z * np + y) * np + x;
+          const double *s0 = sp + t;
+          double        yv[NB], pc[NB];
+          {
+            const double kc = S[t];
+#pragma unroll
+            for (int k = 0; k < NB; ++k)
+              {
+                pc[k] = s0[k * N];
+                yv[k] = kc * pc[k];
+              }
+          }
+#pragma unroll
+          for (int f = 1; f <= 13; ++f)
+            {
+              const int    e = 13 + f, o = ((e / 9 - 1) * np + (e / 3) % 3 - 1) * np + e % 3 - 1;
+              const double kf = S[(size_t)f * N + t], kb = S[(size_t)f * N + t - o];
+#pragma unroll
+              for (int k = 0; k < NB; ++k)
+                {
+                  yv[k] = fma(kf, s0[k * N + o], yv[k]);
+                  yv[k] = fma(kb, s0[k * N - o], yv[k]);
+                }
+            }
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            {
+              if (sdone[k])
+                continue;
+              qg[(size_t)k * N + t] = yv[k];
+              acc[k]                = fma(pc[k], yv[k], acc[k]);
+            }
+        }
+      block_sum_to<NB>(acc, sbuf);
+      if (threadIdx.x == 0)
+        {
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+            if (!sdone[k])
+              part_ptr(P.part, cell * NB + k, P.it & 1, 1)[0] = acc[k];
+        }
+    }
+
     // K3: alpha = rz/pq ; x += alpha p ; r -= alpha q ; partial r.r
     __global__ void __launch_bounds__(THREADS)
     k3_kernel(Params3 P)
@@ -1590,6 +1659,16 @@ namespace msb
       }
     else
       P.nblk2 = P.nblk;
+    // small local meshes: whole-cell K2, one CTA per cell
+    const size_t k2w_smem  = sizeof(double) * NB * (size_t)s.N;
+    const bool   k2_whole  = s.variant != 1 && s.variant != 6 && s.n <= 8 && k2w_smem <= 64 * 1024;
+    if (k2_whole)
+      {
+        P.nblk2 = 1;
+        cudaError_t ea = cudaFuncSetAttribute(k2w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2w_smem);
+        if (ea != cudaSuccess)
+          return ea;
+      }
     P.corners = s.d_corners;
     P.q1coef  = s.d_q1coef;
     P.sten    = s.d_sten;
@@ -1709,7 +1788,9 @@ namespace msb
         ++it;
         P.it = it;
         for_slices([&](const Params3 &Q, int nc) { k1_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
-        if (k2_tiled)
+        if (k2_whole)
+          for_slices([&](const Params3 &Q, int nc) { k2w_kernel<<<dim3(1, nc), THREADS, k2w_smem, st>>>(Q); });
+        else if (k2_tiled)
           for_slices([&](const Params3 &Q, int nc) {
             if (s.variant == 2)
               k2m_kernel<3><<<dim3(P.nblk2, nc), THREADS, k2_smem, st>>>(Q);

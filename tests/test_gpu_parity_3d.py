@@ -204,11 +204,12 @@ def test_more_than_65535_cells_3d(msb, oracle):
             assert _rel(M[c], ref["M"][k]) < TOL_MB
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 def test_alternative_3d_kernels_agree_with_the_default(msb, oracle, variant):
     """variant 1: untiled K2, 2: K2 at 3 CTAs/SM, 3: general trilinear assembly instead of the brick
     tables, 4: one launch per coarse level instead of the fused kernel, 5: separate fine-level
-    kernel.  Same algorithm, so the same iteration counts and bases to rounding."""
+    kernel, 6: plane-marching K2 instead of the whole-cell K2 of small meshes.  Same algorithm, so
+    the same iteration counts and bases to rounding."""
     from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
     cor = msb.coarse_corners3(3, 0, 320)          # >= 296 cells: the fused fine step is active
     cd = coeff_desc(msb.COEFF_REFERENCE)

@@ -89,6 +89,10 @@ namespace msb
                                int *n_launches);
   cudaError_t launch_solve_streamed(Shard &s, double tol, int max_iter, cudaStream_t st,
                                     int *n_launches);
+  // cluster / DSMEM tier (msb_solve_cluster.cu); called by launch_solve_streamed after its setup
+  cudaError_t launch_solve_cluster(const Shard &s, double tol, int max_iter, cudaStream_t st,
+                                   int *n_launches);
+  bool        cluster_tier_supported(int l);
   cudaError_t launch_element_matrices(const Shard &s, cudaStream_t st, int *n_launches);
   cudaError_t launch_apply_operator(const Shard &s, int cell, const double *d_x_lex, double *d_y_lex,
                                     cudaStream_t st);

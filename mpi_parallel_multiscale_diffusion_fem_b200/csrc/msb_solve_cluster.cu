@@ -1,0 +1,714 @@
+// msb_solve_cluster.cu -- thread-block-cluster / distributed-shared-memory tier: the multilevel
+// preconditioned CG of the streamed tier (msb_solve_stream.cu, same mathematics, same stopping
+// rule) for local meshes whose vectors do not fit ONE SM but do fit the shared memory of a
+// cluster of SMs: n = 128, the reference's default run (main.cxx:23-25, n_refine_local = 7).
+//
+// One cluster of CS = n/16 CTAs per coarse cell (8 at n = 128, the portable maximum).  CTA c of
+// the cluster owns the slab of 16 fine node rows [16c, 16c+16); all vectors of the solve live on
+// chip for the whole iteration:
+//     shared memory  the five stencil coefficient arrays of the slab (+ one row below), 1/diag,
+//                    the search direction p with one halo row either side, a staging copy of
+//                    the residual, the slab's part of coarse levels 1 and 2 (+ halo rows), a
+//                    full copy of levels >= 3, reciprocal Galerkin diagonals of all of these
+//     registers      x, r, z / q: a thread owns 4 consecutive rows of one column
+// What crosses CTAs goes through DSMEM, always as a PUSH (remote st.shared::cluster, the latency
+// is hidden behind the following barrier) followed by one cluster barrier:
+//     halo rows of z (-> p), r, r_1, r_2 to the neighbouring slab; the two level-3 rows a CTA owns to
+//     every CTA of the cluster (levels >= 3 are then swept redundantly by all CTAs: no serial
+//     coarse chain across the cluster); the per-CTA partial dot products to every CTA, which
+//     adds them in rank order so that all CTAs take bitwise identical decisions.
+// Six cluster barriers per PCG iteration, HBM traffic = read the stencil once, write Phi.
+// The four bases of a cell are solved two at a time (two passes share the prologue).
+//
+// Replaces, for these local meshes, the per-basis sequence of the reference:
+// diffusion_problem_basis.tpp:450-465 (condense, solve_iterative :293-317, distribute :308).
+#ifndef MSB_EMU // scripts/emu/cluster_emu.cpp compiles this file for the host with its own shims
+#  include <cooperative_groups.h>
+#endif
+#include <limits.h>
+#include <math.h>
+
+#define MSB_STAGE_ARRAY g_msb_stage_cycles_cl
+#include "msb_bpx_common.cuh"
+
+#ifdef MSB_STAGE_TIMERS
+__device__ unsigned long long g_msb_stage_cycles_cl[16];
+extern "C" int
+msb_debug_stage_cycles_cl(unsigned long long *out, int reset)
+{
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_msb_stage_cycles_cl, sizeof(unsigned long long) * 16);
+  if (e == cudaSuccess && reset)
+    {
+      unsigned long long z[16] = {0};
+      e = cudaMemcpyToSymbol(g_msb_stage_cycles_cl, z, sizeof z);
+    }
+  return (int)e;
+}
+#endif
+
+namespace cg = cooperative_groups;
+
+namespace msb
+{
+  namespace clus
+  {
+    constexpr int ROWS = 16; // fine node rows per CTA
+    constexpr int NBP  = 2;  // bases per pass
+
+    struct Params
+    {
+      const double *corners; // [C][8]
+      const double *q1coef;  // [C][16]
+      const double *sten;    // [C][6][N]
+      const double *dinv;    // [C][cn] reciprocal Galerkin diagonals, levels 1.. (stream_galerkin_kernel)
+      double       *phi;     // [C][4][N]
+      int32_t      *iters;   // [C][4]
+      double       *res;     // [C][4]
+      int32_t      *fail;
+      double        tol2;
+      int           max_iter;
+      int           cn;
+    };
+
+    template <int L>
+    struct Lay
+    {
+      static constexpr int n = 1 << L, np = n + 1, N = np * np, CS = n / ROWS, T = 4 * n, NW = T / 32;
+      static constexpr int W = n, W1 = n / 2, W2 = n / 4, W3 = n / 8, NP3 = W3 + 1;
+      static constexpr int LV = L - 1; // coarse levels 1..LV
+      __host__ __device__ static constexpr int
+      npl(int l)
+      {
+        return (n >> l) + 1;
+      }
+      // node offset of level l inside the packed per-cell coarse arrays (make_levels, msb_solve_stream.cu)
+      __host__ __device__ static constexpr int
+      goff(int l)
+      {
+        int o = 0;
+        for (int k = 1; k < l; ++k)
+          o += npl(k) * npl(k);
+        return o;
+      }
+      static constexpr int cn  = goff(LV + 1);
+      static constexpr int cn3 = goff(LV + 1) - goff(3); // nodes of levels 3..LV (full copies)
+      // shared-memory map, in doubles
+      static constexpr int o_cf  = 0;                              // [5][17][W]   rows y0-1 .. y0+15
+      static constexpr int o_d0  = o_cf + 5 * 17 * W;              // [16][W]      1/KC, own rows
+      static constexpr int o_p   = o_d0 + 16 * W;                  // [NBP][18][W] rows y0-1 .. y0+16 (+ pad)
+      static constexpr int o_rs  = o_p + NBP * 18 * W + W;         // [NBP][17][W] rows y0-1 .. y0+15 (+ pad)
+      static constexpr int o_v1  = o_rs + NBP * 17 * W + W;        // [NBP][10][W1] level-1 rows 8c-1 .. 8c+8 (+ pad)
+      static constexpr int o_d1  = o_v1 + NBP * 10 * W1 + W1;      // [9][W1]      level-1 rows 8c .. 8c+8
+      static constexpr int o_v2  = o_d1 + 9 * W1;                  // [NBP][6][W2] level-2 rows 4c-1 .. 4c+4 (+ pad)
+      static constexpr int o_d2  = o_v2 + NBP * 6 * W2 + W2;       // [5][W2]
+      static constexpr int o_v3  = o_d2 + 5 * W2;                  // [NBP][cn3]   levels >= 3, full, stride npl
+      static constexpr int o_d3  = o_v3 + NBP * cn3;               // [cn3]
+      static constexpr int o_red = o_d3 + cn3;                     // [3][CS][NBP] partial dot products
+      static constexpr int o_buf = o_red + 3 * CS * NBP;           // [NBP][NW]    block reduction scratch
+      static constexpr int o_zh  = o_buf + NBP * NW;               // [NBP][2][W]  z of the rows y0-1 and y0+16
+      static constexpr int total = o_zh + NBP * 2 * W;
+      static constexpr size_t smem_bytes = sizeof(double) * (size_t)total;
+      static_assert(L >= 5 && L <= 7, "cluster tier: 32 <= n <= 128 (cluster of 2..8 CTAs)");
+      static_assert(NW <= 32, "block_sum: one lane per warp partial");
+    };
+
+    // full weighting of one coarse node from a buffer with row stride `stride`, centred at s
+    __device__ __forceinline__ double
+    restrict_node(const double *s, int stride)
+    {
+      const double a = fma(0.5, s[-stride - 1] + s[-stride + 1], s[-stride]);
+      const double b = fma(0.5, s[-1] + s[1], s[0]);
+      const double c = fma(0.5, s[stride - 1] + s[stride + 1], s[stride]);
+      return fma(0.5, a + c, b);
+    }
+
+    template <int L>
+    __global__ void __launch_bounds__(Lay<L>::T, 1)
+    solve_cluster_kernel(Params P)
+    {
+      using Y = Lay<L>;
+      constexpr int n = Y::n, np = Y::np, N = Y::N, CS = Y::CS, T = Y::T, NW = Y::NW;
+      constexpr int W = Y::W, W1 = Y::W1, W2 = Y::W2, W3 = Y::W3, NP3 = Y::NP3, LV = Y::LV, cn3 = Y::cn3;
+#ifndef MSB_EMU
+      extern __shared__ __align__(16) double sm[];
+#else
+      double *sm = emu::smem();
+#endif
+      cg::cluster_group cluster = cg::this_cluster();
+      const int rank = (int)cluster.block_rank();
+      const int cell = blockIdx.x / CS;
+      const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+      const int jx = tid & (n - 1), g = tid >> L; // column, group of 4 rows
+      const int y0 = rank * ROWS;
+      const bool colact = jx >= 1;
+
+      double *cf = sm + Y::o_cf, *d0 = sm + Y::o_d0, *pS = sm + Y::o_p, *rS = sm + Y::o_rs;
+      double *v1 = sm + Y::o_v1, *d1 = sm + Y::o_d1, *v2 = sm + Y::o_v2, *d2 = sm + Y::o_d2;
+      double *v3 = sm + Y::o_v3, *d3 = sm + Y::o_d3, *red = sm + Y::o_red, *buf = sm + Y::o_buf;
+      double *zh = sm + Y::o_zh;
+
+      const double *S  = P.sten + (size_t)cell * ST_NARR * N;
+      const double *c  = P.corners + 8 * (size_t)cell;
+      const double *q1 = P.q1coef + 16 * (size_t)cell;
+
+      ST_DECL
+      // ------------------------------------------------------------------ prologue (once per cell)
+      for (int i = tid; i < Y::total; i += T)
+        sm[i] = 0.0;
+      __syncthreads();
+      for (int t = tid; t < 17 * W; t += T)
+        {
+          const int r = t >> L, x = t & (W - 1), y = y0 - 1 + r;
+          if (y >= 0)
+            {
+              const int gi = y * np + x;
+#pragma unroll
+              for (int a = 0; a < 5; ++a)
+                cf[(a * 17 + r) * W + x] = S[(size_t)a * N + gi];
+              if (r >= 1 && y >= 1 && x >= 1)
+                d0[(r - 1) * W + x] = 1.0 / S[(size_t)ST_KC * N + gi];
+            }
+        }
+      {
+        const double *dg = P.dinv + (size_t)cell * P.cn;
+        for (int t = tid; t < 9 * W1; t += T)
+          {
+            const int r = t / W1, X = t % W1;
+            d1[t] = dg[Y::goff(1) + (8 * rank + r) * Y::npl(1) + X];
+          }
+        for (int t = tid; t < 5 * W2; t += T)
+          {
+            const int r = t / W2, X = t % W2;
+            d2[t] = dg[Y::goff(2) + (4 * rank + r) * Y::npl(2) + X];
+          }
+        for (int t = tid; t < cn3; t += T)
+          d3[t] = dg[Y::goff(3) + t];
+      }
+      // nobody may push into a peer's shared memory before that peer has zeroed it
+      cluster.sync();
+      ST_MARK(0)
+
+      // sum of one value per basis over the whole cluster, the same bits in every thread of every CTA
+      auto allreduce = [&](double(&v)[NBP], int slot) {
+        bpx::block_sum<NBP, NW>(v, buf, warp, lane);
+        if (tid < CS)
+          {
+            double *dst = cluster.map_shared_rank(red, tid);
+#pragma unroll
+            for (int k = 0; k < NBP; ++k)
+              dst[(slot * CS + rank) * NBP + k] = v[k];
+          }
+        cluster.sync();
+#pragma unroll
+        for (int k = 0; k < NBP; ++k)
+          {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < CS; ++j)
+              s += red[(slot * CS + j) * NBP + k];
+            v[k] = s;
+          }
+      };
+
+      for (int pass = 0; pass < 4 / NBP; ++pass)
+        {
+          double x[NBP][4], r[NBP][4], z[NBP][4];
+          double rr[NBP], rz[NBP], beta[NBP];
+          int    itc[NBP];
+          bool   done[NBP];
+
+          // ---- x = g on the boundary (distribute, basis.tpp:308), written straight to Phi
+          for (int i = rank * T + tid; i < 4 * n; i += CS * T)
+            {
+              const int side = i / n, o = i % n;
+              const int bx = side == 0 ? o : side == 1 ? n : side == 2 ? n - o : 0;
+              const int by = side == 0 ? 0 : side == 1 ? o : side == 2 ? n : n - o;
+              double    px, py;
+              fine_vertex(c, n, bx, by, px, py);
+#pragma unroll
+              for (int k = 0; k < NBP; ++k)
+                P.phi[((size_t)cell * 4 + NBP * pass + k) * N + by * np + bx] =
+                  basis_q1_value(q1, NBP * pass + k, px, py);
+            }
+          // ---- r = b = -K_IB g_B (condense), x = 0 inside
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            {
+              const int y = y0 + 4 * g + i;
+#pragma unroll
+              for (int k = 0; k < NBP; ++k)
+                x[k][i] = 0.0, r[k][i] = 0.0, z[k][i] = 0.0;
+              if (colact && y >= 1 && (jx == 1 || y == 1 || jx == n - 1 || y == n - 1))
+                {
+                  double rv[NBP];
+#pragma unroll
+                  for (int k = 0; k < NBP; ++k)
+                    rv[k] = 0.0;
+                  for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx)
+                      {
+                        const int bx = jx + dx, by = y + dy;
+                        if ((dx == 0 && dy == 0) || !(bx == 0 || bx == n || by == 0 || by == n))
+                          continue;
+                        const double kij = bpx::sten_get(S, np, N, jx, y, dx, dy);
+                        double       px, py;
+                        fine_vertex(c, n, bx, by, px, py);
+#pragma unroll
+                        for (int k = 0; k < NBP; ++k)
+                          rv[k] -= kij * basis_q1_value(q1, NBP * pass + k, px, py);
+                      }
+#pragma unroll
+                  for (int k = 0; k < NBP; ++k)
+                    r[k][i] = rv[k];
+                }
+            }
+
+          // residual to the staging buffer (+ the slab's last row into the upper neighbour's halo)
+          auto stage_r = [&]() {
+            if (colact)
+              {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                  for (int k = 0; k < NBP; ++k)
+                    rS[(k * 17 + 4 * g + i + 1) * W + jx] = r[k][i];
+                if (g == 3 && rank + 1 < CS)
+                  {
+                    double *dst = cluster.map_shared_rank(rS, rank + 1);
+#pragma unroll
+                    for (int k = 0; k < NBP; ++k)
+                      dst[(k * 17 + 0) * W + jx] = r[k][3];
+                  }
+              }
+          };
+
+          {
+            double acc[NBP];
+#pragma unroll
+            for (int k = 0; k < NBP; ++k)
+              {
+                acc[k] = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  acc[k] = fma(r[k][i], r[k][i], acc[k]);
+              }
+            stage_r();
+            allreduce(acc, 2);
+#pragma unroll
+            for (int k = 0; k < NBP; ++k)
+              rr[k] = acc[k], rz[k] = 1.0, beta[k] = 0.0, itc[k] = -1, done[k] = false;
+          }
+          ST_MARK(1)
+
+          int it = 0;
+          while (true)
+            {
+              // ---- stopping rule of SolverControl (basis.tpp:297): ||r||_2 <= tol, every iteration
+              bool all_done = true;
+#pragma unroll
+              for (int k = 0; k < NBP; ++k)
+                {
+                  if (!done[k] && rr[k] <= P.tol2)
+                    done[k] = true, itc[k] = it;
+                  all_done = all_done && done[k];
+                }
+              if (all_done || it >= P.max_iter)
+                break;
+
+              // ---- z = M^-1 r: additive multilevel preconditioner (exact Galerkin diagonals)
+              // level 1 rows 8c .. 8c+7 from the staged residual (own rows + lower halo)
+              for (int t = tid; t < NBP * 8 * W1; t += T)
+                {
+                  const int X = t & (W1 - 1), qr = (t / W1) & 7, k = t / (8 * W1);
+                  if (X >= 1 && 8 * rank + qr >= 1)
+                    {
+                      const double v = restrict_node(rS + (k * 17 + 2 * qr + 1) * W + 2 * X, W);
+                      v1[(k * 10 + qr + 1) * W1 + X] = v;
+                      if (qr == 0 && rank > 0)
+                        cluster.map_shared_rank(v1, rank - 1)[(k * 10 + 9) * W1 + X] = v;
+                      if (qr == 7 && rank + 1 < CS)
+                        cluster.map_shared_rank(v1, rank + 1)[(k * 10 + 0) * W1 + X] = v;
+                    }
+                }
+              cluster.sync();
+              ST_MARK(2)
+              // level 2 rows 4c .. 4c+3
+              for (int t = tid; t < NBP * 4 * W2; t += T)
+                {
+                  const int X = t & (W2 - 1), qr = (t / W2) & 3, k = t / (4 * W2);
+                  if (X >= 1 && 4 * rank + qr >= 1)
+                    {
+                      const double v = restrict_node(v1 + (k * 10 + 2 * qr + 1) * W1 + 2 * X, W1);
+                      v2[(k * 6 + qr + 1) * W2 + X] = v;
+                      if (qr == 0 && rank > 0)
+                        cluster.map_shared_rank(v2, rank - 1)[(k * 6 + 5) * W2 + X] = v;
+                      if (qr == 3 && rank + 1 < CS)
+                        cluster.map_shared_rank(v2, rank + 1)[(k * 6 + 0) * W2 + X] = v;
+                    }
+                }
+              cluster.sync();
+              ST_MARK(3)
+              // level 3 rows 2c, 2c+1 -> every CTA of the cluster
+              for (int t = tid; t < NBP * 2 * W3; t += T)
+                {
+                  const int X = t & (W3 - 1), qr = (t / W3) & 1, k = t / (2 * W3);
+                  const int Y3 = 2 * rank + qr;
+                  if (X >= 1 && Y3 >= 1)
+                    {
+                      const double v = restrict_node(v2 + (k * 6 + 2 * qr + 1) * W2 + 2 * X, W2);
+#pragma unroll
+                      for (int j = 0; j < CS; ++j)
+                        cluster.map_shared_rank(v3, j)[k * cn3 + Y3 * NP3 + X] = v;
+                    }
+                }
+              cluster.sync();
+              ST_MARK(4)
+              // levels 4 .. LV: down, redundantly in every CTA
+#pragma unroll
+              for (int l = 4; l <= LV; ++l)
+                {
+                  const int npl = Y::npl(l), nin = npl - 2, npf = Y::npl(l - 1);
+                  const int lo = Y::goff(l) - Y::goff(3), lf = Y::goff(l - 1) - Y::goff(3);
+                  for (int t = tid; t < NBP * nin * nin; t += T)
+                    {
+                      const int k = t / (nin * nin), u = t % (nin * nin), cx = 1 + u % nin, cy = 1 + u / nin;
+                      v3[k * cn3 + lo + cy * npl + cx] =
+                        restrict_node(v3 + k * cn3 + lf + 2 * cy * npf + 2 * cx, npf);
+                    }
+                  __syncthreads();
+                }
+              // up: z_l = r_l / D_l + P z_{l+1}, in place
+#pragma unroll
+              for (int l = LV; l >= 3; --l)
+                {
+                  const int npl = Y::npl(l), nin = npl - 2, lo = Y::goff(l) - Y::goff(3);
+                  for (int t = tid; t < NBP * nin * nin; t += T)
+                    {
+                      const int k = t / (nin * nin), u = t % (nin * nin), fx = 1 + u % nin, fy = 1 + u / nin;
+                      const int i = lo + fy * npl + fx;
+                      double    v = v3[k * cn3 + i] * d3[i];
+                      if (l < LV)
+                        {
+                          const int     npc = Y::npl(l + 1);
+                          const double *vc  = v3 + k * cn3 + Y::goff(l + 1) - Y::goff(3);
+                          const int     xl = fx >> 1, xh = (fx + 1) >> 1, yl = fy >> 1, yh = (fy + 1) >> 1;
+                          v += 0.25 * ((vc[yl * npc + xl] + vc[yl * npc + xh]) + (vc[yh * npc + xl] + vc[yh * npc + xh]));
+                        }
+                      v3[k * cn3 + i] = v;
+                    }
+                  __syncthreads();
+                }
+              ST_MARK(5)
+              // level 2: own rows + the upper halo row (needed by level-1 rows of this slab)
+              for (int t = tid; t < NBP * 5 * W2; t += T)
+                {
+                  const int X = t & (W2 - 1), qr = (t / W2) % 5, k = t / (5 * W2);
+                  const int Y2 = 4 * rank + qr;
+                  if (X >= 1 && Y2 >= 1 && Y2 <= W2 - 1)
+                    {
+                      const int     i  = (k * 6 + qr + 1) * W2 + X;
+                      const double *vc = v3 + k * cn3;
+                      const int     xl = X >> 1, xh = (X + 1) >> 1, yl = Y2 >> 1, yh = (Y2 + 1) >> 1;
+                      v2[i] = v2[i] * d2[qr * W2 + X] +
+                              0.25 * ((vc[yl * NP3 + xl] + vc[yl * NP3 + xh]) + (vc[yh * NP3 + xl] + vc[yh * NP3 + xh]));
+                    }
+                }
+              __syncthreads();
+              // level 1: own rows + the upper halo row (needed by the last fine row of this slab)
+              for (int t = tid; t < NBP * 9 * W1; t += T)
+                {
+                  const int X = t & (W1 - 1), qr = (t / W1) % 9, k = t / (9 * W1);
+                  const int Y1 = 8 * rank + qr;
+                  if (X >= 1 && Y1 >= 1 && Y1 <= W1 - 1)
+                    {
+                      const int     i  = (k * 10 + qr + 1) * W1 + X;
+                      const double *vc = v2 + k * 6 * W2;
+                      const int     xl = X >> 1, xh = (X + 1) >> 1;
+                      const int     yl = (Y1 >> 1) - 4 * rank + 1, yh = ((Y1 + 1) >> 1) - 4 * rank + 1;
+                      v1[i] = v1[i] * d1[qr * W1 + X] +
+                              0.25 * ((vc[yl * W2 + xl] + vc[yl * W2 + xh]) + (vc[yh * W2 + xl] + vc[yh * W2 + xh]));
+                    }
+                }
+              __syncthreads();
+              ST_MARK(6)
+              // fine level: z = r / D + P z_1, r.z
+              {
+                double acc[NBP];
+#pragma unroll
+                for (int k = 0; k < NBP; ++k)
+                  acc[k] = 0.0;
+                if (colact)
+                  {
+                    const int xl = jx >> 1, xh = (jx + 1) >> 1;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                      {
+                        const int    yy = 4 * g + i, yl = (yy >> 1) + 1, yh = ((yy + 1) >> 1) + 1;
+                        const double di = d0[yy * W + jx];
+#pragma unroll
+                        for (int k = 0; k < NBP; ++k)
+                          {
+                            const double *vc = v1 + k * 10 * W1;
+                            const double  cv =
+                              0.25 * ((vc[yl * W1 + xl] + vc[yl * W1 + xh]) + (vc[yh * W1 + xl] + vc[yh * W1 + xh]));
+                            const double zv = fma(r[k][i], di, cv);
+                            z[k][i]         = zv;
+                            acc[k]          = fma(r[k][i], zv, acc[k]);
+                          }
+                      }
+                    // z of the slab's first / last row to the neighbours: they update their halo copy
+                    // of p themselves once beta is known (saves the barrier a push of p would need)
+                    if (g == 0 && rank > 0)
+                      {
+                        double *dst = cluster.map_shared_rank(zh, rank - 1);
+#pragma unroll
+                        for (int k = 0; k < NBP; ++k)
+                          dst[(k * 2 + 1) * W + jx] = z[k][0];
+                      }
+                    if (g == 3 && rank + 1 < CS)
+                      {
+                        double *dst = cluster.map_shared_rank(zh, rank + 1);
+#pragma unroll
+                        for (int k = 0; k < NBP; ++k)
+                          dst[(k * 2 + 0) * W + jx] = z[k][3];
+                      }
+                  }
+                allreduce(acc, 0);
+#pragma unroll
+                for (int k = 0; k < NBP; ++k)
+                  {
+                    beta[k] = (it == 0 || done[k]) ? 0.0 : acc[k] / rz[k];
+                    rz[k]   = acc[k];
+                  }
+              }
+              ++it;
+              ST_MARK(7)
+
+              // ---- p = z + beta p on the slab and, with the neighbours' z, on the two halo rows
+              // (the same fma on the same bits as in the owning CTA)
+              if (colact)
+                {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int k = 0; k < NBP; ++k)
+                      {
+                        const int idx = (k * 18 + 4 * g + i + 1) * W + jx;
+                        pS[idx]       = fma(beta[k], pS[idx], z[k][i]);
+                      }
+                  if (g == 1 && rank > 0)
+                    {
+#pragma unroll
+                      for (int k = 0; k < NBP; ++k)
+                        {
+                          const int idx = (k * 18 + 0) * W + jx;
+                          pS[idx]       = fma(beta[k], pS[idx], zh[(k * 2 + 0) * W + jx]);
+                        }
+                    }
+                  if (g == 2 && rank + 1 < CS)
+                    {
+#pragma unroll
+                      for (int k = 0; k < NBP; ++k)
+                        {
+                          const int idx = (k * 18 + 17) * W + jx;
+                          pS[idx]       = fma(beta[k], pS[idx], zh[(k * 2 + 1) * W + jx]);
+                        }
+                    }
+                }
+              __syncthreads();
+              ST_MARK(8)
+
+              // ---- q = K p (9-point stencil, coefficients shared by the bases of the pass), p.q
+              double q[NBP][4], pq[NBP];
+#pragma unroll
+              for (int k = 0; k < NBP; ++k)
+                {
+                  pq[k] = 0.0;
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    q[k][i] = 0.0;
+                }
+              if (colact)
+                {
+                  double w[NBP][3][3];
+#pragma unroll
+                  for (int k = 0; k < NBP; ++k)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                      for (int dx = 0; dx < 3; ++dx)
+                        w[k][a][dx] = pS[(k * 18 + 4 * g + a) * W + jx + dx - 1];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    {
+                      const int cr = 4 * g + i + 1;
+#pragma unroll
+                      for (int k = 0; k < NBP; ++k)
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx)
+                          w[k][2][dx] = pS[(k * 18 + cr + 1) * W + jx + dx - 1];
+                      const double kc = cf[(0 * 17 + cr) * W + jx];
+                      const double kE = cf[(1 * 17 + cr) * W + jx], kW = cf[(1 * 17 + cr) * W + jx - 1];
+                      const double kN = cf[(2 * 17 + cr) * W + jx], kS = cf[(2 * 17 + cr - 1) * W + jx];
+                      const double kNE = cf[(3 * 17 + cr) * W + jx], kSW = cf[(3 * 17 + cr - 1) * W + jx - 1];
+                      const double kNW = cf[(4 * 17 + cr) * W + jx - 1], kSE = cf[(4 * 17 + cr - 1) * W + jx];
+                      const bool   rowact = y0 + 4 * g + i >= 1;
+#pragma unroll
+                      for (int k = 0; k < NBP; ++k)
+                        {
+                          double yv = kc * w[k][1][1];
+                          yv        = fma(kE, w[k][1][2], yv);
+                          yv        = fma(kW, w[k][1][0], yv);
+                          yv        = fma(kN, w[k][2][1], yv);
+                          yv        = fma(kS, w[k][0][1], yv);
+                          yv        = fma(kNE, w[k][2][2], yv);
+                          yv        = fma(kSW, w[k][0][0], yv);
+                          yv        = fma(kNW, w[k][2][0], yv);
+                          yv        = fma(kSE, w[k][0][2], yv);
+                          if (!rowact)
+                            yv = 0.0;
+                          q[k][i] = yv;
+                          pq[k]   = fma(w[k][1][1], yv, pq[k]);
+#pragma unroll
+                          for (int dx = 0; dx < 3; ++dx)
+                            w[k][0][dx] = w[k][1][dx], w[k][1][dx] = w[k][2][dx];
+                        }
+                    }
+                }
+              allreduce(pq, 1);
+              ST_MARK(9)
+
+              // ---- x += alpha p ; r -= alpha q ; r.r
+              {
+                double alpha[NBP], acc[NBP];
+#pragma unroll
+                for (int k = 0; k < NBP; ++k)
+                  alpha[k] = done[k] ? 0.0 : rz[k] / pq[k], acc[k] = 0.0;
+                if (colact)
+                  {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                      for (int k = 0; k < NBP; ++k)
+                        {
+                          const double pv = pS[(k * 18 + 4 * g + i + 1) * W + jx];
+                          x[k][i]         = fma(alpha[k], pv, x[k][i]);
+                          const double rn = fma(-alpha[k], q[k][i], r[k][i]);
+                          r[k][i]         = rn;
+                          acc[k]          = fma(rn, rn, acc[k]);
+                        }
+                  }
+                stage_r();
+                allreduce(acc, 2);
+#pragma unroll
+                for (int k = 0; k < NBP; ++k)
+                  if (!done[k])
+                    rr[k] = acc[k];
+              }
+              ST_MARK(10)
+            }
+
+          // ---- results of the pass
+          if (colact)
+            {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                {
+                  const int y = y0 + 4 * g + i;
+                  if (y >= 1)
+                    {
+#pragma unroll
+                      for (int k = 0; k < NBP; ++k)
+                        P.phi[((size_t)cell * 4 + NBP * pass + k) * N + y * np + jx] = x[k][i];
+                    }
+                }
+            }
+          if (rank == 0 && tid == 0)
+            {
+#pragma unroll
+              for (int k = 0; k < NBP; ++k)
+                {
+                  const int sidx = cell * 4 + NBP * pass + k;
+                  P.iters[sidx]  = itc[k] >= 0 ? itc[k] : it;
+                  P.res[sidx]    = sqrt(rr[k]);
+                  if (!(rr[k] <= P.tol2))
+                    atomicMin(P.fail, sidx);
+                }
+            }
+          // a fast CTA must not start the next pass (or exit) while a peer still reads what it pushed
+          cluster.sync();
+          ST_MARK(11)
+        }
+      ST_FLUSH
+    }
+
+#ifndef MSB_EMU
+    template <int L>
+    static cudaError_t
+    launch(const Params &P, int n_cells, cudaStream_t st)
+    {
+      using Y = Lay<L>;
+      cudaError_t e = cudaFuncSetAttribute(solve_cluster_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)Y::smem_bytes);
+      if (e != cudaSuccess)
+        return e;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim            = dim3((unsigned)(Y::CS * n_cells), 1, 1);
+      cfg.blockDim           = dim3(Y::T, 1, 1);
+      cfg.dynamicSmemBytes   = Y::smem_bytes;
+      cfg.stream             = st;
+      cudaLaunchAttribute at[1];
+      at[0].id               = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = Y::CS;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs              = at;
+      cfg.numAttrs           = 1;
+      return cudaLaunchKernelEx(&cfg, solve_cluster_kernel<L>, P);
+    }
+#endif
+  } // namespace clus
+
+#ifndef MSB_EMU
+  bool
+  cluster_tier_supported(int l)
+  {
+    return l >= 5 && l <= 7;
+  }
+
+  // the solve of all cells of the shard; s.d_dinv must hold the reciprocal Galerkin diagonals
+  // (launch_solve_streamed computes them before dispatching here)
+  cudaError_t
+  launch_solve_cluster(const Shard &s, double tol, int max_iter, cudaStream_t st, int *n_launches)
+  {
+    clus::Params P;
+    P.corners  = s.d_corners;
+    P.q1coef   = s.d_q1coef;
+    P.sten     = s.d_sten;
+    P.dinv     = s.d_dinv;
+    P.phi      = s.d_phi;
+    P.iters    = s.d_iters;
+    P.res      = s.d_res;
+    P.fail     = s.d_fail;
+    P.tol2     = tol * tol;
+    P.max_iter = max_iter;
+    P.cn       = (int)streamed_coarse_nodes(s.l);
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (s.l)
+      {
+        case 5:
+          e = clus::launch<5>(P, s.n_cells, st);
+          break;
+        case 6:
+          e = clus::launch<6>(P, s.n_cells, st);
+          break;
+        case 7:
+          e = clus::launch<7>(P, s.n_cells, st);
+          break;
+      }
+    if (e == cudaSuccess)
+      ++*n_launches;
+    return e;
+  }
+#endif
+} // namespace msb

@@ -21,11 +21,44 @@ NAMES = {0: "prologue (scale + Galerkin)", 1: "rhs init + z0", 2: "stencil q=Ap"
 ORDER = [0, 1, 2, 3, 4, 5, 6, 7, 11, 8, 9, 10]
 
 
+CL_NAMES = {0: "prologue (coefficients to SMEM)", 1: "rhs init + r.r", 2: "restrict level 1 + barrier",
+            3: "restrict level 2 + barrier", 4: "restrict level 3, gather + barrier",
+            5: "levels >= 3 down / up (redundant)", 6: "levels 2, 1 up", 7: "fine z + r.z all-reduce",
+            8: "p update (slab + halo rows)", 9: "stencil q = K p + p.q all-reduce",
+            10: "x, r update, stage r + r.r all-reduce", 11: "epilogue (write phi) + barrier"}
+
+
+def cluster_main(wl, cells, variant):
+    """solve_cluster_kernel: cycles of thread 0 of every CTA, summed over the CTAs of all clusters."""
+    r, l, kind, par, seed = WORKLOADS[wl]
+    lib = pkg.load_library()
+    out = (C.c_ulonglong * 16)()
+    with pkg.BasisShard(l, pkg.coarse_corners(r, 0, cells), coeff_desc(kind, par, seed), variant=variant,
+                        tier=pkg.TIER_STREAMED) as sh:
+        sh.run(1e-12, 5000)
+        lib.msb_debug_stage_cycles_cl(out, 1)
+        sh.run(1e-12, 5000)
+        lib.msb_debug_stage_cycles_cl(out, 1)
+        it, _ = sh.iteration_counts()
+        st = sh.run_stats()
+    cyc = np.array(out[:12], dtype=np.float64)
+    ctas = cells * ((1 << l) // 16)
+    # a pass of two bases iterates until both have converged
+    pass_its = sum(max(row[0], row[1]) + max(row[2], row[3]) for row in it)
+    print("workload %s cells %d l=%d: solve %.3f ms, mean k %.1f, cycles per CTA %.0f" %
+          (wl, cells, l, st["ms_solve"], it.mean(), cyc.sum() / ctas))
+    for idx in range(12):
+        print("  %-42s %5.1f%%   %8.0f cycles/pass-iteration" %
+              (CL_NAMES[idx], 100 * cyc[idx] / cyc.sum(), cyc[idx] / ctas / (pass_its / cells)))
+
+
 def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else "target"
     cells = int(sys.argv[2]) if len(sys.argv) > 2 else 1184
     variant = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     r, l, kind, par, seed = WORKLOADS[wl]
+    if (l == 7 and variant == 0) or variant == 3:
+        return cluster_main(wl, cells, variant)
     lib = pkg.load_library()
     out = (C.c_ulonglong * 16)()
     with pkg.BasisShard(l, pkg.coarse_corners(r, 0, cells), coeff_desc(kind, par, seed), variant=variant) as sh:

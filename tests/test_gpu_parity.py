@@ -407,10 +407,11 @@ def test_more_than_65535_cells_streamed_tier(msb, oracle):
 
 
 def test_streamed_tier_fused_and_unfused_coarse_levels_agree(msb, oracle):
-    """variant 1 of the streamed tier runs one launch per coarse level instead of the fused kernel."""
+    """variant 1 of the streamed tier runs one launch per coarse level instead of the fused kernel
+    (variant 2: the HBM-streamed kernels at n = 128, where the default is the cluster kernel)."""
     cd, _ = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
     cor = msb.coarse_corners(3, 10, 14)
-    with msb.BasisShard(7, cor, cd) as a, msb.BasisShard(7, cor, cd, variant=1) as b:
+    with msb.BasisShard(7, cor, cd, variant=2) as a, msb.BasisShard(7, cor, cd, variant=1) as b:
         a.run(1e-12, 5000)
         b.run(1e-12, 5000)
         ia, _ = a.iteration_counts()
@@ -420,6 +421,57 @@ def test_streamed_tier_fused_and_unfused_coarse_levels_agree(msb, oracle):
         Mb, _ = b.element_matrices()
         assert _rel(Ma, Mb) < 1e-10
         assert a.run_stats()["launches"] < b.run_stats()["launches"]
+
+
+@pytest.mark.parametrize("l,cells", [(7, 21), (6, 5), (5, 3)])
+def test_cluster_tier_matches_streamed_tier(msb, oracle, l, cells):
+    """The thread-block-cluster / DSMEM kernel (default at n = 128; variant 3 of the streamed tier at
+    n = 32, 64: clusters of 2 and 4 CTAs) is the same multilevel PCG as the HBM-streamed kernels
+    (variant 2): same iteration counts, same bases to solver accuracy, ONE solve launch; and the
+    oracle's bases within the north-star tolerance."""
+    cd, co = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    cor = msb.coarse_corners(3, 7, 7 + cells)
+    with msb.BasisShard(l, cor, cd, tier=msb.TIER_STREAMED, variant=0 if l == 7 else 3) as a, \
+            msb.BasisShard(l, cor, cd, tier=msb.TIER_STREAMED, variant=2) as b:
+        a.run(1e-12, 5000)
+        b.run(1e-12, 5000)
+        ia, ra = a.iteration_counts()
+        ib, rb = b.iteration_counts()
+        assert np.all(ra <= 1e-12) and np.all(rb <= 1e-12)
+        assert np.abs(ia - ib).max() <= 1
+        Ma, ba = a.element_matrices()
+        Mb, bb = b.element_matrices()
+        assert _rel(Ma, Mb) < 1e-10 and _rel(ba, bb) < 1e-10
+        for c in (0, cells // 2, cells - 1):
+            for k in range(4):
+                assert _rel(a.basis(c, k), b.basis(c, k)) < 1e-10
+        assert a.run_stats()["launches"] < 20 < b.run_stats()["launches"]
+        ref = oracle.run_cells(l, cor[:1], co)
+        for k in range(4):
+            assert _rel(a.basis(0, k), ref["phi"][0][k]) < TOL_PHI
+        assert _rel(Ma[0], ref["M"][0]) < TOL_MB
+
+
+def test_cluster_tier_no_convergence_and_zero_iterations(msb, oracle):
+    """max_iter reached inside the cluster kernel: error code, iteration counts = max_iter, first failing
+    solve named (the reference throws SolverControl::NoConvergence, basis.tpp:303); a loose tolerance
+    stops at k = 0 like SolverCG's initial check."""
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    with msb.BasisShard(7, msb.coarse_corners(3, 0, 3), cd) as sh:
+        with pytest.raises(msb.MsbError) as e:
+            sh.run(1e-12, 7)
+        assert e.value.code == -5
+        cell, ib, res = sh.failure()
+        assert (cell, ib) == (0, 0) and res > 1e-12
+        it, _ = sh.iteration_counts()
+        assert np.all(it == 7)
+        sh.run(1e3, 1000)
+        it, _ = sh.iteration_counts()
+        assert np.all(it == 0)
+        sh.run(1e-12, 5000)
+        assert sh.failure()[0] == -1
+        M, _ = sh.element_matrices()
+        assert np.abs(M.sum(axis=2)).max() < 1e-9
 
 
 def test_degenerate_coarse_cell_is_rejected(msb, oracle):

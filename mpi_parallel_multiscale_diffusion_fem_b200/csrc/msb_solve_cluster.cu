@@ -11,13 +11,19 @@
 //                    the residual, the slab's part of coarse levels 1 and 2 (+ halo rows), a
 //                    full copy of levels >= 3, reciprocal Galerkin diagonals of all of these
 //     registers      x, r, z / q: a thread owns 4 consecutive rows of one column
-// What crosses CTAs goes through DSMEM, always as a PUSH (remote st.shared::cluster, the latency
-// is hidden behind the following barrier) followed by one cluster barrier:
+// What crosses CTAs goes through DSMEM, always as a PUSH: st.async.shared::cluster with
+// mbarrier complete_tx into the consumer's shared memory; the consumer arms its own mbarrier
+// with the byte count it expects and waits on it -- point-to-point, no cluster-wide barrier and
+// no fence in the iteration (cg::cluster.sync() compiles to MEMBAR.ALL.GPU + barrier + CCTL.IVALL
+// and measured ~1900 cycles per use with 8 x 512 threads; six of them were 45 % of an iteration):
 //     halo rows of z (-> p), r, r_1, r_2 to the neighbouring slab; the two level-3 rows a CTA owns to
 //     every CTA of the cluster (levels >= 3 are then swept redundantly by all CTAs: no serial
 //     coarse chain across the cluster); the per-CTA partial dot products to every CTA, which
 //     adds them in rank order so that all CTAs take bitwise identical decisions.
-// Six cluster barriers per PCG iteration, HBM traffic = read the stencil once, write Phi.
+// The three all-reduces of an iteration are the only cluster-wide synchronisation points; every
+// buffer a CTA pushes into was last read by its owner before an all-reduce the pusher has
+// already completed (see the hazard table in DESIGN.md 3.4).
+// HBM traffic = read the stencil once, write Phi.
 // The four bases of a cell are solved two at a time (two passes share the prologue).
 //
 // Replaces, for these local meshes, the per-basis sequence of the reference:
@@ -47,6 +53,66 @@ msb_debug_stage_cycles_cl(unsigned long long *out, int reset)
 #endif
 
 namespace cg = cooperative_groups;
+
+// ---- distributed-shared-memory primitives (device: PTX; MSB_EMU: scripts/emu/cluster_emu.cpp)
+#ifndef MSB_EMU
+namespace dsm
+{
+  __device__ __forceinline__ uint32_t
+  saddr(const void *p)
+  {
+    return (uint32_t)__cvta_generic_to_shared(p);
+  }
+  // shared::cluster address of CTA `rank`'s copy of a shared::cta address
+  __device__ __forceinline__ uint32_t
+  peer(uint32_t a, int rank)
+  {
+    uint32_t r;
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+  }
+  // store one double into CTA `rank`'s copy of *dst; its mbarrier *mb counts the 8 bytes
+  __device__ __forceinline__ void
+  push(double *dst, uint64_t *mb, int rank, double v)
+  {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 :
+                 : "r"(peer(saddr(dst), rank)), "l"(__double_as_longlong(v)), "r"(peer(saddr(mb), rank))
+                 : "memory");
+  }
+  __device__ __forceinline__ void
+  mbar_init(uint64_t *mb, int count)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" : : "r"(saddr(mb)), "r"(count) : "memory");
+  }
+  __device__ __forceinline__ void
+  mbar_fence_init()
+  {
+    asm volatile("fence.mbarrier_init.release.cluster;" : : : "memory");
+  }
+  // the consumer's single arrival of a phase + the bytes it expects from its producers
+  __device__ __forceinline__ void
+  mbar_expect(uint64_t *mb, uint32_t bytes)
+  {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" : : "r"(saddr(mb)), "r"(bytes) : "memory");
+  }
+  __device__ __forceinline__ void
+  mbar_wait(uint64_t *mb, uint32_t parity)
+  {
+    asm volatile("{\n\t"
+                 ".reg .pred P1;\n\t"
+                 "DSM_WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+                 "@P1 bra DSM_DONE;\n\t"
+                 "bra DSM_WAIT;\n\t"
+                 "DSM_DONE:\n\t"
+                 "}"
+                 :
+                 : "r"(saddr(mb)), "r"(parity)
+                 : "memory");
+  }
+} // namespace dsm
+#endif
 
 namespace msb
 {
@@ -104,9 +170,10 @@ namespace msb
       static constexpr int o_v3  = o_d2 + 5 * W2;                  // [NBP][cn3]   levels >= 3, full, stride npl
       static constexpr int o_d3  = o_v3 + NBP * cn3;               // [cn3]
       static constexpr int o_red = o_d3 + cn3;                     // [3][CS][NBP] partial dot products
-      static constexpr int o_buf = o_red + 3 * CS * NBP;           // [NBP][NW]    block reduction scratch
-      static constexpr int o_zh  = o_buf + NBP * NW;               // [NBP][2][W]  z of the rows y0-1 and y0+16
-      static constexpr int total = o_zh + NBP * 2 * W;
+      static constexpr int o_buf = o_red + 3 * CS * NBP;           // [3][NBP][NW] block reduction scratch
+      static constexpr int o_zh  = o_buf + 3 * NBP * NW;           // [NBP][2][W]  z of the rows y0-1 and y0+16
+      static constexpr int o_mb  = o_zh + NBP * 2 * W;             // [6] mbarriers (64 bit each)
+      static constexpr int total = o_mb + 6;
       static constexpr size_t smem_bytes = sizeof(double) * (size_t)total;
       static_assert(L >= 5 && L <= 7, "cluster tier: 32 <= n <= 128 (cluster of 2..8 CTAs)");
       static_assert(NW <= 32, "block_sum: one lane per warp partial");
@@ -146,6 +213,18 @@ namespace msb
       double *v1 = sm + Y::o_v1, *d1 = sm + Y::o_d1, *v2 = sm + Y::o_v2, *d2 = sm + Y::o_d2;
       double *v3 = sm + Y::o_v3, *d3 = sm + Y::o_d3, *red = sm + Y::o_red, *buf = sm + Y::o_buf;
       double *zh = sm + Y::o_zh;
+      uint64_t *mb = reinterpret_cast<uint64_t *>(sm + Y::o_mb);
+      // one mbarrier per kind of exchange, one phase per use; bit i of ph = parity to wait for next
+      enum { MB_V1 = 0, MB_V2, MB_V3, MB_RZ, MB_PQ, MB_RR };
+      unsigned  ph = 0;
+      const int nn = (rank > 0) + (rank + 1 < CS); // neighbouring slabs
+      // wait until every byte the producers of this exchange push into this CTA has landed
+      auto await = [&](int which, int bytes) {
+        if (tid == 0)
+          dsm::mbar_expect(mb + which, (uint32_t)bytes);
+        dsm::mbar_wait(mb + which, (ph >> which) & 1u);
+        ph ^= 1u << which;
+      };
 
       const double *S  = P.sten + (size_t)cell * ST_NARR * N;
       const double *c  = P.corners + 8 * (size_t)cell;
@@ -156,6 +235,12 @@ namespace msb
       for (int i = tid; i < Y::total; i += T)
         sm[i] = 0.0;
       __syncthreads();
+      if (tid == 0)
+        {
+          for (int i = 0; i < 6; ++i)
+            dsm::mbar_init(mb + i, 1);
+          dsm::mbar_fence_init();
+        }
       for (int t = tid; t < 17 * W; t += T)
         {
           const int r = t >> L, x = t & (W - 1), y = y0 - 1 + r;
@@ -184,21 +269,21 @@ namespace msb
         for (int t = tid; t < cn3; t += T)
           d3[t] = dg[Y::goff(3) + t];
       }
-      // nobody may push into a peer's shared memory before that peer has zeroed it
+      // nobody may push into a peer's shared memory before that peer has zeroed it and set up its mbarriers
       cluster.sync();
       ST_MARK(0)
 
       // sum of one value per basis over the whole cluster, the same bits in every thread of every CTA
-      auto allreduce = [&](double(&v)[NBP], int slot) {
-        bpx::block_sum<NBP, NW>(v, buf, warp, lane);
+      // (slot 0: r.z, 1: p.q, 2: r.r; `extra` = bytes of halo rows that travel with the partials)
+      auto allreduce = [&](double(&v)[NBP], int slot, int extra) {
+        bpx::block_sum<NBP, NW>(v, buf + slot * NBP * NW, warp, lane);
         if (tid < CS)
           {
-            double *dst = cluster.map_shared_rank(red, tid);
 #pragma unroll
             for (int k = 0; k < NBP; ++k)
-              dst[(slot * CS + rank) * NBP + k] = v[k];
+              dsm::push(red + (slot * CS + rank) * NBP + k, mb + MB_RZ + slot, tid, v[k]);
           }
-        cluster.sync();
+        await(MB_RZ + slot, 8 * (CS * NBP + extra));
 #pragma unroll
         for (int k = 0; k < NBP; ++k)
           {
@@ -274,10 +359,9 @@ namespace msb
                     rS[(k * 17 + 4 * g + i + 1) * W + jx] = r[k][i];
                 if (g == 3 && rank + 1 < CS)
                   {
-                    double *dst = cluster.map_shared_rank(rS, rank + 1);
 #pragma unroll
                     for (int k = 0; k < NBP; ++k)
-                      dst[(k * 17 + 0) * W + jx] = r[k][3];
+                      dsm::push(rS + (k * 17 + 0) * W + jx, mb + MB_RR, rank + 1, r[k][3]);
                   }
               }
           };
@@ -293,7 +377,7 @@ namespace msb
                   acc[k] = fma(r[k][i], r[k][i], acc[k]);
               }
             stage_r();
-            allreduce(acc, 2);
+            allreduce(acc, 2, rank > 0 ? NBP * (W - 1) : 0);
 #pragma unroll
             for (int k = 0; k < NBP; ++k)
               rr[k] = acc[k], rz[k] = 1.0, beta[k] = 0.0, itc[k] = -1, done[k] = false;
@@ -325,12 +409,13 @@ namespace msb
                       const double v = restrict_node(rS + (k * 17 + 2 * qr + 1) * W + 2 * X, W);
                       v1[(k * 10 + qr + 1) * W1 + X] = v;
                       if (qr == 0 && rank > 0)
-                        cluster.map_shared_rank(v1, rank - 1)[(k * 10 + 9) * W1 + X] = v;
+                        dsm::push(v1 + (k * 10 + 9) * W1 + X, mb + MB_V1, rank - 1, v);
                       if (qr == 7 && rank + 1 < CS)
-                        cluster.map_shared_rank(v1, rank + 1)[(k * 10 + 0) * W1 + X] = v;
+                        dsm::push(v1 + (k * 10 + 0) * W1 + X, mb + MB_V1, rank + 1, v);
                     }
                 }
-              cluster.sync();
+              __syncthreads();
+              await(MB_V1, 8 * nn * NBP * (W1 - 1));
               ST_MARK(2)
               // level 2 rows 4c .. 4c+3
               for (int t = tid; t < NBP * 4 * W2; t += T)
@@ -341,12 +426,13 @@ namespace msb
                       const double v = restrict_node(v1 + (k * 10 + 2 * qr + 1) * W1 + 2 * X, W1);
                       v2[(k * 6 + qr + 1) * W2 + X] = v;
                       if (qr == 0 && rank > 0)
-                        cluster.map_shared_rank(v2, rank - 1)[(k * 6 + 5) * W2 + X] = v;
+                        dsm::push(v2 + (k * 6 + 5) * W2 + X, mb + MB_V2, rank - 1, v);
                       if (qr == 3 && rank + 1 < CS)
-                        cluster.map_shared_rank(v2, rank + 1)[(k * 6 + 0) * W2 + X] = v;
+                        dsm::push(v2 + (k * 6 + 0) * W2 + X, mb + MB_V2, rank + 1, v);
                     }
                 }
-              cluster.sync();
+              __syncthreads();
+              await(MB_V2, 8 * nn * NBP * (W2 - 1));
               ST_MARK(3)
               // level 3 rows 2c, 2c+1 -> every CTA of the cluster
               for (int t = tid; t < NBP * 2 * W3; t += T)
@@ -358,10 +444,10 @@ namespace msb
                       const double v = restrict_node(v2 + (k * 6 + 2 * qr + 1) * W2 + 2 * X, W2);
 #pragma unroll
                       for (int j = 0; j < CS; ++j)
-                        cluster.map_shared_rank(v3, j)[k * cn3 + Y3 * NP3 + X] = v;
+                        dsm::push(v3 + k * cn3 + Y3 * NP3 + X, mb + MB_V3, j, v);
                     }
                 }
-              cluster.sync();
+              await(MB_V3, 8 * NBP * (W3 - 1) * (W3 - 1));
               ST_MARK(4)
               // levels 4 .. LV: down, redundantly in every CTA
 #pragma unroll
@@ -460,20 +546,18 @@ namespace msb
                     // of p themselves once beta is known (saves the barrier a push of p would need)
                     if (g == 0 && rank > 0)
                       {
-                        double *dst = cluster.map_shared_rank(zh, rank - 1);
 #pragma unroll
                         for (int k = 0; k < NBP; ++k)
-                          dst[(k * 2 + 1) * W + jx] = z[k][0];
+                          dsm::push(zh + (k * 2 + 1) * W + jx, mb + MB_RZ, rank - 1, z[k][0]);
                       }
                     if (g == 3 && rank + 1 < CS)
                       {
-                        double *dst = cluster.map_shared_rank(zh, rank + 1);
 #pragma unroll
                         for (int k = 0; k < NBP; ++k)
-                          dst[(k * 2 + 0) * W + jx] = z[k][3];
+                          dsm::push(zh + (k * 2 + 0) * W + jx, mb + MB_RZ, rank + 1, z[k][3]);
                       }
                   }
-                allreduce(acc, 0);
+                allreduce(acc, 0, nn * NBP * (W - 1));
 #pragma unroll
                 for (int k = 0; k < NBP; ++k)
                   {
@@ -575,7 +659,7 @@ namespace msb
                         }
                     }
                 }
-              allreduce(pq, 1);
+              allreduce(pq, 1, 0);
               ST_MARK(9)
 
               // ---- x += alpha p ; r -= alpha q ; r.r
@@ -599,7 +683,7 @@ namespace msb
                         }
                   }
                 stage_r();
-                allreduce(acc, 2);
+                allreduce(acc, 2, rank > 0 ? NBP * (W - 1) : 0);
 #pragma unroll
                 for (int k = 0; k < NBP; ++k)
                   if (!done[k])

@@ -140,6 +140,80 @@ namespace cooperative_groups
   }
 } // namespace cooperative_groups
 
+// distributed-shared-memory primitives of msb_solve_cluster.cu: st.async + mbarrier complete_tx
+#include <map>
+namespace dsm
+{
+  struct State
+  {
+    long                  tx = 0;
+    int                   pending = 1, count = 1;
+    std::atomic<unsigned> phase{0};
+  };
+  static std::mutex                  mu;
+  static std::map<const void *, State> tab; // keyed by the mbarrier's address in its CTA's memory
+  template <class T>
+  inline T *
+  map_rank(T *p, int rank)
+  {
+    const size_t off = (const char *)p - (const char *)emu::smem();
+    return (T *)((char *)emu::t_cluster->ctas[rank].smem.data() + off);
+  }
+  inline void
+  try_complete(State &s)
+  {
+    if (s.pending == 0 && s.tx == 0)
+      {
+        s.pending = s.count;
+        s.phase.fetch_add(1, std::memory_order_release);
+        s.phase.notify_all();
+      }
+  }
+  inline void
+  mbar_init(uint64_t *mb, int count)
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    State                      &s = tab[mb];
+    s.tx = 0, s.pending = s.count = count, s.phase.store(0);
+  }
+  inline void
+  mbar_fence_init()
+  {}
+  inline void
+  mbar_expect(uint64_t *mb, uint32_t bytes)
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    State                      &s = tab.at(mb);
+    s.tx += bytes, s.pending -= 1;
+    try_complete(s);
+  }
+  inline void
+  push(double *dst, uint64_t *mb, int rank, double v)
+  {
+    *map_rank(dst, rank) = v;
+    std::lock_guard<std::mutex> lk(mu);
+    State                      &s = tab.at(map_rank(mb, rank));
+    s.tx -= 8;
+    try_complete(s);
+  }
+  inline void
+  mbar_wait(uint64_t *mb, uint32_t parity)
+  {
+    State *s;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      s = &tab.at(mb);
+    }
+    for (;;)
+      {
+        const unsigned p = s->phase.load(std::memory_order_acquire);
+        if ((p & 1u) != parity)
+          return;
+        s->phase.wait(p, std::memory_order_acquire);
+      }
+  }
+} // namespace dsm
+
 #include <cuda_runtime.h>
 #undef __launch_bounds__
 #define __launch_bounds__(...)

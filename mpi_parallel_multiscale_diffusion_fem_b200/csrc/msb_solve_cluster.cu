@@ -156,6 +156,18 @@ namespace msb
           o += npl(k) * npl(k);
         return o;
       }
+      // threads the direct restriction to the levels > 3 occupies (whole warps per level)
+      __host__ __device__ static constexpr int
+      deep_threads()
+      {
+        int b = 0;
+        for (int m = 1; m <= LV - 3; ++m)
+          {
+            const int nin = npl(3 + m) - 2, items = NBP * nin * nin, G = m == 1 ? 1 : (2 << m);
+            b += ((items * G + 31) / 32) * 32;
+          }
+        return b;
+      }
       static constexpr int cn  = goff(LV + 1);
       static constexpr int cn3 = goff(LV + 1) - goff(3); // nodes of levels 3..LV (full copies)
       // shared-memory map, in doubles
@@ -177,6 +189,7 @@ namespace msb
       static constexpr size_t smem_bytes = sizeof(double) * (size_t)total;
       static_assert(L >= 5 && L <= 7, "cluster tier: 32 <= n <= 128 (cluster of 2..8 CTAs)");
       static_assert(NW <= 32, "block_sum: one lane per warp partial");
+      static_assert(deep_threads() <= T, "direct restriction: one segment of whole warps per level");
     };
 
     // full weighting of one coarse node from a buffer with row stride `stride`, centred at s
@@ -449,41 +462,70 @@ namespace msb
                 }
               await(MB_V3, 8 * NBP * (W3 - 1) * (W3 - 1));
               ST_MARK(4)
-              // levels 4 .. LV: down, redundantly in every CTA
+              // levels > 3, redundantly in every CTA.  The preconditioner is additive, so the levels are
+              // independent: r_l = (P_3..l)^T r_3 directly (nested hat functions of half width 2^(l-3)),
+              // scaled by 1/D_l, by different warps at the same time; then ONE sweep of level 3 adds the
+              // direct bilinear interpolation of every deeper level.  Two barriers instead of 2 (LV-3) + 1.
+              {
+                int base = 0; // first thread of the level's segment (whole warps)
 #pragma unroll
-              for (int l = 4; l <= LV; ++l)
-                {
-                  const int npl = Y::npl(l), nin = npl - 2, npf = Y::npl(l - 1);
-                  const int lo = Y::goff(l) - Y::goff(3), lf = Y::goff(l - 1) - Y::goff(3);
-                  for (int t = tid; t < NBP * nin * nin; t += T)
-                    {
-                      const int k = t / (nin * nin), u = t % (nin * nin), cx = 1 + u % nin, cy = 1 + u / nin;
-                      v3[k * cn3 + lo + cy * npl + cx] =
-                        restrict_node(v3 + k * cn3 + lf + 2 * cy * npf + 2 * cx, npf);
-                    }
-                  __syncthreads();
-                }
-              // up: z_l = r_l / D_l + P z_{l+1}, in place
+                for (int m = 1; m <= LV - 3; ++m)
+                  {
+                    const int l = 3 + m, npl = Y::npl(l), nin = npl - 2, items = NBP * nin * nin;
+                    const int lo = Y::goff(l) - Y::goff(3), h = 1 << m;
+                    const int G   = m == 1 ? 1 : (2 << m); // lanes per coarse node: one per window row
+                    const int seg = ((items * G + 31) / 32) * 32;
+                    if (tid >= base && tid < base + seg)
+                      {
+                        const int u = tid - base, item = u / G, sub = u % G;
+                        const int k = item / (nin * nin), q2 = item % (nin * nin), cx = 1 + q2 % nin, cy = 1 + q2 / nin;
+                        double    acc = 0.0;
+                        if (item < items)
+                          {
+                            const double *src = v3 + k * cn3 + (cy * h) * NP3 + cx * h;
+                            if (m == 1)
+                              acc = restrict_node(src, NP3);
+                            else if (sub < 2 * h - 1)
+                              {
+                                const int    dy = sub - (h - 1);
+                                const double rh = 1.0 / h;
+                                double       row = 0.0;
+                                for (int dx = -(h - 1); dx <= h - 1; ++dx)
+                                  row = fma(1.0 - abs(dx) * rh, src[dy * NP3 + dx], row);
+                                acc = (1.0 - abs(dy) * rh) * row;
+                              }
+                          }
 #pragma unroll
-              for (int l = LV; l >= 3; --l)
-                {
-                  const int npl = Y::npl(l), nin = npl - 2, lo = Y::goff(l) - Y::goff(3);
-                  for (int t = tid; t < NBP * nin * nin; t += T)
-                    {
-                      const int k = t / (nin * nin), u = t % (nin * nin), fx = 1 + u % nin, fy = 1 + u / nin;
-                      const int i = lo + fy * npl + fx;
-                      double    v = v3[k * cn3 + i] * d3[i];
-                      if (l < LV)
-                        {
-                          const int     npc = Y::npl(l + 1);
-                          const double *vc  = v3 + k * cn3 + Y::goff(l + 1) - Y::goff(3);
-                          const int     xl = fx >> 1, xh = (fx + 1) >> 1, yl = fy >> 1, yh = (fy + 1) >> 1;
-                          v += 0.25 * ((vc[yl * npc + xl] + vc[yl * npc + xh]) + (vc[yh * npc + xl] + vc[yh * npc + xh]));
-                        }
-                      v3[k * cn3 + i] = v;
-                    }
-                  __syncthreads();
-                }
+                        for (int off = G / 2; off > 0; off >>= 1)
+                          acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                        if (item < items && sub == 0)
+                          v3[k * cn3 + lo + cy * npl + cx] = acc * d3[lo + cy * npl + cx];
+                      }
+                    base += seg;
+                  }
+                __syncthreads();
+                const int nin = NP3 - 2;
+                for (int t = tid; t < NBP * nin * nin; t += T)
+                  {
+                    const int k = t / (nin * nin), u = t % (nin * nin), fx = 1 + u % nin, fy = 1 + u / nin;
+                    const int i = fy * NP3 + fx;
+                    double    v = v3[k * cn3 + i] * d3[i];
+#pragma unroll
+                    for (int m = 1; m <= LV - 3; ++m)
+                      {
+                        const int     l = 3 + m, npc = Y::npl(l), h = 1 << m;
+                        const double *vc = v3 + k * cn3 + Y::goff(l) - Y::goff(3);
+                        const int     cx = fx >> m, cy = fy >> m;
+                        const double  tx = (fx & (h - 1)) * (1.0 / h), ty = (fy & (h - 1)) * (1.0 / h);
+                        const double  a = fma(tx, vc[cy * npc + cx + 1] - vc[cy * npc + cx], vc[cy * npc + cx]);
+                        const double  b =
+                          fma(tx, vc[(cy + 1) * npc + cx + 1] - vc[(cy + 1) * npc + cx], vc[(cy + 1) * npc + cx]);
+                        v += fma(ty, b - a, a);
+                      }
+                    v3[k * cn3 + i] = v;
+                  }
+                __syncthreads();
+              }
               ST_MARK(5)
               // level 2: own rows + the upper halo row (needed by level-1 rows of this slab)
               for (int t = tid; t < NBP * 5 * W2; t += T)
@@ -526,17 +568,26 @@ namespace msb
                 if (colact)
                   {
                     const int xl = jx >> 1, xh = (jx + 1) >> 1;
+                    // the 4 fine rows of a thread lie under 3 level-1 rows (buffer rows 2g+1 .. 2g+3)
+                    double c1[NBP][3][2];
+#pragma unroll
+                    for (int k = 0; k < NBP; ++k)
+#pragma unroll
+                      for (int a = 0; a < 3; ++a)
+                        {
+                          const double *vc = v1 + (k * 10 + 2 * g + 1 + a) * W1;
+                          c1[k][a][0] = vc[xl], c1[k][a][1] = vc[xh];
+                        }
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                       {
-                        const int    yy = 4 * g + i, yl = (yy >> 1) + 1, yh = ((yy + 1) >> 1) + 1;
+                        const int    yy = 4 * g + i, al = i >> 1, ah = (i + 1) >> 1;
                         const double di = d0[yy * W + jx];
 #pragma unroll
                         for (int k = 0; k < NBP; ++k)
                           {
-                            const double *vc = v1 + k * 10 * W1;
-                            const double  cv =
-                              0.25 * ((vc[yl * W1 + xl] + vc[yl * W1 + xh]) + (vc[yh * W1 + xl] + vc[yh * W1 + xh]));
+                            const double cv =
+                              0.25 * ((c1[k][al][0] + c1[k][al][1]) + (c1[k][ah][0] + c1[k][ah][1]));
                             const double zv = fma(r[k][i], di, cv);
                             z[k][i]         = zv;
                             acc[k]          = fma(r[k][i], zv, acc[k]);

@@ -384,7 +384,7 @@ def main():
             "gpu_launches": launches_all,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": (("solve_bpx_tm_kernel" if (l == 6 and args.variant in (0, 5)) else "solve_bpx_kernel") if args.variant < 100 else "solve_smem_kernel") if sh.run_stats()["tier"] == 1 else (("solve_cluster_kernel" if (l == 7 and args.variant == 0) or (args.variant == 3 and 5 <= l <= 7) else "stream_k*") if dim == 2 else "d3::k2_kernel + siblings"),
+                         "kernel": (("solve_bpx_tm_kernel" if (l == 6 and args.variant in (0, 5)) else "solve_bpx_kernel") if args.variant < 100 else "solve_smem_kernel") if sh.run_stats()["tier"] == 1 else (("solve_cluster_kernel" if (l == 7 and args.variant == 0) or (args.variant in (3, 4) and 5 <= l <= 7) else "stream_k*") if dim == 2 else "d3::k2_kernel + siblings"),
                          "kernel_ms_per_launch": solve_ms_max,
                          "peak_source": peak_src,
                          "note": "achieved = ALGORITHMIC streaming bytes N(96k+16)/solve (SURVEY 8d) / "

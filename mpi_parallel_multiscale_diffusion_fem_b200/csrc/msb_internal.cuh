@@ -90,7 +90,7 @@ namespace msb
   cudaError_t launch_solve_streamed(Shard &s, double tol, int max_iter, cudaStream_t st,
                                     int *n_launches);
   // cluster / DSMEM tier (msb_solve_cluster.cu); called by launch_solve_streamed after its setup
-  cudaError_t launch_solve_cluster(const Shard &s, double tol, int max_iter, cudaStream_t st,
+  cudaError_t launch_solve_cluster(const Shard &s, double tol, int max_iter, bool tmem, cudaStream_t st,
                                    int *n_launches);
   bool        cluster_tier_supported(int l);
   cudaError_t launch_element_matrices(const Shard &s, cudaStream_t st, int *n_launches);

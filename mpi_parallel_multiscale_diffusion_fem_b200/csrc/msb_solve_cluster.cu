@@ -112,6 +112,77 @@ namespace dsm
                  : "memory");
   }
 } // namespace dsm
+
+// ---- tensor memory as per-thread private storage (32x32b shape: a warp owns a 32-lane quarter, a
+// thread its lane's columns; no tensor-core instruction is issued).  8 doubles = 16 columns.
+namespace tmm
+{
+  constexpr int COLS = 512; // the whole tensor memory of the SM (one CTA per SM)
+  __device__ __forceinline__ void
+  ld8(uint32_t taddr, double (&d)[8])
+  {
+    uint32_t v[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                   "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                   "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      d[i] = __hiloint2double((int)v[2 * i + 1], (int)v[2 * i]);
+  }
+  __device__ __forceinline__ void
+  st8(uint32_t taddr, const double (&d)[8])
+  {
+    uint32_t v[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      {
+        v[2 * i]     = (uint32_t)__double2loint(d[i]);
+        v[2 * i + 1] = (uint32_t)__double2hiint(d[i]);
+      }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+                 "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
+                 "r"(v[15])
+                 : "memory");
+  }
+  __device__ __forceinline__ void
+  wait_st()
+  {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  // all threads of the CTA; returns this thread's base address (lane quarter of its warp in bits
+  // 31:16, the column block of its warp in bits 15:0: warps w, w+4, w+8, .. share a lane quarter)
+  __device__ __forceinline__ uint32_t
+  alloc(uint32_t *s_base, int warp, int cols_per_warp, uint32_t &base_out)
+  {
+    if (warp == 0)
+      {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(s_base)),
+                     "r"(COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+      }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    base_out = *s_base;
+    return base_out + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * cols_per_warp);
+  }
+  __device__ __forceinline__ void
+  release(uint32_t base, int warp)
+  {
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(COLS));
+  }
+} // namespace tmm
 #endif
 
 namespace msb
@@ -119,7 +190,6 @@ namespace msb
   namespace clus
   {
     constexpr int ROWS = 16; // fine node rows per CTA
-    constexpr int NBP  = 2;  // bases per pass
 
     struct Params
     {
@@ -136,7 +206,11 @@ namespace msb
       int           cn;
     };
 
-    template <int L>
+    // NBP = bases per pass.  TM = false: NBP = 2, coefficients in shared memory, x and q in registers.
+    // TM = true: NBP = 4 (one pass), the thread's own stencil coefficients, 1/diag and x in tensor
+    // memory, q parked in the residual staging buffer: frees 100 KB of shared memory for the vectors
+    // of two more bases and takes the coefficient loads off the shared-memory crossbar.
+    template <int L, int NBP, bool TM>
     struct Lay
     {
       static constexpr int n = 1 << L, np = n + 1, N = np * np, CS = n / ROWS, T = 4 * n, NW = T / 32;
@@ -163,7 +237,7 @@ namespace msb
         int b = 0;
         for (int m = 1; m <= LV - 3; ++m)
           {
-            const int nin = npl(3 + m) - 2, items = NBP * nin * nin, G = m == 1 ? 1 : (2 << m);
+            const int nin = npl(3 + m) - 2, items = NBP * nin * nin, G = m == 1 ? 1 : m == 2 ? 4 : 16;
             b += ((items * G + 31) / 32) * 32;
           }
         return b;
@@ -172,8 +246,8 @@ namespace msb
       static constexpr int cn3 = goff(LV + 1) - goff(3); // nodes of levels 3..LV (full copies)
       // shared-memory map, in doubles
       static constexpr int o_cf  = 0;                              // [5][17][W]   rows y0-1 .. y0+15
-      static constexpr int o_d0  = o_cf + 5 * 17 * W;              // [16][W]      1/KC, own rows
-      static constexpr int o_p   = o_d0 + 16 * W;                  // [NBP][18][W] rows y0-1 .. y0+16 (+ pad)
+      static constexpr int o_d0  = o_cf + (TM ? 0 : 5 * 17 * W);   // [16][W]      1/KC, own rows
+      static constexpr int o_p   = o_d0 + (TM ? 0 : 16 * W);       // [NBP][18][W] rows y0-1 .. y0+16 (+ pad)
       static constexpr int o_rs  = o_p + NBP * 18 * W + W;         // [NBP][17][W] rows y0-1 .. y0+15 (+ pad)
       static constexpr int o_v1  = o_rs + NBP * 17 * W + W;        // [NBP][10][W1] level-1 rows 8c-1 .. 8c+8 (+ pad)
       static constexpr int o_d1  = o_v1 + NBP * 10 * W1 + W1;      // [9][W1]      level-1 rows 8c .. 8c+8
@@ -184,8 +258,13 @@ namespace msb
       static constexpr int o_red = o_d3 + cn3;                     // [3][CS][NBP] partial dot products
       static constexpr int o_buf = o_red + 3 * CS * NBP;           // [3][NBP][NW] block reduction scratch
       static constexpr int o_zh  = o_buf + 3 * NBP * NW;           // [NBP][2][W]  z of the rows y0-1 and y0+16
-      static constexpr int o_mb  = o_zh + NBP * 2 * W;             // [6] mbarriers (64 bit each)
-      static constexpr int total = o_mb + 6;
+      static constexpr int o_mb  = o_zh + NBP * 2 * W;             // [6] mbarriers (64 bit each) + TMEM base
+      static constexpr int total = o_mb + 8;
+      // tensor-memory map of a thread (32-bit columns): x [NBP][4] | 8 coefficients per own row | kS of
+      // row 0 and 1/diag of the 4 rows
+      static constexpr int XOFF = 0, COFF = 4 * NBP * 2, EOFF = COFF + 4 * 16, TCOLS = 128;
+      static_assert(!TM || (NBP == 4 && EOFF + 16 <= TCOLS && T / 32 <= 16), "four warps share a lane quarter");
+      static_assert(NBP % 2 == 0 && 4 % NBP == 0, "bases are handled in pairs");
       static constexpr size_t smem_bytes = sizeof(double) * (size_t)total;
       static_assert(L >= 5 && L <= 7, "cluster tier: 32 <= n <= 128 (cluster of 2..8 CTAs)");
       static_assert(NW <= 32, "block_sum: one lane per warp partial");
@@ -202,11 +281,11 @@ namespace msb
       return fma(0.5, a + c, b);
     }
 
-    template <int L>
-    __global__ void __launch_bounds__(Lay<L>::T, 1)
+    template <int L, int NBP, bool TM>
+    __global__ void __launch_bounds__((Lay<L, NBP, TM>::T), 1)
     solve_cluster_kernel(Params P)
     {
-      using Y = Lay<L>;
+      using Y = Lay<L, NBP, TM>;
       constexpr int n = Y::n, np = Y::np, N = Y::N, CS = Y::CS, T = Y::T, NW = Y::NW;
       constexpr int W = Y::W, W1 = Y::W1, W2 = Y::W2, W3 = Y::W3, NP3 = Y::NP3, LV = Y::LV, cn3 = Y::cn3;
 #ifndef MSB_EMU
@@ -254,17 +333,50 @@ namespace msb
             dsm::mbar_init(mb + i, 1);
           dsm::mbar_fence_init();
         }
-      for (int t = tid; t < 17 * W; t += T)
+      uint32_t tm = 0, tm_base = 0; // this thread's tensor-memory base address
+      if constexpr (TM)
         {
-          const int r = t >> L, x = t & (W - 1), y = y0 - 1 + r;
-          if (y >= 0)
-            {
-              const int gi = y * np + x;
+          tm = tmm::alloc(reinterpret_cast<uint32_t *>(mb + 6), warp, Y::TCOLS, tm_base);
+          // the thread's own coefficients straight from HBM (lanes = consecutive columns: coalesced)
+          double e8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-              for (int a = 0; a < 5; ++a)
-                cf[(a * 17 + r) * W + x] = S[(size_t)a * N + gi];
-              if (r >= 1 && y >= 1 && x >= 1)
-                d0[(r - 1) * W + x] = 1.0 / S[(size_t)ST_KC * N + gi];
+          for (int i = 0; i < 4; ++i)
+            {
+              const int y = y0 + 4 * g + i, t = y * np + jx;
+              double    c8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              if (colact && y >= 1)
+                {
+                  c8[0] = S[(size_t)ST_KC * N + t];           // kc
+                  c8[1] = S[(size_t)ST_KE * N + t];           // kE
+                  c8[2] = S[(size_t)ST_KE * N + t - 1];       // kW
+                  c8[3] = S[(size_t)ST_KN * N + t];           // kN
+                  c8[4] = S[(size_t)ST_KD1 * N + t];          // kNE
+                  c8[5] = S[(size_t)ST_KD1 * N + t - np - 1]; // kSW
+                  c8[6] = S[(size_t)ST_KD2 * N + t - 1];      // kNW
+                  c8[7] = S[(size_t)ST_KD2 * N + t - np];     // kSE
+                  e8[1 + i] = 1.0 / c8[0];
+                  if (i == 0)
+                    e8[0] = S[(size_t)ST_KN * N + t - np];    // kS of the first row (then: kN of the row below)
+                }
+              tmm::st8(tm + Y::COFF + 16 * i, c8);
+            }
+          tmm::st8(tm + Y::EOFF, e8);
+          tmm::wait_st();
+        }
+      else
+        {
+          for (int t = tid; t < 17 * W; t += T)
+            {
+              const int r = t >> L, x = t & (W - 1), y = y0 - 1 + r;
+              if (y >= 0)
+                {
+                  const int gi = y * np + x;
+#pragma unroll
+                  for (int a = 0; a < 5; ++a)
+                    cf[(a * 17 + r) * W + x] = S[(size_t)a * N + gi];
+                  if (r >= 1 && y >= 1 && x >= 1)
+                    d0[(r - 1) * W + x] = 1.0 / S[(size_t)ST_KC * N + gi];
+                }
             }
         }
       {
@@ -310,7 +422,7 @@ namespace msb
 
       for (int pass = 0; pass < 4 / NBP; ++pass)
         {
-          double x[NBP][4], r[NBP][4], z[NBP][4];
+          double x[TM ? 1 : NBP][4], r[NBP][4], z[NBP][4]; // TM: x lives in tensor memory
           double rr[NBP], rz[NBP], beta[NBP];
           int    itc[NBP];
           bool   done[NBP];
@@ -335,7 +447,11 @@ namespace msb
               const int y = y0 + 4 * g + i;
 #pragma unroll
               for (int k = 0; k < NBP; ++k)
-                x[k][i] = 0.0, r[k][i] = 0.0, z[k][i] = 0.0;
+                {
+                  r[k][i] = 0.0, z[k][i] = 0.0;
+                  if constexpr (!TM)
+                    x[k][i] = 0.0;
+                }
               if (colact && y >= 1 && (jx == 1 || y == 1 || jx == n - 1 || y == n - 1))
                 {
                   double rv[NBP];
@@ -361,6 +477,14 @@ namespace msb
                 }
             }
 
+          if constexpr (TM)
+            {
+              const double zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+              for (int kp = 0; kp < NBP / 2; ++kp)
+                tmm::st8(tm + Y::XOFF + 16 * kp, zero8);
+              tmm::wait_st();
+            }
           // residual to the staging buffer (+ the slab's last row into the upper neighbour's halo)
           auto stage_r = [&]() {
             if (colact)
@@ -473,7 +597,7 @@ namespace msb
                   {
                     const int l = 3 + m, npl = Y::npl(l), nin = npl - 2, items = NBP * nin * nin;
                     const int lo = Y::goff(l) - Y::goff(3), h = 1 << m;
-                    const int G   = m == 1 ? 1 : (2 << m); // lanes per coarse node: one per window row
+                    const int G   = m == 1 ? 1 : m == 2 ? 4 : 16; // lanes per coarse node, each sums whole window rows
                     const int seg = ((items * G + 31) / 32) * 32;
                     if (tid >= base && tid < base + seg)
                       {
@@ -485,14 +609,17 @@ namespace msb
                             const double *src = v3 + k * cn3 + (cy * h) * NP3 + cx * h;
                             if (m == 1)
                               acc = restrict_node(src, NP3);
-                            else if (sub < 2 * h - 1)
+                            else
                               {
-                                const int    dy = sub - (h - 1);
                                 const double rh = 1.0 / h;
-                                double       row = 0.0;
-                                for (int dx = -(h - 1); dx <= h - 1; ++dx)
-                                  row = fma(1.0 - abs(dx) * rh, src[dy * NP3 + dx], row);
-                                acc = (1.0 - abs(dy) * rh) * row;
+                                for (int wr = sub; wr < 2 * h - 1; wr += G)
+                                  {
+                                    const int dy  = wr - (h - 1);
+                                    double    row = 0.0;
+                                    for (int dx = -(h - 1); dx <= h - 1; ++dx)
+                                      row = fma(1.0 - abs(dx) * rh, src[dy * NP3 + dx], row);
+                                    acc = fma(1.0 - abs(dy) * rh, row, acc);
+                                  }
                               }
                           }
 #pragma unroll
@@ -565,30 +692,41 @@ namespace msb
 #pragma unroll
                 for (int k = 0; k < NBP; ++k)
                   acc[k] = 0.0;
+                double di[4];
+                if constexpr (TM)
+                  {
+                    double e8[8];
+                    tmm::ld8(tm + Y::EOFF, e8); // all lanes: tcgen05.ld is warp-collective
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                      di[i] = e8[1 + i];
+                  }
+                else
+                  {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                      di[i] = d0[(4 * g + i) * W + (colact ? jx : 1)];
+                  }
                 if (colact)
                   {
                     const int xl = jx >> 1, xh = (jx + 1) >> 1;
-                    // the 4 fine rows of a thread lie under 3 level-1 rows (buffer rows 2g+1 .. 2g+3)
-                    double c1[NBP][3][2];
 #pragma unroll
                     for (int k = 0; k < NBP; ++k)
-#pragma unroll
-                      for (int a = 0; a < 3; ++a)
-                        {
-                          const double *vc = v1 + (k * 10 + 2 * g + 1 + a) * W1;
-                          c1[k][a][0] = vc[xl], c1[k][a][1] = vc[xh];
-                        }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
                       {
-                        const int    yy = 4 * g + i, al = i >> 1, ah = (i + 1) >> 1;
-                        const double di = d0[yy * W + jx];
+                        // the 4 fine rows of a thread lie under 3 level-1 rows (buffer rows 2g+1 .. 2g+3)
+                        double c1[3][2];
 #pragma unroll
-                        for (int k = 0; k < NBP; ++k)
+                        for (int a = 0; a < 3; ++a)
                           {
-                            const double cv =
-                              0.25 * ((c1[k][al][0] + c1[k][al][1]) + (c1[k][ah][0] + c1[k][ah][1]));
-                            const double zv = fma(r[k][i], di, cv);
+                            const double *vc = v1 + (k * 10 + 2 * g + 1 + a) * W1;
+                            c1[a][0] = vc[xl], c1[a][1] = vc[xh];
+                          }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                          {
+                            const int    al = i >> 1, ah = (i + 1) >> 1;
+                            const double cv = 0.25 * ((c1[al][0] + c1[al][1]) + (c1[ah][0] + c1[ah][1]));
+                            const double zv = fma(r[k][i], di[i], cv);
                             z[k][i]         = zv;
                             acc[k]          = fma(r[k][i], zv, acc[k]);
                           }
@@ -654,17 +792,74 @@ namespace msb
               ST_MARK(8)
 
               // ---- q = K p (9-point stencil, coefficients shared by the bases of the pass), p.q
-              double q[NBP][4], pq[NBP];
+              double q[TM ? 1 : NBP][4], pq[NBP]; // TM: q is parked in the residual staging buffer
 #pragma unroll
               for (int k = 0; k < NBP; ++k)
+                pq[k] = 0.0;
+              if constexpr (TM)
                 {
-                  pq[k] = 0.0;
+                  double e8[8];
+                  tmm::ld8(tm + Y::EOFF, e8);
 #pragma unroll
-                  for (int i = 0; i < 4; ++i)
-                    q[k][i] = 0.0;
+                  for (int kp = 0; kp < NBP / 2; ++kp) // two bases at a time: 18 window registers
+                    {
+                      double w[2][3][3];
+                      if (colact)
+                        {
+#pragma unroll
+                          for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                              for (int dx = 0; dx < 3; ++dx)
+                                w[kk][a][dx] = pS[((2 * kp + kk) * 18 + 4 * g + a) * W + jx + dx - 1];
+                        }
+                      double kS = e8[0];
+#pragma unroll
+                      for (int i = 0; i < 4; ++i)
+                        {
+                          double c8[8]; // kc kE kW kN kNE kSW kNW kSE of this row
+                          tmm::ld8(tm + Y::COFF + 16 * i, c8);
+                          if (colact)
+                            {
+                              const int  cr     = 4 * g + i + 1;
+                              const bool rowact = y0 + 4 * g + i >= 1;
+#pragma unroll
+                              for (int kk = 0; kk < 2; ++kk)
+                                {
+                                  const int k = 2 * kp + kk;
+#pragma unroll
+                                  for (int dx = 0; dx < 3; ++dx)
+                                    w[kk][2][dx] = pS[(k * 18 + cr + 1) * W + jx + dx - 1];
+                                  double yv = c8[0] * w[kk][1][1];
+                                  yv        = fma(c8[1], w[kk][1][2], yv);
+                                  yv        = fma(c8[2], w[kk][1][0], yv);
+                                  yv        = fma(c8[3], w[kk][2][1], yv);
+                                  yv        = fma(kS, w[kk][0][1], yv);
+                                  yv        = fma(c8[4], w[kk][2][2], yv);
+                                  yv        = fma(c8[5], w[kk][0][0], yv);
+                                  yv        = fma(c8[6], w[kk][2][0], yv);
+                                  yv        = fma(c8[7], w[kk][0][2], yv);
+                                  if (!rowact)
+                                    yv = 0.0;
+                                  rS[(k * 17 + cr) * W + jx] = yv;
+                                  pq[k]                      = fma(w[kk][1][1], yv, pq[k]);
+#pragma unroll
+                                  for (int dx = 0; dx < 3; ++dx)
+                                    w[kk][0][dx] = w[kk][1][dx], w[kk][1][dx] = w[kk][2][dx];
+                                }
+                            }
+                          kS = c8[3];
+                        }
+                    }
                 }
-              if (colact)
+              else if (colact)
                 {
+#pragma unroll
+                  for (int k = 0; k < NBP; ++k)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                      q[k][i] = 0.0;
                   double w[NBP][3][3];
 #pragma unroll
                   for (int k = 0; k < NBP; ++k)
@@ -719,7 +914,34 @@ namespace msb
 #pragma unroll
                 for (int k = 0; k < NBP; ++k)
                   alpha[k] = done[k] ? 0.0 : rz[k] / pq[k], acc[k] = 0.0;
-                if (colact)
+                if constexpr (TM)
+                  {
+#pragma unroll
+                    for (int kp = 0; kp < NBP / 2; ++kp)
+                      {
+                        double x8[8]; // x of bases 2kp, 2kp+1, rows 0..3
+                        tmm::ld8(tm + Y::XOFF + 16 * kp, x8);
+                        if (colact)
+                          {
+#pragma unroll
+                            for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                              for (int i = 0; i < 4; ++i)
+                                {
+                                  const int    k  = 2 * kp + kk;
+                                  const double pv = pS[(k * 18 + 4 * g + i + 1) * W + jx];
+                                  const double qv = rS[(k * 17 + 4 * g + i + 1) * W + jx];
+                                  x8[4 * kk + i]  = fma(alpha[k], pv, x8[4 * kk + i]);
+                                  const double rn = fma(-alpha[k], qv, r[k][i]);
+                                  r[k][i]         = rn;
+                                  acc[k]          = fma(rn, rn, acc[k]);
+                                }
+                          }
+                        tmm::st8(tm + Y::XOFF + 16 * kp, x8);
+                      }
+                    tmm::wait_st();
+                  }
+                else if (colact)
                   {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -744,7 +966,26 @@ namespace msb
             }
 
           // ---- results of the pass
-          if (colact)
+          if constexpr (TM)
+            {
+#pragma unroll
+              for (int kp = 0; kp < NBP / 2; ++kp)
+                {
+                  double x8[8];
+                  tmm::ld8(tm + Y::XOFF + 16 * kp, x8);
+                  if (colact)
+                    {
+#pragma unroll
+                      for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                          if (y0 + 4 * g + i >= 1)
+                            P.phi[((size_t)cell * 4 + NBP * pass + 2 * kp + kk) * N + (y0 + 4 * g + i) * np + jx] =
+                              x8[4 * kk + i];
+                    }
+                }
+            }
+          else if (colact)
             {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
@@ -775,16 +1016,18 @@ namespace msb
           ST_MARK(11)
         }
       ST_FLUSH
+      if constexpr (TM)
+        tmm::release(tm_base, warp);
     }
 
 #ifndef MSB_EMU
-    template <int L>
+    template <int L, int NBP, bool TM>
     static cudaError_t
     launch(const Params &P, int n_cells, cudaStream_t st)
     {
-      using Y = Lay<L>;
-      cudaError_t e = cudaFuncSetAttribute(solve_cluster_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)Y::smem_bytes);
+      using Y = Lay<L, NBP, TM>;
+      cudaError_t e = cudaFuncSetAttribute(solve_cluster_kernel<L, NBP, TM>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y::smem_bytes);
       if (e != cudaSuccess)
         return e;
       cudaLaunchConfig_t cfg = {};
@@ -799,7 +1042,7 @@ namespace msb
       at[0].val.clusterDim.z = 1;
       cfg.attrs              = at;
       cfg.numAttrs           = 1;
-      return cudaLaunchKernelEx(&cfg, solve_cluster_kernel<L>, P);
+      return cudaLaunchKernelEx(&cfg, solve_cluster_kernel<L, NBP, TM>, P);
     }
 #endif
   } // namespace clus
@@ -812,9 +1055,11 @@ namespace msb
   }
 
   // the solve of all cells of the shard; s.d_dinv must hold the reciprocal Galerkin diagonals
-  // (launch_solve_streamed computes them before dispatching here)
+  // (launch_solve_streamed computes them before dispatching here).  tmem = true: all four bases of a
+  // cell in one pass, coefficients and x in tensor memory; false: two passes of two bases, shared
+  // memory and registers only.
   cudaError_t
-  launch_solve_cluster(const Shard &s, double tol, int max_iter, cudaStream_t st, int *n_launches)
+  launch_solve_cluster(const Shard &s, double tol, int max_iter, bool tmem, cudaStream_t st, int *n_launches)
   {
     clus::Params P;
     P.corners  = s.d_corners;
@@ -832,13 +1077,13 @@ namespace msb
     switch (s.l)
       {
         case 5:
-          e = clus::launch<5>(P, s.n_cells, st);
+          e = tmem ? clus::launch<5, 4, true>(P, s.n_cells, st) : clus::launch<5, 2, false>(P, s.n_cells, st);
           break;
         case 6:
-          e = clus::launch<6>(P, s.n_cells, st);
+          e = tmem ? clus::launch<6, 4, true>(P, s.n_cells, st) : clus::launch<6, 2, false>(P, s.n_cells, st);
           break;
         case 7:
-          e = clus::launch<7>(P, s.n_cells, st);
+          e = tmem ? clus::launch<7, 4, true>(P, s.n_cells, st) : clus::launch<7, 2, false>(P, s.n_cells, st);
           break;
       }
     if (e == cudaSuccess)

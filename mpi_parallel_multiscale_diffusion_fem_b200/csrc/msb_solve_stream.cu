@@ -754,10 +754,11 @@ namespace msb
     }
 
     // local meshes that fit the shared memory of a thread-block cluster (n = 128 by default;
-    // variant 3 requests it for n = 32, 64 too, variant 2 declines it): the whole PCG of a cell
-    // runs on chip in ONE launch (msb_solve_cluster.cu); the Galerkin diagonals above are its input
-    if (cluster_tier_supported(s.l) && ((s.l == 7 && s.variant == 0) || s.variant == 3))
-      return launch_solve_cluster(s, tol, max_iter, st, n_launches);
+    // variants 3 / 4 request it for n = 32, 64 too, variant 2 declines it): the whole PCG of a cell
+    // runs on chip in ONE launch (msb_solve_cluster.cu); the Galerkin diagonals above are its input.
+    // Variant 4 = the kernel without tensor memory (two passes of two bases).
+    if (cluster_tier_supported(s.l) && ((s.l == 7 && s.variant == 0) || s.variant == 3 || s.variant == 4))
+      return launch_solve_cluster(s, tol, max_iter, s.variant != 4, st, n_launches);
 
     auto for_slices = [&](auto &&launch) {
       for (int c0 = 0; c0 < C; c0 += 65535)

@@ -214,6 +214,41 @@ namespace dsm
   }
 } // namespace dsm
 
+// tensor memory: per-thread private columns (8 doubles = 16 columns)
+namespace tmm
+{
+  thread_local double t_mem[64];
+  inline void
+  ld8(uint32_t a, double (&d)[8])
+  {
+    for (int i = 0; i < 8; ++i)
+      d[i] = t_mem[a / 2 + i];
+  }
+  inline void
+  st8(uint32_t a, const double (&d)[8])
+  {
+    for (int i = 0; i < 8; ++i)
+      t_mem[a / 2 + i] = d[i];
+  }
+  inline void
+  wait_st()
+  {}
+  inline uint32_t
+  alloc(uint32_t *, int, int, uint32_t &base)
+  {
+    for (double &v : t_mem)
+      v = NAN; // poison
+    base = 0;
+    emu::cta().bar->arrive_and_wait();
+    return 0;
+  }
+  inline void
+  release(uint32_t, int)
+  {
+    emu::cta().bar->arrive_and_wait();
+  }
+} // namespace tmm
+
 #include <cuda_runtime.h>
 #undef __launch_bounds__
 #define __launch_bounds__(...)
@@ -271,7 +306,8 @@ sget(const std::vector<double> &S, int np, int x, int y, int ex, int ey)
 int
 main(int argc, char **argv)
 {
-  const int l = argc > 1 ? atoi(argv[1]) : 5;
+  const int  l  = argc > 1 ? atoi(argv[1]) : 5;
+  const bool tm = argc > 2 ? atoi(argv[2]) != 0 : true; // 1: tensor-memory kernel (4 bases per pass)
   const int n = 1 << l, np = n + 1, N = np * np;
   const int CS = n / 16, T = 4 * n;
   const double H = 1.0 / 8, X0 = 0.25, Y0 = 0.5;
@@ -352,8 +388,10 @@ main(int argc, char **argv)
   P.corners = corners, P.q1coef = q1, P.sten = S.data(), P.dinv = dinv.data(), P.phi = phi.data();
   P.iters = iters.data(), P.res = res.data(), P.fail = fail, P.tol2 = 1e-24, P.max_iter = 500, P.cn = cn;
 
-  size_t smem_doubles = l == 5 ? clus::Lay<5>::total : l == 6 ? clus::Lay<6>::total : clus::Lay<7>::total;
-  printf("l=%d n=%d cluster=%d threads=%d smem=%zu bytes\n", l, n, CS, T, smem_doubles * 8);
+  size_t smem_doubles =
+    tm ? (l == 5 ? clus::Lay<5, 4, true>::total : l == 6 ? clus::Lay<6, 4, true>::total : clus::Lay<7, 4, true>::total) :
+         (l == 5 ? clus::Lay<5, 2, false>::total : l == 6 ? clus::Lay<6, 2, false>::total : clus::Lay<7, 2, false>::total);
+  printf("l=%d n=%d cluster=%d threads=%d tmem=%d smem=%zu bytes\n", l, n, CS, T, (int)tm, smem_doubles * 8);
   emu::Cluster cl;
   cl.bar = std::make_unique<std::barrier<>>(CS * T);
   cl.ctas.resize(CS);
@@ -370,12 +408,24 @@ main(int argc, char **argv)
       th.emplace_back([&, rank, t] {
         emu::t_cluster = &cl, emu::t_rank = rank;
         threadIdx.x = t, blockIdx.x = rank, blockDim.x = T, gridDim.x = CS;
-        if (l == 5)
-          clus::solve_cluster_kernel<5>(P);
-        else if (l == 6)
-          clus::solve_cluster_kernel<6>(P);
+        if (tm)
+          {
+            if (l == 5)
+              clus::solve_cluster_kernel<5, 4, true>(P);
+            else if (l == 6)
+              clus::solve_cluster_kernel<6, 4, true>(P);
+            else
+              clus::solve_cluster_kernel<7, 4, true>(P);
+          }
         else
-          clus::solve_cluster_kernel<7>(P);
+          {
+            if (l == 5)
+              clus::solve_cluster_kernel<5, 2, false>(P);
+            else if (l == 6)
+              clus::solve_cluster_kernel<6, 2, false>(P);
+            else
+              clus::solve_cluster_kernel<7, 2, false>(P);
+          }
       });
   for (auto &t : th)
     t.join();

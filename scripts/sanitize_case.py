@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import mpi_parallel_multiscale_diffusion_fem_b200 as pkg
 from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
 
-cases = [(6, 0, 2), (6, 6, 1), (5, 0, 2), (5, 3, 1), (4, 0, 2), (3, 0, 2), (7, 0, 1), (6, 100, 1)]
+cases = [(6, 0, 2), (6, 6, 1), (5, 0, 2), (5, 3, 1), (4, 0, 2), (3, 0, 2), (7, 0, 1), (7, 4, 1), (6, 100, 1)]
 if len(sys.argv) > 1:   # e.g. "5 4 6:6" = all l=5, l=4 cases and (l=6, variant 6)
     cases = [c for c in cases if str(c[0]) in sys.argv[1:] or "%d:%d" % (c[0], c[1]) in sys.argv[1:]]
 for l, variant, cells in cases:

@@ -423,15 +423,16 @@ def test_streamed_tier_fused_and_unfused_coarse_levels_agree(msb, oracle):
         assert a.run_stats()["launches"] < b.run_stats()["launches"]
 
 
-@pytest.mark.parametrize("l,cells", [(7, 21), (6, 5), (5, 3)])
-def test_cluster_tier_matches_streamed_tier(msb, oracle, l, cells):
-    """The thread-block-cluster / DSMEM kernel (default at n = 128; variant 3 of the streamed tier at
+@pytest.mark.parametrize("l,cells,variant", [(7, 21, 0), (7, 21, 4), (6, 5, 3), (6, 5, 4), (5, 3, 3), (5, 3, 4)])
+def test_cluster_tier_matches_streamed_tier(msb, oracle, l, cells, variant):
+    """The thread-block-cluster / DSMEM kernel (default at n = 128; variants 3 / 4 of the streamed tier at
     n = 32, 64: clusters of 2 and 4 CTAs) is the same multilevel PCG as the HBM-streamed kernels
     (variant 2): same iteration counts, same bases to solver accuracy, ONE solve launch; and the
-    oracle's bases within the north-star tolerance."""
+    oracle's bases within the north-star tolerance.  Variants 0 / 3: four bases per pass, coefficients
+    and x in tensor memory; variant 4: two passes of two bases, shared memory and registers only."""
     cd, co = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
     cor = msb.coarse_corners(3, 7, 7 + cells)
-    with msb.BasisShard(l, cor, cd, tier=msb.TIER_STREAMED, variant=0 if l == 7 else 3) as a, \
+    with msb.BasisShard(l, cor, cd, tier=msb.TIER_STREAMED, variant=variant) as a, \
             msb.BasisShard(l, cor, cd, tier=msb.TIER_STREAMED, variant=2) as b:
         a.run(1e-12, 5000)
         b.run(1e-12, 5000)

@@ -159,6 +159,37 @@ namespace msb
       v1 = __shfl_sync(0xffffffffu, t, 16);
     }
 
+    // block-wide sums of FOUR values: two transposing exchanges leave one value per quarter
+    // warp, so the butterfly costs 6 double shuffles instead of 20
+    template <int NWARP>
+    __device__ __forceinline__ void
+    block_sum4(double (&v)[4], double *buf, int warp, int lane)
+    {
+      static_assert(NWARP <= 16, "two partials per lane in the second stage");
+      const bool up16 = lane & 16, up8 = lane & 8;
+      double     a0 = up16 ? v[2] : v[0], a1 = up16 ? v[3] : v[1];
+      a0 += __shfl_xor_sync(0xffffffffu, up16 ? v[0] : v[2], 16);
+      a1 += __shfl_xor_sync(0xffffffffu, up16 ? v[1] : v[3], 16);
+      double t = (up8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up8 ? a0 : a1, 8);
+#pragma unroll
+      for (int off = 4; off > 0; off >>= 1)
+        t += __shfl_xor_sync(0xffffffffu, t, off);
+      if ((lane & 7) == 0)
+        buf[(lane >> 3) * NWARP + warp] = t;
+      __syncthreads();
+      const int g = lane >> 3, w = lane & 7;
+      double    u = w < NWARP ? buf[g * NWARP + w] : 0.0;
+      if (w + 8 < NWARP)
+        u += buf[g * NWARP + w + 8];
+#pragma unroll
+      for (int off = 4; off > 0; off >>= 1)
+        u += __shfl_xor_sync(0xffffffffu, u, off);
+      v[0] = __shfl_sync(0xffffffffu, u, 0);
+      v[1] = __shfl_sync(0xffffffffu, u, 8);
+      v[2] = __shfl_sync(0xffffffffu, u, 16);
+      v[3] = __shfl_sync(0xffffffffu, u, 24);
+    }
+
     // symmetric 9-point stencil storage (the layout of Shard::d_sten, any level):
     // entry of row node (x,y) towards (x+ex, y+ey); np = nodes per direction, N = np*np
     __device__ __forceinline__ double

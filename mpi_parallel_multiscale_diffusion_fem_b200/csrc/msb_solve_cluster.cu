@@ -401,7 +401,13 @@ namespace msb
       // sum of one value per basis over the whole cluster, the same bits in every thread of every CTA
       // (slot 0: r.z, 1: p.q, 2: r.r; `extra` = bytes of halo rows that travel with the partials)
       auto allreduce = [&](double(&v)[NBP], int slot, int extra) {
-        bpx::block_sum<NBP, NW>(v, buf + slot * NBP * NW, warp, lane);
+        // transposing exchanges: 2 (4) values for the shuffle count of one butterfly
+        if constexpr (NBP == 2 && NW <= 16)
+          bpx::block_sum2<NW>(v[0], v[1], buf + slot * NBP * NW, warp, lane);
+        else if constexpr (NBP == 4 && NW <= 16)
+          bpx::block_sum4<NW>(v, buf + slot * NBP * NW, warp, lane);
+        else
+          bpx::block_sum<NBP, NW>(v, buf + slot * NBP * NW, warp, lane);
         if (tid < CS)
           {
 #pragma unroll

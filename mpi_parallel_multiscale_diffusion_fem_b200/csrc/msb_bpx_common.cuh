@@ -124,7 +124,11 @@ namespace msb
     fast_div(double a, double b)
     {
       double y;
+#ifndef MSB_EMU
       asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+#else
+      y = (double)(1.0f / (float)b); // host emulation of the cluster kernel (scripts/emu)
+#endif
       double e = fma(-b, y, 1.0);
       y        = fma(y, e, y);
       e        = fma(-b, y, 1.0);

@@ -415,15 +415,16 @@ namespace msb
               dsm::push(red + (slot * CS + rank) * NBP + k, mb + MB_RZ + slot, tid, v[k]);
           }
         await(MB_RZ + slot, 8 * (CS * NBP + extra));
+        // lane -> (CTA j = lane % CS, basis k = lane / CS): one load per lane, a butterfly over the CS
+        // partials (the same tree in every warp of every CTA: identical bits), one broadcast per basis
+        static_assert(CS * NBP <= 32, "one lane per partial");
+        double s = lane < CS * NBP ? red[(slot * CS + (lane % CS)) * NBP + lane / CS] : 0.0;
+#pragma unroll
+        for (int off = CS / 2; off > 0; off >>= 1)
+          s += __shfl_xor_sync(0xffffffffu, s, off);
 #pragma unroll
         for (int k = 0; k < NBP; ++k)
-          {
-            double s = 0.0;
-#pragma unroll
-            for (int j = 0; j < CS; ++j)
-              s += red[(slot * CS + j) * NBP + k];
-            v[k] = s;
-          }
+          v[k] = __shfl_sync(0xffffffffu, s, k * CS);
       };
 
       for (int pass = 0; pass < 4 / NBP; ++pass)
@@ -756,7 +757,7 @@ namespace msb
 #pragma unroll
                 for (int k = 0; k < NBP; ++k)
                   {
-                    beta[k] = (it == 0 || done[k]) ? 0.0 : acc[k] / rz[k];
+                    beta[k] = (it == 0 || done[k]) ? 0.0 : bpx::fast_div(acc[k], rz[k]);
                     rz[k]   = acc[k];
                   }
               }
@@ -919,7 +920,7 @@ namespace msb
                 double alpha[NBP], acc[NBP];
 #pragma unroll
                 for (int k = 0; k < NBP; ++k)
-                  alpha[k] = done[k] ? 0.0 : rz[k] / pq[k], acc[k] = 0.0;
+                  alpha[k] = done[k] ? 0.0 : bpx::fast_div(rz[k], pq[k]), acc[k] = 0.0;
                 if constexpr (TM)
                   {
 #pragma unroll

@@ -72,7 +72,9 @@ typedef enum
 {
   MSB_TIER_AUTO     = 0, /* shared-memory resident when the local mesh fits      */
   MSB_TIER_SMEM     = 1, /* one CTA per (cell, right-hand-side group)            */
-  MSB_TIER_STREAMED = 2  /* vectors streamed through HBM/L2, any local mesh size */
+  MSB_TIER_STREAMED = 2  /* any local mesh size: vectors spread over the shared
+                            memory of a thread-block cluster (128x128 fine cells) or
+                            streamed through HBM/L2 (larger, and on request)       */
 } msb_tier;
 
 typedef struct

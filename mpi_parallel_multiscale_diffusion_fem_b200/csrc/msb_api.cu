@@ -210,16 +210,21 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
   if (s.tier == MSB_TIER_STREAMED)
     {
       const size_t cn = s.dim == 2 ? streamed_coarse_nodes(s.l) : dim3_coarse_nodes(s.l);
-      ALLOC(s.d_wr, C * NB * N);
-      ALLOC(s.d_wp, C * NB * N);
-      ALLOC(s.d_wq, C * NB * N);
-      ALLOC(s.d_wz, C * NB * N);
-      ALLOC(s.d_wv, C * NB * cn);
+      // the cluster kernel (n = 128) keeps every vector on chip: no HBM work vectors for it
+      const bool on_chip = s.dim == 2 && streamed_tier_uses_cluster(s.l, s.variant);
+      if (!on_chip)
+        {
+          ALLOC(s.d_wr, C * NB * N);
+          ALLOC(s.d_wp, C * NB * N);
+          ALLOC(s.d_wq, C * NB * N);
+          ALLOC(s.d_wz, C * NB * N);
+          ALLOC(s.d_wv, C * NB * cn);
+          ALLOC(s.d_scal, NB * C);
+          ALLOC(s.d_part, NB * C * (size_t)(s.dim == 2 ? 2 * 3 * 32 : dim3_part_stride()));
+        }
       ALLOC(s.d_dinv, C * cn);
       if (s.dim == 2)
         ALLOC(s.d_gal, streamed_galerkin_scratch_doubles(s.l, s.n_cells));
-      ALLOC(s.d_scal, NB * C);
-      ALLOC(s.d_part, NB * C * (size_t)(s.dim == 2 ? 2 * 3 * 32 : dim3_part_stride()));
     }
 #undef ALLOC
 

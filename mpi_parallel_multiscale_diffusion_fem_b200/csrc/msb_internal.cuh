@@ -93,6 +93,7 @@ namespace msb
   cudaError_t launch_solve_cluster(const Shard &s, double tol, int max_iter, bool tmem, cudaStream_t st,
                                    int *n_launches);
   bool        cluster_tier_supported(int l);
+  bool        streamed_tier_uses_cluster(int l, int variant);
   cudaError_t launch_element_matrices(const Shard &s, cudaStream_t st, int *n_launches);
   cudaError_t launch_apply_operator(const Shard &s, int cell, const double *d_x_lex, double *d_y_lex,
                                     cudaStream_t st);

@@ -654,6 +654,13 @@ namespace msb
     return L;
   }
 
+  // n = 128 runs the cluster kernel by default; variants 3 / 4 request it for n = 32, 64 too
+  bool
+  streamed_tier_uses_cluster(int l, int variant)
+  {
+    return cluster_tier_supported(l) && ((l == 7 && variant == 0) || variant == 3 || variant == 4);
+  }
+
   size_t
   streamed_coarse_nodes(int l)
   {
@@ -722,9 +729,13 @@ namespace msb
   if ((e = (call)) != cudaSuccess) \
   return e
 
+    const bool use_cluster = streamed_tier_uses_cluster(s.l, s.variant);
     TRY(cudaMemsetAsync(s.d_iters, 0xff, sizeof(int32_t) * n_solves, st));
-    TRY(cudaMemsetAsync(s.d_part, 0, sizeof(double) * (size_t)n_solves * PART_STRIDE, st));
-    TRY(cudaMemsetAsync(s.d_wv, 0, sizeof(double) * (size_t)n_solves * L.cn, st));
+    if (!use_cluster) // (the cluster kernel keeps its vectors on chip: these are not even allocated)
+      {
+        TRY(cudaMemsetAsync(s.d_part, 0, sizeof(double) * (size_t)n_solves * PART_STRIDE, st));
+        TRY(cudaMemsetAsync(s.d_wv, 0, sizeof(double) * (size_t)n_solves * L.cn, st));
+      }
     TRY(cudaMemsetAsync(s.d_dinv, 0, sizeof(double) * (size_t)C * L.cn, st));
 
     // ---- setup: Galerkin diagonals of every level, level by level, for all cells
@@ -757,7 +768,7 @@ namespace msb
     // variants 3 / 4 request it for n = 32, 64 too, variant 2 declines it): the whole PCG of a cell
     // runs on chip in ONE launch (msb_solve_cluster.cu); the Galerkin diagonals above are its input.
     // Variant 4 = the kernel without tensor memory (two passes of two bases).
-    if (cluster_tier_supported(s.l) && ((s.l == 7 && s.variant == 0) || s.variant == 3 || s.variant == 4))
+    if (use_cluster)
       return launch_solve_cluster(s, tol, max_iter, s.variant != 4, st, n_launches);
 
     auto for_slices = [&](auto &&launch) {

@@ -1,0 +1,46 @@
+"""Host-side check of the cluster / DSMEM kernel's index and synchronisation logic (no GPU).
+
+scripts/emu/cluster_emu.cpp compiles msb_solve_cluster.cu UNCHANGED for the host: every CUDA
+thread becomes an OS thread, __syncthreads / warp shuffles / st.async + mbarrier complete_tx /
+tensor memory are emulated, shared and tensor memory start NaN-poisoned.  The emulated kernel
+must reproduce a plain full-array multilevel PCG of the same condensed systems (the reference's
+per-basis sequence, diffusion_problem_basis.tpp:450-465): identical iteration counts, bases to
+1e-12, partition of unity, residual below the stopping tolerance.  This is a development / test
+tool: nothing in the library, bench.py or the GPU tests routes through it.
+"""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_INC = "/usr/local/cuda/include"
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if shutil.which("g++") is None or not os.path.isdir(CUDA_INC):
+        pytest.skip("needs g++ and the CUDA headers")
+    exe = str(tmp_path_factory.mktemp("emu") / "cluster_emu")
+    subprocess.check_call(
+        ["g++", "-O1", "-std=c++20", "-pthread", "-DMSB_EMU", "-I" + CUDA_INC, "-I" + os.path.join(ROOT, "include"),
+         "-I" + os.path.join(ROOT, "mpi_parallel_multiscale_diffusion_fem_b200", "csrc"),
+         os.path.join(ROOT, "scripts", "emu", "cluster_emu.cpp"), "-o", exe])
+    return exe
+
+
+@pytest.mark.parametrize("l,tmem", [(5, 1), (5, 0), (6, 1), (6, 0)])
+def test_emulated_cluster_kernel_equals_plain_pcg(emu, l, tmem):
+    """l = 5 / 6: clusters of 2 / 4 CTAs (edge slabs only / edge and interior slabs); tmem = 1: four bases
+    per pass with coefficients and x in (emulated) tensor memory, 0: two passes of two bases."""
+    p = subprocess.run([emu, str(l), str(tmem)], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    rows = re.findall(r"plain PCG basis (\d): iters (\d+) \(kernel (\d+)\)\s+rel diff ([0-9.e+-]+)", p.stdout)
+    assert len(rows) == 4
+    for _, it_plain, it_kernel, diff in rows:
+        assert it_plain == it_kernel and 20 <= int(it_kernel) <= 40
+        assert float(diff) < 1e-12
+    m = re.search(r"partition of unity defect ([0-9.e+-]+), worst residual ([0-9.e+-]+)", p.stdout)
+    assert float(m.group(1)) < 1e-10 and float(m.group(2)) <= 1e-12

@@ -633,7 +633,11 @@ namespace msb
   // Every thread owns one node column and a band of rows and marches up the band with a 3x3
   // register window per basis, so each phi value is loaded three times (by the three column
   // neighbours, from the same cache lines) instead of nine and each stencil coefficient once.
-  __global__ void __launch_bounds__(256, 2)
+  // THREADS = 256 (two CTAs per SM) or 512: local meshes wider than 128 nodes leave half of a 256-thread
+  // CTA idle (one band of rows), which matters when a shard has too few cells to fill the GPU (the
+  // reference's default run: 64 cells of 129 x 129 nodes) -- 512 threads sweep three bands instead.
+  template <int THREADS>
+  __global__ void __launch_bounds__(THREADS, 512 / THREADS)
   element_matrix_kernel(int n, const double *__restrict__ sten, const double *__restrict__ phi,
                         double *__restrict__ M, double *__restrict__ b)
   {
@@ -719,7 +723,7 @@ namespace msb
         if (blockDim.x >= np)
           break;
       }
-    __shared__ double red[8][20];
+    __shared__ double red[THREADS / 32][20];
     const int         lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 20; ++k)
@@ -734,7 +738,7 @@ namespace msb
     if (threadIdx.x < 20)
       {
         double v = 0.0;
-        for (int w = 0; w < 8; ++w)
+        for (int w = 0; w < THREADS / 32; ++w)
           v += red[w][threadIdx.x];
         if (threadIdx.x < 16)
           M[16 * (size_t)cell + threadIdx.x] = v;
@@ -746,7 +750,10 @@ namespace msb
   cudaError_t
   launch_element_matrices(const Shard &s, cudaStream_t st, int *n_launches)
   {
-    element_matrix_kernel<<<s.n_cells, 256, 0, st>>>(s.n, s.d_sten, s.d_phi, s.d_M, s.d_b);
+    if (s.np > 128 && s.np <= 512 / 3 && s.n_cells < 4 * 148)
+      element_matrix_kernel<512><<<s.n_cells, 512, 0, st>>>(s.n, s.d_sten, s.d_phi, s.d_M, s.d_b);
+    else
+      element_matrix_kernel<256><<<s.n_cells, 256, 0, st>>>(s.n, s.d_sten, s.d_phi, s.d_M, s.d_b);
     ++*n_launches;
     return cudaGetLastError();
   }

@@ -33,7 +33,6 @@
 #endif
 #include <limits.h>
 #include <math.h>
-#include <stdlib.h>
 
 #define MSB_STAGE_ARRAY g_msb_stage_cycles_cl
 #include "msb_bpx_common.cuh"
@@ -1043,22 +1042,13 @@ namespace msb
       cfg.blockDim           = dim3(Y::T, 1, 1);
       cfg.dynamicSmemBytes   = Y::smem_bytes;
       cfg.stream             = st;
-      cudaLaunchAttribute at[2];
+      cudaLaunchAttribute at[1];
       at[0].id               = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = Y::CS;
       at[0].val.clusterDim.y = 1;
       at[0].val.clusterDim.z = 1;
       cfg.attrs              = at;
       cfg.numAttrs           = 1;
-      // A/B switch for measurements only: MSB_CLUSTER_POLICY=1 asks for the load-balancing cluster
-      // scheduling policy instead of the default (spread)
-      static const char *pol = getenv("MSB_CLUSTER_POLICY");
-      if (pol && pol[0] == '1')
-        {
-          at[1].id                                         = cudaLaunchAttributeClusterSchedulingPolicyPreference;
-          at[1].val.clusterSchedulingPolicyPreference      = cudaClusterSchedulingPolicyLoadBalancing;
-          cfg.numAttrs                                     = 2;
-        }
       return cudaLaunchKernelEx(&cfg, solve_cluster_kernel<L, NBP, TM>, P);
     }
 #endif

@@ -44,3 +44,32 @@ def test_emulated_cluster_kernel_equals_plain_pcg(emu, l, tmem):
         assert float(diff) < 1e-12
     m = re.search(r"partition of unity defect ([0-9.e+-]+), worst residual ([0-9.e+-]+)", p.stdout)
     assert float(m.group(1)) < 1e-10 and float(m.group(2)) <= 1e-12
+
+
+@pytest.fixture(scope="module")
+def emu_tsan(tmp_path_factory):
+    if shutil.which("g++") is None or not os.path.isdir(CUDA_INC):
+        pytest.skip("needs g++ and the CUDA headers")
+    exe = str(tmp_path_factory.mktemp("emu_tsan") / "cluster_emu_tsan")
+    p = subprocess.run(
+        ["g++", "-O1", "-g", "-fsanitize=thread", "-std=c++20", "-pthread", "-DMSB_EMU", "-I" + CUDA_INC,
+         "-I" + os.path.join(ROOT, "include"),
+         "-I" + os.path.join(ROOT, "mpi_parallel_multiscale_diffusion_fem_b200", "csrc"),
+         os.path.join(ROOT, "scripts", "emu", "cluster_emu.cpp"), "-o", exe], capture_output=True, text=True)
+    if p.returncode != 0:
+        pytest.skip("ThreadSanitizer runtime not available: " + p.stderr[-200:])
+    return exe
+
+
+@pytest.mark.parametrize("tmem", [1, 0])
+def test_emulated_cluster_kernel_is_race_free_under_thread_sanitizer(emu_tsan, tmem):
+    """Every cross-CTA exchange of the kernel (st.async pushes into a peer's shared memory, mbarrier waits,
+    buffer reuse from one iteration to the next) under ThreadSanitizer: a write that is not ordered after
+    the owner's last read of the old content -- the hazard table of DESIGN.md 3.4 -- would be reported as
+    a data race.  Cluster of 2 CTAs x 128 threads (l = 5), both kernel flavours."""
+    p = subprocess.run([emu_tsan, "5", str(tmem)], capture_output=True, text=True, timeout=900)
+    out = p.stdout + p.stderr
+    if "unexpected memory mapping" in out or "FATAL: ThreadSanitizer" in out:
+        pytest.skip("ThreadSanitizer cannot run in this container")
+    assert "WARNING: ThreadSanitizer" not in out, out[-3000:]
+    assert p.returncode == 0, out[-2000:]

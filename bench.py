@@ -214,6 +214,9 @@ def main():
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL's own banner ("NCCL version ...", printed to stdout when
+        # the environment sets NCCL_DEBUG) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     r, l, kind, par, seed, dim = workload(args.workload)

@@ -4,13 +4,17 @@
 // cluster of SMs: n = 128, the reference's default run (main.cxx:23-25, n_refine_local = 7).
 //
 // One cluster of CS = n/16 CTAs per coarse cell (8 at n = 128, the portable maximum).  CTA c of
-// the cluster owns the slab of 16 fine node rows [16c, 16c+16); all vectors of the solve live on
-// chip for the whole iteration:
-//     shared memory  the five stencil coefficient arrays of the slab (+ one row below), 1/diag,
-//                    the search direction p with one halo row either side, a staging copy of
-//                    the residual, the slab's part of coarse levels 1 and 2 (+ halo rows), a
-//                    full copy of levels >= 3, reciprocal Galerkin diagonals of all of these
-//     registers      x, r, z / q: a thread owns 4 consecutive rows of one column
+// the cluster owns the slab of 16 fine node rows [16c, 16c+16), a thread 4 consecutive rows of one
+// column; all vectors of the solve live on chip for the whole iteration.  Two flavours:
+//   <L, 4, true> (default)  all four bases of the cell in ONE pass
+//     shared memory  the search direction p with one halo row either side; a staging copy of the
+//                    residual that also parks q = K p; the slab's part of coarse levels 1 and 2
+//                    (+ halo rows), a full copy of levels >= 3, reciprocal Galerkin diagonals
+//     tensor memory  per-thread private columns (tcgen05.ld/st.32x32b, no MMA is issued): the
+//                    thread's own 33 stencil coefficients, 1/diag and x
+//     registers      r, z
+//   <L, 2, false> (variant 4)  two passes of two bases; the five coefficient arrays of the slab
+//                    and 1/diag in shared memory, x, r, z / q in registers, no tensor memory
 // What crosses CTAs goes through DSMEM, always as a PUSH: st.async.shared::cluster with
 // mbarrier complete_tx into the consumer's shared memory; the consumer arms its own mbarrier
 // with the byte count it expects and waits on it -- point-to-point, no cluster-wide barrier and
@@ -19,12 +23,11 @@
 //     halo rows of z (-> p), r, r_1, r_2 to the neighbouring slab; the two level-3 rows a CTA owns to
 //     every CTA of the cluster (levels >= 3 are then swept redundantly by all CTAs: no serial
 //     coarse chain across the cluster); the per-CTA partial dot products to every CTA, which
-//     adds them in rank order so that all CTAs take bitwise identical decisions.
+//     adds them with the same butterfly so that all CTAs take bitwise identical decisions.
 // The three all-reduces of an iteration are the only cluster-wide synchronisation points; every
 // buffer a CTA pushes into was last read by its owner before an all-reduce the pusher has
 // already completed (see the hazard table in DESIGN.md 3.4).
 // HBM traffic = read the stencil once, write Phi.
-// The four bases of a cell are solved two at a time (two passes share the prologue).
 //
 // Replaces, for these local meshes, the per-basis sequence of the reference:
 // diffusion_problem_basis.tpp:450-465 (condense, solve_iterative :293-317, distribute :308).

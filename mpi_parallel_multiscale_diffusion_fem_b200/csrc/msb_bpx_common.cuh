@@ -379,54 +379,115 @@ namespace msb
     };
 
     // Dense inverse of the Galerkin operator of the 7x7-unknown level (9-point stencil Gl on 9x9
-    // nodes, layout of Shard::d_sten), built in place in sGi[49][49] by a Gauss-Jordan sweep without
-    // pivoting (the operator is SPD).  With it the levels below 15x15 are solved EXACTLY instead of
-    // being diagonally scaled: the preconditioner becomes D^-1 + ... + P_7 A_7^-1 P_7^T, which
-    // removes the contrast dependence of the coarse part (cfg4: 67 -> 38 iterations).
+    // nodes, layout of Shard::d_sten) into sGi[49][49].  With it the levels below 15x15 are solved
+    // EXACTLY instead of being diagonally scaled: the preconditioner becomes
+    // D^-1 + ... + P_7 A_7^-1 P_7^T, which removes the contrast dependence of the coarse part
+    // (cfg4: 67 -> 38 iterations).
+    // The operator is SPD and banded (lexicographic 7x7 grid, 9-point stencil: half bandwidth 8), so
+    // the inverse is built from a banded L D L^T factorisation (warp 0: 49 steps of <= 36 entry updates,
+    // __syncwarp only) followed by 49 independent pairs of band substitutions, one column of the
+    // inverse per thread: ~15 k cycles instead of the ~55 k of a dense Gauss-Jordan sweep with two CTA
+    // barriers per pivot, which was 20 % of the n = 32 kernel (profiles/r01s_stage_timers_cfg4_2368.txt).
+    // sBand: scratch of EXACT7_SCRATCH doubles (band storage [49 + 8][9], zero padded).
+    constexpr int EXACT7_SCRATCH = (49 + 8) * 9;
     template <int THREADS>
     __device__ __forceinline__ void
-    exact7_build(const double *Gl, double *sGi, int tid)
+    exact7_build(const double *Gl, double *sGi, double *sBand, int tid)
     {
-      for (int t = tid; t < 49 * 49; t += THREADS)
-        sGi[t] = 0.0;
+      constexpr int BW = 8, LD = BW + 1;
+      // lower band: sBand[i * LD + b] = A(i, i - b), b = 0 .. 8, i = (Y-1) * 7 + (X-1)
+      for (int t = tid; t < EXACT7_SCRATCH; t += THREADS)
+        sBand[t] = 0.0;
       __syncthreads();
       if (tid < 49)
         {
           const int X = 1 + tid % 7, Y = 1 + tid / 7;
-#pragma unroll
-          for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx)
-              {
-                const int bx = X + dx, by = Y + dy;
-                if (bx >= 1 && bx <= 7 && by >= 1 && by <= 7)
-                  sGi[tid * 49 + (by - 1) * 7 + bx - 1] = sten_get(Gl, 9, 81, X, Y, dx, dy);
-              }
+          sBand[tid * LD + 0] = sten_get(Gl, 9, 81, X, Y, 0, 0);
+          if (X > 1)
+            sBand[tid * LD + 1] = sten_get(Gl, 9, 81, X, Y, -1, 0);
+          if (Y > 1)
+            {
+              if (X < 7)
+                sBand[tid * LD + 6] = sten_get(Gl, 9, 81, X, Y, 1, -1);
+              sBand[tid * LD + 7] = sten_get(Gl, 9, 81, X, Y, 0, -1);
+              if (X > 1)
+                sBand[tid * LD + 8] = sten_get(Gl, 9, 81, X, Y, -1, -1);
+            }
         }
       __syncthreads();
-#pragma unroll 1
-      for (int k = 0; k < 49; ++k)
+      // ---- A = L D L^T in place (right looking): after step k column k holds L(.,k), sBand[k*LD] = 1/D_k
+      if (tid < 32)
         {
-          const double piv = 1.0 / sGi[k * 49 + k];
-          for (int t = tid; t < 49 * 49; t += THREADS)
+          // a step updates the entries (k+a, k+c), 1 <= c <= a <= 8: 36 pairs, lanes 0..3 take two
+          int pa[2], pc[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
             {
-              const int i = t / 49, j = t - 49 * i;
-              if (i != k && j != k)
-                sGi[t] = fma(-sGi[i * 49 + k] * piv, sGi[k * 49 + j], sGi[t]);
+              int q = tid + 32 * u, a = 1;
+              while (q >= a)
+                q -= a, ++a;
+              pa[u] = a, pc[u] = q + 1; // (u = 1 is only meaningful for lanes 0..3: a = 8)
             }
-          __syncthreads();
-          if (tid < 49)
+#pragma unroll 1
+          for (int k = 0; k < 49; ++k)
             {
-              if (tid != k)
-                {
-                  sGi[k * 49 + tid] *= piv;
-                  sGi[tid * 49 + k] *= -piv;
-                }
-              else
-                sGi[k * 49 + k] = piv;
+              const double rd = fast_div(1.0, sBand[k * LD]);
+#pragma unroll
+              for (int u = 0; u < 2; ++u)
+                if ((u == 0 || tid < 4) && k + pa[u] < 49)
+                  {
+                    const int a = pa[u], c = pc[u];
+                    sBand[(k + a) * LD + (a - c)] =
+                      fma(-(sBand[(k + a) * LD + a] * rd), sBand[(k + c) * LD + c], sBand[(k + a) * LD + (a - c)]);
+                  }
+              __syncwarp();
+              if (tid >= 1 && tid <= BW && k + tid < 49)
+                sBand[(k + tid) * LD + tid] *= rd;
+              if (tid == 0)
+                sBand[k * LD] = rd;
+              __syncwarp();
             }
-          __syncthreads();
         }
+      __syncthreads();
+      // ---- column c of the inverse: L y = e_c, z = D^-1 y, L^T x = z (window of the last 8 values in registers)
+      if (tid < 49)
+        {
+          const int c = tid;
+          double    w[BW];
+#pragma unroll
+          for (int b = 0; b < BW; ++b)
+            w[b] = 0.0;
+#pragma unroll 7
+          for (int i = 0; i < 49; ++i)
+            {
+              double s = i == c ? 1.0 : 0.0;
+#pragma unroll
+              for (int b = BW; b >= 1; --b) // the newest value last: shortest dependency chain
+                s = fma(-sBand[i * LD + b], w[b - 1], s);
+#pragma unroll
+              for (int b = BW - 1; b >= 1; --b)
+                w[b] = w[b - 1];
+              w[0]            = s;
+              sGi[i * 49 + c] = s * sBand[i * LD];
+            }
+#pragma unroll
+          for (int b = 0; b < BW; ++b)
+            w[b] = 0.0;
+#pragma unroll 7
+          for (int i = 48; i >= 0; --i)
+            {
+              double s = sGi[i * 49 + c];
+#pragma unroll
+              for (int b = BW; b >= 1; --b) // rows beyond 48 are the zero padding of sBand
+                s = fma(-sBand[(i + b) * LD + b], w[b - 1], s);
+#pragma unroll
+              for (int b = BW - 1; b >= 1; --b)
+                w[b] = w[b - 1];
+              w[0]            = s;
+              sGi[i * 49 + c] = s;
+            }
+        }
+      __syncthreads();
     }
 
     // RPT > 0: sU holds the pre-summed strips of Presum<NL,NRHS,RPT>; RPT == 0: sU holds u itself.

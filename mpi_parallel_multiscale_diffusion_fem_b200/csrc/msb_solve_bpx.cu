@@ -152,7 +152,11 @@ namespace msb
           }
       }
       if constexpr (C::EXACT7)
-        exact7_build<THREADS>(sP + 5 * C::lvl_off(C::LW + 1), sGi, tid);
+        {
+          // scratch: the u buffer (free until the scaling pass below)
+          static_assert(EXACT7_SCRATCH <= NRHS * N, "band scratch must fit the residual staging buffer");
+          exact7_build<THREADS>(sP + 5 * C::lvl_off(C::LW + 1), sGi, sU, tid);
+        }
       // (b) s = d^-1/2 on every node into the u buffer (p buffer still holds the hierarchy,
       //     which is dead from here on)
       double *sS = sU;

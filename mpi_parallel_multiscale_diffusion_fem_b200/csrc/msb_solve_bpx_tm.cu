@@ -235,7 +235,7 @@ namespace msb
                             (uint32_t)(C::MOFF + (warp >> 2) * 16 * X7::NCHK);
       if constexpr (EXACT)
         {
-          exact7_build<THREADS>(sP + 5 * L::lvl_off(L::LW + 1), sE, tid);
+          exact7_build<THREADS>(sP + 5 * L::lvl_off(L::LW + 1), sE, sN, tid); // scratch: the next coefficient array
           if (warp < X7::WARPS)
             {
 #pragma unroll

@@ -73,3 +73,19 @@ def test_emulated_cluster_kernel_is_race_free_under_thread_sanitizer(emu_tsan, t
         pytest.skip("ThreadSanitizer cannot run in this container")
     assert "WARNING: ThreadSanitizer" not in out, out[-3000:]
     assert p.returncode == 0, out[-2000:]
+
+
+def test_emulated_banded_inverse_of_the_7x7_level(tmp_path):
+    """bpx::exact7_build (banded L D L^T + 49 parallel substitutions, used by the n = 32 kernel for the exact
+    solve of its 7x7 coarse level) run by 128 emulated threads: A * A^-1 = I for a 9-point operator with
+    coefficient jumps of 1, 1e4 and 1e6."""
+    if shutil.which("g++") is None or not os.path.isdir(CUDA_INC):
+        pytest.skip("needs g++ and the CUDA headers")
+    exe = str(tmp_path / "exact7_emu")
+    subprocess.check_call(
+        ["g++", "-O1", "-std=c++20", "-pthread", "-DMSB_EMU", "-I" + CUDA_INC, "-I" + os.path.join(ROOT, "include"),
+         "-I" + os.path.join(ROOT, "mpi_parallel_multiscale_diffusion_fem_b200", "csrc"),
+         os.path.join(ROOT, "scripts", "emu", "exact7_emu.cpp"), "-o", exe])
+    for contrast in ("1", "1e4", "1e6"):
+        p = subprocess.run([exe, contrast], capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout + p.stderr

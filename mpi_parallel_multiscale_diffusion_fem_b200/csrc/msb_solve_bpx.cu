@@ -153,9 +153,9 @@ namespace msb
       }
       if constexpr (C::EXACT7)
         {
-          // scratch: the u buffer (free until the scaling pass below)
-          static_assert(EXACT7_SCRATCH <= NRHS * N, "band scratch must fit the residual staging buffer");
-          exact7_build<THREADS>(sP + 5 * C::lvl_off(C::LW + 1), sGi, sU, tid);
+          // scratch: the first coefficient array (filled in (c) below; the p/u buffers hold the hierarchy)
+          static_assert(EXACT7_SCRATCH <= n * n, "band scratch must fit a coefficient array");
+          exact7_build<THREADS>(sP + 5 * C::lvl_off(C::LW + 1), sGi, sE, tid);
         }
       // (b) s = d^-1/2 on every node into the u buffer (p buffer still holds the hierarchy,
       //     which is dead from here on)

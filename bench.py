@@ -380,14 +380,16 @@ def main():
                               "write of a 512 MB buffer), each step timed by the stage's own CUDA events on its stream"
                               % (ws_bytes / 1e6)),
                        "mean_pcg_iterations": iters_all / n_solves,
-                       "preconditioner": ("multilevel diagonal scaling (BPX), exact Galerkin diagonals" if args.variant < 100 else "Jacobi (symmetric diagonal scaling)"),
+                       "preconditioner": ("multilevel diagonal scaling (BPX), exact Galerkin diagonals"
+                                          + (", exact solve of the 7x7 coarse level" if (dim == 2 and l == 5) or (dim == 2 and l == 6 and args.variant == 0) else "")
+                                          if args.variant < 100 else "Jacobi (symmetric diagonal scaling)"),
                        "variant": args.variant},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches_all,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": (("solve_bpx_tm_kernel" if (l == 6 and args.variant in (0, 5)) else "solve_bpx_kernel") if args.variant < 100 else "solve_smem_kernel") if sh.run_stats()["tier"] == 1 else (("solve_cluster_kernel" if (l == 7 and args.variant == 0) or (args.variant in (3, 4) and 5 <= l <= 7) else "stream_k*") if dim == 2 else "d3::k2_kernel + siblings"),
+                         "kernel": (("solve_bpx_tm_kernel" if (l == 6 and args.variant in (0, 5, 7)) else "solve_bpx_kernel") if args.variant < 100 else "solve_smem_kernel") if sh.run_stats()["tier"] == 1 else (("solve_cluster_kernel" if (l == 7 and args.variant == 0) or (args.variant in (3, 4) and 5 <= l <= 7) else "stream_k*") if dim == 2 else "d3::k2_kernel + siblings"),
                          "kernel_ms_per_launch": solve_ms_max,
                          "peak_source": peak_src,
                          "note": "achieved = ALGORITHMIC streaming bytes N(96k+16)/solve (SURVEY 8d) / "

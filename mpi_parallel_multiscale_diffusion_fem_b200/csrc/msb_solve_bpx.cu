@@ -593,16 +593,18 @@ namespace msb
           return bpx::launch_one<5, 2, 128>(P, st);
         case 6:
           // default: two bases in flight per CTA, tensor memory as spill space (1.07M vs 0.89M
-          // solves/s on the target configuration against one basis per pass)
+          // solves/s on the target configuration against one basis per pass) + exact solve of the
+          // 7x7 coarse level (26.0 instead of 27.8 iterations; pays since its inverse is built by the
+          // banded factorisation: 16.94 vs 17.44 ms on 5920 cells; it lost with the Gauss-Jordan sweep)
           if (s.variant == 5)
             return launch_solve_bpx_tm(P, 256, false, st);
           if (s.variant == 7)
-            return launch_solve_bpx_tm(P, 512, true, st); // + exact 7x7 coarse solve (A/B)
+            return launch_solve_bpx_tm(P, 512, false, st); // without the exact 7x7 coarse solve (A/B)
           if (s.variant == 6)
             return bpx::launch_one<6, 1, 512>(P, st);
           if (s.variant == 1)
             return bpx::launch_one<6, 1, 256>(P, st);
-          return launch_solve_bpx_tm(P, 512, false, st);
+          return launch_solve_bpx_tm(P, 512, true, st);
         default:
           return cudaErrorInvalidValue;
       }

@@ -63,7 +63,7 @@ def main():
     out = (C.c_ulonglong * 16)()
     with pkg.BasisShard(l, pkg.coarse_corners(r, 0, cells), coeff_desc(kind, par, seed), variant=variant) as sh:
         sh.run(1e-12, 5000)
-        fn = lib.msb_debug_stage_cycles_tm if (l == 6 and variant in (0, 5)) else lib.msb_debug_stage_cycles
+        fn = lib.msb_debug_stage_cycles_tm if (l == 6 and variant in (0, 5, 7)) else lib.msb_debug_stage_cycles
         fn(out, 1)
         sh.run(1e-12, 5000)
         fn(out, 1)
@@ -74,7 +74,7 @@ def main():
     n_iter = it.sum() / (4.0 / max(1, 4 // (4 if l <= 5 and variant == 0 else 1)))  # per solve-group iterations
     print("workload %s cells %d l=%d variant %d: solve kernel %.3f ms, mean k %.1f" %
           (wl, cells, l, variant, st["ms_solve"], it.mean()))
-    nrhs = 2 if (l == 6 and variant in (0, 5)) or (l == 5 and variant == 0) else (4 if l <= 5 and variant == 3 else 1)
+    nrhs = 2 if (l == 6 and variant in (0, 5, 7)) or (l == 5 and variant == 0) else (4 if l <= 5 and variant == 3 else 1)
     group_its = it.sum() / nrhs
     print("cycles per CTA: %.0f  (per pass-iteration of %d bases: %.0f)" % (tot / cells, nrhs, tot / group_its))
     for idx in ORDER:

@@ -460,10 +460,15 @@ namespace msb
 #pragma unroll 7
           for (int i = 0; i < 49; ++i)
             {
-              double s = i == c ? 1.0 : 0.0;
+              // two partial sums (even / odd offsets), the newest value last: half the dependency chain
+              double s = i == c ? 1.0 : 0.0, s2 = 0.0;
 #pragma unroll
-              for (int b = BW; b >= 1; --b) // the newest value last: shortest dependency chain
-                s = fma(-sBand[i * LD + b], w[b - 1], s);
+              for (int b = BW; b >= 2; b -= 2)
+                {
+                  s2 = fma(-sBand[i * LD + b], w[b - 1], s2);
+                  s  = fma(-sBand[i * LD + b - 1], w[b - 2], s);
+                }
+              s += s2;
 #pragma unroll
               for (int b = BW - 1; b >= 1; --b)
                 w[b] = w[b - 1];
@@ -476,10 +481,14 @@ namespace msb
 #pragma unroll 7
           for (int i = 48; i >= 0; --i)
             {
-              double s = sGi[i * 49 + c];
+              double s = sGi[i * 49 + c], s2 = 0.0;
 #pragma unroll
-              for (int b = BW; b >= 1; --b) // rows beyond 48 are the zero padding of sBand
-                s = fma(-sBand[(i + b) * LD + b], w[b - 1], s);
+              for (int b = BW; b >= 2; b -= 2) // rows beyond 48 are the zero padding of sBand
+                {
+                  s2 = fma(-sBand[(i + b) * LD + b], w[b - 1], s2);
+                  s  = fma(-sBand[(i + b - 1) * LD + b - 1], w[b - 2], s);
+                }
+              s += s2;
 #pragma unroll
               for (int b = BW - 1; b >= 1; --b)
                 w[b] = w[b - 1];

@@ -206,6 +206,12 @@ def main():
     import mpi_parallel_multiscale_diffusion_fem_b200 as pkg
     from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
 
+    # stdout carries exactly ONE JSON line: anything a library prints to file descriptor 1 from here on
+    # (NCCL's "NCCL version ..." banner when the environment sets NCCL_DEBUG, ...) is sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -214,9 +220,6 @@ def main():
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL's own banner ("NCCL version ...", printed to stdout when
-        # the environment sets NCCL_DEBUG) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     r, l, kind, par, seed, dim = workload(args.workload)
@@ -400,7 +403,8 @@ def main():
             cb = cpu_baseline(args.workload)
             cb.pop("seconds"), cb.pop("solves")
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     sh.close()
     if world > 1:
         dist.barrier()

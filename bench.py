@@ -182,6 +182,266 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------ GPU arm
+PER_CONFIG = ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "3d-16x16"]   # BASELINE.json configs 1-5 + the 3D path
+
+
+def kernel_name(dim, l, variant, tier):
+    if dim == 3:
+        return "d3::k2m_kernel + siblings (HBM-streamed)"
+    if tier == 1:
+        if variant >= 100:
+            return "solve_smem_kernel"
+        return "solve_bpx_tm_kernel" if (l == 6 and variant in (0, 5, 7, 8, 9)) else "solve_bpx_kernel"
+    if (l == 7 and variant == 0) or (variant in (3, 4) and 5 <= l <= 7):
+        return "solve_cluster_kernel"
+    return "stream_k* (HBM-streamed)"
+
+
+def binding_resource(dim, l, variant, tier):
+    """What actually bounds the dominant kernel (ncu evidence in profiles/): the HBM model of SURVEY 8(d)
+    only BINDS the tiers whose vectors stream through HBM."""
+    name = kernel_name(dim, l, variant, tier)
+    if "HBM-streamed" in name:
+        return "hbm"
+    return "shared-memory crossbar (LSU wavefronts) + dependency latency; HBM is not binding (vectors stay on chip)"
+
+
+class Ctx:
+    pass
+
+
+def measure(cx, name, steps, warmup, variant=0, cells=0, max_iter=5000, e2e=True, with_bases=False):
+    """One workload on this rank's Morton range: kernel-resident leg, optional end-to-end legs, invariants.
+    Returns a dict (identical on every rank for the reduced quantities)."""
+    torch, dist, pkg = cx.torch, cx.dist, cx.pkg
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
+    world, rank, local_rank = cx.world, cx.rank, cx.local_rank
+    r, l, kind, par, seed, dim = workload(name)
+    nb = 1 << dim
+    total_cells = (1 << r) ** dim
+    if cells:
+        total_cells = min(total_cells, cells)
+    lo, hi = pkg.morton_partition(total_cells, rank, world)
+    n_local = hi - lo
+    N = ((1 << l) + 1) ** dim
+    dev = torch.device("cuda", local_rank)
+
+    corners_np = pkg.coarse_corners(r, lo, hi) if dim == 2 else pkg.coarse_corners3(r, lo, hi)
+    h_corners = torch.from_numpy(corners_np).pin_memory()
+    h_M = torch.empty((total_cells, nb, nb), dtype=torch.float64, pin_memory=True)
+    h_b = torch.empty((total_cells, nb), dtype=torch.float64, pin_memory=True)
+    h_it = torch.empty((n_local, nb), dtype=torch.int32, pin_memory=True)
+
+    sh = pkg.BasisShard(l, corners_np, coeff_desc(kind, par, seed), device_id=local_rank, variant=variant, dim=dim)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        sh.run_async(1e-12, max_iter, sptr)
+
+    # working sets that could survive in the 126 MB L2 from one step to the next (the reference's
+    # default run: 64 cells) are flushed out between timed steps by writing a 512 MB buffer
+    ws_bytes = n_local * (10 if dim == 2 else 23) * N * 8
+    flush = ws_bytes < (512 << 20)
+    if flush and cx.flush_buf is None:
+        cx.flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    # ---- kernel-resident leg: inputs already in HBM -----------------------------------
+    for _ in range(warmup):
+        step()
+    sh.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    solve_ms, launches = [], 0
+    ms_total = 0.0
+    if not flush:
+        ev0.record(stream)
+    for _ in range(steps):
+        if flush:
+            cx.flush_buf.zero_()            # untimed
+            torch.cuda.synchronize()
+        step()
+        # per-step device-side stats need the events of this run: sync this rank's stream
+        sh.sync()
+        st = sh.run_stats()
+        solve_ms.append(st["ms_solve"])
+        launches += st["launches"]
+        if flush:
+            # the stage's own CUDA events, recorded on the stream the kernels run on
+            # (msb_get_run_stats: first launch of the assembly -> end of the element matrices)
+            ms_total += st["ms_total"]
+    if not flush:
+        ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    if not flush:
+        ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / steps
+    it_np, res_np = sh.iteration_counts()
+    alg_bytes, mean_k = sh.algorithmic_bytes()
+    stats = torch.tensor([alg_bytes, float(it_np.sum()), float(launches), float(np.mean(solve_ms))],
+                         dtype=torch.float64, device=dev)
+    if world > 1:
+        smax = stats.clone()
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        dist.all_reduce(smax, op=dist.ReduceOp.MAX)
+        solve_ms_max = float(smax[3].item())
+    else:
+        solve_ms_max = float(stats[3].item())
+    n_solves = nb * total_cells
+    out = {
+        "name": name, "dim": dim, "r": r, "l": l, "N": N, "total_cells": total_cells, "n_local": n_local,
+        "n_solves": n_solves, "ms_step": ms_step, "value": n_solves / (ms_step * 1e-3),
+        "alg_bytes_all": float(stats[0]), "iters_all": float(stats[1]), "launches_all": int(stats[2]),
+        "solve_ms_max": solve_ms_max, "clocks": clocks, "tier": sh.run_stats()["tier"], "ws_bytes": ws_bytes,
+        "flush": flush, "steps": steps, "warmup": warmup, "e2e": None, "e2e_with_bases": None,
+    }
+
+    # ---- end-to-end leg: host buffers in, host buffers out, through the C ABI -------------
+    if e2e:
+        from mpi_parallel_multiscale_diffusion_fem_b200 import parallel
+        d_M = d_b = None
+        if world > 1:
+            d_M = torch.empty((total_cells, nb, nb), dtype=torch.float64, device=dev)
+            d_b = torch.empty((total_cells, nb), dtype=torch.float64, device=dev)
+        h_phi = None
+        if with_bases:
+            h_phi = torch.empty((n_local, nb, N), dtype=torch.float64, pin_memory=True)
+
+        def e2e_step(bases):
+            sh.set_cells_ptr(h_corners.data_ptr())                 # H2D corners; BasisQ1 data on device
+            sh.run_async(1e-12, max_iter, sptr)
+            sh.sync()
+            if world > 1:
+                # the reference's compress(add) exchange (ms.tpp:253-254): every rank obtains the per-cell
+                # coarse contributions of all ranks over NVLink -- NCCL all_gather straight out of the
+                # library's device buffers (msb_get_device_results), then ONE device->host copy
+                parallel.gather_coarse_contributions_device(sh, total_cells, dev, d_M, d_b)
+                h_M.copy_(d_M, non_blocking=True)
+                h_b.copy_(d_b, non_blocking=True)
+                sh.iteration_counts_into(h_it.data_ptr())
+                torch.cuda.current_stream().synchronize()
+            else:
+                sh.element_matrices_into(h_M.data_ptr(), h_b.data_ptr())   # D2H
+                sh.iteration_counts_into(h_it.data_ptr())
+            if bases:
+                # the 2^dim solution_vectors of every cell to the host, where the reference keeps them
+                # (basis.hpp:216): one bulk call, chunked reordering + overlapped D2H
+                sh.bases_into(0, n_local, h_phi.data_ptr())
+
+        def timed(bases, k):
+            e2e_step(bases)
+            barrier()
+            t0 = torch.cuda.Event(enable_timing=True)
+            t1 = torch.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
+            t0.record(stream)
+            for _ in range(k):
+                e2e_step(bases)          # (no L2 flush here: every step starts from host buffers)
+            t1.record(stream)
+            barrier()
+            wall_ms = (time.perf_counter() - w0) * 1e3
+            # the copies run on the library's streams: take the larger of device and wall time
+            tt = torch.tensor([max(t0.elapsed_time(t1), wall_ms)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item()) / k
+
+        e2e_ms = timed(False, steps)
+        d2h = int((h_M.numel() + h_b.numel()) * 8 + h_it.numel() * 4)
+        out["e2e"] = {
+            "value": n_solves / (e2e_ms * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": int(h_corners.numel() * 8), "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+            "api": "msb_set_cells + msb_run_async + msb_sync + msb_get_element_matrices + "
+                   "msb_get_iteration_counts (pinned host buffers; bases stay device-resident); at N>1 the "
+                   "NCCL all_gather reads msb_get_device_results and the gathered (M, b) go to the host once"}
+        if with_bases:
+            kb = max(1, min(steps, 3))
+            wb_ms = timed(True, kb)
+            out["e2e_with_bases"] = {
+                "value": n_solves / (wb_ms * 1e-3), "unit": UNIT, "ms_per_step": wb_ms, "steps": kb,
+                "h2d_bytes_per_step": int(h_corners.numel() * 8),
+                "d2h_bytes_per_step": d2h + int(h_phi.numel() * 8),
+                "api": "the e2e step + msb_get_bases of every local cell into pinned host memory (deal.II DoF "
+                       "order): what a caller pays who needs the bases host-side like the reference's "
+                       "output_global_fine (ms.tpp:386-393)"}
+            # spot check of the bulk copy: partition of unity on the last cell
+            pu = float((h_phi[-1].sum(dim=0) - 1.0).abs().max())
+            if not pu < 1e-9:
+                raise SystemExit("bench.py: bulk bases failed the partition-of-unity check (%g)" % pu)
+            del h_phi
+
+    # ---- checks that make the number meaningful -----------------------------------------
+    M, b = sh.element_matrices()
+    H = 1.0 / (1 << r)
+    ok = bool(np.all(res_np <= 1e-12) and np.abs(M.sum(axis=2)).max() < 1e-8 * np.abs(M).max()
+              and np.abs(b.sum(axis=1) - 2 * H ** dim).max() < 1e-9 * H ** dim)
+    if not ok:
+        raise SystemExit("bench.py: %s failed the invariants (zero row sums / load / residual)" % name)
+    sh.close()
+    del sh
+    return out
+
+
+def load_profile_facts(name, build_id):
+    """profiles/traffic.json: per-cell DRAM bytes and pipe utilisations of the dominant kernel from the committed
+    ncu --set full page -- quoted ONLY when it was captured on the binary that is running (msb_build_id)."""
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tpath):
+        return None, "profiles/traffic.json missing"
+    tj = json.load(open(tpath))
+    ent = tj.get("workloads", {}).get(name)
+    if ent is None:
+        return None, "no ncu capture of this workload"
+    if tj.get("build_id") != build_id:
+        return None, ("ncu capture is of build %s, running build %s: not quoted" % (tj.get("build_id"), build_id))
+    return ent, None
+
+
+def roofline_of(m, variant, build_id, peaks):
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if "hbm_gbs" in peaks:
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    world_share = m["alg_bytes_all"] * m["n_local"] / max(1, m["total_cells"])   # rank 0's launch
+    achieved = world_share / (m["solve_ms_max"] * 1e-3) / 1e9
+    ent, why = load_profile_facts(m["name"], build_id)
+    bind = binding_resource(m["dim"], m["l"], variant, m["tier"])
+    rf = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+          "traffic": None if ent is None else ent["dram_bytes_per_cell"] * m["n_local"],
+          "kernel": kernel_name(m["dim"], m["l"], variant, m["tier"]),
+          "kernel_ms_per_launch": m["solve_ms_max"], "peak_source": peak_src,
+          "binding_resource": bind,
+          "note": "achieved = ALGORITHMIC streaming bytes N(96k+16)/solve (SURVEY 8d) of the solves ONE launch of "
+                  "this rank processes / solve-kernel time: a MODEL throughput.  For the on-chip tiers the vectors "
+                  "never leave the SM, real DRAM traffic (`traffic`, ncu, per launch of this rank) is ~1 % of HBM "
+                  "peak and frac > 1 says nothing about kernel quality -- `secondary` (ncu pipe utilisations "
+                  "against the measured on-chip peaks) does"}
+    if ent is None:
+        rf["traffic_note"] = why
+    else:
+        rf["traffic_source"] = ent.get("source")
+        rf["secondary"] = {k: ent[k] for k in ("smem_wavefront_frac", "fp64_pipe_frac", "issue_slot_frac",
+                                                "bank_conflict_wavefront_frac") if k in ent}
+    ppath = os.path.join(ROOT, "profiles", "onchip_peaks.json")
+    if os.path.exists(ppath):
+        op = json.load(open(ppath))
+        rf["onchip_peaks"] = {"fp64_tflops": op.get("fp64", {}).get("tflops"),
+                              "smem_bytes_per_clk_per_sm": op.get("smem", {}).get("lds128", {}).get("bytes_per_clk_per_sm"),
+                              "source": "scripts/probes/onchip_peaks.cu on this pool's B200 (profiles/onchip_peaks.json)"}
+    return rf
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -194,6 +454,9 @@ def main():
     ap.add_argument("--max-iter", type=int, default=5000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true",
+                    help="skip the per_config block (BASELINE configs 1-5 + 3D after the headline leg)")
+    ap.add_argument("--no-bases", action="store_true", help="skip the e2e_with_bases leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 3) if not args.cells else args.warmup
@@ -204,7 +467,7 @@ def main():
     import torch
     import torch.distributed as dist
     import mpi_parallel_multiscale_diffusion_fem_b200 as pkg
-    from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
+    from mpi_parallel_multiscale_diffusion_fem_b200 import binding
 
     # stdout carries exactly ONE JSON line: anything a library prints to file descriptor 1 from here on
     # (NCCL's "NCCL version ..." banner when the environment sets NCCL_DEBUG, ...) is sent to stderr
@@ -212,200 +475,82 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cx = Ctx()
+    cx.torch, cx.dist, cx.pkg = torch, dist, pkg
+    cx.world = world = int(os.environ.get("WORLD_SIZE", "1"))
+    cx.rank = rank = int(os.environ.get("RANK", "0"))
+    cx.local_rank = local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cx.flush_buf = None
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the basis stage has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    build_id = binding.build_id()
 
-    r, l, kind, par, seed, dim = workload(args.workload)
-    nb = 1 << dim
-    total_cells = (1 << r) ** dim
-    if args.cells:
-        total_cells = min(total_cells, args.cells)
-    lo, hi = pkg.morton_partition(total_cells, rank, world)
-    n_local = hi - lo
-    N = ((1 << l) + 1) ** dim
+    m = measure(cx, args.workload, args.steps, args.warmup, variant=args.variant, cells=args.cells,
+                max_iter=args.max_iter, e2e=not args.no_e2e,
+                with_bases=not (args.no_e2e or args.no_bases))
 
-    # host inputs/outputs in pinned memory (the e2e leg copies them every step)
-    corners_np = pkg.coarse_corners(r, lo, hi) if dim == 2 else pkg.coarse_corners3(r, lo, hi)
-    h_corners = torch.from_numpy(corners_np).pin_memory()
-    h_M = torch.empty((n_local, nb, nb), dtype=torch.float64).pin_memory()
-    h_b = torch.empty((n_local, nb), dtype=torch.float64).pin_memory()
-    h_it = torch.empty((n_local, nb), dtype=torch.int32).pin_memory()
-
-    sh = pkg.BasisShard(l, corners_np, coeff_desc(kind, par, seed), device_id=local_rank,
-                        variant=args.variant, dim=dim)
-    stream = torch.cuda.current_stream()
-    sptr = stream.cuda_stream
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step():
-        sh.run_async(1e-12, args.max_iter, sptr)
-
-    # working sets that could survive in the 126 MB L2 from one step to the next (the reference's
-    # default run: 64 cells) are flushed out between timed steps by writing a 512 MB buffer
-    ws_bytes = n_local * (10 if dim == 2 else 23) * N * 8
-    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda") if ws_bytes < (512 << 20) else None
-
-    # ---- kernel-resident leg: inputs already in HBM -----------------------------------
-    for _ in range(args.warmup):
-        step()
-    sh.sync()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    solve_ms, launches = [], 0
-    ms_total = 0.0
-    if flush_buf is None:
-        ev0.record(stream)
-    for _ in range(args.steps):
-        if flush_buf is not None:
-            flush_buf.zero_()            # untimed
-            torch.cuda.synchronize()
-        step()
-        # per-step device-side stats need the events of this run: sync this rank's stream
-        sh.sync()
-        st = sh.run_stats()
-        solve_ms.append(st["ms_solve"])
-        launches += st["launches"]
-        if flush_buf is not None:
-            # the stage's own CUDA events, recorded on the stream the kernels run on
-            # (msb_get_run_stats: first launch of the assembly -> end of the element matrices)
-            ms_total += st["ms_total"]
-    if flush_buf is None:
-        ev1.record(stream)
-    barrier()
-    clocks = sampler.stop()
-    if flush_buf is None:
-        ms_total = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    it_np, res_np = sh.iteration_counts()
-    alg_bytes, mean_k = sh.algorithmic_bytes()
-    stats = torch.tensor([alg_bytes, float(it_np.sum()), float(launches), float(np.mean(solve_ms))],
-                         dtype=torch.float64, device="cuda")
-    if world > 1:
-        smax = stats.clone()
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-        dist.all_reduce(smax, op=dist.ReduceOp.MAX)
-        solve_ms_max = float(smax[3].item())
-    else:
-        solve_ms_max = float(stats[3].item())
-    alg_bytes_all, iters_all, launches_all = float(stats[0]), float(stats[1]), int(stats[2])
-    n_solves = nb * total_cells
-    value = n_solves / (ms_step * 1e-3)
-
-    # ---- end-to-end leg: host buffers in, host buffers out, through the C ABI -------------
-    e2e = None
-    if not args.no_e2e:
-        from mpi_parallel_multiscale_diffusion_fem_b200 import parallel
-
-        def e2e_step():
-            sh.set_cells_ptr(h_corners.data_ptr())                 # H2D corners; BasisQ1 data on device
-            sh.run_async(1e-12, args.max_iter, sptr)
-            sh.sync()
-            sh.element_matrices_into(h_M.data_ptr(), h_b.data_ptr())   # D2H
-            sh.iteration_counts_into(h_it.data_ptr())
-            if world > 1:
-                # the reference's compress(add) exchange (ms.tpp:253-254): every rank obtains the
-                # per-cell coarse contributions of all ranks over NVLink (NCCL all_gather)
-                parallel.gather_coarse_contributions(h_M, h_b, total_cells, device="cuda")
-
-        e2e_step()
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        w0 = time.perf_counter()
-        t0.record(stream)
-        for _ in range(args.steps):
-            e2e_step()                   # (no L2 flush here: every step starts from host buffers)
-        t1.record(stream)
-        barrier()
-        wall_ms = (time.perf_counter() - w0) * 1e3
-        # the D2H copies run on the library's stream: take the larger of device and wall time
-        tt = torch.tensor([max(t0.elapsed_time(t1), wall_ms)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item()) / args.steps
-        e2e = {"value": n_solves / (e2e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h_corners.numel() * 8),
-               "d2h_bytes_per_step": int(h_M.numel() * 8 + h_b.numel() * 8 + h_it.numel() * 4),
-               "ms_per_step": e2e_ms,
-               "api": "msb_set_cells + msb_run_async + msb_sync + msb_get_element_matrices + "
-                      "msb_get_iteration_counts (pinned host buffers; bases stay device-resident "
-                      "as in the reference, where they live inside the basis objects)"}
-
-    # ---- checks that make the number meaningful -----------------------------------------
-    M, b = sh.element_matrices()
-    H = 1.0 / (1 << r)
-    ok = bool(np.all(res_np <= 1e-12) and np.abs(M.sum(axis=2)).max() < 1e-8 * np.abs(M).max()
-              and np.abs(b.sum(axis=1) - 2 * H ** dim).max() < 1e-9 * H ** dim)
-    if not ok:
-        raise SystemExit("bench.py: results failed the invariants (zero row sums / load / residual)")
+    # ---- the other BASELINE configurations, each at the rank count of this run -------------
+    per_config = None
+    if not args.no_per_config and not args.cells and args.workload == "target" and args.variant == 0:
+        per_config = {}
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        for name in PER_CONFIG:
+            k = 2 if name == "cfg5" else 3
+            pm = measure(cx, name, k, 3, e2e=False)
+            rf = roofline_of(pm, 0, build_id, peaks)
+            per_config[name] = {
+                "workload": describe(name, pm["total_cells"]), "value": pm["value"], "unit": UNIT,
+                "ms_per_step": pm["ms_step"], "steps": k, "warmup": 3,
+                "mean_pcg_iterations": pm["iters_all"] / pm["n_solves"],
+                "model_frac": rf["frac"], "model_gbs": rf["achieved"], "kernel": rf["kernel"],
+                "binding_resource": rf["binding_resource"], "kernel_ms_per_launch": pm["solve_ms_max"],
+                "gpu_launches": pm["launches_all"], "clocks": pm["clocks"],
+                "l2": "flushed between steps" if pm["flush"] else "working set >> L2"}
 
     if rank == 0:
+        r, l, kind, par, seed, dim = workload(args.workload)
         peaks = {}
         ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         if os.path.exists(ppath):
             peaks = json.load(open(ppath))
-            peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-        # dominant kernel: the PCG solve kernel; algorithmic bytes N(96k+16) per solve
-        #  of the solves ONE launch processes / its CUDA-event duration
-        achieved = (alg_bytes_all / world) / (solve_ms_max * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            traffic = tj.get(args.workload, {}).get("dram_bytes_per_launch")
+        rf = roofline_of(m, args.variant, build_id, peaks)
+        n_solves = m["n_solves"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": m["ms_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": describe(args.workload, total_cells),
+            "config": {"workload": describe(args.workload, m["total_cells"]),
                        "partition": "contiguous Morton ranges over %d rank(s) (p4est rule)" % world,
                        "l2": ("working set (stencil + bases = %.1f GB per GPU) far larger than L2; "
-                              "no flush needed" % (ws_bytes / 1e9)) if flush_buf is None else
+                              "no flush needed" % (m["ws_bytes"] / 1e9)) if not m["flush"] else
                              ("working set %.0f MB per GPU: L2 flushed between timed steps (untimed "
                               "write of a 512 MB buffer), each step timed by the stage's own CUDA events on its stream"
-                              % (ws_bytes / 1e6)),
-                       "mean_pcg_iterations": iters_all / n_solves,
-                       "preconditioner": ("multilevel diagonal scaling (BPX), exact Galerkin diagonals"
-                                          + (", exact solve of the 7x7 coarse level" if (dim == 2 and l == 5) or (dim == 2 and l == 6 and args.variant == 0) else "")
+                              % (m["ws_bytes"] / 1e6)),
+                       "mean_pcg_iterations": m["iters_all"] / n_solves,
+                       "preconditioner": ("multilevel diagonal scaling (BPX), exact Galerkin diagonals (the reciprocal "
+                                          "diagonals of the coarse levels are STORED as float; all arithmetic f64)"
+                                          + (", exact solve of the 7x7 coarse level" if (dim == 2 and l == 5) or (dim == 2 and l == 6 and args.variant in (0, 8, 9)) else "")
                                           if args.variant < 100 else "Jacobi (symmetric diagonal scaling)"),
-                       "variant": args.variant},
-            "clocks": clocks,
-            "e2e": e2e,
-            "gpu_launches": launches_all,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "kernel": (("solve_bpx_tm_kernel" if (l == 6 and args.variant in (0, 5, 7)) else "solve_bpx_kernel") if args.variant < 100 else "solve_smem_kernel") if sh.run_stats()["tier"] == 1 else (("solve_cluster_kernel" if (l == 7 and args.variant == 0) or (args.variant in (3, 4) and 5 <= l <= 7) else "stream_k*") if dim == 2 else "d3::k2_kernel + siblings"),
-                         "kernel_ms_per_launch": solve_ms_max,
-                         "peak_source": peak_src,
-                         "note": "achieved = ALGORITHMIC streaming bytes N(96k+16)/solve (SURVEY 8d) / "
-                                 "solve-kernel time; vectors live on chip, so real DRAM traffic "
-                                 "(`traffic`, ncu) is far smaller and frac may exceed 1"},
+                       "variant": args.variant, "build_id": build_id},
+            "clocks": m["clocks"],
+            "e2e": m["e2e"],
+            "e2e_with_bases": m["e2e_with_bases"],
+            "gpu_launches": m["launches_all"],
+            "roofline": rf,
         }
+        if per_config is not None:
+            line["per_config"] = per_config
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(args.workload)
             cb.pop("seconds"), cb.pop("solves")
             line["cpu_baseline"] = cb
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    sh.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

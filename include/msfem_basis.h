@@ -123,7 +123,11 @@ int msb_set_cells(msb_handle h, const double *corners, const double *coeff_table
  * tested every iteration). */
 int msb_run(msb_handle h, double tol_abs, int32_t max_iter);
 
-/* Same, enqueued on `cuda_stream` without synchronising; pair with msb_sync. */
+/* Same, enqueued on `cuda_stream`; pair with msb_sync.  The shared-memory and cluster
+ * tiers (n_refine_local <= 7 in 2D) are one asynchronous launch sequence: the call returns
+ * without synchronising.  The HBM-streamed kernels (2D n_refine_local >= 8, dim 3) test
+ * convergence from the host every few iterations and therefore block the calling thread
+ * until the solves have finished (the stream is still the caller's). */
 int msb_run_async(msb_handle h, double tol_abs, int32_t max_iter, void *cuda_stream);
 int msb_sync(msb_handle h);
 
@@ -141,6 +145,14 @@ int msb_get_iteration_counts(msb_handle h, int32_t *iters, double *residuals);
 /* solution_vector[index_basis] of one cell (basis.hpp:216), N doubles in the
  * deal.II DoF order. */
 int msb_get_basis(msb_handle h, int32_t cell, int32_t index_basis, double *out);
+
+/* Bulk form: the 2^dim solution_vectors (basis.hpp:216) of the cells [cell0, cell0 + n_cells)
+ * in ONE call, out [n_cells][2^dim][N] in the deal.II DoF order.  The reference keeps these
+ * vectors host-side inside every basis object; a caller that walks all cells
+ * (output_global_fine, ms.tpp:386-393) gets them with one reordering launch per staging
+ * chunk and chunked device->host copies that overlap it (fully asynchronous when `out` is
+ * page-locked), instead of one launch + one synchronisation per (cell, basis). */
+int msb_get_bases(msb_handle h, int32_t cell0, int32_t n_cells, double *out);
 
 /* DoF map of the local mesh (basis.tpp:106): dof_of_vertex[jy*(n+1)+jx]
  * (dim 3: [(jz*(n+1)+jy)*(n+1)+jx]). */
@@ -165,6 +177,19 @@ int msb_set_global_weights(msb_handle h, const double *w);
 /* global_solution of one cell (basis.hpp, basis.tpp:421-435), deal.II order. */
 int msb_get_global_solution(msb_handle h, int32_t cell, double *out);
 
+/* Bulk form for the walk over all cells in output_global_fine (ms.tpp:386-393):
+ * global_solution of the cells [cell0, cell0 + n_cells), out [n_cells][N], deal.II order. */
+int msb_get_global_solutions(msb_handle h, int32_t cell0, int32_t n_cells, double *out);
+
+/* Device addresses (as integers of the handle's device) of the stage results of the last
+ * run: M [n_cells][2^dim][2^dim], b [n_cells][2^dim], iteration counts [n_cells][2^dim]
+ * (int32).  For the exchange that follows the stage -- the reference's
+ * compress(VectorOperation::add), ms.tpp:253-254 -- so that an NCCL collective can read the
+ * contributions where they are instead of through a host round trip.  The memory stays
+ * owned by the handle and valid until msb_set_cells / msb_run / msb_destroy.  Any of the
+ * out-pointers may be NULL. */
+int msb_get_device_results(msb_handle h, uint64_t *d_M, uint64_t *d_b, uint64_t *d_iters);
+
 /* Device-side timing of the last run (CUDA events on the run's stream), ms;
  * and the number of kernels the run launched. */
 int msb_get_run_stats(msb_handle h, float *ms_total, float *ms_solve_kernel, int32_t *n_launches,
@@ -179,9 +204,12 @@ int msb_destroy(msb_handle h);
 /* Thread-local description of the last error. */
 const char *msb_last_error(void);
 
-/* Library / device identification. */
+/* Library / device identification.  msb_build_id: first 16 hex digits of the SHA-256 of the
+ * kernel sources this binary was compiled from (csrc/Makefile), so that a profile captured
+ * on one binary is never quoted beside a run of another (bench.py roofline.traffic). */
 int msb_device_count(void);
 const char *msb_version(void);
+const char *msb_build_id(void);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "msb_get_constraints", "msb_apply_operator", "msb_get_load_vector", "msb_set_global_weights",
     "msb_get_global_solution", "msb_get_run_stats", "msb_get_algorithmic_bytes", "msb_destroy",
     "msb_last_error", "msb_device_count", "msb_version",
+    "msb_get_bases", "msb_get_global_solutions", "msb_get_device_results", "msb_build_id",
 ]
 
 
@@ -63,12 +64,18 @@ def load_library():
         lib = C.CDLL(p)
         lib.msb_last_error.restype = C.c_char_p
         lib.msb_version.restype = C.c_char_p
+        lib.msb_build_id.restype = C.c_char_p
         lib.msb_run.argtypes = [C.c_void_p, C.c_double, C.c_int32]
         lib.msb_run_async.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_void_p]
         for name in ("msb_sync", "msb_destroy"):
             getattr(lib, name).argtypes = [C.c_void_p]
         _lib = lib
     return _lib
+
+
+def build_id():
+    """Identity of the kernel sources the loaded library was compiled from (msb_build_id)."""
+    return load_library().msb_build_id().decode()
 
 
 def _dp(a):
@@ -186,6 +193,29 @@ class BasisShard:
         out = np.empty(self.N, dtype=np.float64)
         self._check(self._lib.msb_get_basis(self._h, C.c_int32(cell), C.c_int32(index_basis), _dp(out)))
         return out
+
+    def bases(self, cell0=0, n_cells=None, out=None):
+        """msb_get_bases: [n_cells, 2^dim, N] in the deal.II DoF order, one call."""
+        n_cells = self.n_cells - cell0 if n_cells is None else n_cells
+        if out is None:
+            out = np.empty((n_cells, self.nb, self.N), dtype=np.float64)
+        self._check(self._lib.msb_get_bases(self._h, C.c_int32(cell0), C.c_int32(n_cells), _dp(out)))
+        return out
+
+    def bases_into(self, cell0, n_cells, out_addr):
+        self._check(self._lib.msb_get_bases(self._h, C.c_int32(cell0), C.c_int32(n_cells), C.c_void_p(out_addr)))
+
+    def global_solutions(self, cell0=0, n_cells=None):
+        n_cells = self.n_cells - cell0 if n_cells is None else n_cells
+        out = np.empty((n_cells, self.N), dtype=np.float64)
+        self._check(self._lib.msb_get_global_solutions(self._h, C.c_int32(cell0), C.c_int32(n_cells), _dp(out)))
+        return out
+
+    def device_results(self):
+        """Device addresses of (M, b, iteration counts) of the last run (msb_get_device_results)."""
+        m, b, it = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.msb_get_device_results(self._h, C.byref(m), C.byref(b), C.byref(it)))
+        return m.value, b.value, it.value
 
     def dof_map(self):
         out = np.empty(self.N, dtype=np.uint32)

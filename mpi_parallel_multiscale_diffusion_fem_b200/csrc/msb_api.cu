@@ -56,6 +56,15 @@ msb_version(void)
   return "msfem_basis 0.1 (sm_100a)";
 }
 
+#ifndef MSB_BUILD_ID
+#  define MSB_BUILD_ID "unknown"
+#endif
+extern "C" const char *
+msb_build_id(void)
+{
+  return MSB_BUILD_ID;
+}
+
 extern "C" int
 msb_device_count(void)
 {
@@ -85,6 +94,36 @@ all_bricks(const double *corners, size_t n_cells)
   return true;
 }
 
+// MSB_COEFF_TABLE: the stiffness matrix is assembled from the symmetric part of the tensor
+// (K must be symmetric for the reference's SolverCG as well, basis.tpp:299-306), so a table
+// whose tensors are not symmetric up to rounding is rejected instead of being silently
+// symmetrised.  The reference MatrixCoeff is asymmetric by ~6e-17 a.
+// Returns the index of the first offending tensor or -1.
+static long long
+first_unsymmetric_tensor(const double *table, size_t n_tensors, int dim)
+{
+  const int e = dim * dim;
+  for (size_t t = 0; t < n_tensors; ++t)
+    {
+      const double *a = table + e * t;
+      double        big = 0.0;
+      for (int i = 0; i < e; ++i)
+        big = fabs(a[i]) > big ? fabs(a[i]) : big;
+      for (int i = 0; i < dim; ++i)
+        for (int j = i + 1; j < dim; ++j)
+          if (!(fabs(a[dim * i + j] - a[dim * j + i]) <= 1e-12 * big))
+            return (long long)t;
+    }
+  return -1;
+}
+
+// doubles of the coefficient table per coarse cell: fine cells x 2^dim q-points x dim*dim entries
+static size_t
+ncoef_table_doubles(const Shard &s)
+{
+  return ((size_t)1 << (s.dim * s.l)) * (size_t)s.nb * (size_t)(s.dim * s.dim);
+}
+
 static void
 free_shard(Shard &s)
 {
@@ -92,10 +131,13 @@ free_shard(Shard &s)
   void *ptrs[] = {s.d_corners, s.d_q1coef, s.d_table, s.d_sten, s.d_phi,  s.d_M,    s.d_b,
                   s.d_iters,   s.d_res,    s.d_fail,  s.d_dofmap, s.d_invmap, s.d_gsol, s.d_tmp,
                   s.d_wr,      s.d_wp,     s.d_wq,    s.d_scal, s.d_part, s.d_flags,
-                  s.d_wz,      s.d_wv,     s.d_dinv,  s.d_gal};
+                  s.d_wz,      s.d_wv,     s.d_dinv,  s.d_gal,  s.d_w,    s.d_stage[0], s.d_stage[1]};
   for (void *p : ptrs)
     if (p)
       cudaFree(p);
+  for (auto &q : s.stage_stream)
+    if (q)
+      cudaStreamDestroy(q);
   for (auto &e : s.ev)
     if (e)
       cudaEventDestroy(e);
@@ -128,6 +170,15 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
     return fail(MSB_ERR_INVALID_ARG, "msb_create: coefficient kind %d", cfg->coeff.kind);
   if (cfg->coeff.kind == MSB_COEFF_TABLE && !coeff_table)
     return fail(MSB_ERR_INVALID_ARG, "msb_create: MSB_COEFF_TABLE needs coeff_table");
+  if (cfg->coeff.kind == MSB_COEFF_TABLE)
+    {
+      const size_t    ncell_f = (size_t)1 << (cfg->dim * cfg->n_refine_local);
+      const long long bad = first_unsymmetric_tensor(coeff_table, (size_t)cfg->n_cells * ncell_f * (1u << cfg->dim), cfg->dim);
+      if (bad >= 0)
+        return fail(MSB_ERR_INVALID_ARG,
+                    "msb_create: coefficient tensor %lld of the table is not symmetric (|a_ij - a_ji| > 1e-12 max|a|): "
+                    "the stage, like the reference's SolverCG, needs a symmetric stiffness matrix", bad);
+    }
   if (cfg->coeff.kind == MSB_COEFF_PERIODIC && !(cfg->coeff.par[0] > 0.0))
     return fail(MSB_ERR_INVALID_ARG, "msb_create: periodic coefficient needs eps > 0");
   if (cfg->coeff.kind == MSB_COEFF_INCLUSIONS && !(cfg->coeff.par[0] > 0.0))
@@ -206,7 +257,7 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
   ALLOC(s.d_tmp, 3 * N);
   ALLOC(s.d_flags, 4);
   if (s.coeff.kind == MSB_COEFF_TABLE)
-    ALLOC(s.d_table, C * (size_t)s.n * s.n * 16);
+    ALLOC(s.d_table, C * ncoef_table_doubles(s));
   if (s.tier == MSB_TIER_STREAMED)
     {
       const size_t cn = s.dim == 2 ? streamed_coarse_nodes(s.l) : dim3_coarse_nodes(s.l);
@@ -237,7 +288,7 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
   if (e == cudaSuccess)
     e = launch_basis_q1(s, s.stream, &bad_cell); // BasisQ1 coefficient matrices, on the device
   if (e == cudaSuccess && s.d_table)
-    e = cudaMemcpyAsync(s.d_table, coeff_table, sizeof(double) * C * (size_t)s.n * s.n * 16,
+    e = cudaMemcpyAsync(s.d_table, coeff_table, sizeof(double) * C * ncoef_table_doubles(s),
                         cudaMemcpyHostToDevice, s.stream);
   if (e == cudaSuccess)
     e = cudaStreamSynchronize(s.stream);
@@ -269,19 +320,40 @@ msb_set_cells(msb_handle h, const double *corners, const double *coeff_table)
     return fail(MSB_ERR_INVALID_ARG, "msb_set_cells: MSB_COEFF_TABLE needs coeff_table");
   CUDA_TRY(cudaSetDevice(s.device));
   if (s.run_pending)
-    CUDA_TRY(cudaStreamSynchronize(s.run_stream));
+    {
+      // results of the run in flight belong to the old cells: wait for it, then drop them
+      const cudaError_t e = cudaStreamSynchronize(s.run_stream);
+      s.run_pending       = false;
+      if (e != cudaSuccess)
+        {
+          s.valid = false;
+          return fail(MSB_ERR_CUDA, "msb_set_cells: pending run failed: %s", cudaGetErrorString(e));
+        }
+    }
   const size_t C = (size_t)s.n_cells, NB = (size_t)s.nb, NCORN = NB * s.dim;
+  if (s.coeff.kind == MSB_COEFF_TABLE)
+    {
+      const size_t    ncell_f = (size_t)1 << (s.dim * s.l);
+      const long long bad     = first_unsymmetric_tensor(coeff_table, C * ncell_f * NB, s.dim);
+      if (bad >= 0) // nothing on the device has been touched yet: the handle keeps its old cells
+        return fail(MSB_ERR_INVALID_ARG, "msb_set_cells: coefficient tensor %lld of the table is not symmetric", bad);
+    }
+  // from here on device state is overwritten: every result of the previous batch is void, and
+  // a failure leaves the handle unusable until a later msb_set_cells succeeds
+  s.assembled = s.ran = s.weights_set = false;
+  s.valid     = false;
+  s.last_status = MSB_OK;
   CUDA_TRY(cudaMemcpyAsync(s.d_corners, corners, sizeof(double) * NCORN * C, cudaMemcpyHostToDevice, s.stream));
   int32_t bad_cell = INT_MAX;
   CUDA_TRY(launch_basis_q1(s, s.stream, &bad_cell));
   if (bad_cell != INT_MAX)
     return fail(MSB_ERR_INVALID_ARG, "msb_set_cells: coarse cell %d is degenerate", bad_cell);
   if (s.d_table)
-    CUDA_TRY(cudaMemcpyAsync(s.d_table, coeff_table, sizeof(double) * C * (size_t)s.n * s.n * 16,
+    CUDA_TRY(cudaMemcpyAsync(s.d_table, coeff_table, sizeof(double) * C * (size_t)ncoef_table_doubles(s),
                              cudaMemcpyHostToDevice, s.stream));
   CUDA_TRY(cudaStreamSynchronize(s.stream));
-  s.bricks    = s.dim == 3 && all_bricks(corners, C);
-  s.assembled = s.ran = s.weights_set = s.run_pending = false;
+  s.bricks = s.dim == 3 && all_bricks(corners, C);
+  s.valid  = true;
   return MSB_OK;
 }
 
@@ -306,6 +378,8 @@ msb_run_async(msb_handle h, double tol_abs, int32_t max_iter, void *cuda_stream)
   if (!(tol_abs >= 0.0) || max_iter < 0)
     return fail(MSB_ERR_INVALID_ARG, "msb_run: tol_abs=%g max_iter=%d", tol_abs, max_iter);
   Shard &s = h->s;
+  if (!s.valid)
+    return fail(MSB_ERR_STATE, "msb_run: the last msb_set_cells failed; set valid cells first");
   CUDA_TRY(cudaSetDevice(s.device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s.stream;
   s.run_stream    = st;
@@ -377,6 +451,8 @@ need_ran(msb_handle h, const char *who)
 {
   if (!h)
     return fail(MSB_ERR_INVALID_ARG, "%s: null handle", who);
+  if (!h->s.valid)
+    return fail(MSB_ERR_STATE, "%s: the last msb_set_cells failed; set valid cells first", who);
   if (h->s.run_pending)
     {
       const int rc = msb_sync(h);
@@ -488,6 +564,8 @@ msb_get_constraints(msb_handle h, int32_t cell, int32_t ib, uint32_t *dofs, doub
   if (rc != MSB_OK)
     return rc;
   Shard &s = h->s;
+  if (!s.valid)
+    return fail(MSB_ERR_STATE, "msb_get_constraints: the last msb_set_cells failed; set valid cells first");
   CUDA_TRY(cudaSetDevice(s.device));
   const int nb    = s.dim == 2 ? 4 * s.n : s.N - (s.n - 1) * (s.n - 1) * (s.n - 1);
   uint32_t *d_dof = reinterpret_cast<uint32_t *>(s.d_tmp);       // nb uint32 <= N doubles
@@ -506,6 +584,8 @@ static int
 ensure_assembled(msb_handle h)
 {
   Shard &s = h->s;
+  if (!s.valid)
+    return fail(MSB_ERR_STATE, "the last msb_set_cells failed; set valid cells first");
   if (s.run_pending)
     {
       const int rc = msb_sync(h);
@@ -580,14 +660,13 @@ msb_set_global_weights(msb_handle h, const double *w)
   const size_t C = (size_t)s.n_cells;
   if (!s.d_gsol)
     CUDA_TRY(cudaMalloc((void **)&s.d_gsol, sizeof(double) * C * s.N));
-  double *d_w = nullptr;
-  CUDA_TRY(cudaMalloc((void **)&d_w, sizeof(double) * s.nb * C));
-  cudaError_t e = cudaMemcpyAsync(d_w, w, sizeof(double) * s.nb * C, cudaMemcpyHostToDevice, s.stream);
+  if (!s.d_w) // allocated once, with the global-solution array, on the first call
+    CUDA_TRY(cudaMalloc((void **)&s.d_w, sizeof(double) * s.nb * C));
+  cudaError_t e = cudaMemcpyAsync(s.d_w, w, sizeof(double) * s.nb * C, cudaMemcpyHostToDevice, s.stream);
   if (e == cudaSuccess)
-    e = launch_global_solution(s, d_w, s.stream);
+    e = launch_global_solution(s, s.d_w, s.stream);
   if (e == cudaSuccess)
     e = cudaStreamSynchronize(s.stream);
-  cudaFree(d_w);
   if (e != cudaSuccess)
     return fail(MSB_ERR_CUDA, "msb_set_global_weights: %s", cudaGetErrorString(e));
   s.weights_set = true;
@@ -611,6 +690,100 @@ msb_get_global_solution(msb_handle h, int32_t cell, double *out)
   CUDA_TRY(launch_permute(s, s.d_gsol + (size_t)cell * s.N, s.d_tmp, true, s.stream));
   CUDA_TRY(cudaMemcpyAsync(out, s.d_tmp, sizeof(double) * s.N, cudaMemcpyDeviceToHost, s.stream));
   CUDA_TRY(cudaStreamSynchronize(s.stream));
+  return MSB_OK;
+}
+
+// n_vec consecutive device vectors (lexicographic) -> host, deal.II DoF order.  Two staging buffers on two
+// streams: the device->host copy of chunk k overlaps the reordering launch of chunk k+1.
+static int
+bulk_to_host(Shard &s, const double *d_src, size_t n_vec, double *out, const char *who)
+{
+  if (n_vec == 0)
+    return MSB_OK;
+  if (!s.d_stage[0])
+    {
+      // 64 MB per staging buffer, at least one vector, at most what is asked for
+      size_t vecs = ((size_t)64 << 20) / (sizeof(double) * (size_t)s.N);
+      vecs        = vecs < 1 ? 1 : vecs;
+      const size_t most = (size_t)s.nb * (size_t)s.n_cells;
+      vecs        = vecs > most ? most : vecs;
+      for (int k = 0; k < 2; ++k)
+        {
+          CUDA_TRY(cudaMalloc((void **)&s.d_stage[k], sizeof(double) * vecs * (size_t)s.N));
+          CUDA_TRY(cudaStreamCreateWithFlags(&s.stage_stream[k], cudaStreamNonBlocking));
+        }
+      s.stage_vecs = vecs;
+    }
+  CUDA_TRY(cudaStreamSynchronize(s.stream)); // whatever produced d_src on the library stream
+  int k = 0;
+  for (size_t v0 = 0; v0 < n_vec; v0 += s.stage_vecs, k ^= 1)
+    {
+      const size_t nv = n_vec - v0 < s.stage_vecs ? n_vec - v0 : s.stage_vecs;
+      // stream order protects the staging buffer: the previous copy out of it is on the same stream
+      CUDA_TRY(launch_permute_batch(s, d_src + v0 * (size_t)s.N, s.d_stage[k], nv, s.stage_stream[k]));
+      CUDA_TRY(cudaMemcpyAsync(out + v0 * (size_t)s.N, s.d_stage[k], sizeof(double) * nv * (size_t)s.N,
+                               cudaMemcpyDeviceToHost, s.stage_stream[k]));
+    }
+  for (int q = 0; q < 2; ++q)
+    {
+      const cudaError_t e = cudaStreamSynchronize(s.stage_stream[q]);
+      if (e != cudaSuccess)
+        return fail(MSB_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e));
+    }
+  return MSB_OK;
+}
+
+static int
+check_range(msb_handle h, int32_t cell0, int32_t n, const char *who)
+{
+  if (cell0 < 0 || n < 0 || (long long)cell0 + n > h->s.n_cells)
+    return fail(MSB_ERR_INVALID_ARG, "%s: cells [%d, %d) outside the shard's %d cells", who, cell0, cell0 + n,
+                h->s.n_cells);
+  return MSB_OK;
+}
+
+extern "C" int
+msb_get_bases(msb_handle h, int32_t cell0, int32_t n_cells, double *out)
+{
+  int rc = need_ran(h, "msb_get_bases");
+  if (rc != MSB_OK)
+    return rc;
+  if ((rc = check_range(h, cell0, n_cells, "msb_get_bases")) != MSB_OK)
+    return rc;
+  if (!out && n_cells > 0)
+    return fail(MSB_ERR_INVALID_ARG, "msb_get_bases: null out");
+  Shard &s = h->s;
+  return bulk_to_host(s, s.d_phi + (size_t)cell0 * s.nb * s.N, (size_t)n_cells * s.nb, out, "msb_get_bases");
+}
+
+extern "C" int
+msb_get_global_solutions(msb_handle h, int32_t cell0, int32_t n_cells, double *out)
+{
+  int rc = need_ran(h, "msb_get_global_solutions");
+  if (rc != MSB_OK)
+    return rc;
+  if ((rc = check_range(h, cell0, n_cells, "msb_get_global_solutions")) != MSB_OK)
+    return rc;
+  Shard &s = h->s;
+  if (!s.weights_set) // the reference asserts is_set_global_weights (basis.tpp:425-426)
+    return fail(MSB_ERR_STATE, "msb_get_global_solutions: global weights must be set first");
+  if (!out && n_cells > 0)
+    return fail(MSB_ERR_INVALID_ARG, "msb_get_global_solutions: null out");
+  return bulk_to_host(s, s.d_gsol + (size_t)cell0 * s.N, (size_t)n_cells, out, "msb_get_global_solutions");
+}
+
+extern "C" int
+msb_get_device_results(msb_handle h, uint64_t *d_M, uint64_t *d_b, uint64_t *d_iters)
+{
+  int rc = need_ran(h, "msb_get_device_results");
+  if (rc != MSB_OK)
+    return rc;
+  if (d_M)
+    *d_M = (uint64_t)(uintptr_t)h->s.d_M;
+  if (d_b)
+    *d_b = (uint64_t)(uintptr_t)h->s.d_b;
+  if (d_iters)
+    *d_iters = (uint64_t)(uintptr_t)h->s.d_iters;
   return MSB_OK;
 }
 

@@ -60,6 +60,13 @@ namespace msb
     uint32_t     *d_invmap  = nullptr; // deal.II dof -> lex
     double       *d_gsol    = nullptr; // [C][N] global solution (after set_global_weights)
     double       *d_tmp     = nullptr; // 2*N scratch for single-vector calls
+    double       *d_w       = nullptr; // [C][nb] coarse weights (set_global_weights)
+    // bulk accessors (msb_get_bases / msb_get_global_solutions): two staging buffers for the
+    // reordered vectors, each on its own stream so that the device->host copy of one chunk
+    // overlaps the reordering launch of the next
+    double       *d_stage[2]   = {nullptr, nullptr};
+    size_t        stage_vecs   = 0;    // vectors of N doubles per staging buffer
+    cudaStream_t  stage_stream[2] = {nullptr, nullptr};
     // streamed tier work vectors [C][4][N] each
     double       *d_wr = nullptr, *d_wp = nullptr, *d_wq = nullptr, *d_wz = nullptr;
     double       *d_wv = nullptr;     // streamed tier coarse-level vectors [C][4][cn]
@@ -73,6 +80,7 @@ namespace msb
     cudaStream_t run_stream = nullptr;
     cudaEvent_t  ev[4]  = {nullptr, nullptr, nullptr, nullptr};
     bool         assembled = false, ran = false, weights_set = false, run_pending = false;
+    bool         valid = true;        // false after a failed msb_set_cells: only set_cells / destroy work
     bool         bricks = false;      // dim 3: every coarse cell is an axis-aligned brick
     int          n_launches = 0;
     int          tier_used  = 0;
@@ -99,6 +107,9 @@ namespace msb
                                     cudaStream_t st);
   cudaError_t launch_permute(const Shard &s, const double *d_src, double *d_dst, bool lex_to_dof,
                              cudaStream_t st);
+  // n_vec consecutive vectors of N doubles, lexicographic -> deal.II DoF order, one launch
+  cudaError_t launch_permute_batch(const Shard &s, const double *d_src, double *d_dst, size_t n_vec,
+                                   cudaStream_t st);
   cudaError_t launch_global_solution(const Shard &s, const double *d_w, cudaStream_t st);
   cudaError_t launch_constraints(const Shard &s, int cell, int ib, uint32_t *d_dofs, double *d_vals,
                                  cudaStream_t st);

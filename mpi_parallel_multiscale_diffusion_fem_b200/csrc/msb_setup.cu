@@ -781,6 +781,32 @@ namespace msb
     return cudaGetLastError();
   }
 
+  // Bulk form (msb_get_bases / msb_get_global_solutions): n_vec consecutive vectors in one launch.
+  // Reads are coalesced; the scattered writes stay inside one vector (<= 0.5 MB: L2 resident).
+  __global__ void __launch_bounds__(256)
+  permute_batch_kernel(int N, const uint32_t *__restrict__ dofmap, const double *__restrict__ src,
+                       double *__restrict__ dst, size_t n_vec)
+  {
+    for (size_t v = blockIdx.y; v < n_vec; v += gridDim.y)
+      {
+        const double *s = src + v * (size_t)N;
+        double       *d = dst + v * (size_t)N;
+        for (int lex = blockIdx.x * blockDim.x + threadIdx.x; lex < N; lex += gridDim.x * blockDim.x)
+          d[dofmap[lex]] = s[lex];
+      }
+  }
+
+  cudaError_t
+  launch_permute_batch(const Shard &s, const double *d_src, double *d_dst, size_t n_vec, cudaStream_t st)
+  {
+    if (n_vec == 0)
+      return cudaSuccess;
+    const int bx = (s.N + 255) / 256 < 16 ? (s.N + 255) / 256 : 16;
+    const int by = n_vec < 32768 ? (int)n_vec : 32768;
+    permute_batch_kernel<<<dim3(bx, by), 256, 0, st>>>(s.N, s.d_dofmap, d_src, d_dst, n_vec);
+    return cudaGetLastError();
+  }
+
   // ======================================================================================
   // set_global_weights (basis.tpp:352-377) for all cells: gsol = sum_i w_i phi_i.
   // Purely bandwidth bound: reads 4N, writes N doubles per cell.

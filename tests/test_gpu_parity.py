@@ -491,3 +491,160 @@ def test_degenerate_coarse_cell_is_rejected(msb, oracle):
         sh.set_cells(good)
         sh.run()
         assert np.abs(sh.element_matrices()[0].sum(axis=2)).max() < 1e-12
+
+
+# ---------------------------------------------------------------------------- accepted sizes that round 1 never ran
+def test_largest_accepted_2d_local_mesh_l9(msb, oracle):
+    """msb_create accepts n_refine_local = 9 in 2D (512 x 512 fine cells, 263 169 DoFs per solve, HBM-streamed
+    kernels): DoF map bit-exact, bases / M / b of one cell against the oracle."""
+    cd, co = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    cor = msb.coarse_corners(3, 37, 38)
+    ref = oracle.run_cells(9, cor, co)
+    with msb.BasisShard(9, cor, cd) as sh:
+        assert np.array_equal(sh.dof_map(), oracle.dof_map(9))
+        sh.run(1e-12, 5000)
+        it, res = sh.iteration_counts()
+        assert np.all(res <= 1e-12) and np.all(it > 0)
+        phis = sh.bases()[0]
+        for ib in range(4):
+            assert _rel(phis[ib], ref["phi"][0][ib]) < TOL_PHI, ib
+        assert np.abs(phis.sum(axis=0) - 1.0).max() < 1e-9
+        M, b = sh.element_matrices()
+        assert _rel(M[0], ref["M"][0]) < TOL_MB and _rel(b[0], ref["b"][0]) < TOL_MB
+        assert sh.run_stats()["tier"] == msb.TIER_STREAMED
+
+
+def test_cfg5_full_size_slice_invariants(msb, oracle):
+    """BASELINE cfg5 (64x64 coarse x 256x256 fine, periodic eps = 1/64) on a 192-cell slice of the Morton curve:
+    the size-independent invariants on every cell, oracle parity on two sampled cells."""
+    r, l, lo, hi = 6, 8, 2000, 2192
+    cd, co = _coeffs(msb, oracle, msb.COEFF_PERIODIC, (1.0 / 64, 0.9999))
+    cor = msb.coarse_corners(r, lo, hi)
+    H = 1.0 / (1 << r)
+    with msb.BasisShard(l, cor, cd) as sh:
+        sh.run(1e-12, 5000)
+        M, b = sh.element_matrices()
+        it, res = sh.iteration_counts()
+        assert np.all(res <= 1e-12)
+        scale = np.abs(M).max()
+        assert np.abs(M.sum(axis=2)).max() < 1e-9 * scale
+        assert np.abs(M - M.transpose(0, 2, 1)).max() < 1e-9 * scale
+        assert np.abs(b.sum(axis=1) - 2.0 * H * H).max() < 1e-9 * H * H
+        sample = [0, hi - lo - 1]
+        ref = oracle.run_cells(l, cor[sample], co, n_threads=2)
+        for k, c in enumerate(sample):
+            phis = sh.bases(c, 1)[0]
+            assert np.abs(phis.sum(axis=0) - 1.0).max() < 1e-9
+            assert _rel(phis, ref["phi"][k]) < TOL_PHI
+            assert _rel(M[c], ref["M"][k]) < TOL_MB and _rel(b[c], ref["b"][k]) < TOL_MB
+
+
+# ---------------------------------------------------------------------------- bulk accessors
+@pytest.mark.parametrize("l,cells", [(5, 37), (7, 5)])
+def test_bulk_bases_and_global_solutions_equal_the_per_cell_getters(msb, oracle, l, cells):
+    """msb_get_bases / msb_get_global_solutions (one call, chunked staging) return bit for bit what the
+    per-(cell, basis) getters return, for full and partial cell ranges."""
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    cor = msb.coarse_corners(4, 11, 11 + cells)
+    rng = np.random.default_rng(5)
+    w = rng.standard_normal((cells, 4))
+    with msb.BasisShard(l, cor, cd) as sh:
+        sh.run(1e-12, 5000)
+        allb = sh.bases()
+        assert allb.shape == (cells, 4, sh.N)
+        for c in (0, cells // 2, cells - 1):
+            for ib in range(4):
+                assert np.array_equal(allb[c, ib], sh.basis(c, ib))
+        part = sh.bases(3, 2)
+        assert np.array_equal(part, allb[3:5])
+        assert sh.bases(cells, 0).shape == (0, 4, sh.N)
+        with pytest.raises(msb.MsbError) as e:
+            sh.bases(cells - 1, 2)
+        assert e.value.code == -1
+        with pytest.raises(msb.MsbError) as e:
+            sh.global_solutions()          # the reference asserts is_set_global_weights
+        assert e.value.code == -6
+        sh.set_global_weights(w)
+        g = sh.global_solutions()
+        for c in (0, cells - 1):
+            assert np.array_equal(g[c], sh.global_solution(c))
+        assert np.array_equal(sh.global_solutions(2, 2), g[2:4])
+
+
+def test_bulk_bases_more_vectors_than_one_staging_buffer(msb, oracle):
+    """4 x 2100 vectors of 1089 doubles = 73 MB > the 64 MB staging buffer: the ping-pong path."""
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_PERIODIC, (1.0 / 64, 0.9999))
+    cells = 2100
+    cor = msb.coarse_corners(7, 3000, 3000 + cells)
+    with msb.BasisShard(5, cor, cd) as sh:
+        sh.run(1e-12, 5000)
+        allb = sh.bases()
+        assert np.abs(allb.sum(axis=1) - 1.0).max() < 1e-9          # partition of unity on every cell
+        for c in (0, 1927, 1928, cells - 1):                        # around the chunk boundary (7704 vectors)
+            assert np.array_equal(allb[c, 2], sh.basis(c, 2))
+
+
+def test_device_results_alias_the_host_getters(msb, oracle):
+    import torch
+    from mpi_parallel_multiscale_diffusion_fem_b200 import parallel
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    with msb.BasisShard(5, msb.coarse_corners(4, 0, 50), cd) as sh:
+        with pytest.raises(msb.MsbError):
+            sh.device_results()
+        sh.run(1e-12, 5000)
+        M, b = sh.element_matrices()
+        it, _ = sh.iteration_counts()
+        dM, db, dit = parallel.device_result_tensors(sh, torch.device("cuda", 0))
+        assert dM.is_cuda and np.array_equal(dM.cpu().numpy(), M) and np.array_equal(db.cpu().numpy(), b)
+        assert np.array_equal(dit.cpu().numpy(), it)
+
+
+def test_failed_set_cells_invalidates_the_handle(msb, oracle):
+    """A msb_set_cells that fails after touching device state must not leave the previous batch's results
+    readable against the new corners: every accessor and msb_run report MSB_ERR_STATE until a
+    later msb_set_cells succeeds."""
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_CONSTANT, (1.0,))
+    good = msb.coarse_corners(2, 0, 3)
+    bad = good.copy()
+    bad[2, 1] = bad[2, 0]
+    with msb.BasisShard(3, good, cd) as sh:
+        sh.run()
+        sh.element_matrices()
+        with pytest.raises(msb.MsbError) as e:
+            sh.set_cells(bad)
+        assert e.value.code == -1
+        for call in (sh.element_matrices, sh.run, lambda: sh.basis(0, 0), lambda: sh.constraints(0, 0),
+                     lambda: sh.apply_operator(0, np.zeros(sh.N)), sh.bases):
+            with pytest.raises(msb.MsbError) as e:
+                call()
+            assert e.value.code == -6, call
+        sh.set_cells(good)
+        with pytest.raises(msb.MsbError) as e:
+            sh.element_matrices()          # valid again, but not run yet
+        assert e.value.code == -6
+        sh.run()
+        assert np.abs(sh.element_matrices()[0].sum(axis=2)).max() < 1e-12
+
+
+def test_unsymmetric_coefficient_table_is_rejected(msb, oracle):
+    """The stiffness matrix is assembled from the symmetric part of the tensor; a table with a01 != a10 would
+    silently differ from the reference's grad_i . A . grad_j (basis.tpp:213-216), so it is refused."""
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
+    l, n = 3, 8
+    cor = msb.coarse_corners(2, 0, 2)
+    table = np.zeros((2, n * n, 4, 4))
+    table[..., 0] = 1.0
+    table[..., 3] = 2.0
+    table[..., 1] = 0.25
+    table[..., 2] = 0.25 * (1 + 1e-15)       # rounding-level asymmetry (the reference tensor has it) is fine
+    with msb.BasisShard(l, cor, coeff_desc(msb.COEFF_TABLE), table=table) as sh:
+        sh.run()
+        bad = table.copy()
+        bad[1, 17, 2, 2] = 0.3
+        with pytest.raises(msb.MsbError) as e:
+            sh.set_cells(cor, bad)
+        assert e.value.code == -1 and "not symmetric" in str(e.value)
+        sh.element_matrices()                # refused before any device write: the old results stay valid
+    with pytest.raises(msb.MsbError) as e:
+        msb.BasisShard(l, cor, coeff_desc(msb.COEFF_TABLE), table=bad)
+    assert e.value.code == -1

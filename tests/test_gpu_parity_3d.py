@@ -224,3 +224,25 @@ def test_alternative_3d_kernels_agree_with_the_default(msb, oracle, variant):
         assert _rel(Ma, Mb) < 1e-10 and _rel(ba, bb) < 1e-10
         for c in (0, 319):
             assert _rel(a.basis(c, 5), b.basis(c, 5)) < 1e-10
+
+
+def test_largest_accepted_3d_local_mesh_l6(msb, oracle):
+    """msb_create accepts n_refine_local = 6 for dim 3 (64^3 fine hexahedra, 274 625 DoFs per solve): DoF map
+    bit-exact, the 8 bases / M / b of one coarse cell against the oracle, partition of unity."""
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
+    cor = msb.coarse_corners3(1, 6, 7)
+    co = oracle.coeff(oracle.COEFF_REFERENCE)
+    ref = oracle.run_cells3(6, cor, co)
+    with msb.BasisShard(6, cor, coeff_desc(msb.COEFF_REFERENCE), dim=3) as sh:
+        assert np.array_equal(sh.dof_map(), oracle.dof_map3(6))
+        sh.run(1e-12, 5000)
+        it, res = sh.iteration_counts()
+        assert np.all(res <= 1e-12) and np.all(it > 0)
+        phis = sh.bases()[0]
+        for ib in range(8):
+            e = np.linalg.norm(phis[ib] - ref["phi"][0][ib]) / np.linalg.norm(ref["phi"][0][ib])
+            assert e < 1e-8, (ib, e)
+        assert np.abs(phis.sum(axis=0) - 1.0).max() < 1e-9
+        M, b = sh.element_matrices()
+        assert np.abs(M[0] - ref["M"][0]).max() < 1e-8 * np.abs(ref["M"][0]).max()
+        assert np.abs(b[0] - ref["b"][0]).max() < 1e-8 * np.abs(ref["b"][0]).max()

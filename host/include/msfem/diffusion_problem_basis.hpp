@@ -18,6 +18,7 @@
 // of one and exists for interface parity, not for speed.
 #pragma once
 
+#include <algorithm>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -112,6 +113,21 @@ namespace DiffusionProblem
           {
             check(msb_set_global_weights(handle, weights.data()));
             weights_dirty = false;
+            gsol_valid    = false;
+          }
+      }
+
+      // global_solution of EVERY cell of the batch with one bulk call (msb_get_global_solutions)
+      // instead of one reordering launch + synchronisation per cell: what the walk over all cells
+      // in output_global_fine (ms.tpp:386-393) needs
+      void fetch_global_solutions(std::size_t n_dofs)
+      {
+        upload_weights();
+        if (!gsol_valid)
+          {
+            gsol_cache.resize(n_cells * n_dofs);
+            check(msb_get_global_solutions(handle, 0, (int32_t)n_cells, gsol_cache.data()));
+            gsol_valid = true;
           }
       }
 
@@ -120,6 +136,8 @@ namespace DiffusionProblem
       unsigned            n_refine_local;
       std::vector<double> weights;
       bool                weights_dirty = true;
+      std::vector<double> gsol_cache; // [n_cells][N], deal.II DoF order
+      bool                gsol_valid = false;
     };
   } // namespace internal
 
@@ -234,8 +252,27 @@ namespace DiffusionProblem
       require_batch();
       batch->upload_weights();
       out.resize(n_dofs());
-      internal::check(msb_get_global_solution(batch->handle, (int32_t)index_in_batch, out.data()));
+      if (batch->gsol_valid) // prefetched in bulk (prefetch_global_solutions)
+        std::copy(batch->gsol_cache.begin() + index_in_batch * n_dofs(),
+                  batch->gsol_cache.begin() + (index_in_batch + 1) * n_dofs(), out.begin());
+      else
+        internal::check(msb_get_global_solution(batch->handle, (int32_t)index_in_batch, out.data()));
     }
+    // Bring the global solutions of all cells of this object's batch to the host in one call; the
+    // per-object getters / output_global_solution_in_cell() then read the host copy.
+    void prefetch_global_solutions() const
+    {
+      require_batch();
+      batch->fetch_global_solutions(n_dofs());
+    }
+    // the 2^dim bases of the cells [first, first + count) of this object's batch, [count][2^dim][N]
+    void get_bases_of_batch(std::size_t first, std::size_t count, std::vector<double> &out) const
+    {
+      require_batch();
+      out.resize(count * NB * n_dofs());
+      internal::check(msb_get_bases(batch->handle, (int32_t)first, (int32_t)count, out.data()));
+    }
+    std::size_t batch_size() const { return batch ? batch->n_cells : 0; }
     std::size_t n_dofs() const
     {
       const std::size_t np = (std::size_t(1) << n_refine_local) + 1;

@@ -414,6 +414,10 @@ namespace DiffusionProblem
     void output_global_fine()
     {
       std::vector<std::string> filenames;
+      // one bulk device->host transfer per GPU batch (msb_get_global_solutions) instead of one
+      // launch + synchronisation per coarse cell; repeated calls on the same batch are no-ops
+      for (auto &kv : cell_basis_map)
+        kv.second.prefetch_global_solutions();
       for (auto &kv : cell_basis_map)
         {
           kv.second.output_global_solution_in_cell();

@@ -89,7 +89,8 @@ smem_kernel(int iters, double *out, unsigned long long *cycles)
             }
           else
             {
-              const int idx = ((r * THREADS + threadIdx.x) * 2) & (words - 2);
+              // (the address depends on the iteration so that no store is dead)
+              const int idx = ((r * THREADS + threadIdx.x) * 2 + it * 2) & (words - 2);
               *reinterpret_cast<ulonglong2 *>(sm + idx) = make_ulonglong2(acc0 + it, acc1 + r);
             }
         }

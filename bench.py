@@ -191,7 +191,9 @@ def kernel_name(dim, l, variant, tier):
     if tier == 1:
         if variant >= 100:
             return "solve_smem_kernel"
-        return "solve_bpx_tm_kernel" if (l == 6 and variant in (0, 5, 7, 8, 9)) else "solve_bpx_kernel"
+        if l == 6 and variant == 0:
+            return "solve_fused_kernel (assembly + 4 solves + element matrices in one launch)"
+        return "solve_bpx_tm_kernel" if (l == 6 and variant in (5, 7, 9)) else "solve_bpx_kernel"
     if (l == 7 and variant == 0) or (variant in (3, 4) and 5 <= l <= 7):
         return "solve_cluster_kernel"
     return "stream_k* (HBM-streamed)"
@@ -534,7 +536,7 @@ def main():
                        "mean_pcg_iterations": m["iters_all"] / n_solves,
                        "preconditioner": ("multilevel diagonal scaling (BPX), exact Galerkin diagonals (the reciprocal "
                                           "diagonals of the coarse levels are STORED as float; all arithmetic f64)"
-                                          + (", exact solve of the 7x7 coarse level" if (dim == 2 and l == 5) or (dim == 2 and l == 6 and args.variant in (0, 8, 9)) else "")
+                                          + (", exact solve of the 7x7 coarse level" if (dim == 2 and l == 5) or (dim == 2 and l == 6 and args.variant in (0, 9)) else "")
                                           if args.variant < 100 else "Jacobi (symmetric diagonal scaling)"),
                        "variant": args.variant, "build_id": build_id},
             "clocks": m["clocks"],

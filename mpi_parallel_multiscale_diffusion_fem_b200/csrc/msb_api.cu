@@ -94,6 +94,38 @@ all_bricks(const double *corners, size_t n_cells)
   return true;
 }
 
+// dim 2: are all coarse cells axis-aligned rectangles with positive extent (the only kind the reference's
+// refined hyper_cube produces, ms.tpp:97-99)?  Same test as assemble_kernel's.
+static bool
+all_rectangles(const double *corners, size_t n_cells)
+{
+  for (size_t k = 0; k < n_cells; ++k)
+    {
+      const double *c = corners + 8 * k;
+      if (!(c[0] == c[4] && c[2] == c[6] && c[1] == c[3] && c[5] == c[7] && c[2] > c[0] && c[5] > c[1]))
+        return false;
+    }
+  return true;
+}
+
+// does msb_run take the fused one-kernel stage?
+static bool
+fused_eligible(const Shard &s)
+{
+  return s.dim == 2 && s.l == 6 && s.tier == MSB_TIER_SMEM && s.variant == 0 && s.aligned &&
+         s.coeff.kind != MSB_COEFF_TABLE;
+}
+
+// the HBM copy of the stencil (203 KB per cell at n = 64) is only needed by the three-kernel path and by the
+// operator-level accessors: allocated on first use
+static cudaError_t
+ensure_sten(Shard &s)
+{
+  if (s.d_sten)
+    return cudaSuccess;
+  return cudaMalloc((void **)&s.d_sten, sizeof(double) * (size_t)s.n_cells * s.nst * (size_t)s.N);
+}
+
 // MSB_COEFF_TABLE: the stiffness matrix is assembled from the symmetric part of the tensor
 // (K must be symmetric for the reference's SolverCG as well, basis.tpp:299-306), so a table
 // whose tensors are not symmetric up to rounding is rejected instead of being silently
@@ -218,7 +250,8 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
   s.tier      = cfg->tier;
   if (s.dim == 3)
     s.tier = MSB_TIER_STREAMED;
-  s.bricks = s.dim == 3 && all_bricks(corners, (size_t)s.n_cells);
+  s.bricks  = s.dim == 3 && all_bricks(corners, (size_t)s.n_cells);
+  s.aligned = s.dim == 2 && all_rectangles(corners, (size_t)s.n_cells);
   if (s.tier == MSB_TIER_AUTO)
     s.tier = smem_tier_supported(s.l) ? MSB_TIER_SMEM : MSB_TIER_STREAMED;
   if (s.tier == MSB_TIER_SMEM && !smem_tier_supported(s.l))
@@ -245,7 +278,8 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
 
   ALLOC(s.d_corners, NCORN * C);
   ALLOC(s.d_q1coef, NB * NB * C);
-  ALLOC(s.d_sten, C * s.nst * N);
+  if (!fused_eligible(s)) // the fused stage keeps the stencil on chip
+    ALLOC(s.d_sten, C * s.nst * N);
   ALLOC(s.d_phi, C * NB * N);
   ALLOC(s.d_M, NB * NB * C);
   ALLOC(s.d_b, NB * C);
@@ -352,8 +386,9 @@ msb_set_cells(msb_handle h, const double *corners, const double *coeff_table)
     CUDA_TRY(cudaMemcpyAsync(s.d_table, coeff_table, sizeof(double) * C * (size_t)ncoef_table_doubles(s),
                              cudaMemcpyHostToDevice, s.stream));
   CUDA_TRY(cudaStreamSynchronize(s.stream));
-  s.bricks = s.dim == 3 && all_bricks(corners, C);
-  s.valid  = true;
+  s.bricks  = s.dim == 3 && all_bricks(corners, C);
+  s.aligned = s.dim == 2 && all_rectangles(corners, C);
+  s.valid   = true;
   return MSB_OK;
 }
 
@@ -388,6 +423,21 @@ msb_run_async(msb_handle h, double tol_abs, int32_t max_iter, void *cuda_stream)
   const int32_t init_fail[2] = {INT_MAX, 0};
   CUDA_TRY(cudaMemcpyAsync(s.d_fail, init_fail, sizeof init_fail, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaEventRecord(s.ev[0], st));
+  s.fused_last = fused_eligible(s);
+  if (s.fused_last)
+    {
+      // assemble_system + 4 x (condense, PCG, distribute) + assemble_global_element_matrix of every cell
+      // in ONE launch; nothing but Phi, M, b leaves the SM
+      CUDA_TRY(cudaEventRecord(s.ev[1], st));
+      CUDA_TRY(launch_stage_fused(s, tol_abs, max_iter, st, &s.n_launches));
+      s.tier_used = s.tier;
+      CUDA_TRY(cudaEventRecord(s.ev[2], st));
+      CUDA_TRY(cudaEventRecord(s.ev[3], st));
+      s.run_pending = true;
+      s.weights_set = false;
+      return MSB_OK;
+    }
+  CUDA_TRY(ensure_sten(s));
   if (s.dim == 3)
     CUDA_TRY(launch_assemble3(s, st, &s.n_launches));
   else
@@ -595,6 +645,7 @@ ensure_assembled(msb_handle h)
   if (!s.assembled)
     {
       int nl = 0;
+      CUDA_TRY(ensure_sten(s));
       if (s.dim == 3)
         CUDA_TRY(launch_assemble3(s, s.stream, &nl));
       else

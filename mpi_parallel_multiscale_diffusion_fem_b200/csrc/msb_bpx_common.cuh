@@ -8,6 +8,7 @@
 #include <type_traits>
 
 #include "msb_internal.cuh"
+#include "msb_tmem.cuh"
 
 // Optional per-stage cycle timers (profiling build only: make EXTRA=-DMSB_STAGE_TIMERS).
 #ifdef MSB_STAGE_TIMERS
@@ -214,8 +215,10 @@ namespace msb
     // entry A(i, i+e), i = 2I + a, is loaded once and scattered (at compile time) into the
     // entries it contributes to: (P^T A P)(I, I+d) = sum_a sum_e w(a) w(b) A(2I+a, 2I+a+e)
     // with b = a + e - 2d, |b| <= 1.
+    // get(ix, iy, ex, ey): entry of fine row node (ix,iy) towards (ix+ex, iy+ey)
+    template <class Get>
     __device__ __forceinline__ void
-    galerkin_row(const double *Sf, int npf, int Nf, int X, int Y, double (&acc)[5])
+    galerkin_row_of(Get &&get, int X, int Y, double (&acc)[5])
     {
       constexpr int ddx[5] = {0, 1, 0, 1, -1}, ddy[5] = {0, 0, 1, 1, 1};
 #pragma unroll
@@ -233,7 +236,7 @@ namespace msb
 #pragma unroll
               for (int ex = -1; ex <= 1; ++ex)
                 {
-                  const double v = wa * sten_get(Sf, npf, Nf, ix, iy, ex, ey);
+                  const double v = wa * get(ix, iy, ex, ey);
 #pragma unroll
                   for (int d = 0; d < 5; ++d)
                     {
@@ -243,6 +246,13 @@ namespace msb
                     }
                 }
           }
+    }
+
+    __device__ __forceinline__ void
+    galerkin_row(const double *Sf, int npf, int Nf, int X, int Y, double (&acc)[5])
+    {
+      galerkin_row_of([&](int ix, int iy, int ex, int ey) { return sten_get(Sf, npf, Nf, ix, iy, ex, ey); }, X, Y,
+                      acc);
     }
 
     // compile-time loops over levels (ascending / descending, inclusive bounds)
@@ -304,15 +314,21 @@ namespace msb
     //     into TB[strip][col(X)],
     // with the columns de-interleaved (odd X in the upper half of a row) so that the horizontal
     // 3-point combination of the level-1 stage reads consecutive addresses.
-    template <int NL, int NRHS, int RPT>
+    // PAD > 0 shifts the odd-column half of a row by PAD entries: a quarter warp stores four even and four
+    // odd columns at once, and with PAD = 5 (mod 8) entries of 16 bytes the two groups fall into disjoint
+    // banks (PAD = 0: 2-way conflicts on every store of two right-hand sides, 20 % of the store wavefronts
+    // of the round-1 kernel, profiles/r01u_ncu_full_*).
+    template <int NL, int NRHS, int RPT, int PAD = 0>
     struct Presum
     {
-      static constexpr int n = 1 << NL, ROW = n, HALF = RPT / 2;
+      static constexpr int n = 1 << NL, ROW = n + PAD, HALF = RPT / 2;
+      static constexpr int HOFF = n / 2 + PAD; // entry offset of the odd columns inside a row
       static constexpr int TB = (n / 2) * ROW; // entry offset of the strip-edge contributions
+      static constexpr int ENTRIES = (n / 2 + (n - 1 + RPT - 1) / RPT) * ROW; // staging footprint
       __device__ static __forceinline__ int
       col(int X)
       {
-        return (X & 1) * (n / 2) + (X >> 1);
+        return (X & 1) * HOFF + (X >> 1);
       }
       // Streaming form: call for j = 0 .. RPT-1 in order (j is a compile-time constant after
       // unrolling) with u_j = the unscaled residual of row Y0+j (zero beyond the mesh); `acc`
@@ -503,10 +519,15 @@ namespace msb
     // EXACT7: gi(c, g) delivers rows 8c..8c+7 of column tid of the inverse built by exact7_build
     // (from shared memory or from tensor memory; called by all lanes of warps 0-1); the 3x3 and
     // 1x1 levels are not used.
-    template <int NL, int NRHS, int THREADS, int RPT, bool EXACT7 = false, class DiT, class Mark, class GiChunk = int>
+    // PAD: the Presum padding the staging was written with.  dot1 != nullptr: the caller wants
+    // sum_{level-1 nodes} u_1 z_1 (restricted residual times final level-1 correction = r.z minus the fine-level
+    // part, see msb_solve_fused.cu) accumulated into dot1[NRHS] per thread, and does the block barrier that
+    // publishes z_1 itself (inside its block reduction): the final __syncthreads is skipped.
+    template <int NL, int NRHS, int THREADS, int RPT, bool EXACT7 = false, int PAD = 0, class DiT, class Mark,
+              class GiChunk = int>
     __device__ __forceinline__ void
     coarse_correction(const double *sU, double *sV, const DiT *sDi, int tid, int warp, int lane, Mark &&mark,
-                      GiChunk &&gi = 0)
+                      GiChunk &&gi = 0, double *dot1 = nullptr)
     {
       using L             = Levels<NL>;
       constexpr int NWARP = THREADS / 32;
@@ -559,6 +580,13 @@ namespace msb
             const int i = fy * npl + fx;
             double    v[NRHS];
             ldv<NRHS>(Vl, i, v);
+            [[maybe_unused]] double v_in[NRHS];
+            if constexpr (l == 1)
+              {
+#pragma unroll
+                for (int k = 0; k < NRHS; ++k)
+                  v_in[k] = v[k];
+              }
             const double di = Dl[i];
             if constexpr (l < L::LEVELS)
               {
@@ -581,6 +609,15 @@ namespace msb
                   v[k] *= di;
               }
             stv<NRHS>(Vl, i, v);
+            if constexpr (l == 1)
+              {
+                if (dot1)
+                  {
+#pragma unroll
+                    for (int k = 0; k < NRHS; ++k)
+                      dot1[k] = fma(v_in[k], v[k], dot1[k]);
+                  }
+              }
           }
       };
       // down: wide levels
@@ -588,7 +625,7 @@ namespace msb
         {
           // level 1 from the pre-summed strips: horizontal 3-point combination, conflict-free
           static_assert(L::LW >= 1, "pre-summed staging needs a wide level 1");
-          using PS          = Presum<NL, NRHS, RPT>;
+          using PS          = Presum<NL, NRHS, RPT, PAD>;
           constexpr int W   = n >> 1, LG = NL - 1, np1 = W + 1;
           for (int t = tid; t < W * W; t += THREADS)
             {
@@ -597,16 +634,16 @@ namespace msb
                 continue;
               const double *row = sU + (size_t)NRHS * (cy * PS::ROW);
               double        a[NRHS], b[NRHS], c[NRHS];
-              ldv<NRHS>(row, W + cx - 1, a); // X = 2cx-1
-              ldv<NRHS>(row, cx, b);         // X = 2cx
-              ldv<NRHS>(row, W + cx, c);     // X = 2cx+1
+              ldv<NRHS>(row, PS::HOFF + cx - 1, a); // X = 2cx-1
+              ldv<NRHS>(row, cx, b);                // X = 2cx
+              ldv<NRHS>(row, PS::HOFF + cx, c);     // X = 2cx+1
               if (cy % PS::HALF == 0)
                 {
                   const double *rb = sU + (size_t)NRHS * (PS::TB + (cy / PS::HALF) * PS::ROW);
                   double        a2[NRHS], b2[NRHS], c2[NRHS];
-                  ldv<NRHS>(rb, W + cx - 1, a2);
+                  ldv<NRHS>(rb, PS::HOFF + cx - 1, a2);
                   ldv<NRHS>(rb, cx, b2);
-                  ldv<NRHS>(rb, W + cx, c2);
+                  ldv<NRHS>(rb, PS::HOFF + cx, c2);
 #pragma unroll
                   for (int k = 0; k < NRHS; ++k)
                     a[k] += a2[k], b[k] += b2[k], c[k] += c2[k];
@@ -675,7 +712,7 @@ namespace msb
                         o[k] = fma(0.5, row[0][k] + row[2][k], row[1][k]);
                       stv<NRHS>(V1, cy * 9 + cx, o);
                     }
-                  asm volatile("bar.sync 1, %0;" ::"n"(32 * X::WARPS) : "memory");
+                  named_barrier<1, 32 * X::WARPS>();
                   const int r7 = tid / X::PARTS, q7 = tid % X::PARTS;
                   double    acc0[NRHS], acc1[NRHS];
 #pragma unroll
@@ -712,7 +749,7 @@ namespace msb
                       for (int off = 1; off < X::PARTS; off <<= 1)
                         acc0[k] += __shfl_xor_sync(0xffffffffu, acc0[k], off);
                     }
-                  asm volatile("bar.sync 1, %0;" ::"n"(32 * X::WARPS) : "memory");
+                  named_barrier<1, 32 * X::WARPS>();
                   if (r7 < 49 && q7 == 0)
                     stv<NRHS>(V1, (1 + r7 / 7) * 9 + 1 + r7 % 7, acc0);
                 }
@@ -860,7 +897,8 @@ namespace msb
           // up: the wide levels above B
           for_levels_down<L::LW - 1, 1>([&](auto lc) {
             prolong_level(lc, tid, THREADS);
-            __syncthreads();
+            if (!(decltype(lc)::value == 1 && dot1))
+              __syncthreads();
           });
         }
       else

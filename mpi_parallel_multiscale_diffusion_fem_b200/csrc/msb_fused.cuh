@@ -1,0 +1,28 @@
+// msb_fused.cuh -- parameters of the fused basis-stage kernel (msb_solve_fused.cu)
+#pragma once
+
+#include "msb_coeff.cuh"
+#include "msb_internal.cuh"
+
+namespace msb
+{
+  struct FusedParams
+  {
+    const double *corners; // [C][8]
+    const double *q1coef;  // [C][16]
+    double       *phi;     // [C][4][N]
+    double       *M;       // [C][16]
+    double       *b;       // [C][4]
+    int32_t      *iters;   // [C][4]
+    double       *res;     // [C][4]
+    int32_t      *fail;
+    double        tol2;
+    int           max_iter;
+    int           n_cells;
+    double        rhs_value;
+    CoeffEval     coef;
+  };
+
+  // the whole stage (assembly, 4 solves, element matrices) of every cell in ONE launch; 64 x 64 local meshes
+  cudaError_t launch_solve_fused(const FusedParams &P, cudaStream_t st);
+} // namespace msb

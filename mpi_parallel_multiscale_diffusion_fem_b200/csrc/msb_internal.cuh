@@ -82,6 +82,8 @@ namespace msb
     bool         assembled = false, ran = false, weights_set = false, run_pending = false;
     bool         valid = true;        // false after a failed msb_set_cells: only set_cells / destroy work
     bool         bricks = false;      // dim 3: every coarse cell is an axis-aligned brick
+    bool         aligned = false;     // dim 2: every coarse cell is an axis-aligned rectangle
+    bool         fused_last = false;  // the last run used the fused one-kernel stage
     int          n_launches = 0;
     int          tier_used  = 0;
     int          last_status = 0;
@@ -125,6 +127,9 @@ namespace msb
   size_t      dim3_coarse_nodes(int l);
   int         dim3_part_stride();
   bool        smem_tier_supported(int l);
+  // the fused one-kernel stage (msb_solve_fused.cu): 64 x 64 local meshes, axis-aligned cells,
+  // analytic coefficient, default variant
+  cudaError_t launch_stage_fused(const Shard &s, double tol, int max_iter, cudaStream_t st, int *n_launches);
   size_t      streamed_coarse_nodes(int l);
   size_t      streamed_galerkin_scratch_doubles(int l, int n_cells);
 

@@ -19,6 +19,7 @@
 // staging/restriction/prolongation 7, direction update 2) and executes 7 block barriers.
 #define MSB_STAGE_ARRAY g_msb_stage_cycles
 #include "msb_bpx_common.cuh"
+#include "msb_fused.cuh"
 
 #ifdef MSB_STAGE_TIMERS
 __device__ unsigned long long g_msb_stage_cycles[16];
@@ -596,6 +597,8 @@ namespace msb
           // solves/s on the target configuration against one basis per pass) + exact solve of the
           // 7x7 coarse level (26.0 instead of 27.8 iterations; pays since its inverse is built by the
           // banded factorisation: 16.94 vs 17.44 ms on 5920 cells; it lost with the Gauss-Jordan sweep)
+          // (variant 0 on axis-aligned cells with an analytic coefficient never gets here: msb_run takes the
+          //  fused one-kernel stage, msb_solve_fused.cu; variant 9 = this three-kernel path for A/B)
           if (s.variant == 5)
             return launch_solve_bpx_tm(P, 256, false, st);
           if (s.variant == 7)
@@ -608,5 +611,26 @@ namespace msb
         default:
           return cudaErrorInvalidValue;
       }
+  }
+  // the fused one-kernel stage (msb_solve_fused.cu)
+  cudaError_t
+  launch_stage_fused(const Shard &s, double tol, int max_iter, cudaStream_t st, int *n_launches)
+  {
+    FusedParams P;
+    P.corners   = s.d_corners;
+    P.q1coef    = s.d_q1coef;
+    P.phi       = s.d_phi;
+    P.M         = s.d_M;
+    P.b         = s.d_b;
+    P.iters     = s.d_iters;
+    P.res       = s.d_res;
+    P.fail      = s.d_fail;
+    P.tol2      = tol * tol;
+    P.max_iter  = max_iter;
+    P.n_cells   = s.n_cells;
+    P.rhs_value = s.rhs_value;
+    P.coef      = make_coeff_eval(s.coeff);
+    ++*n_launches;
+    return launch_solve_fused(P, st);
   }
 } // namespace msb

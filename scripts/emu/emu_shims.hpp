@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -48,6 +50,27 @@ namespace emu
   {
     return cta().smem.data();
   }
+  // bar.sync ID, COUNT: a barrier over the first COUNT threads of the CTA (created on first use)
+  inline std::mutex &
+  named_mutex()
+  {
+    static std::mutex m;
+    return m;
+  }
+  inline void
+  named_barrier(int id, int count)
+  {
+    static std::map<std::pair<const void *, int>, std::unique_ptr<std::barrier<>>> bars;
+    std::barrier<> *b;
+    {
+      std::lock_guard<std::mutex> lk(named_mutex());
+      auto &slot = bars[{(const void *)&cta(), id}];
+      if (!slot)
+        slot = std::make_unique<std::barrier<>>(count);
+      b = slot.get();
+    }
+    b->arrive_and_wait();
+  }
 } // namespace emu
 
 inline void
@@ -86,6 +109,16 @@ inline long long
 clock64()
 {
   return 0;
+}
+inline double
+rsqrt(double x)
+{
+  return 1.0 / std::sqrt(x);
+}
+inline int
+min(int a, int b)
+{
+  return a < b ? a : b;
 }
 #include <atomic>
 #include <mutex>

@@ -14,6 +14,8 @@ import mpi_parallel_multiscale_diffusion_fem_b200 as pkg  # noqa: E402
 from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc  # noqa: E402
 from bench import WORKLOADS  # noqa: E402
 
+# (fused kernel, l = 6 variant 0: stage 0 also holds the on-chip stencil assembly, stage 1 is unused, stage 9 is the
+#  fused fine prolongation + direction update, stage 10 the epilogue with the element-matrix sums)
 NAMES = {0: "prologue (scale + Galerkin)", 1: "rhs init + z0", 2: "stencil q=Ap", 3: "reduce p.q",
          4: "r update + stage u (+barrier)", 5: "restrict 0->1->2 (wide levels)",
          6: "direct restrict to 7x7/3x3/1x1", 7: "direct interpolate to 15x15", 11: "prolong 2->1 (wide)",
@@ -63,22 +65,32 @@ def main():
     out = (C.c_ulonglong * 16)()
     with pkg.BasisShard(l, pkg.coarse_corners(r, 0, cells), coeff_desc(kind, par, seed), variant=variant) as sh:
         sh.run(1e-12, 5000)
-        fn = lib.msb_debug_stage_cycles_tm if (l == 6 and variant in (0, 5, 7)) else lib.msb_debug_stage_cycles
+        fn = lib.msb_debug_stage_cycles_fu if (l == 6 and variant == 0) else (
+            lib.msb_debug_stage_cycles_tm if (l == 6 and variant in (5, 7, 9)) else lib.msb_debug_stage_cycles)
         fn(out, 1)
         sh.run(1e-12, 5000)
         fn(out, 1)
         it, _ = sh.iteration_counts()
         st = sh.run_stats()
-    cyc = np.array(out[:12], dtype=np.float64)
+    fused = l == 6 and variant == 0
+    cyc = np.array(out[:16 if fused else 12], dtype=np.float64)
     tot = cyc.sum()
     n_iter = it.sum() / (4.0 / max(1, 4 // (4 if l <= 5 and variant == 0 else 1)))  # per solve-group iterations
     print("workload %s cells %d l=%d variant %d: solve kernel %.3f ms, mean k %.1f" %
           (wl, cells, l, variant, st["ms_solve"], it.mean()))
-    nrhs = 2 if (l == 6 and variant in (0, 5, 7)) or (l == 5 and variant == 0) else (4 if l <= 5 and variant == 3 else 1)
+    nrhs = 2 if (l == 6 and variant in (0, 5, 7, 9)) or (l == 5 and variant == 0) else (4 if l <= 5 and variant == 3 else 1)
     group_its = it.sum() / nrhs
     print("cycles per CTA: %.0f  (per pass-iteration of %d bases: %.0f)" % (tot / cells, nrhs, tot / group_its))
-    for idx in ORDER:
-        nm, c = NAMES[idx], cyc[idx]
+    names = dict(NAMES)
+    order = list(ORDER)
+    if fused:
+        names.update({12: "prologue: sine tables + node stencils", 13: "prologue: Galerkin level 1, sqrt(d), scaling",
+                      14: "prologue: Galerkin levels 2..5", 0: "prologue: exact 7x7 inverse -> TMEM",
+                      1: "Dirichlet table + rhs init (per pass)", 8: "reduce r.z, |r| (+ level-1 barrier)",
+                      9: "fine prolong + x, p update (+barrier)", 10: "epilogue (phi, M, b)"})
+        order = [12, 13, 14] + order
+    for idx in order:
+        nm, c = names[idx], cyc[idx]
         per_it = c / group_its
         print("  %-34s %5.1f%%   %8.0f cycles/iteration" % (nm, 100 * c / tot, per_it))
 

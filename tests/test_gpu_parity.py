@@ -648,3 +648,105 @@ def test_unsymmetric_coefficient_table_is_rejected(msb, oracle):
     with pytest.raises(msb.MsbError) as e:
         msb.BasisShard(l, cor, coeff_desc(msb.COEFF_TABLE), table=bad)
     assert e.value.code == -1
+
+
+# ---------------------------------------------------------------------------- the fused one-kernel stage (n = 64)
+def test_fused_stage_equals_the_three_kernel_path(msb, oracle):
+    """Default at n = 64 on axis-aligned cells: assembly, the four solves and the element matrices of a cell in
+    ONE kernel (msb_solve_fused.cu).  Variant 9 is the round-1 path (assemble_kernel -> solve_bpx_tm_kernel ->
+    element_matrix_kernel) with the same preconditioner: same iteration counts, same bases / M / b to solver
+    accuracy, ONE launch instead of three."""
+    cd, co = _coeffs(msb, oracle, msb.COEFF_PERIODIC, (1.0 / 64, 0.9999))
+    cor = msb.coarse_corners(8, 40000, 40000 + 300)
+    with msb.BasisShard(6, cor, cd, variant=9) as a, msb.BasisShard(6, cor, cd) as b:
+        a.run(1e-12, 5000)
+        b.run(1e-12, 5000)
+        ita, ra = a.iteration_counts()
+        itb, rb = b.iteration_counts()
+        assert np.all(ra <= 1e-12) and np.all(rb <= 1e-12)
+        assert np.abs(ita - itb).max() <= 1
+        Ma, ba = a.element_matrices()
+        Mb, bb = b.element_matrices()
+        assert _rel(Mb, Ma) < 1e-10 and _rel(bb, ba) < 1e-10
+        pa, pb = a.bases(), b.bases()
+        assert _rel(pb, pa) < 1e-10
+        assert a.run_stats()["launches"] == 3 and b.run_stats()["launches"] == 1
+
+
+@pytest.mark.parametrize("kind,par,seed,r", [
+    (0, (), 0, 3), (1, (1.0 / 64, 0.9999), 0, 8), (2, (2.0 ** -12, 0.2, 1e4, 1.0), 1234, 8), (3, (2.5,), 0, 4)])
+def test_fused_stage_against_the_oracle_every_coefficient_kind(msb, oracle, kind, par, seed, r):
+    cd, co = _coeffs(msb, oracle, kind, par, seed)
+    total = 4 ** r
+    cor = msb.coarse_corners(r, total // 3, total // 3 + 3)
+    ref = oracle.run_cells(6, cor, co, rhs_value=3.5, n_threads=3)
+    with msb.BasisShard(6, cor, cd, rhs_value=3.5) as sh:
+        sh.run(1e-12, 5000)
+        assert sh.run_stats()["launches"] == 1
+        it, res = sh.iteration_counts()
+        assert np.all(res <= 1e-12)
+        M, b = sh.element_matrices()
+        phis = sh.bases()
+        for c in range(3):
+            assert _rel(phis[c], ref["phi"][c]) < TOL_PHI, c
+            assert _rel(M[c], ref["M"][c]) < TOL_MB and _rel(b[c], ref["b"][c]) < TOL_MB
+        # the operator-level accessors assemble the HBM stencil on demand
+        import scipy.sparse as sp
+        rowptr, col, val, F = oracle.assemble(6, cor[1], co, rhs_value=3.5)
+        N = oracle.n_dofs(6)
+        K = sp.csr_matrix((val, col.astype(np.int64), rowptr.astype(np.int64)), shape=(N, N))
+        x = np.random.default_rng(3).standard_normal(N)
+        # (5e-12: at H = 1/256 the sine arguments are ~1e2 and a(x) comes close to 1e-4, so the last bits of the
+        #  argument reduction show in K; the default-run cells of test_matrix_free_operator_matches_csr_vmult reach 5e-14)
+        assert _rel(sh.apply_operator(1, x), K @ x) < 5e-12
+        assert np.abs(sh.load_vector(1) - F).max() < 1e-15 * max(1.0, np.abs(F).max() / 1e-6)
+        # ... and do not disturb the results of the run
+        M2, _ = sh.element_matrices()
+        assert np.array_equal(M, M2)
+
+
+def test_fused_stage_rectangular_cells_and_fallback_for_general_quadrilaterals(msb, oracle):
+    """hx != hy goes through the fused kernel; one skewed cell in the shard sends the whole shard down the
+    three-kernel path (general Q1 mapping in assemble_kernel)."""
+    cd, co = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    rect = np.array([
+        [[0.50, 0.25], [0.75, 0.25], [0.50, 0.375], [0.75, 0.375]],
+        [[0.25, 0.50], [0.3125, 0.50], [0.25, 0.75], [0.3125, 0.75]]])
+    skew = np.array([[[0.10, 0.20], [0.35, 0.22], [0.12, 0.41], [0.38, 0.47]]])
+    ref = oracle.run_cells(6, rect, co, n_threads=2)
+    with msb.BasisShard(6, rect, cd) as sh:
+        sh.run(1e-12, 5000)
+        assert sh.run_stats()["launches"] == 1
+        M, b = sh.element_matrices()
+        for c in range(2):
+            assert _rel(sh.bases(c, 1)[0], ref["phi"][c]) < TOL_PHI
+            assert _rel(M[c], ref["M"][c]) < TOL_MB and _rel(b[c], ref["b"][c]) < TOL_MB
+        # re-target the same handle at a batch with a skewed cell: falls back, still correct
+        mixed = np.concatenate([rect[:1], skew])
+        sh.set_cells(mixed)
+        sh.run(1e-12, 5000)
+        assert sh.run_stats()["launches"] == 3
+        ref2 = oracle.run_cells(6, mixed, co, n_threads=2)
+        M, b = sh.element_matrices()
+        for c in range(2):
+            assert _rel(sh.bases(c, 1)[0], ref2["phi"][c]) < TOL_PHI
+            assert _rel(M[c], ref2["M"][c]) < TOL_MB and _rel(b[c], ref2["b"][c]) < TOL_MB
+
+
+def test_fused_stage_no_convergence_and_zero_iterations(msb, oracle):
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    with msb.BasisShard(6, msb.coarse_corners(3, 0, 3), cd) as sh:
+        with pytest.raises(msb.MsbError) as e:
+            sh.run(1e-12, 7)
+        assert e.value.code == -5
+        cell, ib, res = sh.failure()
+        assert (cell, ib) == (0, 0) and res > 1e-12
+        it, _ = sh.iteration_counts()
+        assert np.all(it == 7)
+        sh.run(1e3, 1000)
+        it, _ = sh.iteration_counts()
+        assert np.all(it == 0)
+        sh.run(1e-12, 5000)
+        assert sh.failure()[0] == -1
+        M, _ = sh.element_matrices()
+        assert np.abs(M.sum(axis=2)).max() < 1e-9

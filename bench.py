@@ -191,7 +191,7 @@ def kernel_name(dim, l, variant, tier):
     if tier == 1:
         if variant >= 100:
             return "solve_smem_kernel"
-        if l == 6 and variant == 0:
+        if l == 6 and (variant == 0 or 10 <= variant <= 12):
             return "solve_fused_kernel (assembly + 4 solves + element matrices in one launch)"
         return "solve_bpx_tm_kernel" if (l == 6 and variant in (5, 7, 9)) else "solve_bpx_kernel"
     if (l == 7 and variant == 0) or (variant in (3, 4) and 5 <= l <= 7):
@@ -212,7 +212,7 @@ class Ctx:
     pass
 
 
-def measure(cx, name, steps, warmup, variant=0, cells=0, max_iter=5000, e2e=True, with_bases=False):
+def measure(cx, name, steps, warmup, variant=0, cells=0, max_iter=5000, e2e=True, with_bases=False, tier=0):
     """One workload on this rank's Morton range: kernel-resident leg, optional end-to-end legs, invariants.
     Returns a dict (identical on every rank for the reduced quantities)."""
     torch, dist, pkg = cx.torch, cx.dist, cx.pkg
@@ -234,7 +234,8 @@ def measure(cx, name, steps, warmup, variant=0, cells=0, max_iter=5000, e2e=True
     h_b = torch.empty((total_cells, nb), dtype=torch.float64, pin_memory=True)
     h_it = torch.empty((n_local, nb), dtype=torch.int32, pin_memory=True)
 
-    sh = pkg.BasisShard(l, corners_np, coeff_desc(kind, par, seed), device_id=local_rank, variant=variant, dim=dim)
+    sh = pkg.BasisShard(l, corners_np, coeff_desc(kind, par, seed), device_id=local_rank, variant=variant, dim=dim,
+                        tier=tier)
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
 
@@ -453,6 +454,7 @@ def main():
     ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
     ap.add_argument("--cells", type=int, default=0, help="limit the number of coarse cells (debug)")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--tier", type=int, default=0, help="msb_tier: 0 auto, 1 shared memory, 2 streamed / cluster")
     ap.add_argument("--max-iter", type=int, default=5000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -493,7 +495,7 @@ def main():
 
     m = measure(cx, args.workload, args.steps, args.warmup, variant=args.variant, cells=args.cells,
                 max_iter=args.max_iter, e2e=not args.no_e2e,
-                with_bases=not (args.no_e2e or args.no_bases))
+                with_bases=not (args.no_e2e or args.no_bases), tier=args.tier)
 
     # ---- the other BASELINE configurations, each at the rank count of this run -------------
     per_config = None

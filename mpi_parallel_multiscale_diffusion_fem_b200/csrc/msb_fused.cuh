@@ -20,6 +20,7 @@ namespace msb
     int           max_iter;
     int           n_cells;
     double        rhs_value;
+    int           flavor; // A/B: 0 default, 1 residual in tensor memory, 2 q through tensor memory (variants 10-12)
     CoeffEval     coef;
   };
 

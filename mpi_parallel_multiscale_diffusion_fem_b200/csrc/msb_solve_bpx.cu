@@ -629,6 +629,7 @@ namespace msb
     P.max_iter  = max_iter;
     P.n_cells   = s.n_cells;
     P.rhs_value = s.rhs_value;
+    P.flavor    = s.variant >= 10 && s.variant <= 12 ? s.variant - 10 : 0;
     P.coef      = make_coeff_eval(s.coeff);
     ++*n_launches;
     return launch_solve_fused(P, st);

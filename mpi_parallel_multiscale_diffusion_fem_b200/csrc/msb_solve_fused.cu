@@ -102,20 +102,45 @@ namespace msb
       return k;
     }
 
-    // edge coefficient of node (x,y) towards (x+ex, y+ey) in the pair layout
-    //   sA[(y n + x)] = { E: (x,y)-(x+1,y),  D2: (x+1,y)-(x,y+1) },  sB[(y n + x)] = { N: (x,y)-(x,y+1),  D1: (x,y)-(x+1,y+1) }
-    // for edges that live inside the n x n cell arrays (every edge with at least one interior end)
+    // The four edge-coefficient arrays of the n x n fine cells, cell index i = y n + x:
+    //   E  (x,y)-(x+1,y)    D2 (x+1,y)-(x,y+1)    N  (x,y)-(x,y+1)    D1 (x,y)-(x+1,y+1)
+    // MSB_FUSED_PAIRED = 0 (default): four planes, sA = [E | D2], sB = [N | D1]: a stencil row costs 7 LDS.64 =
+    // 14 shared-memory wavefronts per warp.  = 1: interleaved pairs sA[i] = {E, D2}, sB[i] = {N, D1}: 4 LDS.128
+    // per row, but 16 wavefronts (one of the four is half used) -- the stencil sweep runs at ~0.9 wavefronts per
+    // cycle (ncu, profiles/r02c_*), so bytes count, not instructions; kept for the A/B only.
+#ifndef MSB_FUSED_PAIRED
+#  define MSB_FUSED_PAIRED 0
+#endif
+    template <int n>
+    struct Coef
+    {
+      static constexpr bool PAIRED = MSB_FUSED_PAIRED != 0;
+      __device__ static __forceinline__ int
+      e(int i)
+      {
+        return PAIRED ? 2 * i : i;
+      }
+      __device__ static __forceinline__ int
+      hi(int i) // D2 in sA, D1 in sB
+      {
+        return PAIRED ? 2 * i + 1 : n * n + i;
+      }
+    };
+
+    // edge coefficient of node (x,y) towards (x+ex, y+ey), for edges that live inside the n x n cell arrays
+    // (every edge with at least one interior end)
     template <int n>
     __device__ __forceinline__ double
     eget(const double *sA, const double *sB, int x, int y, int ex, int ey)
     {
+      using K = Coef<n>;
       if (ey == 0)
-        return sA[2 * (y * n + (ex > 0 ? x : x - 1))];
+        return sA[K::e(y * n + (ex > 0 ? x : x - 1))];
       if (ex == 0)
-        return sB[2 * ((ey > 0 ? y : y - 1) * n + x)];
+        return sB[K::e((ey > 0 ? y : y - 1) * n + x)];
       if (ex == ey)
-        return sB[2 * ((ey > 0 ? y : y - 1) * n + (ex > 0 ? x : x - 1)) + 1];
-      return sA[2 * ((ey > 0 ? y * n + x - 1 : (y - 1) * n + x)) + 1];
+        return sB[K::hi((ey > 0 ? y : y - 1) * n + (ex > 0 ? x : x - 1))];
+      return sA[K::hi(ey > 0 ? y * n + x - 1 : (y - 1) * n + x)];
     }
     // ... and any edge of the mesh, including the boundary-boundary edges of the top row / right column
     template <int n>
@@ -127,6 +152,30 @@ namespace msb
       if (ex == 0 && x == n)
         return sNb[ey > 0 ? y : y - 1];
       return eget<n>(sA, sB, x, y, ex, ey);
+    }
+
+    // Warp-level sums of TEN values for the element-matrix epilogue: three transposing exchanges leave one of the
+    // first eight values per group of four lanes (9 double shuffles instead of 40), the last two share one
+    // butterfly (5 instead of 10).  Lane l with (l & 3) == 0 returns the warp total of value (l >> 2) & 7 in `e`;
+    // lanes 0 and 16 return the totals of values 8 and 9 in `t`.
+    __device__ __forceinline__ void
+    warp_sum10(const double (&v)[10], int lane, double &e, double &t)
+    {
+      const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+      double     a[4], c[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        a[i] = (b4 ? v[4 + i] : v[i]) + __shfl_xor_sync(0xffffffffu, b4 ? v[i] : v[4 + i], 16);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        c[i] = (b3 ? a[2 + i] : a[i]) + __shfl_xor_sync(0xffffffffu, b3 ? a[i] : a[2 + i], 8);
+      e = (b2 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, b2 ? c[0] : c[1], 4);
+      e += __shfl_xor_sync(0xffffffffu, e, 2);
+      e += __shfl_xor_sync(0xffffffffu, e, 1);
+      t = (b4 ? v[9] : v[8]) + __shfl_xor_sync(0xffffffffu, b4 ? v[8] : v[9], 16);
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1)
+        t += __shfl_xor_sync(0xffffffffu, t, off);
     }
 
     struct Cfg
@@ -143,8 +192,11 @@ namespace msb
       static constexpr int CN    = L::CN;
       static constexpr int PAD   = 5;
       using PS                   = Presum<NL, NRHS, RPT, PAD>;
-      // per-thread TMEM columns: x | p_old | sqrt(d)
-      static constexpr int XOFF = 0, POFF = 2 * RPT * NRHS, SOFF = 4 * RPT * NRHS;
+      // per-thread TMEM columns: x | p_old | rhat | sqrt(d).  The residual lives in tensor memory as well: with it
+      // in registers the kernel spilled ~20 words, and with 227 KB of the L1 carved out as shared memory a
+      // spill load goes to L2 -- eight of them sat on the critical path of the coarse chain (5400 cycles per
+      // iteration, profiles/r02b_stage_timers_*)
+      static constexpr int XOFF = 0, POFF = 2 * RPT * NRHS, ROFF = 4 * RPT * NRHS, SOFF = 6 * RPT * NRHS;
       static constexpr int TCOLS = SOFF + 2 * RPT;
       static constexpr int TMEM_COLS = 512;
       using X7 = Exact7<THREADS>;
@@ -166,9 +218,19 @@ namespace msb
       static_assert(smem_bytes <= 232448, "shared memory");
     };
 
+    // RMODE (A/B flavours, FusedParams::flavor; measured on 5920 target cells, profiles/r02c_ab_flavours.txt):
+    //   0  residual and q = Ahat p in registers                                   17.78 ms   <- default
+    //   1  residual in tensor memory (fewest registers, two more TMEM round trips) 18.16 ms
+    //   2  residual in registers, q through tensor memory four rows at a time      17.93 ms
+    // A flattened coarse chain (level 2 and the 7x7 level restricted straight from level 1 by different warps,
+    // both interpolated straight back: two block barriers instead of five) was 3 % SLOWER than
+    // bpx::coarse_correction in every flavour and is not kept: the stages it removes are short, the ones it
+    // fattens (all threads) are not.
+    template <int RMODE>
     __global__ void __launch_bounds__(Cfg::THREADS, 1)
     solve_fused_kernel(FusedParams P)
     {
+      constexpr bool RTMEM = RMODE == 1, QTMEM = RMODE == 2;
       using C             = Cfg;
       using L             = typename C::L;
       using PS            = typename C::PS;
@@ -285,8 +347,9 @@ namespace msb
             sKC[t] = kc;
             if (jx < n && jy < n)
               {
-                st2(sA, jy * n + jx, kE, kd2);
-                st2(sB, jy * n + jx, kN, kd1);
+                using K = Coef<n>;
+                sA[K::e(jy * n + jx)] = kE, sA[K::hi(jy * n + jx)] = kd2;
+                sB[K::e(jy * n + jx)] = kN, sB[K::hi(jy * n + jx)] = kd1;
               }
             else if (jx < n)
               sEb[jx] = kE; // top boundary row: boundary-boundary edges
@@ -354,11 +417,11 @@ namespace msb
         {
           const int    x = i % n, y = i / n, g = y * np + x;
           const double s00 = sKC[g], s10 = sKC[g + 1], s01 = sKC[g + np], s11 = sKC[g + np + 1];
-          double       e, d2, nn, d1;
-          ld2(sA, i, e, d2);
-          ld2(sB, i, nn, d1);
-          st2(sA, i, e * s00 * s10, d2 * s10 * s01);
-          st2(sB, i, nn * s00 * s01, d1 * s00 * s11);
+          using K = Coef<n>;
+          sA[K::e(i)] *= s00 * s10;
+          sA[K::hi(i)] *= s10 * s01;
+          sB[K::e(i)] *= s00 * s01;
+          sB[K::hi(i)] *= s00 * s11;
         }
       __syncthreads();
       ST_MARK(13)
@@ -477,15 +540,20 @@ namespace msb
           fill_boundary_table();
           __syncthreads();
 
-          double r[RPT][NRHS];
           // (b) rhat_0 = -D^-1/2 K_IB g_B: the interior-boundary edges carry the factor d^-1/2 already
+          [[maybe_unused]] double rreg[RPT][NRHS]; // the residual when it lives in registers (!RTMEM)
 #pragma unroll
-          for (int j = 0; j < RPT; ++j)
+          for (int c = 0; c < NCH; ++c)
             {
+            double r8[8];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            {
+              const int j = 4 * c + jj;
               const int y = Y0 + j;
 #pragma unroll
               for (int k = 0; k < NRHS; ++k)
-                r[j][k] = 0.0;
+                r8[2 * jj + k] = 0.0;
               if (colok && y <= n - 1 && (X == 1 || X == n - 1 || y == 1 || y == n - 1))
                 {
                   double acc[NRHS] = {0.0, 0.0};
@@ -505,8 +573,17 @@ namespace msb
                       }
 #pragma unroll
                   for (int k = 0; k < NRHS; ++k)
-                    r[j][k] = -acc[k];
+                    r8[2 * jj + k] = -acc[k];
                 }
+            }
+            if constexpr (RTMEM)
+              tmem::st8(tm + C::ROFF + 16 * c, r8);
+            else
+              {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                  rreg[4 * c + jj][0] = r8[2 * jj], rreg[4 * c + jj][1] = r8[2 * jj + 1];
+              }
             }
           __syncthreads(); // the Dirichlet table has been read
           for (int i = tid; i < NRHS * CN; i += THREADS)
@@ -520,6 +597,8 @@ namespace msb
               {
                 tmem::st8(tm + C::XOFF + 16 * c, zero8);
                 tmem::st8(tm + C::POFF + 16 * c, zero8);
+                if constexpr (QTMEM)
+                  tmem::st8(tm + C::ROFF + 16 * c, zero8); // q of the threads beyond the last column stays 0
               }
             tmem::wait_st();
           }
@@ -536,87 +615,164 @@ namespace msb
 #pragma unroll 1
           for (;;)
             {
+              double q[RPT][NRHS];
               if (it > 0)
                 {
                   // ---- q = Ahat p for both bases: one set of coefficient loads per stencil row
-                  double q[RPT][NRHS];
                   double pq[NRHS] = {0.0, 0.0};
 #pragma unroll
                   for (int j = 0; j < RPT; ++j)
                     q[j][0] = q[j][1] = 0.0;
-                  if (colok)
-                    {
-                      double a0[NRHS], a1[NRHS], a2[NRHS];
-                      double b0[NRHS], b1[NRHS], b2[NRHS];
-                      ldv<NRHS>(sP, (Y0 - 1) * np + X - 1, a0);
-                      ldv<NRHS>(sP, (Y0 - 1) * np + X, a1);
-                      ldv<NRHS>(sP, (Y0 - 1) * np + X + 1, a2);
-                      ldv<NRHS>(sP, Y0 * np + X - 1, b0);
-                      ldv<NRHS>(sP, Y0 * np + X, b1);
-                      ldv<NRHS>(sP, Y0 * np + X + 1, b2);
-                      // couplings towards the row below the current one, carried up the strip
-                      double cS, cSE, cSW, unused;
-                      ld2(sB, (Y0 - 1) * n + X, cS, unused);      // N(X, y-1)
-                      ld2(sA, (Y0 - 1) * n + X, unused, cSE);     // D2(X, y-1)
-                      ld2(sB, (Y0 - 1) * n + X - 1, unused, cSW); // D1(X-1, y-1)
+                  {
+                    // Every lane runs the sweep (tcgen05.st is .sync.aligned: no divergence around it): the one
+                    // lane beyond the last interior column (X = n) re-reads column n-1 and its results are
+                    // discarded.
+                    const int Xc = colok ? X : n - 1;
+                    double    a0[NRHS], a1[NRHS], a2[NRHS];
+                    double    b0[NRHS], b1[NRHS], b2[NRHS];
+                    ldv<NRHS>(sP, (Y0 - 1) * np + Xc - 1, a0);
+                    ldv<NRHS>(sP, (Y0 - 1) * np + Xc, a1);
+                    ldv<NRHS>(sP, (Y0 - 1) * np + Xc + 1, a2);
+                    ldv<NRHS>(sP, Y0 * np + Xc - 1, b0);
+                    ldv<NRHS>(sP, Y0 * np + Xc, b1);
+                    ldv<NRHS>(sP, Y0 * np + Xc + 1, b2);
+                    // couplings towards the row below the current one, carried up the strip
+                    using K = Coef<n>;
+                    double cS  = sB[K::e((Y0 - 1) * n + Xc)];       // N(X, y-1)
+                    double cSE = sA[K::hi((Y0 - 1) * n + Xc)];      // D2(X, y-1)
+                    double cSW = sB[K::hi((Y0 - 1) * n + Xc - 1)];  // D1(X-1, y-1)
 #pragma unroll
-                      for (int j = 0; j < RPT; ++j)
-                        {
-                          const int y = Y0 + j;
-                          if (y <= n - 1)
-                            {
-                              double c0[NRHS], c1[NRHS], c2[NRHS];
-                              ldv<NRHS>(sP, (y + 1) * np + X - 1, c0);
-                              ldv<NRHS>(sP, (y + 1) * np + X, c1);
-                              ldv<NRHS>(sP, (y + 1) * np + X + 1, c2);
-                              double cE, d2o, cW, cNW, cN, cNE, d1w;
-                              ld2(sA, y * n + X, cE, d2o);
-                              ld2(sA, y * n + X - 1, cW, cNW);
-                              ld2(sB, y * n + X, cN, cNE);
-                              ld2(sB, y * n + X - 1, unused, d1w);
+                    for (int j = 0; j < RPT; ++j)
+                      {
+                        const int y = Y0 + j;
+                        if (y <= n - 1) // (uniform over the warp)
+                          {
+                            double c0[NRHS], c1[NRHS], c2[NRHS];
+                            ldv<NRHS>(sP, (y + 1) * np + Xc - 1, c0);
+                            ldv<NRHS>(sP, (y + 1) * np + Xc, c1);
+                            ldv<NRHS>(sP, (y + 1) * np + Xc + 1, c2);
+                            double cE, d2o, cW, cNW, cN, cNE, d1w;
+                            if constexpr (K::PAIRED)
+                              {
+                                double unused;
+                                ld2(sA, y * n + Xc, cE, d2o);
+                                ld2(sA, y * n + Xc - 1, cW, cNW);
+                                ld2(sB, y * n + Xc, cN, cNE);
+                                ld2(sB, y * n + Xc - 1, unused, d1w);
+                              }
+                            else
+                              {
+                                const int i = y * n + Xc;
+                                cE = sA[i], cW = sA[i - 1];
+                                d2o = sA[n * n + i], cNW = sA[n * n + i - 1];
+                                cN = sB[i];
+                                cNE = sB[n * n + i], d1w = sB[n * n + i - 1];
+                              }
 #pragma unroll
-                              for (int k = 0; k < NRHS; ++k)
-                                {
-                                  double t = b1[k];
-                                  t        = fma(cE, b2[k], t);
-                                  t        = fma(cW, b0[k], t);
-                                  t        = fma(cN, c1[k], t);
-                                  t        = fma(cS, a1[k], t);
-                                  t        = fma(cNE, c2[k], t);
-                                  t        = fma(cSW, a0[k], t);
-                                  t        = fma(cNW, c0[k], t);
-                                  t        = fma(cSE, a2[k], t);
-                                  q[j][k]  = t;
-                                  pq[k]    = fma(b1[k], t, pq[k]);
-                                  a0[k] = b0[k], a1[k] = b1[k], a2[k] = b2[k];
-                                  b0[k] = c0[k], b1[k] = c1[k], b2[k] = c2[k];
-                                }
-                              cS = cN, cSE = d2o, cSW = d1w;
-                            }
-                        }
-                    }
+                            for (int k = 0; k < NRHS; ++k)
+                              {
+                                double t = b1[k];
+                                t        = fma(cE, b2[k], t);
+                                t        = fma(cW, b0[k], t);
+                                t        = fma(cN, c1[k], t);
+                                t        = fma(cS, a1[k], t);
+                                t        = fma(cNE, c2[k], t);
+                                t        = fma(cSW, a0[k], t);
+                                t        = fma(cNW, c0[k], t);
+                                t        = fma(cSE, a2[k], t);
+                                t        = colok ? t : 0.0;
+                                q[j][k]  = t;
+                                pq[k]    = fma(b1[k], t, pq[k]);
+                                a0[k] = b0[k], a1[k] = b1[k], a2[k] = b2[k];
+                                b0[k] = c0[k], b1[k] = c1[k], b2[k] = c2[k];
+                              }
+                            cS = cN, cSE = d2o, cSW = d1w;
+                          }
+                        if constexpr (QTMEM)
+                          {
+                            if ((j & 3) == 3) // rows 4c .. 4c+3 are complete (zero beyond the mesh)
+                              {
+                                double q8[8];
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj)
+                                  q8[2 * jj] = q[j - 3 + jj][0], q8[2 * jj + 1] = q[j - 3 + jj][1];
+                                tmem::st8(tm + C::ROFF + 16 * (j >> 2), q8);
+                              }
+                          }
+                      }
+                    if constexpr (QTMEM)
+                      tmem::wait_st();
+                  }
                   ST_MARK(2)
                   block_sum2<NWARP>(pq[0], pq[1], sRed, warp, lane);
                   ST_MARK(3)
 #pragma unroll
                   for (int k = 0; k < NRHS; ++k)
                     alpha[k] = done[k] ? 0.0 : fast_div(rho[k], pq[k]);
-                  // ---- r -= alpha q
+                  if constexpr (RMODE == 0)
+                    {
 #pragma unroll
-                  for (int j = 0; j < RPT; ++j)
+                      for (int j = 0; j < RPT; ++j)
 #pragma unroll
-                    for (int k = 0; k < NRHS; ++k)
-                      r[j][k] = fma(-alpha[k], q[j][k], r[j][k]);
+                        for (int k = 0; k < NRHS; ++k)
+                          rreg[j][k] = fma(-alpha[k], q[j][k], rreg[j][k]);
+                    }
                 }
 
-              // ---- u = D^1/2 rhat, pre-summed per strip into the vector buffer (p is dead there: every warp has
-              //      passed the barrier of the p.q reduction); |u|^2 for the stopping rule, |rhat|^2 for r.z
+              // ---- rhat -= alpha q (tensor memory); u = D^1/2 rhat, pre-summed per strip into the vector buffer
+              //      (p is dead there: every warp has passed the barrier of the p.q reduction); |u|^2 for the
+              //      stopping rule, |rhat|^2 for r.z
               double rz[NRHS] = {0.0, 0.0}, rr[NRHS] = {0.0, 0.0};
               {
                 double    acc[NRHS];
                 const int pc = PS::col(X);
-                double    sq8[8];
-                tmem::ld8(tm + C::SOFF, sq8);
+                double    sq8[8], ra[8], rb[8];
+                if constexpr (RTMEM)
+                  tmem::ld8x3(tm + C::SOFF, tm + C::ROFF, tm + C::ROFF + 16, sq8, ra, rb);
+                else
+                  {
+                    if constexpr (QTMEM)
+                      {
+                        double qa[8], qb[8];
+                        tmem::ld8x3(tm + C::SOFF, tm + C::ROFF, tm + C::ROFF + 16, sq8, qa, qb);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                          for (int k = 0; k < NRHS; ++k)
+                            q[jj][k] = qa[2 * jj + k], q[4 + jj][k] = qb[2 * jj + k];
+                      }
+                    else
+                      tmem::ld8(tm + C::SOFF, sq8);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                      for (int k = 0; k < NRHS; ++k)
+                        ra[2 * jj + k] = rreg[jj][k], rb[2 * jj + k] = rreg[4 + jj][k];
+                  }
+                if (RMODE != 0 && it > 0)
+                  {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                      for (int k = 0; k < NRHS; ++k)
+                        {
+                          ra[2 * jj + k] = fma(-alpha[k], q[jj][k], ra[2 * jj + k]);
+                          rb[2 * jj + k] = fma(-alpha[k], q[4 + jj][k], rb[2 * jj + k]);
+                        }
+                    if constexpr (RTMEM)
+                      {
+                        tmem::st8(tm + C::ROFF, ra);
+                        tmem::st8(tm + C::ROFF + 16, rb);
+                      }
+                    else
+                      {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                          for (int k = 0; k < NRHS; ++k)
+                            rreg[jj][k] = ra[2 * jj + k], rreg[4 + jj][k] = rb[2 * jj + k];
+                      }
+                  }
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj)
                   {
@@ -624,23 +780,37 @@ namespace msb
 #pragma unroll
                     for (int k = 0; k < NRHS; ++k)
                       {
-                        u[k]  = sq8[jj] * r[jj][k]; // zero beyond the mesh
+                        const double rv = jj < 4 ? ra[2 * jj + k] : rb[2 * (jj - 4) + k];
+                        u[k]  = sq8[jj] * rv; // zero beyond the mesh
                         rr[k] = fma(u[k], u[k], rr[k]);
-                        rz[k] = fma(r[jj][k], r[jj][k], rz[k]);
+                        rz[k] = fma(rv, rv, rz[k]);
                       }
                     PS::push(sP, jj, u, acc, pc, wy, colok);
                   }
+                if constexpr (RTMEM)
+                  tmem::wait_st(); // rhat is re-read after the coarse levels
               }
               __syncthreads();
               ST_MARK(4)
               // ---- coarse levels; r.z = |rhat|^2 + u_1 . z_1 is completed while level 1 is prolonged
-              coarse_correction<NL, NRHS, THREADS, RPT, true, C::PAD>(
-                sP, sV, sDi, tid, warp, lane,
-                [&](int st_k) {
-                  (void)st_k;
-                  ST_MARK(st_k)
-                },
-                [&](int c, double(&g)[8]) { tmem::ld8(tmat + 16 * c, g); }, rz);
+                {
+                  // The index arithmetic of the coarse stages is loop invariant; hoisted out of the PCG loop it
+                  // stays live across the whole iteration and is SPILLED (the kernel sits at the 128-register
+                  // cap), and with 227 KB of the L1 carved out as shared memory a spill load goes to L2: eight of
+                  // them in front of one coarse stage cost ~3500 cycles per iteration.  Laundering the thread
+                  // index through an empty asm keeps the arithmetic inside the loop.
+                  int tl = tid;
+#ifndef MSB_EMU
+                  asm volatile("" : "+r"(tl));
+#endif
+                  coarse_correction<NL, NRHS, THREADS, RPT, true, C::PAD>(
+                  sP, sV, sDi, tl, tl >> 5, tl & 31,
+                  [&](int st_k) {
+                    (void)st_k;
+                    ST_MARK(st_k)
+                  },
+                  [&](int c, double(&g)[8]) { tmem::ld8(tmat + 16 * c, g); }, rz);
+                }
               ST_MARK(11)
               {
                 double four[4] = {rz[0], rz[1], rr[0], rr[1]};
@@ -696,9 +866,16 @@ namespace msb
 #pragma unroll
                 for (int c = 0; c < NCH; ++c)
                   {
-                    double x8[8], p8[8];
-                    tmem::ld8(tm + C::XOFF + 16 * c, x8);
-                    tmem::ld8(tm + C::POFF + 16 * c, p8);
+                    double x8[8], p8[8], r8[8];
+                    if constexpr (RTMEM)
+                      tmem::ld8x3(tm + C::XOFF + 16 * c, tm + C::POFF + 16 * c, tm + C::ROFF + 16 * c, x8, p8, r8);
+                    else
+                      {
+                        tmem::ld8x2(tm + C::XOFF + 16 * c, tm + C::POFF + 16 * c, x8, p8);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                          r8[2 * jj] = rreg[4 * c + jj][0], r8[2 * jj + 1] = rreg[4 * c + jj][1];
+                      }
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj)
                       {
@@ -708,7 +885,7 @@ namespace msb
                         for (int k = 0; k < NRHS; ++k)
                           {
                             const double cc = (j & 1) ? h[(j + 1) / 2][k] : 0.5 * (h[j / 2][k] + h[j / 2 + 1][k]);
-                            const double z  = fma(sq8[j], cc, r[j][k]);
+                            const double z  = fma(sq8[j], cc, r8[2 * jj + k]);
                             const double po = p8[2 * jj + k];
                             x8[2 * jj + k]  = fma(alpha[k], po, x8[2 * jj + k]);
                             pn[k]           = (done[k] && beta[k] == 0.0) ? po : fma(beta[k], po, z);
@@ -756,7 +933,7 @@ namespace msb
                 if (colok && y <= n - 1)
                   {
                     const int    i = y * np + X;
-                    const double s = 1.0 / sq8[jj];
+                    const double s = fast_div(1.0, sq8[jj]);
                     double       xh[NRHS];
 #pragma unroll
                     for (int k = 0; k < NRHS; ++k)
@@ -834,23 +1011,34 @@ namespace msb
                 }
             }
           {
-            double ten[10];
+            double ten[10], e, t;
 #pragma unroll
             for (int i2 = 0; i2 < 4; ++i2)
               ten[2 * i2] = macc[i2][0], ten[2 * i2 + 1] = macc[i2][1];
             ten[8] = bsum[0], ten[9] = bsum[1];
-            block_sum<10, NWARP>(ten, sRed, warp, lane);
+            warp_sum10(ten, lane, e, t);
+            if ((lane & 3) == 0)
+              sRed[((lane >> 2) & 7) * NWARP + warp] = e;
+            if ((lane & 15) == 0)
+              sRed[(8 + (lane >> 4)) * NWARP + warp] = t;
+            __syncthreads();
+            // ten threads add the warp partials in a fixed order (deterministic) and write the results
+            if (tid < 10)
+              {
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < NWARP; ++w)
+                  sum += sRed[tid * NWARP + w];
+                if (tid < 8)
+                  P.M[16 * (size_t)cell + 4 * (tid >> 1) + rhs0 + (tid & 1)] = sum;
+                else
+                  P.b[4 * (size_t)cell + rhs0 + (tid - 8)] = P.rhs_value * hx * hy * sum;
+              }
             if (tid == 0)
               {
 #pragma unroll
-                for (int i2 = 0; i2 < 4; ++i2)
-#pragma unroll
-                  for (int k = 0; k < NRHS; ++k)
-                    P.M[16 * (size_t)cell + 4 * i2 + rhs0 + k] = ten[2 * i2 + k];
-#pragma unroll
                 for (int k = 0; k < NRHS; ++k)
                   {
-                    P.b[4 * (size_t)cell + rhs0 + k] = P.rhs_value * hx * hy * ten[8 + k];
                     const int sidx = cell * 4 + rhs0 + k;
                     P.iters[sidx]  = kit[k];
                     P.res[sidx]    = sqrt(exact[k]);
@@ -871,12 +1059,23 @@ namespace msb
   cudaError_t
   launch_solve_fused(const FusedParams &P, cudaStream_t st)
   {
-    using C        = fused::Cfg;
-    cudaError_t e  = cudaFuncSetAttribute(fused::solve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)C::smem_bytes);
+    using C = fused::Cfg;
+    void (*kern)(FusedParams);
+    switch (P.flavor)
+      {
+        case 1:
+          kern = fused::solve_fused_kernel<1>;
+          break;
+        case 2:
+          kern = fused::solve_fused_kernel<2>;
+          break;
+        default:
+          kern = fused::solve_fused_kernel<0>;
+      }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
     if (e != cudaSuccess)
       return e;
-    fused::solve_fused_kernel<<<P.n_cells, C::THREADS, C::smem_bytes, st>>>(P);
+    kern<<<P.n_cells, C::THREADS, C::smem_bytes, st>>>(P);
     return cudaGetLastError();
   }
 #endif

@@ -59,6 +59,42 @@ namespace msb
         }
     }
 
+    // three independent loads in flight, one wait
+    __device__ __forceinline__ void
+    ld8x3(uint32_t ta, uint32_t tb, uint32_t tc, double (&da)[8], double (&db)[8], double (&dc)[8])
+    {
+      uint32_t v[16], w[16], z[16];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                   "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                     "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                     "=r"(v[14]), "=r"(v[15])
+                   : "r"(ta)
+                   : "memory");
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                   "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]),
+                     "=r"(w[7]), "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]),
+                     "=r"(w[14]), "=r"(w[15])
+                   : "r"(tb)
+                   : "memory");
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                   "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(z[0]), "=r"(z[1]), "=r"(z[2]), "=r"(z[3]), "=r"(z[4]), "=r"(z[5]), "=r"(z[6]),
+                     "=r"(z[7]), "=r"(z[8]), "=r"(z[9]), "=r"(z[10]), "=r"(z[11]), "=r"(z[12]), "=r"(z[13]),
+                     "=r"(z[14]), "=r"(z[15])
+                   : "r"(tc)
+                   : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        {
+          da[i] = __hiloint2double((int)v[2 * i + 1], (int)v[2 * i]);
+          db[i] = __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]);
+          dc[i] = __hiloint2double((int)z[2 * i + 1], (int)z[2 * i]);
+        }
+    }
+
     __device__ __forceinline__ void
     st8(uint32_t taddr, const double (&d)[8])
     {
@@ -139,9 +175,13 @@ namespace msb
       thread_local double t[256];
       return t;
     }
+    // tcgen05.ld / st / wait are .sync.aligned: every lane of the warp must execute them together.  The
+    // emulation enforces it with a warp barrier, so a call from divergent code deadlocks HERE instead of
+    // hanging the GPU (it did: a tcgen05.st inside `if (colok)` cost ten GPU-minutes in round 2).
     inline void
     ld8(uint32_t a, double (&d)[8])
     {
+      __syncwarp();
       for (int i = 0; i < 8; ++i)
         d[i] = priv()[(a & 0xffffu) / 2 + i];
     }
@@ -152,14 +192,24 @@ namespace msb
       ld8(b, db);
     }
     inline void
+    ld8x3(uint32_t a, uint32_t b, uint32_t c, double (&da)[8], double (&db)[8], double (&dc)[8])
+    {
+      ld8(a, da);
+      ld8(b, db);
+      ld8(c, dc);
+    }
+    inline void
     st8(uint32_t a, const double (&d)[8])
     {
+      __syncwarp();
       for (int i = 0; i < 8; ++i)
         priv()[(a & 0xffffu) / 2 + i] = d[i];
     }
     inline void
     wait_st()
-    {}
+    {
+      __syncwarp();
+    }
     inline uint32_t
     alloc(uint32_t *, int, int)
     {

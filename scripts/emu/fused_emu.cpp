@@ -19,6 +19,7 @@ main(int argc, char **argv)
 {
   const int kind     = argc > 1 ? atoi(argv[1]) : 1;
   const int max_iter = argc > 2 ? atoi(argv[2]) : 500;
+  const int flavor   = argc > 3 ? atoi(argv[3]) : 0;
   constexpr int n = 64, np = 65, N = np * np;
   // a coarse cell of the target configuration (256 x 256 coarse mesh), or a 2:1 rectangle for kind 3
   const double H = 1.0 / 256, X0 = 37 * H, Y0 = 101 * H, HY = kind == 3 ? 0.5 * H : H;
@@ -202,7 +203,7 @@ main(int argc, char **argv)
   FusedParams          P;
   P.corners = corners, P.q1coef = q1, P.phi = phi.data(), P.M = M.data(), P.b = b.data();
   P.iters = iters.data(), P.res = res.data(), P.fail = fail, P.tol2 = 1e-24, P.max_iter = max_iter, P.n_cells = 1;
-  P.rhs_value = f, P.coef = coef;
+  P.rhs_value = f, P.coef = coef, P.flavor = flavor;
   constexpr int T = fused::Cfg::THREADS;
   emu::Cluster  cl;
   cl.bar = std::make_unique<std::barrier<>>(T);
@@ -216,7 +217,12 @@ main(int argc, char **argv)
     th.emplace_back([&, t] {
       emu::t_cluster = &cl, emu::t_rank = 0;
       threadIdx.x = t, blockIdx.x = 0, blockDim.x = T, gridDim.x = 1;
-      fused::solve_fused_kernel(P);
+      if (flavor == 1)
+        fused::solve_fused_kernel<1>(P);
+      else if (flavor == 2)
+        fused::solve_fused_kernel<2>(P);
+      else
+        fused::solve_fused_kernel<0>(P);
     });
   for (auto &t : th)
     t.join();

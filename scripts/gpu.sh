@@ -30,17 +30,26 @@ for step in "$@"; do
       timeout 900 $PY bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; cat gpurun_out/bench_reference.json ;;
     probes)
       (cd scripts/probes && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o onchip_peaks onchip_peaks.cu) && timeout 300 scripts/probes/onchip_peaks | tee gpurun_out/onchip_peaks.json ;;
+    latency)
+      (cd scripts/probes && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o latency_probe latency_probe.cu) && timeout 120 scripts/probes/latency_probe | tee gpurun_out/latency_probe.json ;;
     ncu-launches)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 12 --csv --log-file gpurun_out/launches_target5920.csv $PY bench.py --workload target --cells 5920 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch_target.log 2>&1; tail -8 gpurun_out/launches_target5920.csv ;;
     ncu-full)
-      timeout 900 ncu --set full --import-source on --clock-control none -k regex:solve_bpx_tm -c 1 -f -o gpurun_out/bpx_tm_1184 $PY bench.py --workload target --cells 1184 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_target.log 2>&1
-      ncu -i gpurun_out/bpx_tm_1184.ncu-rep --page raw --csv > gpurun_out/ncu_full_solve_bpx_tm_1184.csv 2>/dev/null; ls -la gpurun_out/*.ncu-rep | tail -2 ;;
+      V=${NCU_VARIANT:-0}
+      timeout 900 ncu --set full --import-source on --clock-control none -k regex:'solve_fused|solve_bpx_tm' -c 1 -f -o gpurun_out/solve_n64_v${V}_1184 $PY bench.py --workload target --cells 1184 --steps 1 --warmup 3 --variant $V --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_target.log 2>&1
+      ncu -i gpurun_out/solve_n64_v${V}_1184.ncu-rep --page raw --csv > gpurun_out/ncu_full_solve_n64_v${V}_1184.csv 2>/dev/null; ls -la gpurun_out/*.ncu-rep | tail -2 ;;
     timers)
       MSB_LIBRARY=$PWD/mpi_parallel_multiscale_diffusion_fem_b200/libmsfem_basis_prof.so timeout 300 $PY scripts/stage_timers.py target 1184 ${TIMER_VARIANT:-0} 2>&1 | tee gpurun_out/stage_timers_target_1184_v${TIMER_VARIANT:-0}.txt ;;
     ab:*)
       for v in $(echo "${step#ab:}" | tr ',' ' '); do
-        timeout 300 $PY bench.py --workload target --cells 5920 --steps 5 --warmup 3 --variant $v --no-cpu-baseline --no-e2e > gpurun_out/ab_target5920_v$v.json 2> gpurun_out/ab_v$v.err
+        timeout 90 $PY bench.py --workload target --cells 5920 --steps 5 --warmup 3 --variant $v --no-cpu-baseline --no-e2e > gpurun_out/ab_target5920_v$v.json 2> gpurun_out/ab_v$v.err
         $PY -c "import json,sys; d=json.load(open('gpurun_out/ab_target5920_v$v.json')); print('variant $v: %.1f k solves/s, %.3f ms/step, solve kernel %.3f ms, k=%.2f' % (d['value']/1e3, d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['mean_pcg_iterations']))" || tail -3 gpurun_out/ab_v$v.err
+      done ;;
+    abt:*)
+      # A/B through the streamed / cluster tier: abt:V1,V2
+      for v in $(echo "${step#abt:}" | tr ',' ' '); do
+        timeout 90 $PY bench.py --workload target --cells 5920 --steps 5 --warmup 3 --variant $v --tier 2 --no-cpu-baseline --no-e2e > gpurun_out/abt_target5920_v$v.json 2> gpurun_out/abt_v$v.err
+        $PY -c "import json,sys; d=json.load(open('gpurun_out/abt_target5920_v$v.json')); print('tier 2 variant $v: %.1f k solves/s, %.3f ms/step, solve kernel %.3f ms, k=%.2f' % (d['value']/1e3, d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['mean_pcg_iterations']))" || tail -3 gpurun_out/abt_v$v.err
       done ;;
     wl:*)
       spec="${step#wl:}"; name="${spec%%:*}"; var=0; [[ "$spec" == *:* ]] && var="${spec#*:}"

@@ -79,25 +79,33 @@ namespace msb
       *reinterpret_cast<double2 *>(p + 2 * (size_t)idx) = make_double2(a, b);
     }
 
-    // ---- reference-cell gradients of the bilinear shape functions at the 2x2 Gauss points, and one entry of
-    // a fine element matrix on an hx x hy rectangle from the per-point coefficients
-    //   c00 = a00 hy / (4 hx),  c01 = (a01 + a10) / 8,  c11 = a11 hx / (4 hy)
-    // in the summation order of assemble_kernel (msb_setup.cu): q outermost, three fused multiply-adds each.
-    template <int I, int J>
+    // ---- One entry of a fine element matrix on an hx x hy rectangle from the tensor coefficient at the 2x2 Gauss
+    // points q = qx + 2 qy (abscissae g_qx, g_qy):
+    //   K_ij = sum_q [ dNx_i dNx_j a00 hy/(4hx) + (dNx_i dNy_j + dNy_i dNx_j) (a01+a10)/8 + dNy_i dNy_j a11 hx/(4hy) ]_q .
+    // The x-gradients of the bilinear shape functions depend on eta_q only and the y-gradients on xi_q only, so the
+    // first and the last term need the coefficient only SUMMED over qx resp. qy:
+    //   S[0] = c00_0 + c00_1 (eta = g0), S[1] = c00_2 + c00_3 (eta = g1), S[2] = c11_0 + c11_2 (xi = g0), S[3] = c11_1 + c11_3
+    // -- 4 fused multiply-adds per entry for an isotropic coefficient (c01 = 0), 8 for a full tensor, instead
+    // of 12 (assemble_kernel's order; the results differ in the last bits).
+    template <int I, int J, bool ISO>
     __device__ __forceinline__ double
-    kentry(const double (&c00)[4], const double (&c01)[4], const double (&c11)[4])
+    kentry(const double (&S)[4], const double (&c01)[4])
     {
       constexpr double G0 = 0.21132486540518711775, G1 = 0.78867513459481288225;
-      double           k  = 0.0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
+      constexpr double dx0[4] = {-(1 - G0), (1 - G0), -G0, G0}, dx1[4] = {-(1 - G1), (1 - G1), -G1, G1}; // dNx at eta = g0, g1
+      constexpr double dy0[4] = {-(1 - G0), -G0, (1 - G0), G0}, dy1[4] = {-(1 - G1), -G1, (1 - G1), G1}; // dNy at xi = g0, g1
+      double           k = dx0[I] * dx0[J] * S[0];
+      k                  = fma(dx1[I] * dx1[J], S[1], k);
+      k                  = fma(dy0[I] * dy0[J], S[2], k);
+      k                  = fma(dy1[I] * dy1[J], S[3], k);
+      if constexpr (!ISO)
         {
-          const double xi = (q & 1) ? G1 : G0, eta = (q >> 1) ? G1 : G0;
-          const double dNx[4] = {-(1 - eta), (1 - eta), -eta, eta};
-          const double dNy[4] = {-(1 - xi), -xi, (1 - xi), xi};
-          k = fma(dNx[I] * dNx[J], c00[q], k);
-          k = fma(dNx[I] * dNy[J] + dNy[I] * dNx[J], c01[q], k);
-          k = fma(dNy[I] * dNy[J], c11[q], k);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            {
+              const double *dx = (q >> 1) ? dx1 : dx0, *dy = (q & 1) ? dy1 : dy0;
+              k = fma(dx[I] * dy[J] + dy[I] * dx[J], c01[q], k);
+            }
         }
       return k;
     }
@@ -299,63 +307,73 @@ namespace msb
       // (1) node stencils: K_e entries of the <= 4 adjacent fine cells, gathered in the order SW, SE, NW, NE
       {
         const double rxx = 0.25 * hy / hx, ryy = 0.25 * hx / hy;
-        for (int t = tid; t < N; t += THREADS)
-          {
-            const int jx = t % np, jy = t / np;
-            double    kc = 0, kE = 0, kN = 0, kd1 = 0, kd2 = 0;
-            auto cell_coef = [&](int ix, int iy, double(&c00)[4], double(&c01)[4], double(&c11)[4]) {
+        // every kind but the reference's rotated tensor is a scalar times the identity
+        const bool iso = P.coef.kind != MSB_COEFF_REFERENCE;
+        auto node_stencil = [&](auto iso_c, int t) {
+          constexpr bool ISO = decltype(iso_c)::value;
+          const int      jx = t % np, jy = t / np;
+          double         kc = 0, kE = 0, kN = 0, kd1 = 0, kd2 = 0;
+          auto cell_sums = [&](int ix, int iy, double(&S)[4], double(&c01)[4]) {
+            double c00[4], c11[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                {
-                  constexpr double G0 = 0.21132486540518711775, G1 = 0.78867513459481288225;
-                  double           a00, a01, a10, a11;
-                  if (separable)
-                    P.coef.from_sines(tsx[4 * ix + q], tsy[4 * iy + q], a00, a01, a10, a11);
-                  else
-                    P.coef(crn[0] + (ix + ((q & 1) ? G1 : G0)) * hx, crn[1] + (iy + ((q >> 1) ? G1 : G0)) * hy, a00,
-                           a01, a10, a11);
-                  c00[q] = a00 * rxx, c01[q] = 0.125 * (a01 + a10), c11[q] = a11 * ryy;
-                }
-            };
-            double c00[4], c01[4], c11[4];
-            if (jx > 0 && jy > 0) // SW cell: the node is its vertex 3
+            for (int q = 0; q < 4; ++q)
               {
-                cell_coef(jx - 1, jy - 1, c00, c01, c11);
-                kc += kentry<3, 3>(c00, c01, c11);
+                constexpr double G0 = 0.21132486540518711775, G1 = 0.78867513459481288225;
+                double           a00, a01, a10, a11;
+                if (separable)
+                  P.coef.from_sines(tsx[4 * ix + q], tsy[4 * iy + q], a00, a01, a10, a11);
+                else
+                  P.coef(crn[0] + (ix + ((q & 1) ? G1 : G0)) * hx, crn[1] + (iy + ((q >> 1) ? G1 : G0)) * hy, a00, a01,
+                         a10, a11);
+                c00[q] = a00 * rxx, c01[q] = 0.125 * (a01 + a10), c11[q] = a11 * ryy;
               }
-            if (jx < n && jy > 0) // SE cell: vertex 2
-              {
-                cell_coef(jx, jy - 1, c00, c01, c11);
-                kc += kentry<2, 2>(c00, c01, c11);
-                kE += kentry<2, 3>(c00, c01, c11);
-              }
-            if (jx > 0 && jy < n) // NW cell: vertex 1
-              {
-                cell_coef(jx - 1, jy, c00, c01, c11);
-                kc += kentry<1, 1>(c00, c01, c11);
-                kN += kentry<1, 3>(c00, c01, c11);
-              }
-            if (jx < n && jy < n) // NE cell: vertex 0
-              {
-                cell_coef(jx, jy, c00, c01, c11);
-                kc += kentry<0, 0>(c00, c01, c11);
-                kE += kentry<0, 1>(c00, c01, c11);
-                kN += kentry<0, 2>(c00, c01, c11);
-                kd1 = kentry<0, 3>(c00, c01, c11);
-                kd2 = kentry<1, 2>(c00, c01, c11);
-              }
-            sKC[t] = kc;
-            if (jx < n && jy < n)
-              {
-                using K = Coef<n>;
-                sA[K::e(jy * n + jx)] = kE, sA[K::hi(jy * n + jx)] = kd2;
-                sB[K::e(jy * n + jx)] = kN, sB[K::hi(jy * n + jx)] = kd1;
-              }
-            else if (jx < n)
-              sEb[jx] = kE; // top boundary row: boundary-boundary edges
-            else if (jy < n)
-              sNb[jy] = kN; // right boundary column
-          }
+            S[0] = c00[0] + c00[1], S[1] = c00[2] + c00[3], S[2] = c11[0] + c11[2], S[3] = c11[1] + c11[3];
+          };
+          double S[4], c01[4];
+          if (jx > 0 && jy > 0) // SW cell: the node is its vertex 3
+            {
+              cell_sums(jx - 1, jy - 1, S, c01);
+              kc += kentry<3, 3, ISO>(S, c01);
+            }
+          if (jx < n && jy > 0) // SE cell: vertex 2
+            {
+              cell_sums(jx, jy - 1, S, c01);
+              kc += kentry<2, 2, ISO>(S, c01);
+              kE += kentry<2, 3, ISO>(S, c01);
+            }
+          if (jx > 0 && jy < n) // NW cell: vertex 1
+            {
+              cell_sums(jx - 1, jy, S, c01);
+              kc += kentry<1, 1, ISO>(S, c01);
+              kN += kentry<1, 3, ISO>(S, c01);
+            }
+          if (jx < n && jy < n) // NE cell: vertex 0
+            {
+              cell_sums(jx, jy, S, c01);
+              kc += kentry<0, 0, ISO>(S, c01);
+              kE += kentry<0, 1, ISO>(S, c01);
+              kN += kentry<0, 2, ISO>(S, c01);
+              kd1 = kentry<0, 3, ISO>(S, c01);
+              kd2 = kentry<1, 2, ISO>(S, c01);
+            }
+          sKC[t] = kc;
+          if (jx < n && jy < n)
+            {
+              using K = Coef<n>;
+              sA[K::e(jy * n + jx)] = kE, sA[K::hi(jy * n + jx)] = kd2;
+              sB[K::e(jy * n + jx)] = kN, sB[K::hi(jy * n + jx)] = kd1;
+            }
+          else if (jx < n)
+            sEb[jx] = kE; // top boundary row: boundary-boundary edges
+          else if (jy < n)
+            sNb[jy] = kN; // right boundary column
+        };
+        if (iso)
+          for (int t = tid; t < N; t += THREADS)
+            node_stencil(std::true_type{}, t);
+        else
+          for (int t = tid; t < N; t += THREADS)
+            node_stencil(std::false_type{}, t);
       }
       __syncthreads();
       ST_MARK(12)

@@ -750,3 +750,39 @@ def test_fused_stage_no_convergence_and_zero_iterations(msb, oracle):
         assert sh.failure()[0] == -1
         M, _ = sh.element_matrices()
         assert np.abs(M.sum(axis=2)).max() < 1e-9
+
+
+# ---------------------------------------------------------------------------- the second, independent restatement
+INDEP = json.load(open(os.path.join(GOLD, "independent_golden.json")))
+
+
+@pytest.mark.parametrize("name", sorted(INDEP))
+def test_independent_restatement_on_gpu(msb, oracle, name):
+    """The CUDA path against vectors that do NOT come from oracle/msfem_oracle.c: tests/golden/independent_restatement.py
+    (numpy / scipy, own DoF numbering and assembly, sparse direct solve).  DoF map and constraint index set bit for
+    bit, bases / M / b within the north-star tolerance."""
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
+    g = INDEP[name]
+    l, n = g["l"], 1 << g["l"]
+    cor = np.array(g["corners"], dtype=np.float64)[None]
+
+    def checksum(a):
+        return int(sum((i + 1) * int(d) for i, d in enumerate(np.asarray(a).ravel())) % (1 << 61))
+
+    with msb.BasisShard(l, cor, coeff_desc(g["kind"], g["par"], g["seed"]), rhs_value=g["f"]) as sh:
+        d = sh.dof_map()
+        assert checksum(d) == g["dof_checksum"]
+        dofs, vals = sh.constraints(0, 2)
+        assert dofs.size == g["n_boundary"] and checksum(dofs) == g["boundary_dofs_checksum"]
+        assert np.abs(vals[:6] - np.array(g["constraint_values_head"][2])).max() < 1e-9
+        sh.run(1e-12, 5000)
+        it, res = sh.iteration_counts()
+        assert np.all(res <= 1e-12)
+        M, b = sh.element_matrices()
+        assert _rel(M[0], np.array(g["M"])) < TOL_MB and _rel(b[0], np.array(g["b"])) < TOL_MB
+        phis = sh.bases()[0]
+        for (jx, jy), want in zip(g["probes"], g["phi_probes"]):
+            got = np.array([phis[ib][d[jy, jx]] for ib in range(4)])
+            assert np.abs(got - np.array(want)).max() < TOL_PHI
+        for ib in range(4):
+            assert abs(np.linalg.norm(phis[ib]) - g["phi_norms"][ib]) < TOL_PHI * g["phi_norms"][ib]

@@ -148,8 +148,17 @@ namespace DiffusionProblem
     DiffusionProblemBasis() = delete;
     static constexpr unsigned NB = 1u << dim; // GeometryInfo<dim>::vertices_per_cell
 
+#ifdef MSFEM_WITH_DEALII
+    // The reference's constructor, argument for argument (diffusion_problem_basis.hpp:79-83), so that the
+    // construction loop diffusion_problem_ms.tpp:54-66 compiles against this class unchanged.
+    DiffusionProblemBasis(unsigned int                                               n_refine_local,
+                          typename dealii::Triangulation<dim>::active_cell_iterator &global_cell,
+                          unsigned int local_subdomain, MPI_Comm mpi_communicator)
+      : DiffusionProblemBasis(n_refine_local, CoarseCell<dim>::from(global_cell), local_subdomain, mpi_communicator)
+    {}
+#endif
     DiffusionProblemBasis(unsigned int n_refine_local, const CoarseCell<dim> &global_cell,
-                          unsigned int local_subdomain, MPI_Comm_shim mpi_communicator = 0)
+                          unsigned int local_subdomain, MPI_Comm_shim mpi_communicator = MPI_Comm_shim())
       : mpi_communicator(mpi_communicator)
       , corner_points(1 << dim)
       , filename_global("")
@@ -330,35 +339,43 @@ namespace DiffusionProblem
 
       const msb_coeff_desc desc = coeff.device_descriptor();
       std::vector<double>  table;
-      if (desc.kind == MSB_COEFF_TABLE && dim != 2)
-        throw BasisStageError(MSB_ERR_UNSUPPORTED, "tabulated coefficients are built for dim 2 only");
       if (desc.kind == MSB_COEFF_TABLE)
         {
           // a coefficient class the device has no formula for: evaluate its value_list at the
-          // fine quadrature points (what assemble_system does per cell, basis.tpp:202-203)
+          // fine quadrature points (what assemble_system does per cell, basis.tpp:202-203);
+          // dim 2: [cell][iy n + ix][4 q][2x2], dim 3: [cell][(iz n + iy) n + ix][8 q][3x3], q with x fastest
           const double g[2] = {0.5 - 0.5 / std::sqrt(3.0), 0.5 + 0.5 / std::sqrt(3.0)};
-          std::vector<Point<dim>>     pts(4);
-          std::vector<Tensor<2, dim>> vals(4);
-          table.reserve(objs.size() * n * n * 16);
+          std::vector<Point<dim>>     pts(NB);
+          std::vector<Tensor<2, dim>> vals(NB);
+          const unsigned              nz = dim == 3 ? n : 1;
+          table.reserve(objs.size() * std::size_t(n) * n * nz * NB * dim * dim);
           for (auto &kv : objs)
             {
               const auto &c = kv.second->corner_points;
-              for (unsigned iy = 0; iy < n; ++iy)
-                for (unsigned ix = 0; ix < n; ++ix)
-                  {
-                    for (int q = 0; q < 4; ++q)
-                      {
-                        const double s = (ix + g[q & 1]) / n, t = (iy + g[q >> 1]) / n;
-                        for (int d = 0; d < dim; ++d)
-                          pts[q](d) = c[0](d) + s * (c[1](d) - c[0](d)) + t * (c[2](d) - c[0](d)) +
-                                      s * t * ((c[3](d) - c[2](d)) - (c[1](d) - c[0](d)));
-                      }
-                    coeff.value_list(pts, vals);
-                    for (int q = 0; q < 4; ++q)
-                      for (int i = 0; i < 2; ++i)
-                        for (int j = 0; j < 2; ++j)
-                          table.push_back(vals[q][i][j]);
-                  }
+              for (unsigned iz = 0; iz < nz; ++iz)
+                for (unsigned iy = 0; iy < n; ++iy)
+                  for (unsigned ix = 0; ix < n; ++ix)
+                    {
+                      for (unsigned q = 0; q < NB; ++q)
+                        {
+                          // multilinear image of the reference point: sum_v c_v N_v(s, t, u)
+                          const double s = (ix + g[q & 1]) / n, t = (iy + g[(q >> 1) & 1]) / n,
+                                       u = dim == 3 ? (iz + g[q >> 2]) / n : 0.0;
+                          for (int d = 0; d < dim; ++d)
+                            {
+                              double x = 0.0;
+                              for (unsigned v = 0; v < NB; ++v)
+                                x += c[v](d) * ((v & 1) ? s : 1 - s) * (((v >> 1) & 1) ? t : 1 - t) *
+                                     (dim == 3 ? ((v >> 2) ? u : 1 - u) : 1.0);
+                              pts[q](d) = x;
+                            }
+                        }
+                      coeff.value_list(pts, vals);
+                      for (unsigned q = 0; q < NB; ++q)
+                        for (int i = 0; i < dim; ++i)
+                          for (int j = 0; j < dim; ++j)
+                            table.push_back(vals[q][i][j]);
+                    }
             }
         }
 

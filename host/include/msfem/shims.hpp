@@ -6,12 +6,16 @@
 // define MSFEM_WITH_DEALII and the real types are used instead.
 #pragma once
 
+#include <array>
+
 #ifdef MSFEM_WITH_DEALII
 #  include <deal.II/base/point.h>
 #  include <deal.II/base/tensor.h>
 #  include <deal.II/grid/cell_id.h>
+#  include <deal.II/grid/tria.h>
 #  include <deal.II/lac/full_matrix.h>
 #  include <deal.II/lac/vector.h>
+#  include <mpi.h>
 namespace msfem
 {
   using dealii::CellId;
@@ -19,168 +23,17 @@ namespace msfem
   using dealii::Point;
   using dealii::Tensor;
   using dealii::Vector;
+  using MPI_Comm_shim = MPI_Comm;
 } // namespace msfem
 #else
-
-#  include <array>
-#  include <cstddef>
-#  include <cstdint>
-#  include <string>
-#  include <vector>
-
+#  define MSFEM_SHIM_NAMESPACE msfem
+#  include "msfem/shim_types.hpp"
+#  undef MSFEM_SHIM_NAMESPACE
 namespace msfem
 {
-  template <int dim>
-  class Point
-  {
-  public:
-    Point() { c_.fill(0.0); }
-    Point(double x, double y)
-    {
-      static_assert(dim == 2, "2-argument Point is 2D");
-      c_[0] = x, c_[1] = y;
-    }
-    Point(double x, double y, double z)
-    {
-      static_assert(dim == 3, "3-argument Point is 3D");
-      c_[0] = x, c_[1] = y, c_[2] = z;
-    }
-    double  operator()(unsigned i) const { return c_[i]; }
-    double &operator()(unsigned i) { return c_[i]; }
-    double  operator[](unsigned i) const { return c_[i]; }
-    double &operator[](unsigned i) { return c_[i]; }
-
-  private:
-    std::array<double, dim> c_;
-  };
-
-  // rank-2 tensor only (the diffusion coefficient)
-  template <int rank, int dim>
-  class Tensor;
-
-  template <int dim>
-  class Tensor<2, dim>
-  {
-  public:
-    Tensor() { clear(); }
-    void clear()
-    {
-      for (auto &row : a_)
-        row.fill(0.0);
-    }
-    std::array<double, dim>       &operator[](unsigned i) { return a_[i]; }
-    const std::array<double, dim> &operator[](unsigned i) const { return a_[i]; }
-
-  private:
-    std::array<std::array<double, dim>, dim> a_;
-  };
-
-  template <int dim>
-  Tensor<2, dim>
-  operator*(const Tensor<2, dim> &A, const Tensor<2, dim> &B)
-  {
-    Tensor<2, dim> C;
-    for (int i = 0; i < dim; ++i)
-      for (int j = 0; j < dim; ++j)
-        {
-          double s = 0.0;
-          for (int k = 0; k < dim; ++k)
-            s += A[i][k] * B[k][j];
-          C[i][j] = s;
-        }
-    return C;
-  }
-
-  template <int dim>
-  Tensor<2, dim>
-  transpose(const Tensor<2, dim> &A)
-  {
-    Tensor<2, dim> T;
-    for (int i = 0; i < dim; ++i)
-      for (int j = 0; j < dim; ++j)
-        T[i][j] = A[j][i];
-    return T;
-  }
-
-  template <typename number>
-  class Vector
-  {
-  public:
-    Vector() = default;
-    explicit Vector(std::size_t n)
-      : v_(n, number(0))
-    {}
-    void        reinit(std::size_t n) { v_.assign(n, number(0)); }
-    std::size_t size() const { return v_.size(); }
-    number      operator()(std::size_t i) const { return v_[i]; }
-    number     &operator()(std::size_t i) { return v_[i]; }
-    number      operator[](std::size_t i) const { return v_[i]; }
-    number     &operator[](std::size_t i) { return v_[i]; }
-    number     *data() { return v_.data(); }
-    const number *data() const { return v_.data(); }
-    number      operator*(const Vector &o) const
-    {
-      number s = 0;
-      for (std::size_t i = 0; i < v_.size(); ++i)
-        s += v_[i] * o.v_[i];
-      return s;
-    }
-
-  private:
-    std::vector<number> v_;
-  };
-
-  // row-major dense matrix, FullMatrix<double>-like
-  template <typename number>
-  class FullMatrix
-  {
-  public:
-    FullMatrix() = default;
-    FullMatrix(std::size_t m, std::size_t n)
-      : m_(m)
-      , n_(n)
-      , v_(m * n, number(0))
-    {}
-    std::size_t m() const { return m_; }
-    std::size_t n() const { return n_; }
-    number      operator()(std::size_t i, std::size_t j) const { return v_[i * n_ + j]; }
-    number     &operator()(std::size_t i, std::size_t j) { return v_[i * n_ + j]; }
-    number     *data() { return v_.data(); }
-    const number *data() const { return v_.data(); }
-
-  private:
-    std::size_t         m_ = 0, n_ = 0;
-    std::vector<number> v_;
-  };
-
-  // identifies a coarse cell of the refined hyper_cube: Morton index at a given depth;
-  // to_string() follows deal.II's "coarse_depth:child digits" form
-  class CellId
-  {
-  public:
-    CellId() = default;
-    CellId(unsigned depth, std::uint64_t morton, unsigned dim = 2)
-      : depth_(depth)
-      , dim_(dim)
-      , morton_(morton)
-    {}
-    std::string to_string() const
-    {
-      std::string s = "0_" + std::to_string(depth_) + ":";
-      for (unsigned k = 0; k < depth_; ++k)
-        s += char('0' + ((morton_ >> (dim_ * (depth_ - 1 - k))) & ((1u << dim_) - 1u)));
-      return s;
-    }
-    bool          operator<(const CellId &o) const { return morton_ < o.morton_; }
-    bool          operator==(const CellId &o) const { return depth_ == o.depth_ && morton_ == o.morton_; }
-    std::uint64_t morton() const { return morton_; }
-    unsigned      depth() const { return depth_; }
-
-  private:
-    unsigned      depth_  = 0;
-    unsigned      dim_    = 2;
-    std::uint64_t morton_ = 0;
-  };
+  // MPI is not needed on one box; the reference stores the communicator without using it
+  // (basis.tpp:24, SURVEY section 1)
+  using MPI_Comm_shim = int;
 } // namespace msfem
 #endif
 
@@ -197,9 +50,20 @@ namespace msfem
 
     const Point<dim> &vertex(unsigned i) const { return vertices[i]; }
     CellId            id() const { return cell_id; }
-  };
 
-  // MPI is not needed on one box; the reference stores the communicator without using it
-  // (basis.tpp:24, SURVEY section 1)
-  using MPI_Comm_shim = int;
+#ifdef MSFEM_WITH_DEALII
+    // from the reference's own argument type (basis.hpp:79-83, caller ms.tpp:54-66)
+    static CoarseCell
+    from(const typename dealii::Triangulation<dim>::active_cell_iterator &cell)
+    {
+      CoarseCell c;
+      for (unsigned v = 0; v < (1u << dim); ++v)
+        c.vertices[v] = cell->vertex(v);
+      c.cell_id = cell->id();
+      for (unsigned f = 0; f < 2 * dim; ++f)
+        c.boundary_id[f] = cell->face(f)->at_boundary() ? (unsigned)cell->face(f)->boundary_id() : 255u;
+      return c;
+    }
+#endif
+  };
 } // namespace msfem

@@ -103,9 +103,15 @@ typedef struct msb_handle_s *msb_handle;
 /* Replaces the construction loop ms.tpp:50-73 (DiffusionProblemBasis ctor,
  * basis.tpp:18-50).  corners: [n_cells][2^dim][dim] doubles, deal.II vertex
  * order.  dim 3 (hexahedral cells, 8 bases, 1 <= n_refine_local <= 6) takes
- * MSB_COEFF_REFERENCE (MatrixCoeff<3>, matrix_coeff.tpp:28-41) or MSB_COEFF_CONSTANT
- * and always runs in the streamed tier.  coeff_table: NULL unless coeff.kind == MSB_COEFF_TABLE, then
- * [n_cells][n*n fine cells, iy*n+ix][4 q-points, x fastest][a00,a01,a10,a11]. */
+ * MSB_COEFF_REFERENCE (MatrixCoeff<3>, matrix_coeff.tpp:28-41), MSB_COEFF_CONSTANT or
+ * MSB_COEFF_TABLE and always runs in the streamed tier.  coeff_table: NULL unless
+ * coeff.kind == MSB_COEFF_TABLE, then what TensorFunction<2,dim>::value_list returned at the fine
+ * quadrature points (basis.tpp:202-203):
+ *   dim 2: [n_cells][n*n fine cells, iy*n+ix][4 q-points, x fastest][a00,a01,a10,a11]
+ *   dim 3: [n_cells][n^3 fine cells, (iz*n+iy)*n+ix][8 q-points, x fastest][a00,a01,a02,a10,...,a22]
+ * A tensor that is not symmetric up to 1e-12 max|a| is rejected (MSB_ERR_INVALID_ARG): the stiffness
+ * matrix must be symmetric for CG -- the reference's SolverCG needs that too -- and the 2D kernels
+ * assemble from the symmetric part only. */
 int msb_create(const msb_config *cfg, const double *corners, const double *coeff_table,
                msb_handle *out);
 

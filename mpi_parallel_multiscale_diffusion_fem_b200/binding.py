@@ -114,7 +114,7 @@ class BasisShard:
         tab = None
         if table is not None:
             tab = np.ascontiguousarray(table, dtype=np.float64)
-            assert tab.size == self.n_cells * self.n * self.n * 16
+            assert tab.size == self.n_cells * self.n ** self.dim * self.nb * self.dim * self.dim
         self._check(self._lib.msb_create(C.byref(cfg), _dp(corners),
                                          None if tab is None else _dp(tab), C.byref(self._h)))
 

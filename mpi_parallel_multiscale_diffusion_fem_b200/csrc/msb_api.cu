@@ -193,8 +193,10 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
   if (cfg->n_refine_local < 1 || cfg->n_refine_local > max_l)
     return fail(MSB_ERR_UNSUPPORTED, "msb_create: n_refine_local=%d outside 1..%d for dim=%d",
                 cfg->n_refine_local, max_l, cfg->dim);
-  if (cfg->dim == 3 && cfg->coeff.kind != MSB_COEFF_REFERENCE && cfg->coeff.kind != MSB_COEFF_CONSTANT)
-    return fail(MSB_ERR_UNSUPPORTED, "msb_create: dim=3 supports MSB_COEFF_REFERENCE and MSB_COEFF_CONSTANT");
+  if (cfg->dim == 3 && cfg->coeff.kind != MSB_COEFF_REFERENCE && cfg->coeff.kind != MSB_COEFF_CONSTANT &&
+      cfg->coeff.kind != MSB_COEFF_TABLE)
+    return fail(MSB_ERR_UNSUPPORTED,
+                "msb_create: dim=3 supports MSB_COEFF_REFERENCE, MSB_COEFF_CONSTANT and MSB_COEFF_TABLE");
   if (cfg->dim == 3 && cfg->tier == MSB_TIER_SMEM)
     return fail(MSB_ERR_UNSUPPORTED, "msb_create: dim=3 runs in the streamed tier");
   if (cfg->n_cells < 1)

@@ -276,8 +276,8 @@ namespace msb
     // stores the diagonal, the 13 forward couplings and the load entry.  No atomics: the sum
     // order is fixed (cells in local-vertex order, quadrature points in order).
     __global__ void __launch_bounds__(128)
-    assemble3_kernel(int n, const double *__restrict__ corners, Coeff3 cf, double rhs_value,
-                     double *__restrict__ sten)
+    assemble3_kernel(int n, const double *__restrict__ corners, Coeff3 cf, const double *__restrict__ table,
+                     double rhs_value, double *__restrict__ sten)
     {
       const int np = n + 1, N = np * np * np, cell = blockIdx.y;
       const int t  = blockIdx.x * blockDim.x + threadIdx.x;
@@ -381,7 +381,18 @@ namespace msb
                       G[v][a] = Ji[0][a] * dN[v][0] + Ji[1][a] * dN[v][1] + Ji[2][a] * dN[v][2];
                 }
               double A[9];
-              coeff3_eval(cf, xq[0], xq[1], A);
+              if (table)
+                {
+                  // MSB_COEFF_TABLE: what TensorFunction<2,3>::value_list returned for this quadrature point
+                  // (basis.tpp:202-203): [cell][(iz n + iy) n + ix][q][9]
+                  const double *tp =
+                    table + ((((size_t)cell * n + iz) * n + iy) * n + ix) * 72 + (size_t)q * 9;
+#pragma unroll
+                  for (int a = 0; a < 9; ++a)
+                    A[a] = tp[a];
+                }
+              else
+                coeff3_eval(cf, xq[0], xq[1], A);
               // own gradient and shape value, selected without dynamic register indexing
               double gi[3] = {0, 0, 0}, ni = 0.0;
 #pragma unroll
@@ -1612,12 +1623,15 @@ namespace msb
     for (int c0 = 0; c0 < s.n_cells; c0 += 65535)
       {
         const int nc = s.n_cells - c0 < 65535 ? s.n_cells - c0 : 65535;
-        if (s.bricks && s.variant != 3)
+        const bool tab = s.coeff.kind == MSB_COEFF_TABLE;
+        if (s.bricks && s.variant != 3 && !tab)
           d3::assemble3_brick_kernel<<<dim3((s.N + 127) / 128, nc), 128, 0, st>>>(
             s.n, s.d_corners + 24 * (size_t)c0, cf, s.rhs_value, s.d_sten + (size_t)c0 * ST3_NARR * s.N);
         else
           d3::assemble3_kernel<<<dim3((s.N + 127) / 128, nc), 128, 0, st>>>(
-            s.n, s.d_corners + 24 * (size_t)c0, cf, s.rhs_value, s.d_sten + (size_t)c0 * ST3_NARR * s.N);
+            s.n, s.d_corners + 24 * (size_t)c0, cf,
+            tab ? s.d_table + (size_t)c0 * (size_t)s.n * s.n * s.n * 72 : nullptr, s.rhs_value,
+            s.d_sten + (size_t)c0 * ST3_NARR * s.N);
         ++*n_launches;
       }
     return cudaGetLastError();

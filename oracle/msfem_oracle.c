@@ -961,9 +961,11 @@ build_sparsity3(int l, const uint32_t *dof, uint64_t *rowptr, uint32_t *col)
 }
 
 /* assemble_system for dim = 3: QGauss<3>(2), FE_Q<3>(1), MappingQ1 */
+/* table: NULL, or the tensor values a user TensorFunction<2,3>::value_list produced at the fine quadrature
+ * points (basis.tpp:202-203): [(iz n + iy) n + ix][q, x fastest][a00 a01 a02 a10 ... a22] */
 static void
-assemble3(int l, const double corners[24], const orc_coeff *c, double rhs_value, const uint32_t *dof,
-          const uint64_t *rowptr, const uint32_t *col, double *val, double *F)
+assemble3(int l, const double corners[24], const orc_coeff *c, const double *table, double rhs_value,
+          const uint32_t *dof, const uint64_t *rowptr, const uint32_t *col, double *val, double *F)
 {
   const uint32_t n = 1u << l, np = n + 1, N = np * np * np;
   memset(val, 0, sizeof(double) * rowptr[N]);
@@ -1023,7 +1025,10 @@ assemble3(int l, const double corners[24], const orc_coeff *c, double rhs_value,
             for (int a = 0; a < 3; ++a)
               G[v][a] = Ji[0][a] * dN[v][0] + Ji[1][a] * dN[v][1] + Ji[2][a] * dN[v][2];
           double A[9];
-          orc3_coeff_eval(c, xq[0], xq[1], xq[2], A);
+          if (table)
+            memcpy(A, table + ((((size_t)iz * n + iy) * n + ix) * 8 + (size_t)q) * 9, sizeof A);
+          else
+            orc3_coeff_eval(c, xq[0], xq[1], xq[2], A);
           for (int i = 0; i < 8; ++i)
             {
               double t[3];
@@ -1051,13 +1056,13 @@ orc3_assemble(int l, const double corners[24], const orc_coeff *c, double rhs_va
   uint32_t *dof = (uint32_t *)malloc(sizeof(uint32_t) * np * np * np);
   orc3_dof_map(l, dof);
   const uint64_t nnz = build_sparsity3(l, dof, rowptr, col);
-  assemble3(l, corners, c, rhs_value, dof, rowptr, col, val, F);
+  assemble3(l, corners, c, NULL, rhs_value, dof, rowptr, col, val, F);
   free(dof);
   return nnz;
 }
 
 static int
-run_cell3(int l, const double corners[24], const orc_coeff *c, double rhs_value, double tol,
+run_cell3(int l, const double corners[24], const orc_coeff *c, const double *table, double rhs_value, double tol,
           int max_iter, int precond, double omega, double *phi_out, double *M, double *b, int32_t *iters,
           double *res)
 {
@@ -1085,7 +1090,7 @@ run_cell3(int l, const double corners[24], const orc_coeff *c, double rhs_value,
         ++k;
       rod[r] = k;
     }
-  assemble3(l, corners, c, rhs_value, dof, rowptr, col, K, F);
+  assemble3(l, corners, c, table, rhs_value, dof, rowptr, col, K, F);
   orc3_basis_q1_coeffs(corners, coef);
   for (uint32_t jz = 0; jz < np; ++jz)
     for (uint32_t jy = 0; jy < np; ++jy)
@@ -1145,6 +1150,15 @@ orc3_run_cells(int l, int n_cells, const double *corners, const orc_coeff *c, do
                double tol, int max_iter, int precond, double omega, int n_threads, double *phi, double *M,
                double *b, int32_t *iters, double *res)
 {
+  return orc3_run_cells_table(l, n_cells, corners, c, NULL, rhs_value, tol, max_iter, precond, omega, n_threads,
+                              phi, M, b, iters, res);
+}
+
+int
+orc3_run_cells_table(int l, int n_cells, const double *corners, const orc_coeff *c, const double *table,
+                     double rhs_value, double tol, int max_iter, int precond, double omega, int n_threads,
+                     double *phi, double *M, double *b, int32_t *iters, double *res)
+{
   const size_t n = (size_t)1 << l, N = (n + 1) * (n + 1) * (n + 1);
   int          failed = 0;
   if (n_threads < 1)
@@ -1152,7 +1166,8 @@ orc3_run_cells(int l, int n_cells, const double *corners, const orc_coeff *c, do
 #pragma omp parallel for num_threads(n_threads) schedule(static) reduction(+ : failed)
   for (int k = 0; k < n_cells; ++k)
     {
-      const int f = run_cell3(l, corners + 24 * (size_t)k, c, rhs_value, tol, max_iter, precond, omega,
+      const int f = run_cell3(l, corners + 24 * (size_t)k, c, table ? table + (size_t)k * n * n * n * 72 : NULL,
+                              rhs_value, tol, max_iter, precond, omega,
                               phi ? phi + (size_t)k * 8 * N : NULL, M + 64 * (size_t)k, b + 8 * (size_t)k,
                               iters + 8 * (size_t)k, res + 8 * (size_t)k);
       failed += (f != 0);

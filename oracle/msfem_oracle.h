@@ -118,6 +118,10 @@ uint64_t orc3_assemble(int l, const double corners[24], const orc_coeff *c, doub
 int orc3_run_cells(int l, int n_cells, const double *corners, const orc_coeff *c, double rhs_value,
                    double tol, int max_iter, int precond, double omega, int n_threads, double *phi,
                    double *M, double *b, int32_t *iters, double *res);
+/* Same with tabulated tensors: table [n_cells][n^3 fine cells, (iz n + iy) n + ix][8 q-points, x fastest][9] or NULL */
+int orc3_run_cells_table(int l, int n_cells, const double *corners, const orc_coeff *c, const double *table,
+                         double rhs_value, double tol, int max_iter, int precond, double omega, int n_threads,
+                         double *phi, double *M, double *b, int32_t *iters, double *res);
 
 #ifdef __cplusplus
 }

@@ -222,8 +222,9 @@ def assemble3(l, corners, c, rhs_value=2.0):
 
 
 def run_cells3(l, corners, c, rhs_value=2.0, tol=1e-12, max_iter=1000, precond=PRECOND_SSOR,
-               omega=1.6, n_threads=1, keep_phi=True):
-    """DiffusionProblemBasis<3>::run() over the given coarse hexes.  corners: [C,8,3]."""
+               omega=1.6, n_threads=1, keep_phi=True, table=None):
+    """DiffusionProblemBasis<3>::run() over the given coarse hexes.  corners: [C,8,3]; table: tabulated tensors
+    [C][n^3][8][9] (a user TensorFunction<2,3>::value_list at the fine quadrature points) or None."""
     corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(-1, 8, 3)
     nc = corners.shape[0]
     N = n_dofs3(l)
@@ -232,8 +233,10 @@ def run_cells3(l, corners, c, rhs_value=2.0, tol=1e-12, max_iter=1000, precond=P
     b = np.empty((nc, 8), dtype=np.float64)
     iters = np.empty((nc, 8), dtype=np.int32)
     res = np.empty((nc, 8), dtype=np.float64)
-    failed = lib().orc3_run_cells(
-        C.c_int(l), C.c_int(nc), _p(corners, C.c_double), C.byref(c), C.c_double(rhs_value),
+    tab = None if table is None else np.ascontiguousarray(table, dtype=np.float64)
+    failed = lib().orc3_run_cells_table(
+        C.c_int(l), C.c_int(nc), _p(corners, C.c_double), C.byref(c),
+        None if tab is None else _p(tab, C.c_double), C.c_double(rhs_value),
         C.c_double(tol), C.c_int(max_iter), C.c_int(precond), C.c_double(omega), C.c_int(n_threads),
         None if phi is None else _p(phi, C.c_double), _p(M, C.c_double), _p(b, C.c_double),
         _p(iters, C.c_int32), _p(res, C.c_double))

@@ -96,3 +96,19 @@ def test_coarse_mesh_helpers(msb):
         ranges = [msb.morton_partition(64, r, world) for r in range(world)]
         assert ranges[0][0] == 0 and ranges[-1][1] == 64
         assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+
+
+def test_dealii_branch_of_the_host_mirror_compiles():
+    """MSFEM_WITH_DEALII: the mirror's constructor with the reference's exact signature
+    (diffusion_problem_basis.hpp:79-83) and the reference's construction loop (ms.tpp:54-66) written against it,
+    compiled against API-compatible stubs of the deal.II headers (tests/fake_dealii; deal.II itself is absent)."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    p = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-DMSFEM_WITH_DEALII",
+                        "-I" + os.path.join(ROOT, "tests", "fake_dealii"), "-I" + os.path.join(ROOT, "host", "include"),
+                        "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "fake_dealii", "check_reference_ctor.cxx")],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-3000:]

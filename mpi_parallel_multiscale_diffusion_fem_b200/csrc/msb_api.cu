@@ -164,7 +164,7 @@ free_shard(Shard &s)
   void *ptrs[] = {s.d_corners, s.d_q1coef, s.d_table, s.d_sten, s.d_phi,  s.d_M,    s.d_b,
                   s.d_iters,   s.d_res,    s.d_fail,  s.d_dofmap, s.d_invmap, s.d_gsol, s.d_tmp,
                   s.d_wr,      s.d_wp,     s.d_wq,    s.d_scal, s.d_part, s.d_flags,
-                  s.d_wz,      s.d_wv,     s.d_dinv,  s.d_gal,  s.d_w,    s.d_stage[0], s.d_stage[1]};
+                  s.d_wz,      s.d_wv,     s.d_dinv,  s.d_gal,  s.d_w,    s.d_stage[0], s.d_stage[1], s.d_wr2};
   for (void *p : ptrs)
     if (p)
       cudaFree(p);
@@ -308,7 +308,9 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
           ALLOC(s.d_wz, C * NB * N);
           ALLOC(s.d_wv, C * NB * cn);
           ALLOC(s.d_scal, NB * C);
-          ALLOC(s.d_part, NB * C * (size_t)(s.dim == 2 ? 2 * 3 * 32 : dim3_part_stride()));
+          ALLOC(s.d_part, NB * C * (size_t)(s.dim == 2 ? 2 * 4 * 64 : dim3_part_stride()));
+          if (s.dim == 2)
+            ALLOC(s.d_wr2, C * NB * N);
         }
       ALLOC(s.d_dinv, C * cn);
       if (s.dim == 2)

@@ -69,6 +69,7 @@ namespace msb
     cudaStream_t  stage_stream[2] = {nullptr, nullptr};
     // streamed tier work vectors [C][4][N] each
     double       *d_wr = nullptr, *d_wp = nullptr, *d_wq = nullptr, *d_wz = nullptr;
+    double       *d_wr2 = nullptr;    // 2D streamed tier: second residual buffer (fused iteration kernels)
     double       *d_wv = nullptr;     // streamed tier coarse-level vectors [C][4][cn]
     double       *d_dinv = nullptr;   // streamed tier reciprocal Galerkin diagonals [C][cn]
     double       *d_gal = nullptr;    // streamed tier Galerkin scratch (two coarse stencil buffers)

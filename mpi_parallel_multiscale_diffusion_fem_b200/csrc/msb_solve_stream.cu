@@ -32,8 +32,8 @@
 namespace msb
 {
   constexpr int STREAM_THREADS = 256;
-  constexpr int STREAM_MAXBLK  = 32;                    // max CTAs per coarse cell (fine kernels)
-  constexpr int PART_STRIDE    = 2 * 3 * STREAM_MAXBLK; // doubles per solve: [parity][rz|pq|rr][blk]
+  constexpr int STREAM_MAXBLK  = 64;                    // max CTAs per coarse cell (fine kernels)
+  constexpr int PART_STRIDE    = 2 * 4 * STREAM_MAXBLK; // doubles per solve: [parity][rz|pq|rr|rz coarse part][blk]
   constexpr int MAX_LEVELS     = 10;
 
   struct LevelInfo
@@ -47,9 +47,14 @@ namespace msb
   struct StreamParams
   {
     int           n, nblk, rows; // fine kernels: rows of nodes per CTA
+    int           tr, tc, ntx;   // fused kernels (stream_ka / kb / p1): tiles of tr x tc interior nodes, ntx per row
     const double *corners, *q1coef, *sten;
     double       *x;             // phi buffer [C][4][N]
     double       *r, *p, *q, *z; // [C][4][N]
+    // fused kernels: r and p are double buffered (a CTA re-reads the halo of its tile from the OLD vector
+    // while the owner of those nodes writes the NEW one)
+    const double *r_in, *p_in;
+    double       *r_out, *p_out;
     double       *v;             // [C][4][cn] coarse residuals / corrections
     const double *dinv;          // [C][cn] reciprocal Galerkin diagonals
     double       *part;          // [C][4][PART_STRIDE]
@@ -64,7 +69,7 @@ namespace msb
   __device__ __forceinline__ double *
   part_ptr(double *part, int sidx, int parity, int which)
   {
-    return part + (size_t)sidx * PART_STRIDE + (parity * 3 + which) * STREAM_MAXBLK;
+    return part + (size_t)sidx * PART_STRIDE + (parity * 4 + which) * STREAM_MAXBLK;
   }
 
   // deterministic sum of the nblk (<= 32) partials of one quantity by ONE WARP: a fixed
@@ -74,6 +79,8 @@ namespace msb
   {
     const int lane = threadIdx.x & 31;
     double    v    = lane < nblk ? part[lane] : 0.0;
+    if (lane + 32 < nblk)
+      v += part[lane + 32];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1)
       v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -605,6 +612,392 @@ namespace msb
       }
   }
 
+  // ================================================================================================
+  // The fused iteration (default): 12.6 vector passes per iteration instead of 15.8, 6 launches instead of 9.
+  //   KA   p = (r / D + P z_1) + beta p and q = K p in ONE kernel: the preconditioned residual z is never
+  //        stored -- a CTA rebuilds p_new on its tile plus a one-node halo in shared memory and applies the
+  //        stencil from there (reads r, p, the five coefficient arrays, level 1; writes p, q);
+  //   KB   x += alpha p, r -= alpha q, |r|^2, sum r^2 / d, and the restriction of the NEW residual to level 1
+  //        from a shared-memory tile with a halo of one row / column (reads p, q, r, x; writes x, r, r_1);
+  //   P1   the prolongation to level 1 also accumulates u_1 . z_1, so that
+  //        r . z = sum r^2 / d + u_1 . z_1   (z = r / D + P z_1, u_1 = P^T r)
+  //        is known without a pass over the fine vectors.
+  // Tiles: tr x tc interior nodes starting at odd coordinates, so the 3x3 restriction windows of the coarse
+  // nodes whose centre lies in a tile need only the row above and the column to the right of it.
+  // ================================================================================================
+  struct TileGeom
+  {
+    int x0, x1, y0, y1; // own interior nodes [x0, x1) x [y0, y1)
+  };
+  __device__ __forceinline__ TileGeom
+  tile_of(const StreamParams &P, int blk)
+  {
+    TileGeom g;
+    const int tx = blk % P.ntx, ty = blk / P.ntx;
+    g.x0 = 1 + P.tc * tx, g.x1 = min(P.n, g.x0 + P.tc);
+    g.y0 = 1 + P.tr * ty, g.y1 = min(P.n, g.y0 + P.tr);
+    return g;
+  }
+
+  // per-basis scalars of iteration P.it from the partial sums: done flags, rho = r.z of the previous
+  // iteration (both parts), beta, alpha.  Warp k evaluates basis k; one block barrier.
+  struct IterScalars
+  {
+    int    done[4];
+    double rho[4], beta[4], alpha[4];
+  };
+  __device__ __forceinline__ bool
+  iter_scalars(const StreamParams &P, int cell, bool need_alpha, IterScalars *S /*shared*/)
+  {
+    const int par = (P.it - 1) & 1, warp = threadIdx.x >> 5;
+    if (warp < 4)
+      {
+        const int    sidx = cell * 4 + warp;
+        const double rr   = warp_sum_part(part_ptr(P.part, sidx, par, 2), P.nblk);
+        const double rz   = warp_sum_part(part_ptr(P.part, sidx, par, 0), P.nblk) +
+                          warp_sum_part(part_ptr(P.part, sidx, par, 3), P.nblk);
+        double pq = 1.0;
+        if (need_alpha)
+          pq = warp_sum_part(part_ptr(P.part, sidx, P.it & 1, 1), P.nblk);
+        if ((threadIdx.x & 31) == 0)
+          {
+            const int dn   = (P.iters[sidx] >= 0) || (rr <= P.tol2);
+            S->done[warp]  = dn;
+            S->rho[warp]   = rz;
+            S->beta[warp]  = P.it <= 1 ? 0.0 : rz / P.rzprev[sidx];
+            S->alpha[warp] = (dn || !need_alpha) ? 0.0 : rz / pq;
+            if (!need_alpha && blockIdx.x == 0 && dn && P.iters[sidx] < 0)
+              {
+                P.iters[sidx] = P.it - 1;
+                P.res[sidx]   = sqrt(rr);
+              }
+          }
+      }
+    __syncthreads();
+    return S->done[0] && S->done[1] && S->done[2] && S->done[3];
+  }
+
+  // TC_, TR_ > 0: the tile dimensions as compile-time constants (the index arithmetic of the loops below
+  // divides by the tile width); 0: run-time P.tc, P.tr
+  template <int TC_, int TR_>
+  __global__ void __launch_bounds__(STREAM_THREADS)
+  stream_ka_kernel(StreamParams P)
+  {
+    extern __shared__ double sp[]; // [4][H][W]: p_new on the tile + halo, then [4][CH][CW]: level-1 z_1 around the tile
+    __shared__ IterScalars   S;
+    __shared__ double        sbuf[8 * 4];
+    const int n = P.n, np = n + 1, N = np * np, cell = blockIdx.y, blk = blockIdx.x;
+    if (iter_scalars(P, cell, false, &S))
+      return;
+    const TileGeom g  = tile_of(P, blk);
+    const int      tc = TC_ > 0 ? TC_ : P.tc, tr = TR_ > 0 ? TR_ : P.tr;
+    const int      W = tc + 2, H = tr + 2, WH = W * H;
+    const double  *St = P.sten + (size_t)cell * ST_NARR * N;
+    const int      np1 = P.L.levels >= 1 ? P.L.npl[1] : 0;
+    // ---- phase 0: the level-1 correction z_1 on the coarse nodes around the tile, once per CTA (coalesced),
+    //      instead of four scattered loads per fine node and basis
+    const int cx0 = (g.x0 - 1) >> 1, cy0 = (g.y0 - 1) >> 1;
+    const int CW = (tc >> 1) + 2, CH = (tr >> 1) + 2, CWH = CW * CH;
+    double   *sc = sp + 4 * WH;
+    if (np1 > 0)
+      for (int idx = threadIdx.x; idx < 4 * CWH; idx += STREAM_THREADS)
+        {
+          const int k = idx / CWH, u = idx - k * CWH, cx = cx0 + u % CW, cy = cy0 + u / CW;
+          sc[idx] = (cx < np1 && cy < np1) ? P.v[((size_t)cell * 4 + k) * P.L.cn + P.L.off[1] + cy * np1 + cx] : 0.0;
+        }
+    __syncthreads();
+    // ---- phase 1: p_new on rows y0-1 .. y1, columns x0-1 .. x1.  U nodes per thread and pass: every global
+    //      load of the pass is issued before the first use (bytes in flight are what a streaming kernel lives on)
+    const double *__restrict__ r_in = P.r_in;
+    const double *__restrict__ p_in = P.p_in;
+    double *__restrict__       p_out = P.p_out;
+    constexpr int U = 3;
+    for (int base = 0; base < WH; base += U * STREAM_THREADS)
+      {
+        double rv[U][4], pv[U][4], kcv[U];
+        int    tt[U];
+        bool   in[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          {
+            const int idx = base + u * STREAM_THREADS + threadIdx.x;
+            const int lx = idx % W, ly = idx / W, x = g.x0 - 1 + lx, y = g.y0 - 1 + ly;
+            in[u] = idx < WH && x >= 1 && y >= 1 && x <= n - 1 && y <= n - 1 && x <= g.x1 && y <= g.y1;
+            tt[u] = in[u] ? y * np + x : np + 1; // (any valid interior node: loads stay unconditional)
+            kcv[u] = St[ST_KC * N + tt[u]];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              {
+                const size_t o = ((size_t)cell * 4 + k) * N + tt[u];
+                rv[u][k] = r_in[o], pv[u][k] = p_in[o];
+              }
+          }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          {
+            const int idx = base + u * STREAM_THREADS + threadIdx.x;
+            if (idx >= WH)
+              continue;
+            double pn[4] = {0, 0, 0, 0};
+            if (in[u])
+              {
+                const int    x = tt[u] % np, y = tt[u] / np;
+                const bool   own = x >= g.x0 && x < g.x1 && y >= g.y0 && y < g.y1;
+                const double dinv = 1.0 / kcv[u];
+                const int    xl = (x >> 1) - cx0, xh = ((x + 1) >> 1) - cx0, yl = (y >> 1) - cy0, yh = ((y + 1) >> 1) - cy0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  {
+                    const double *v1 = sc + k * CWH;
+                    const double  cv = np1 == 0 ? 0.0 :
+                                                  0.25 * ((v1[yl * CW + xl] + v1[yl * CW + xh]) + (v1[yh * CW + xl] + v1[yh * CW + xh]));
+                    pn[k] = S.done[k] ? pv[u][k] : fma(S.beta[k], pv[u][k], fma(rv[u][k], dinv, cv));
+                    if (own && !S.done[k])
+                      p_out[((size_t)cell * 4 + k) * N + tt[u]] = pn[k];
+                  }
+              }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              sp[k * WH + idx] = pn[k];
+          }
+      }
+    __syncthreads();
+    // ---- phase 2: q = K p_new on the own nodes, partial p.q
+    double    acc[4] = {0, 0, 0, 0};
+    const int tw = g.x1 - g.x0, th = g.y1 - g.y0;
+    double *__restrict__ qo = P.q;
+    constexpr int U2 = 2;
+    for (int base = 0; base < tw * th; base += U2 * STREAM_THREADS)
+      {
+        double kf[U2][9];
+        int    tt[U2], cc[U2];
+        bool   ok[U2];
+#pragma unroll
+        for (int u = 0; u < U2; ++u)
+          {
+            const int idx = base + u * STREAM_THREADS + threadIdx.x;
+            ok[u]         = idx < tw * th;
+            const int lx = ok[u] ? idx % tw : 0, ly = ok[u] ? idx / tw : 0, t = (g.y0 + ly) * np + g.x0 + lx;
+            tt[u] = t, cc[u] = (ly + 1) * W + lx + 1;
+            kf[u][0] = St[ST_KC * N + t], kf[u][1] = St[ST_KE * N + t], kf[u][2] = St[ST_KE * N + t - 1];
+            kf[u][3] = St[ST_KN * N + t], kf[u][4] = St[ST_KN * N + t - np];
+            kf[u][5] = St[ST_KD1 * N + t], kf[u][6] = St[ST_KD1 * N + t - np - 1];
+            kf[u][7] = St[ST_KD2 * N + t - 1], kf[u][8] = St[ST_KD2 * N + t - np];
+          }
+#pragma unroll
+        for (int u = 0; u < U2; ++u)
+          {
+            if (!ok[u])
+              continue;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              {
+                if (S.done[k])
+                  continue;
+                const double *p = sp + k * WH + cc[u];
+                double        yv = kf[u][0] * p[0];
+                yv = fma(kf[u][1], p[1], yv);
+                yv = fma(kf[u][2], p[-1], yv);
+                yv = fma(kf[u][3], p[W], yv);
+                yv = fma(kf[u][4], p[-W], yv);
+                yv = fma(kf[u][5], p[W + 1], yv);
+                yv = fma(kf[u][6], p[-W - 1], yv);
+                yv = fma(kf[u][7], p[W - 1], yv);
+                yv = fma(kf[u][8], p[-W + 1], yv);
+                qo[((size_t)cell * 4 + k) * N + tt[u]] = yv;
+                acc[k] = fma(p[0], yv, acc[k]);
+              }
+          }
+      }
+    block_sum_to<4>(acc, sbuf);
+    if (threadIdx.x == 0)
+      {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (!S.done[k])
+            part_ptr(P.part, cell * 4 + k, P.it & 1, 1)[blk] = acc[k];
+      }
+  }
+
+  // P.it == 0: initialisation pass (no update: alpha = 0, q is not read)
+  template <int TC_, int TR_>
+  __global__ void __launch_bounds__(STREAM_THREADS)
+  stream_kb_kernel(StreamParams P)
+  {
+    extern __shared__ double sr[]; // [4][tr+1][tc+1]: the new residual on the tile + upper / right halo
+    __shared__ IterScalars   S;
+    __shared__ double        sbuf[8 * 8];
+    const int n = P.n, np = n + 1, N = np * np, cell = blockIdx.y, blk = blockIdx.x;
+    if (P.it == 0)
+      {
+        if (threadIdx.x < 4)
+          S.done[threadIdx.x] = 0, S.alpha[threadIdx.x] = 0.0, S.rho[threadIdx.x] = 0.0;
+        __syncthreads();
+      }
+    else if (iter_scalars(P, cell, true, &S))
+      return;
+    const TileGeom g  = tile_of(P, blk);
+    const int      W = (TC_ > 0 ? TC_ : P.tc) + 1, H = (TR_ > 0 ? TR_ : P.tr) + 1, WH = W * H;
+    const double  *KC = P.sten + (size_t)cell * ST_NARR * N + ST_KC * N;
+    double         acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // |r|^2 [4], sum r^2 / d [4]
+    const double *__restrict__ r_in = P.r_in;
+    const double *__restrict__ p_in = P.p_in;
+    const double *__restrict__ q_in = P.q;
+    double *__restrict__       r_out = P.r_out;
+    double *__restrict__       x_io  = P.x;
+    constexpr int U = 2;
+    for (int base = 0; base < WH; base += U * STREAM_THREADS)
+      {
+        double rv[U][4], qv[U][4], pv[U][4], xv[U][4], kcv[U];
+        int    tt[U];
+        bool   in[U], own[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          {
+            const int idx = base + u * STREAM_THREADS + threadIdx.x;
+            const int lx = idx % W, ly = idx / W, x = g.x0 + lx, y = g.y0 + ly;
+            in[u]  = idx < WH && x <= n - 1 && y <= n - 1 && x <= g.x1 && y <= g.y1;
+            own[u] = in[u] && x < g.x1 && y < g.y1;
+            tt[u]  = in[u] ? y * np + x : np + 1;
+            kcv[u] = KC[tt[u]];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              {
+                const size_t o = ((size_t)cell * 4 + k) * N + tt[u];
+                rv[u][k] = r_in[o];
+                qv[u][k] = P.it > 0 ? q_in[o] : 0.0;
+                pv[u][k] = (P.it > 0 && own[u]) ? p_in[o] : 0.0;
+                xv[u][k] = (P.it > 0 && own[u]) ? x_io[o] : 0.0;
+              }
+          }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          {
+            const int idx = base + u * STREAM_THREADS + threadIdx.x;
+            if (idx >= WH)
+              continue;
+            double rn[4] = {0, 0, 0, 0};
+            if (in[u])
+              {
+                const double dinv = own[u] ? 1.0 / kcv[u] : 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  {
+                    const double a = S.alpha[k];
+                    rn[k]          = (S.done[k] || P.it == 0) ? rv[u][k] : fma(-a, qv[u][k], rv[u][k]);
+                    if (own[u] && !S.done[k])
+                      {
+                        const size_t o = ((size_t)cell * 4 + k) * N + tt[u];
+                        if (P.it > 0)
+                          {
+                            x_io[o]  = fma(a, pv[u][k], xv[u][k]);
+                            r_out[o] = rn[k];
+                          }
+                        acc[k]     = fma(rn[k], rn[k], acc[k]);
+                        acc[4 + k] = fma(rn[k] * rn[k], dinv, acc[4 + k]);
+                      }
+                  }
+              }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              sr[k * WH + idx] = rn[k];
+          }
+      }
+    __syncthreads();
+    // restriction to level 1: the coarse nodes whose centre (2cx, 2cy) is an own node of this tile
+    if (P.L.levels >= 1)
+      {
+        const int np1 = P.L.npl[1];
+        const int cx_lo = (g.x0 + 1) >> 1, cx_hi = (g.x1 - 1) >> 1, cy_lo = (g.y0 + 1) >> 1, cy_hi = (g.y1 - 1) >> 1;
+        const int cw = cx_hi - cx_lo + 1, ch = cy_hi - cy_lo + 1;
+        for (int idx = threadIdx.x; idx < cw * ch; idx += STREAM_THREADS)
+          {
+            const int cx = cx_lo + idx % cw, cy = cy_lo + idx / cw;
+            const int c  = (2 * cy - g.y0) * W + 2 * cx - g.x0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              {
+                if (S.done[k])
+                  continue;
+                const double *s = sr + k * WH + c;
+                const double  lo = fma(0.5, s[-W - 1] + s[-W + 1], s[-W]);
+                const double  mi = fma(0.5, s[-1] + s[1], s[0]);
+                const double  hi = fma(0.5, s[W - 1] + s[W + 1], s[W]);
+                P.v[((size_t)cell * 4 + k) * P.L.cn + P.L.off[1] + cy * np1 + cx] = fma(0.5, lo + hi, mi);
+              }
+          }
+      }
+    block_sum_to<8>(acc, sbuf);
+    if (threadIdx.x == 0)
+      {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (!S.done[k])
+            {
+              const int sidx = cell * 4 + k;
+              part_ptr(P.part, sidx, P.it & 1, 2)[blk] = acc[k];
+              part_ptr(P.part, sidx, P.it & 1, 0)[blk] = acc[4 + k];
+              // r.z of the iteration just consumed becomes "previous" for the next beta
+              if (blk == 0 && P.it > 0)
+                P.rzprev[sidx] = S.rho[k];
+            }
+      }
+  }
+
+  // prolongation to level 1, z_1 = r_1 / D_1 + P z_2 in place, tiled like the fine kernels; the partial
+  // u_1 . z_1 (coarse part of r.z) goes to slot 3 of parity rpar
+  __global__ void __launch_bounds__(STREAM_THREADS)
+  stream_p1_kernel(StreamParams P, int rpar)
+  {
+    const int cell = blockIdx.y, blk = blockIdx.x;
+    __shared__ int    sdone[4];
+    __shared__ double sbuf[8 * 4];
+    if (cell_done(P, cell, rpar, sdone))
+      return;
+    // (gridDim.x <= P.nblk CTAs per cell: CTA blk sweeps the level-1 nodes of the fine tiles blk, blk + gridDim.x, ...
+    //  -- a level-1 tile alone is too little work for a CTA -- and owns partial-sum slot blk; the slots beyond
+    //  gridDim.x stay zero)
+    const int np1 = P.L.npl[1];
+    double    acc[4] = {0, 0, 0, 0};
+    for (int tile = blk; tile < P.nblk; tile += gridDim.x)
+    {
+    const TileGeom g  = tile_of(P, tile);
+    const int      cx_lo = (g.x0 + 1) >> 1, cx_hi = (g.x1 - 1) >> 1, cy_lo = (g.y0 + 1) >> 1, cy_hi = (g.y1 - 1) >> 1;
+    const int      cw = cx_hi - cx_lo + 1, ch = cy_hi - cy_lo + 1;
+    for (int idx = threadIdx.x; idx < cw * ch; idx += STREAM_THREADS)
+      {
+        const int    fx = cx_lo + idx % cw, fy = cy_lo + idx / cw, i = fy * np1 + fx;
+        const double di = P.dinv[(size_t)cell * P.L.cn + P.L.off[1] + i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          {
+            if (sdone[k])
+              continue;
+            double      *vl = P.v + ((size_t)cell * 4 + k) * P.L.cn + P.L.off[1];
+            const double u  = vl[i];
+            double       v  = u * di;
+            if (P.L.levels > 1)
+              {
+                const int     npc = P.L.npl[2];
+                const double *vc  = P.v + ((size_t)cell * 4 + k) * P.L.cn + P.L.off[2];
+                const int     xl = fx >> 1, xh = (fx + 1) >> 1, yl = fy >> 1, yh = (fy + 1) >> 1;
+                v += 0.25 * ((vc[yl * npc + xl] + vc[yl * npc + xh]) + (vc[yh * npc + xl] + vc[yh * npc + xh]));
+              }
+            vl[i]  = v;
+            acc[k] = fma(u, v, acc[k]);
+          }
+      }
+    }
+    block_sum_to<4>(acc, sbuf);
+    if (threadIdx.x == 0)
+      {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (!sdone[k])
+            part_ptr(P.part, cell * 4 + k, rpar, 3)[blk] = acc[k];
+      }
+  }
+
   // after the loop (P.it = last executed iteration): record every solve not yet recorded
   // (one warp per solve)
   __global__ void
@@ -687,6 +1080,9 @@ namespace msb
     Q.corners += 8 * (size_t)c0, Q.q1coef += 16 * (size_t)c0, Q.sten += (size_t)c0 * ST_NARR * s.N;
     Q.x += (size_t)c0 * 4 * s.N, Q.r += (size_t)c0 * 4 * s.N, Q.p += (size_t)c0 * 4 * s.N;
     Q.q += (size_t)c0 * 4 * s.N, Q.z += (size_t)c0 * 4 * s.N, Q.v += (size_t)c0 * 4 * P.L.cn;
+    if (Q.r_in)
+      Q.r_in += (size_t)c0 * 4 * s.N, Q.r_out += (size_t)c0 * 4 * s.N, Q.p_in += (size_t)c0 * 4 * s.N,
+        Q.p_out += (size_t)c0 * 4 * s.N;
     Q.dinv += (size_t)c0 * P.L.cn, Q.part += (size_t)c0 * 4 * PART_STRIDE;
     Q.rzprev += 4 * (size_t)c0, Q.iters += 4 * (size_t)c0, Q.res += 4 * (size_t)c0;
     return Q;
@@ -711,6 +1107,8 @@ namespace msb
     P.p       = s.d_wp;
     P.q       = s.d_wq;
     P.z       = s.d_wz;
+    P.r_in = P.p_in = nullptr, P.r_out = P.p_out = nullptr;
+    P.tr = P.tc = P.ntx = 0;
     P.v       = s.d_wv;
     P.dinv    = s.d_dinv;
     P.part    = s.d_part;
@@ -818,6 +1216,103 @@ namespace msb
         stream_fine_kernel<<<dim3(P.nblk, nc), STREAM_THREADS, 0, st>>>(Q, rpar);
       });
     };
+
+    // ---- the fused iteration (default; variants 1 and 5 keep the round-1 kernel sequence for comparison)
+    const bool fused_iteration = s.variant != 1 && s.variant != 5 && s.d_wr2 != nullptr;
+    if (fused_iteration)
+      {
+        const int nint = s.n - 1;
+        P.tc  = nint < 128 ? (nint < 1 ? 1 : nint) : 128;
+        P.tr  = nint < 8 ? (nint < 1 ? 1 : nint) : 8;
+        P.ntx = (nint + P.tc - 1) / P.tc;
+        while (P.ntx * ((nint + P.tr - 1) / P.tr) > STREAM_MAXBLK)
+          P.tr *= 2;
+        P.nblk = P.ntx * ((nint + P.tr - 1) / P.tr);
+        P.rows = (s.np + P.nblk - 1) / P.nblk; // (the initialisation kernel covers the mesh with the same CTA count)
+        const size_t smem_a = sizeof(double) * 4 * ((size_t)(P.tc + 2) * (P.tr + 2) + (size_t)(P.tc / 2 + 2) * (P.tr / 2 + 2));
+        const size_t smem_b = sizeof(double) * 4 * (size_t)(P.tc + 1) * (P.tr + 1);
+        const bool   std_tile = P.tc == 128 && P.tr == 8;
+        auto         ka = std_tile ? stream_ka_kernel<128, 8> : stream_ka_kernel<0, 0>;
+        auto         kb = std_tile ? stream_kb_kernel<128, 8> : stream_kb_kernel<0, 0>;
+        TRY(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+        TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        const int p1_blocks = P.nblk < 8 ? P.nblk : 8;
+        // levels >= lf run fused in shared memory; level 1 belongs to KB (restriction) and P1 (prolongation)
+        const int lf = l0 < 2 ? 2 : l0;
+        const size_t lf_smem = lf <= L.levels ? sizeof(double) * 4 * (size_t)(L.off[L.levels + 1] - L.off[lf]) : 0;
+        if (lf_smem)
+          TRY(cudaFuncSetAttribute(stream_coarse_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lf_smem));
+        auto coarse_part = [&](int rpar) {
+          for (int l = 2; l < lf && l <= L.levels; ++l)
+            {
+              const int nin = L.npl[l] - 2;
+              for_slices([&](const StreamParams &Q, int nc) {
+                stream_restrict_kernel<<<dim3((nin * nin + STREAM_THREADS - 1) / STREAM_THREADS, nc),
+                                         STREAM_THREADS, 0, st>>>(Q, l, rpar);
+              });
+            }
+          if (lf_smem)
+            for_slices([&](const StreamParams &Q, int nc) {
+              stream_coarse_fused_kernel<<<nc, STREAM_THREADS, lf_smem, st>>>(Q, lf, rpar);
+            });
+          for (int l = (lf <= L.levels ? lf - 1 : L.levels); l >= 2; --l)
+            {
+              const int nin = L.npl[l] - 2;
+              for_slices([&](const StreamParams &Q, int nc) {
+                stream_prolong_kernel<<<dim3((nin * nin + STREAM_THREADS - 1) / STREAM_THREADS, nc),
+                                        STREAM_THREADS, 0, st>>>(Q, l, rpar);
+              });
+            }
+          if (L.levels >= 1)
+            for_slices([&](const StreamParams &Q, int nc) {
+              stream_p1_kernel<<<dim3(p1_blocks, nc), STREAM_THREADS, 0, st>>>(Q, rpar);
+            });
+        };
+        double *Ra = s.d_wr, *Rb = s.d_wr2, *Pa = s.d_wp, *Pb = s.d_wz;
+        P.it = 0;
+        for_slices([&](const StreamParams &Q, int nc) {
+          stream_init_kernel<<<dim3(P.nblk, nc), STREAM_THREADS, 0, st>>>(Q); // x = g, r -> Ra, p = 0 -> Pa
+        });
+        P.r_in = Ra, P.r_out = Ra, P.p_in = Pa, P.p_out = Pa;
+        for_slices([&](const StreamParams &Q, int nc) {
+          kb<<<dim3(P.nblk, nc), STREAM_THREADS, smem_b, st>>>(Q); // |r|^2, sum r^2/d, level 1
+        });
+        coarse_part(0);
+        int32_t   h_rem = 1;
+        int       it    = 0;
+        const int check_every = 4;
+        while (it < max_iter)
+          {
+            if (it % check_every == 0)
+              {
+                P.it = it;
+                TRY(cudaMemsetAsync(s.d_flags, 0, sizeof(int32_t), st));
+                stream_count_kernel<<<(n_solves + 7) / 8, 256, 0, st>>>(P, n_solves, s.d_flags);
+                ++*n_launches;
+                TRY(cudaMemcpyAsync(&h_rem, s.d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                TRY(cudaStreamSynchronize(st));
+                if (h_rem == 0)
+                  break;
+              }
+            ++it;
+            P.it = it;
+            // the residual of iteration it-1 is in Ra (it odd) / Rb (it even); p likewise
+            P.r_in = (it & 1) ? Ra : Rb, P.r_out = (it & 1) ? Rb : Ra;
+            P.p_in = (it & 1) ? Pa : Pb, P.p_out = (it & 1) ? Pb : Pa;
+            for_slices([&](const StreamParams &Q, int nc) {
+              ka<<<dim3(P.nblk, nc), STREAM_THREADS, smem_a, st>>>(Q);
+            });
+            P.p_in = P.p_out; // KB reads the direction KA has just written
+            for_slices([&](const StreamParams &Q, int nc) {
+              kb<<<dim3(P.nblk, nc), STREAM_THREADS, smem_b, st>>>(Q);
+            });
+            coarse_part(it & 1);
+          }
+        P.it = it;
+        stream_finalize_kernel<<<(n_solves + 7) / 8, 256, 0, st>>>(P, n_solves, s.d_fail);
+        ++*n_launches;
+        return cudaGetLastError();
+      }
 
     for_slices([&](const StreamParams &Q, int nc) {
       stream_init_kernel<<<dim3(P.nblk, nc), STREAM_THREADS, 0, st>>>(Q);

@@ -308,7 +308,7 @@ msb_create(const msb_config *cfg, const double *corners, const double *coeff_tab
           ALLOC(s.d_wz, C * NB * N);
           ALLOC(s.d_wv, C * NB * cn);
           ALLOC(s.d_scal, NB * C);
-          ALLOC(s.d_part, NB * C * (size_t)(s.dim == 2 ? 2 * 4 * 64 : dim3_part_stride()));
+          ALLOC(s.d_part, NB * C * (size_t)(s.dim == 2 ? 2 * 4 * 128 : dim3_part_stride()));
           if (s.dim == 2)
             ALLOC(s.d_wr2, C * NB * N);
         }

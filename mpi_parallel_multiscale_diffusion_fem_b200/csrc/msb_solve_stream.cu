@@ -32,7 +32,7 @@
 namespace msb
 {
   constexpr int STREAM_THREADS = 256;
-  constexpr int STREAM_MAXBLK  = 64;                    // max CTAs per coarse cell (fine kernels)
+  constexpr int STREAM_MAXBLK  = 128;                   // max CTAs per coarse cell (fine kernels)
   constexpr int PART_STRIDE    = 2 * 4 * STREAM_MAXBLK; // doubles per solve: [parity][rz|pq|rr|rz coarse part][blk]
   constexpr int MAX_LEVELS     = 10;
 
@@ -78,9 +78,9 @@ namespace msb
   warp_sum_part(const double *part, int nblk)
   {
     const int lane = threadIdx.x & 31;
-    double    v    = lane < nblk ? part[lane] : 0.0;
-    if (lane + 32 < nblk)
-      v += part[lane + 32];
+    double    v    = 0.0;
+    for (int i = lane; i < nblk; i += 32) // (fixed order: every CTA of the cell obtains the same bits)
+      v += part[i];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1)
       v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -1222,6 +1222,9 @@ namespace msb
     if (fused_iteration)
       {
         const int nint = s.n - 1;
+        // 128 x 8 interior nodes per CTA: measured on cfg5 (64x64 coarse x 256x256 fine, ms per step):
+        // 128 x 16 (3 CTAs/SM) 1060, 128 x 8 (4 CTAs/SM) 887, 64 x 8 (8 CTAs/SM, twice the per-CTA scalar
+        // prologues and reductions) 1176; the round-1 kernel sequence (variant 5) 924
         P.tc  = nint < 128 ? (nint < 1 ? 1 : nint) : 128;
         P.tr  = nint < 8 ? (nint < 1 ? 1 : nint) : 8;
         P.ntx = (nint + P.tc - 1) / P.tc;

@@ -324,8 +324,14 @@ def measure(cx, name, steps, warmup, variant=0, cells=0, max_iter=5000, e2e=True
 
         def e2e_step(bases):
             sh.set_cells_ptr(h_corners.data_ptr())                 # H2D corners; BasisQ1 data on device
-            sh.run_async(1e-12, max_iter, sptr)
-            sh.sync()
+            if bases:
+                # the stage with the 2^dim solution_vectors of every cell brought to the host, where the reference
+                # keeps them (basis.hpp:216): msb_run_with_bases pipelines the reordering + D2H of chunk k behind
+                # the solves of chunk k+1
+                sh.run_with_bases(1e-12, max_iter, out_addr=h_phi.data_ptr())
+            else:
+                sh.run_async(1e-12, max_iter, sptr)
+                sh.sync()
             if world > 1:
                 # the reference's compress(add) exchange (ms.tpp:253-254): every rank obtains the per-cell
                 # coarse contributions of all ranks over NVLink -- NCCL all_gather straight out of the
@@ -338,10 +344,6 @@ def measure(cx, name, steps, warmup, variant=0, cells=0, max_iter=5000, e2e=True
             else:
                 sh.element_matrices_into(h_M.data_ptr(), h_b.data_ptr())   # D2H
                 sh.iteration_counts_into(h_it.data_ptr())
-            if bases:
-                # the 2^dim solution_vectors of every cell to the host, where the reference keeps them
-                # (basis.hpp:216): one bulk call, chunked reordering + overlapped D2H
-                sh.bases_into(0, n_local, h_phi.data_ptr())
 
         def timed(bases, k):
             e2e_step(bases)
@@ -376,9 +378,10 @@ def measure(cx, name, steps, warmup, variant=0, cells=0, max_iter=5000, e2e=True
                 "value": n_solves / (wb_ms * 1e-3), "unit": UNIT, "ms_per_step": wb_ms, "steps": kb,
                 "h2d_bytes_per_step": int(h_corners.numel() * 8),
                 "d2h_bytes_per_step": d2h + int(h_phi.numel() * 8),
-                "api": "the e2e step + msb_get_bases of every local cell into pinned host memory (deal.II DoF "
-                       "order): what a caller pays who needs the bases host-side like the reference's "
-                       "output_global_fine (ms.tpp:386-393)"}
+                "api": "msb_set_cells + msb_run_with_bases (the stage with the bases of every local cell delivered into "
+                       "pinned host memory in deal.II DoF order, reordering + D2H of chunk k pipelined behind the "
+                       "solves of chunk k+1) + msb_get_element_matrices + msb_get_iteration_counts: what a caller "
+                       "pays who keeps the bases host-side like the reference (basis.hpp:216, ms.tpp:386-393)"}
             # spot check of the bulk copy: partition of unity on the last cell
             pu = float((h_phi[-1].sum(dim=0) - 1.0).abs().max())
             if not pu < 1e-9:

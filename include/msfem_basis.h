@@ -137,6 +137,15 @@ int msb_run(msb_handle h, double tol_abs, int32_t max_iter);
 int msb_run_async(msb_handle h, double tol_abs, int32_t max_iter, void *cuda_stream);
 int msb_sync(msb_handle h);
 
+/* msb_run followed by msb_get_bases of every cell, PIPELINED: the shard is processed in chunks of coarse
+ * cells, and while chunk k+1 is being solved the bases of chunk k are reordered to the deal.II DoF order and
+ * copied to bases_out ([n_cells][2^dim][N]; page-locked memory makes the copy overlap the solves).  For a
+ * caller that keeps the 2^dim solution_vectors host-side like the reference does (basis.hpp:216; all of them are
+ * walked in output_global_fine, ms.tpp:386-393) this hides the PCIe time of the bases (8.9 GB for the
+ * 256x256 x 64x64 problem) behind the stage instead of paying it afterwards.  Synchronous on return; same
+ * return codes as msb_run.  Shards that do not run the fused one-kernel stage take msb_run + msb_get_bases. */
+int msb_run_with_bases(msb_handle h, double tol_abs, int32_t max_iter, double *bases_out);
+
 /* First non-converged solve of the last run (cell = -1 if none). */
 int msb_get_failure(msb_handle h, int32_t *cell, int32_t *index_basis, double *residual);
 

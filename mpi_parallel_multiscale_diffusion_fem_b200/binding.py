@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "msb_get_global_solution", "msb_get_run_stats", "msb_get_algorithmic_bytes", "msb_destroy",
     "msb_last_error", "msb_device_count", "msb_version",
     "msb_get_bases", "msb_get_global_solutions", "msb_get_device_results", "msb_build_id",
+    "msb_run_with_bases",
 ]
 
 
@@ -154,6 +155,16 @@ class BasisShard:
 
     def run_async(self, tol=1e-12, max_iter=1000, stream=None):
         self._check(self._lib.msb_run_async(self._h, tol, max_iter, C.c_void_p(stream or 0)))
+
+    def run_with_bases(self, tol=1e-12, max_iter=1000, out=None, out_addr=None):
+        """msb_run_with_bases: the stage with the device->host copy of the bases pipelined behind the solves."""
+        if out_addr is None:
+            if out is None:
+                out = np.empty((self.n_cells, self.nb, self.N), dtype=np.float64)
+            out_addr = out.ctypes.data
+        self._lib.msb_run_with_bases.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_void_p]
+        self._check(self._lib.msb_run_with_bases(self._h, tol, max_iter, C.c_void_p(out_addr)))
+        return out
 
     def sync(self, allow_no_convergence=False):
         allow = (MSB_ERR_NO_CONVERGENCE,) if allow_no_convergence else ()

@@ -174,6 +174,9 @@ free_shard(Shard &s)
   for (auto &e : s.ev)
     if (e)
       cudaEventDestroy(e);
+  for (auto &e : s.ev_chunk)
+    if (e)
+      cudaEventDestroy(e);
   if (s.stream)
     cudaStreamDestroy(s.stream);
 }
@@ -499,6 +502,91 @@ msb_run(msb_handle h, double tol_abs, int32_t max_iter)
   if (rc != MSB_OK)
     return rc;
   return msb_sync(h);
+}
+
+extern "C" int msb_get_bases(msb_handle h, int32_t cell0, int32_t n_cells, double *out);
+
+// msb_run + msb_get_bases, pipelined over chunks of cells (fused one-kernel stage only): chunk k is reordered
+// and copied device -> host on the staging streams while chunk k+1 is being solved on the library stream.
+extern "C" int
+msb_run_with_bases(msb_handle h, double tol_abs, int32_t max_iter, double *bases_out)
+{
+  if (!h || !bases_out)
+    return fail(MSB_ERR_INVALID_ARG, "msb_run_with_bases: null argument");
+  if (!(tol_abs >= 0.0) || max_iter < 0)
+    return fail(MSB_ERR_INVALID_ARG, "msb_run_with_bases: tol_abs=%g max_iter=%d", tol_abs, max_iter);
+  Shard &s = h->s;
+  if (!s.valid)
+    return fail(MSB_ERR_STATE, "msb_run_with_bases: the last msb_set_cells failed; set valid cells first");
+  if (!fused_eligible(s))
+    {
+      const int rc = msb_run(h, tol_abs, max_iter);
+      if (rc != MSB_OK && rc != MSB_ERR_NO_CONVERGENCE)
+        return rc;
+      const int rc2 = msb_get_bases(h, 0, s.n_cells, bases_out);
+      return rc2 != MSB_OK ? rc2 : rc;
+    }
+  CUDA_TRY(cudaSetDevice(s.device));
+  if (s.run_pending)
+    CUDA_TRY(cudaStreamSynchronize(s.run_stream));
+  // chunks of ~28 waves of CTAs: long enough to hide the launch, short enough that the last copy is small
+  int ndev_sm = 148;
+  cudaDeviceGetAttribute(&ndev_sm, cudaDevAttrMultiProcessorCount, s.device);
+  const int    chunk = 28 * ndev_sm < s.n_cells ? 28 * ndev_sm : s.n_cells;
+  const size_t vecs  = (size_t)chunk * s.nb;
+  if (s.stage_vecs < vecs)
+    {
+      for (int k = 0; k < 2; ++k)
+        {
+          if (s.d_stage[k])
+            CUDA_TRY(cudaFree(s.d_stage[k]));
+          s.d_stage[k] = nullptr;
+          CUDA_TRY(cudaMalloc((void **)&s.d_stage[k], sizeof(double) * vecs * (size_t)s.N));
+          if (!s.stage_stream[k])
+            CUDA_TRY(cudaStreamCreateWithFlags(&s.stage_stream[k], cudaStreamNonBlocking));
+        }
+      s.stage_vecs = vecs;
+    }
+  if (!s.ev_chunk[0])
+    for (auto &e : s.ev_chunk)
+      CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaStream_t st = s.stream;
+  s.run_stream    = st;
+  s.n_launches    = 0;
+  s.ran           = false;
+  s.fused_last    = true;
+  const int32_t init_fail[2] = {INT_MAX, 0};
+  CUDA_TRY(cudaMemcpyAsync(s.d_fail, init_fail, sizeof init_fail, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(s.ev[0], st));
+  CUDA_TRY(cudaEventRecord(s.ev[1], st));
+  int k = 0;
+  for (int c0 = 0; c0 < s.n_cells; c0 += chunk, k ^= 1)
+    {
+      const int nc = s.n_cells - c0 < chunk ? s.n_cells - c0 : chunk;
+      CUDA_TRY(launch_stage_fused_range(s, c0, nc, tol_abs, max_iter, st, &s.n_launches));
+      CUDA_TRY(cudaEventRecord(s.ev_chunk[k], st));
+      // staging buffer k was last used two chunks ago on the same staging stream: stream order protects it
+      CUDA_TRY(cudaStreamWaitEvent(s.stage_stream[k], s.ev_chunk[k], 0));
+      const size_t v0 = (size_t)c0 * s.nb, nv = (size_t)nc * s.nb;
+      CUDA_TRY(launch_permute_batch(s, s.d_phi + v0 * (size_t)s.N, s.d_stage[k], nv, s.stage_stream[k]));
+      CUDA_TRY(cudaMemcpyAsync(bases_out + v0 * (size_t)s.N, s.d_stage[k], sizeof(double) * nv * (size_t)s.N,
+                               cudaMemcpyDeviceToHost, s.stage_stream[k]));
+      // (the event of buffer k is re-recorded two chunks later: the copy that waits on it has been enqueued
+      //  behind the wait, and cudaStreamWaitEvent captured the event's state at the time of the call)
+    }
+  s.tier_used = s.tier;
+  CUDA_TRY(cudaEventRecord(s.ev[2], st));
+  CUDA_TRY(cudaEventRecord(s.ev[3], st));
+  s.run_pending = true;
+  s.weights_set = false;
+  const int rc = msb_sync(h);
+  for (int q = 0; q < 2; ++q)
+    {
+      const cudaError_t e = cudaStreamSynchronize(s.stage_stream[q]);
+      if (e != cudaSuccess)
+        return fail(MSB_ERR_CUDA, "msb_run_with_bases: %s", cudaGetErrorString(e));
+    }
+  return rc;
 }
 
 static int

@@ -16,6 +16,7 @@ namespace msb
     int32_t      *iters;   // [C][4]
     double       *res;     // [C][4]
     int32_t      *fail;
+    int           fail_base; // index of this launch's first solve in the shard (ranges of cells)
     double        tol2;
     int           max_iter;
     int           n_cells;

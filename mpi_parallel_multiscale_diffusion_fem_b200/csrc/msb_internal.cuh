@@ -80,6 +80,7 @@ namespace msb
     cudaStream_t stream = nullptr;    // library-owned stream
     cudaStream_t run_stream = nullptr;
     cudaEvent_t  ev[4]  = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t  ev_chunk[2] = {nullptr, nullptr}; // msb_run_with_bases: "chunk solved" per staging buffer
     bool         assembled = false, ran = false, weights_set = false, run_pending = false;
     bool         valid = true;        // false after a failed msb_set_cells: only set_cells / destroy work
     bool         bricks = false;      // dim 3: every coarse cell is an axis-aligned brick
@@ -131,6 +132,9 @@ namespace msb
   // the fused one-kernel stage (msb_solve_fused.cu): 64 x 64 local meshes, axis-aligned cells,
   // analytic coefficient, default variant
   cudaError_t launch_stage_fused(const Shard &s, double tol, int max_iter, cudaStream_t st, int *n_launches);
+  // the same for the cells [c0, c0 + nc) of the shard only (pipelined msb_run_with_bases)
+  cudaError_t launch_stage_fused_range(const Shard &s, int c0, int nc, double tol, int max_iter, cudaStream_t st,
+                                       int *n_launches);
   size_t      streamed_coarse_nodes(int l);
   size_t      streamed_galerkin_scratch_doubles(int l, int n_cells);
 

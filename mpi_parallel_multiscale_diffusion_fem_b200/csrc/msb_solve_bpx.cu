@@ -612,26 +612,33 @@ namespace msb
           return cudaErrorInvalidValue;
       }
   }
-  // the fused one-kernel stage (msb_solve_fused.cu)
+  // the fused one-kernel stage (msb_solve_fused.cu) for the cells [c0, c0 + nc) of the shard
   cudaError_t
-  launch_stage_fused(const Shard &s, double tol, int max_iter, cudaStream_t st, int *n_launches)
+  launch_stage_fused_range(const Shard &s, int c0, int nc, double tol, int max_iter, cudaStream_t st, int *n_launches)
   {
     FusedParams P;
-    P.corners   = s.d_corners;
-    P.q1coef    = s.d_q1coef;
-    P.phi       = s.d_phi;
-    P.M         = s.d_M;
-    P.b         = s.d_b;
-    P.iters     = s.d_iters;
-    P.res       = s.d_res;
+    P.corners   = s.d_corners + 8 * (size_t)c0;
+    P.q1coef    = s.d_q1coef + 16 * (size_t)c0;
+    P.phi       = s.d_phi + (size_t)c0 * 4 * s.N;
+    P.M         = s.d_M + 16 * (size_t)c0;
+    P.b         = s.d_b + 4 * (size_t)c0;
+    P.iters     = s.d_iters + 4 * (size_t)c0;
+    P.res       = s.d_res + 4 * (size_t)c0;
     P.fail      = s.d_fail;
+    P.fail_base = 4 * c0;
     P.tol2      = tol * tol;
     P.max_iter  = max_iter;
-    P.n_cells   = s.n_cells;
+    P.n_cells   = nc;
     P.rhs_value = s.rhs_value;
     P.flavor    = s.variant >= 10 && s.variant <= 12 ? s.variant - 10 : 0;
     P.coef      = make_coeff_eval(s.coeff);
     ++*n_launches;
     return launch_solve_fused(P, st);
+  }
+
+  cudaError_t
+  launch_stage_fused(const Shard &s, double tol, int max_iter, cudaStream_t st, int *n_launches)
+  {
+    return launch_stage_fused_range(s, 0, s.n_cells, tol, max_iter, st, n_launches);
   }
 } // namespace msb

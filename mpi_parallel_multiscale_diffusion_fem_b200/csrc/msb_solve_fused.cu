@@ -1061,7 +1061,7 @@ namespace msb
                     P.iters[sidx]  = kit[k];
                     P.res[sidx]    = sqrt(exact[k]);
                     if (!done[k])
-                      atomicMin(P.fail, sidx);
+                      atomicMin(P.fail, P.fail_base + sidx);
                   }
               }
           }

@@ -202,7 +202,7 @@ main(int argc, char **argv)
   int32_t              fail[2] = {INT_MAX, 0};
   FusedParams          P;
   P.corners = corners, P.q1coef = q1, P.phi = phi.data(), P.M = M.data(), P.b = b.data();
-  P.iters = iters.data(), P.res = res.data(), P.fail = fail, P.tol2 = 1e-24, P.max_iter = max_iter, P.n_cells = 1;
+  P.iters = iters.data(), P.res = res.data(), P.fail = fail, P.fail_base = 0, P.tol2 = 1e-24, P.max_iter = max_iter, P.n_cells = 1;
   P.rhs_value = f, P.coef = coef, P.flavor = flavor;
   constexpr int T = fused::Cfg::THREADS;
   emu::Cluster  cl;

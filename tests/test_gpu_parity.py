@@ -786,3 +786,27 @@ def test_independent_restatement_on_gpu(msb, oracle, name):
             assert np.abs(got - np.array(want)).max() < TOL_PHI
         for ib in range(4):
             assert abs(np.linalg.norm(phis[ib]) - g["phi_norms"][ib]) < TOL_PHI * g["phi_norms"][ib]
+
+
+@pytest.mark.parametrize("l,cells", [(6, 4500), (6, 7), (5, 60)])
+def test_run_with_bases_equals_run_then_get_bases(msb, oracle, l, cells):
+    """msb_run_with_bases (chunks of cells; reordering + device->host copy of chunk k behind the solves of chunk k+1)
+    delivers bit for bit what msb_run + msb_get_bases deliver: more cells than one chunk (28 x 148 = 4144) with a
+    ragged last chunk, fewer cells than a chunk, and the fallback for shards that do not run the fused stage (l = 5)."""
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_PERIODIC, (1.0 / 64, 0.9999))
+    cor = msb.coarse_corners(8, 20000, 20000 + cells)
+    with msb.BasisShard(l, cor, cd) as sh:
+        sh.run(1e-12, 5000)
+        want = sh.bases()
+        M0, b0 = sh.element_matrices()
+        it0, _ = sh.iteration_counts()
+        got = sh.run_with_bases(1e-12, 5000)
+        M1, b1 = sh.element_matrices()
+        it1, res1 = sh.iteration_counts()
+        assert np.array_equal(got, want)
+        assert np.array_equal(M0, M1) and np.array_equal(b0, b1) and np.array_equal(it0, it1)
+        assert np.all(res1 <= 1e-12)
+        # no-convergence is reported like msb_run reports it, the bases are still delivered
+        with pytest.raises(msb.MsbError) as e:
+            sh.run_with_bases(1e-12, 5)
+        assert e.value.code == -5 and sh.failure()[0] == 0

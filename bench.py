@@ -191,7 +191,7 @@ def kernel_name(dim, l, variant, tier):
     if tier == 1:
         if variant >= 100:
             return "solve_smem_kernel"
-        if l == 6 and (variant == 0 or 10 <= variant <= 12):
+        if l in (5, 6) and (variant == 0 or 10 <= variant <= 12):
             return "solve_fused_kernel (assembly + 4 solves + element matrices in one launch)"
         return "solve_bpx_tm_kernel" if (l == 6 and variant in (5, 7, 9)) else "solve_bpx_kernel"
     if (l == 7 and variant == 0) or (variant in (3, 4) and 5 <= l <= 7):
@@ -543,6 +543,8 @@ def main():
                                           "diagonals of the coarse levels are STORED as float; all arithmetic f64)"
                                           + (", exact solve of the 7x7 coarse level" if (dim == 2 and l == 5) or (dim == 2 and l == 6 and args.variant in (0, 9)) else "")
                                           if args.variant < 100 else "Jacobi (symmetric diagonal scaling)"),
+                       "initial_guess": ("coarse Q1 shape function (fused stage)" if "solve_fused" in kernel_name(dim, l, args.variant, m["tier"])
+                                         else "zero"),
                        "variant": args.variant, "build_id": build_id},
             "clocks": m["clocks"],
             "e2e": m["e2e"],

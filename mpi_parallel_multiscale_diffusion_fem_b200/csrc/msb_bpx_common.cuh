@@ -867,6 +867,13 @@ namespace msb
               const int i = fy * npB + fx;
               double    v[NRHS];
               ldv<NRHS>(VB, i, v);
+              [[maybe_unused]] double v_in[NRHS]; // n = 32: level B IS level 1, the u_1 . z_1 sum is formed here
+              if constexpr (B == 1)
+                {
+#pragma unroll
+                  for (int k = 0; k < NRHS; ++k)
+                    v_in[k] = v[k];
+                }
               const double di = DB[i];
 #pragma unroll
               for (int k = 0; k < NRHS; ++k)
@@ -891,6 +898,15 @@ namespace msb
                     }
                 }
               stv<NRHS>(VB, i, v);
+              if constexpr (B == 1)
+                {
+                  if (dot1)
+                    {
+#pragma unroll
+                      for (int k = 0; k < NRHS; ++k)
+                        dot1[k] = fma(v_in[k], v[k], dot1[k]);
+                    }
+                }
             }
           __syncthreads();
           mark(7);

@@ -25,6 +25,6 @@ namespace msb
     CoeffEval     coef;
   };
 
-  // the whole stage (assembly, 4 solves, element matrices) of every cell in ONE launch; 64 x 64 local meshes
-  cudaError_t launch_solve_fused(const FusedParams &P, cudaStream_t st);
+  // the whole stage (assembly, 4 solves, element matrices) of every cell in ONE launch; l = 5, 6 (32 x 32 and 64 x 64 local meshes)
+  cudaError_t launch_solve_fused(const FusedParams &P, int l, cudaStream_t st);
 } // namespace msb

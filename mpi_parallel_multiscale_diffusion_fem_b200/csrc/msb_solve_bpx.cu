@@ -633,7 +633,7 @@ namespace msb
     P.flavor    = s.variant >= 10 && s.variant <= 12 ? s.variant - 10 : 0;
     P.coef      = make_coeff_eval(s.coeff);
     ++*n_launches;
-    return launch_solve_fused(P, st);
+    return launch_solve_fused(P, s.l, st);
   }
 
   cudaError_t

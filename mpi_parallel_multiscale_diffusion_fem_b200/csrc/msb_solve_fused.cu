@@ -186,43 +186,48 @@ namespace msb
         t += __shfl_xor_sync(0xffffffffu, t, off);
     }
 
+    // NL = 6: 64 x 64 local mesh, 512 threads, one CTA per SM, the inverse of the 7x7 level in tensor memory.
+    // NL = 5: 32 x 32 local mesh, 128 threads, two or three CTAs per SM, the inverse in shared memory.
+    template <int NL_>
     struct Cfg
     {
-      static constexpr int THREADS = 512;
-      static constexpr int NL = 6, NRHS = 2;
+      static constexpr int NL = NL_, NRHS = 2;
+      static_assert(NL == 5 || NL == 6, "fused stage: 32 x 32 and 64 x 64 local meshes");
       using L                    = Levels<NL>;
-      static constexpr int n     = 64, np = 65, N = np * np;
-      static constexpr int NWARP = THREADS / 32;
-      static constexpr int WX    = 2;
-      static constexpr int WY    = NWARP / WX;
+      static constexpr int n     = 1 << NL, np = n + 1, N = np * np;
       static constexpr int RPT   = 8;
+      static constexpr int WX    = (n - 1 + 31) / 32;
+      static constexpr int WY    = n / RPT;
+      static constexpr int NWARP = WX * WY;
+      static constexpr int THREADS = 32 * NWARP;
       static constexpr int NCH   = RPT / 4; // TMEM chunks of 4 rows x 2 bases = 8 doubles
       static constexpr int CN    = L::CN;
       static constexpr int PAD   = 5;
       using PS                   = Presum<NL, NRHS, RPT, PAD>;
-      // per-thread TMEM columns: x | p_old | rhat | sqrt(d).  The residual lives in tensor memory as well: with it
-      // in registers the kernel spilled ~20 words, and with 227 KB of the L1 carved out as shared memory a
-      // spill load goes to L2 -- eight of them sat on the critical path of the coarse chain (5400 cycles per
-      // iteration, profiles/r02b_stage_timers_*)
+      // per-thread TMEM columns: x | p_old | rhat or q (flavours 1, 2) | sqrt(d)
       static constexpr int XOFF = 0, POFF = 2 * RPT * NRHS, ROFF = 4 * RPT * NRHS, SOFF = 6 * RPT * NRHS;
       static constexpr int TCOLS = SOFF + 2 * RPT;
-      static constexpr int TMEM_COLS = 512;
       using X7 = Exact7<THREADS>;
-      static constexpr int MOFF = (NWARP / 4) * TCOLS, MCOLS = ((X7::WARPS + 3) / 4) * 16 * X7::NCHK;
-      static constexpr int RED  = 10 * NWARP + 8; // the widest reduction: 10 values (element matrix columns)
+      static constexpr bool GI_TMEM = NL == 6; // where the 49 x 49 inverse of the 7x7 level lives
+      static constexpr int  MOFF = (NWARP / 4) * TCOLS, MCOLS = GI_TMEM ? ((X7::WARPS + 3) / 4) * 16 * X7::NCHK : 0;
+      static constexpr int  TMEM_COLS = NL == 6 ? 512 : 128; // per CTA (a power of two)
+      static constexpr int  RED = 10 * NWARP + 8; // the widest reduction: 10 values (element matrix columns)
       // shared memory, in doubles
       static constexpr int o_A = 0, o_B = o_A + 2 * n * n, o_P = o_B + 2 * n * n, o_V = o_P + NRHS * N;
-      static constexpr int o_red = o_V + NRHS * CN, o_eb = o_red + RED, o_nb = o_eb + n, o_di = o_nb + n;
+      static constexpr int o_red = o_V + NRHS * CN, o_eb = o_red + RED, o_nb = o_eb + n, o_gi = o_nb + n;
+      static constexpr int o_di  = o_gi + (GI_TMEM ? 0 : 49 * 49 + 1);
       static constexpr size_t smem_bytes = sizeof(double) * (size_t)o_di + sizeof(float) * (size_t)CN;
-      // prologue scratch inside the vector buffers
-      static constexpr int o_kc  = o_P + 5 * L::lvl_off(2);  // fine diagonal, N doubles (dead before level 2 is built)
-      static constexpr int o_tab = o_V + 1300;               // sine tables, 8 n doubles
-      static_assert(o_kc + N <= o_tab, "fine diagonal and sine tables overlap");
+      // prologue scratch inside the vector buffers (o_P .. o_red is one contiguous area)
+      static constexpr int o_kc  = o_P + 5 * L::lvl_off(2); // fine diagonal, N doubles (dead before level 2 is built)
+      static constexpr int o_tab = o_kc + N;                // sine tables, 8 n doubles
+      // scratch of the banded factorisation (and, NL = 6, of the inverse before it moves to tensor memory)
+      static constexpr int o_x7  = o_V;
       static_assert(o_tab + 8 * n <= o_red, "sine tables");
       static_assert(5 * CN <= NRHS * N, "Galerkin scratch must fit the vector buffer");
-      static_assert(49 * 49 + EXACT7_SCRATCH <= NRHS * CN, "scratch of the 7x7 inverse must fit the coarse vectors");
+      static_assert((GI_TMEM ? 49 * 49 : 0) + EXACT7_SCRATCH <= NRHS * CN, "scratch of the 7x7 inverse must fit the coarse vectors");
       static_assert(NRHS * PS::ENTRIES <= NRHS * N, "pre-summed staging must fit the vector buffer");
-      static_assert(MOFF + MCOLS <= TMEM_COLS, "tensor memory columns");
+      static_assert(4 * 4 * n <= NRHS * CN, "Dirichlet table must fit the coarse vectors");
+      static_assert((NWARP + 3) / 4 * TCOLS + MCOLS <= TMEM_COLS, "tensor memory columns");
       static_assert(smem_bytes <= 232448, "shared memory");
     };
 
@@ -234,12 +239,12 @@ namespace msb
     // both interpolated straight back: two block barriers instead of five) was 3 % SLOWER than
     // bpx::coarse_correction in every flavour and is not kept: the stages it removes are short, the ones it
     // fattens (all threads) are not.
-    template <int RMODE>
-    __global__ void __launch_bounds__(Cfg::THREADS, 1)
+    template <int NL_, int RMODE>
+    __global__ void __launch_bounds__(Cfg<NL_>::THREADS, NL_ == 6 ? 1 : 2)
     solve_fused_kernel(FusedParams P)
     {
       constexpr bool RTMEM = RMODE == 1, QTMEM = RMODE == 2;
-      using C             = Cfg;
+      using C             = Cfg<NL_>;
       using L             = typename C::L;
       using PS            = typename C::PS;
       constexpr int THREADS = C::THREADS, NL = C::NL, NRHS = C::NRHS, n = C::n, np = C::np, N = C::N;
@@ -484,25 +489,30 @@ namespace msb
       // (6) exact coarse solve: the 49 x 49 inverse of the 7x7-level operator, built in the coarse-vector
       //     area and parked in tensor memory
       using X7            = typename C::X7;
-      const uint32_t tmat = tmem_base + tmem::lane_quarter(warp) + (uint32_t)(C::MOFF + (warp >> 2) * 16 * X7::NCHK);
-      {
-        double *sGi = sV, *sBand = sV + 49 * 49;
-        exact7_build<THREADS>(G + 5 * L::lvl_off(L::LW + 1), sGi, sBand, tid);
-        if (warp < X7::WARPS)
-          {
+      [[maybe_unused]] const uint32_t tmat =
+        tmem_base + tmem::lane_quarter(warp) + (uint32_t)(C::MOFF + (warp >> 2) * 16 * X7::NCHK);
+      [[maybe_unused]] const double *sGiv = smem + C::o_gi; // NL = 5: the inverse stays in shared memory
+      if constexpr (C::GI_TMEM)
+        {
+          double *sGi = smem + C::o_x7, *sBand = sGi + 49 * 49;
+          exact7_build<THREADS>(G + 5 * L::lvl_off(L::LW + 1), sGi, sBand, tid);
+          if (warp < X7::WARPS)
+            {
 #pragma unroll
-            for (int c = 0; c < X7::NCHK; ++c)
-              {
-                double g[8];
+              for (int c = 0; c < X7::NCHK; ++c)
+                {
+                  double g[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  g[i] = X7::fetch(sGi, tid, c, i);
-                tmem::st8(tmat + 16 * c, g);
-              }
-          }
-        tmem::wait_st();
-        __syncthreads();
-      }
+                  for (int i = 0; i < 8; ++i)
+                    g[i] = X7::fetch(sGi, tid, c, i);
+                  tmem::st8(tmat + 16 * c, g);
+                }
+            }
+          tmem::wait_st();
+          __syncthreads();
+        }
+      else
+        exact7_build<THREADS>(G + 5 * L::lvl_off(L::LW + 1), smem + C::o_gi, smem + C::o_x7, tid);
       ST_MARK(0)
 
       // boundary nodes in walking order (4 n of them)
@@ -551,75 +561,60 @@ namespace msb
       for (int grp = 0; grp < 4 / NRHS; ++grp)
         {
           const int rhs0 = grp * NRHS;
-          // (a) clear the vector buffer (halos stay zero for the solve); the coarse-vector area holds the
-          //     Dirichlet data until the right-hand side is formed
-          for (int i = tid; i < NRHS * N; i += THREADS)
-            sP[i] = 0.0;
-          fill_boundary_table();
-          __syncthreads();
-
-          // (b) rhat_0 = -D^-1/2 K_IB g_B: the interior-boundary edges carry the factor d^-1/2 already
+          // (a) Initial guess: the coarse Q1 shape function itself, x_0 = g on the interior nodes (the exact
+          //     solution for a constant coefficient; for the oscillating coefficients of the target workload it
+          //     saves 4-5 of 26 iterations, profiles/r02e_*).  In the scaled variables what = S^-1 g (sqrt(d) g
+          //     inside, g on the boundary) and rhat_0 = -S K g = -(S K S) what: ONE pass of the stencil sweep
+          //     below over what, boundary values in the halo, gives the initial residual -- iteration 0 runs
+          //     it with p = what and alpha = 1 (x_0 = 0 + 1 * what, rhat_0 = 0 - 1 * Ahat what, beta = 0).
+          //     The condensed right-hand side -D^-1/2 K_IB g_B is the boundary part of that product.
           [[maybe_unused]] double rreg[RPT][NRHS]; // the residual when it lives in registers (!RTMEM)
-#pragma unroll
-          for (int c = 0; c < NCH; ++c)
-            {
-            double r8[8];
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            {
-              const int j = 4 * c + jj;
-              const int y = Y0 + j;
-#pragma unroll
-              for (int k = 0; k < NRHS; ++k)
-                r8[2 * jj + k] = 0.0;
-              if (colok && y <= n - 1 && (X == 1 || X == n - 1 || y == 1 || y == n - 1))
-                {
-                  double acc[NRHS] = {0.0, 0.0};
-#pragma unroll
-                  for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx)
-                      {
-                        const int bx = X + dx, by = y + dy;
-                        if ((dx == 0 && dy == 0) || !(bx == 0 || bx == n || by == 0 || by == n))
-                          continue;
-                        const double kij = eget<n>(sA, sB, X, y, dx, dy);
-                        double       g0, g1;
-                        ld2(sG, 2 * boundary_index(bx, by) + grp, g0, g1);
-                        acc[0] = fma(kij, g0, acc[0]);
-                        acc[1] = fma(kij, g1, acc[1]);
-                      }
-#pragma unroll
-                  for (int k = 0; k < NRHS; ++k)
-                    r8[2 * jj + k] = -acc[k];
-                }
-            }
-            if constexpr (RTMEM)
-              tmem::st8(tm + C::ROFF + 16 * c, r8);
-            else
-              {
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-                  rreg[4 * c + jj][0] = r8[2 * jj], rreg[4 * c + jj][1] = r8[2 * jj + 1];
-              }
-            }
-          __syncthreads(); // the Dirichlet table has been read
-          for (int i = tid; i < NRHS * CN; i += THREADS)
-            sV[i] = 0.0;
-          ST_MARK(1)
-          // x = 0, p_old = 0 in tensor memory
           {
-            const double zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            double sq8[8];
+            tmem::ld8(tm + C::SOFF, sq8);
 #pragma unroll
             for (int c = 0; c < NCH; ++c)
               {
+                double w8[8];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                  {
+                    const int j = 4 * c + jj, y = Y0 + j;
+                    double    px, py, w[NRHS];
+                    fine_vertex(crn, n, colok ? X : n - 1, y <= n - 1 ? y : n - 1, px, py);
+#pragma unroll
+                    for (int k = 0; k < NRHS; ++k)
+                      {
+                        w[k]           = sq8[j] * basis_q1_value(q1, rhs0 + k, px, py); // sqrt(d) = 0 beyond the mesh
+                        w8[2 * jj + k] = w[k];
+                        rreg[j][k]     = 0.0;
+                      }
+                    if (colok && y <= n - 1)
+                      stv<NRHS>(sP, y * np + X, w);
+                  }
+                const double zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                tmem::st8(tm + C::POFF + 16 * c, w8);
                 tmem::st8(tm + C::XOFF + 16 * c, zero8);
-                tmem::st8(tm + C::POFF + 16 * c, zero8);
-                if constexpr (QTMEM)
-                  tmem::st8(tm + C::ROFF + 16 * c, zero8); // q of the threads beyond the last column stays 0
+                if constexpr (RMODE != 0)
+                  tmem::st8(tm + C::ROFF + 16 * c, zero8); // rhat (1) / q of the threads beyond the last column (2)
               }
+            for (int t = tid; t < 4 * n; t += THREADS)
+              {
+                int jx, jy;
+                boundary_node(t, jx, jy);
+                double px, py, w[NRHS];
+                fine_vertex(crn, n, jx, jy, px, py);
+#pragma unroll
+                for (int k = 0; k < NRHS; ++k)
+                  w[k] = basis_q1_value(q1, rhs0 + k, px, py);
+                stv<NRHS>(sP, jy * np + jx, w);
+              }
+            for (int i = tid; i < NRHS * CN; i += THREADS)
+              sV[i] = 0.0;
             tmem::wait_st();
           }
+          __syncthreads();
+          ST_MARK(1)
 
           double rho[NRHS] = {1.0, 1.0}, exact[NRHS] = {0.0, 0.0}, alpha[NRHS] = {0.0, 0.0};
           bool   done[NRHS] = {false, false};
@@ -628,13 +623,12 @@ namespace msb
           int    it         = 0;
 
           // ------------------------------------------------------------ one PCG iteration =
-          //   [stencil, alpha, r update]   (skipped for it = 0)
+          //   [stencil, alpha, r update]   (it = 0: the initial residual, see (a))
           //   stage u = D^1/2 rhat -> coarse levels -> (r.z, |r|^2) -> beta -> p = z + beta p_old, x += alpha p_old
 #pragma unroll 1
           for (;;)
             {
               double q[RPT][NRHS];
-              if (it > 0)
                 {
                   // ---- q = Ahat p for both bases: one set of coefficient loads per stencil row
                   double pq[NRHS] = {0.0, 0.0};
@@ -726,7 +720,7 @@ namespace msb
                   ST_MARK(3)
 #pragma unroll
                   for (int k = 0; k < NRHS; ++k)
-                    alpha[k] = done[k] ? 0.0 : fast_div(rho[k], pq[k]);
+                    alpha[k] = it == 0 ? 1.0 : (done[k] ? 0.0 : fast_div(rho[k], pq[k]));
                   if constexpr (RMODE == 0)
                     {
 #pragma unroll
@@ -767,7 +761,7 @@ namespace msb
                       for (int k = 0; k < NRHS; ++k)
                         ra[2 * jj + k] = rreg[jj][k], rb[2 * jj + k] = rreg[4 + jj][k];
                   }
-                if (RMODE != 0 && it > 0)
+                if constexpr (RMODE != 0)
                   {
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj)
@@ -827,7 +821,17 @@ namespace msb
                     (void)st_k;
                     ST_MARK(st_k)
                   },
-                  [&](int c, double(&g)[8]) { tmem::ld8(tmat + 16 * c, g); }, rz);
+                  [&](int c, double(&g)[8]) {
+                    if constexpr (C::GI_TMEM)
+                      tmem::ld8(tmat + 16 * c, g);
+                    else
+                      {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                          g[i] = X7::fetch(sGiv, tl, c, i);
+                      }
+                  },
+                  rz);
                 }
               ST_MARK(11)
               {
@@ -1074,27 +1078,37 @@ namespace msb
   } // namespace fused
 
 #ifndef MSB_EMU
-  cudaError_t
-  launch_solve_fused(const FusedParams &P, cudaStream_t st)
+  namespace fused
   {
-    using C = fused::Cfg;
-    void (*kern)(FusedParams);
-    switch (P.flavor)
-      {
-        case 1:
-          kern = fused::solve_fused_kernel<1>;
-          break;
-        case 2:
-          kern = fused::solve_fused_kernel<2>;
-          break;
-        default:
-          kern = fused::solve_fused_kernel<0>;
-      }
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
-    if (e != cudaSuccess)
-      return e;
-    kern<<<P.n_cells, C::THREADS, C::smem_bytes, st>>>(P);
-    return cudaGetLastError();
+    template <int NL>
+    static cudaError_t
+    launch(const FusedParams &P, cudaStream_t st)
+    {
+      using C = Cfg<NL>;
+      void (*kern)(FusedParams);
+      switch (P.flavor)
+        {
+          case 1:
+            kern = solve_fused_kernel<NL, 1>;
+            break;
+          case 2:
+            kern = solve_fused_kernel<NL, 2>;
+            break;
+          default:
+            kern = solve_fused_kernel<NL, 0>;
+        }
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
+      if (e != cudaSuccess)
+        return e;
+      kern<<<P.n_cells, C::THREADS, C::smem_bytes, st>>>(P);
+      return cudaGetLastError();
+    }
+  } // namespace fused
+
+  cudaError_t
+  launch_solve_fused(const FusedParams &P, int l, cudaStream_t st)
+  {
+    return l == 5 ? fused::launch<5>(P, st) : fused::launch<6>(P, st);
   }
 #endif
 } // namespace msb

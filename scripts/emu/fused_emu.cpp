@@ -8,7 +8,7 @@
 //
 //   g++ -O1 -std=c++20 -pthread -DMSB_EMU -I/usr/local/cuda/include -I include \
 //       -I mpi_parallel_multiscale_diffusion_fem_b200/csrc scripts/emu/fused_emu.cpp -o /tmp/fused_emu
-//   /tmp/fused_emu [kind 0|1|2|3] [max_iter]
+//   /tmp/fused_emu [kind 0|1|2|3] [max_iter] [flavour]          (-DEMU_NL=5 for the 32 x 32 instantiation)
 #include "emu_shims.hpp"
 #include "msb_solve_fused.cu"
 
@@ -20,7 +20,10 @@ main(int argc, char **argv)
   const int kind     = argc > 1 ? atoi(argv[1]) : 1;
   const int max_iter = argc > 2 ? atoi(argv[2]) : 500;
   const int flavor   = argc > 3 ? atoi(argv[3]) : 0;
-  constexpr int n = 64, np = 65, N = np * np;
+#ifndef EMU_NL
+#  define EMU_NL 6 // -DEMU_NL=5: the 32 x 32 instantiation (128 threads)
+#endif
+  constexpr int NL = EMU_NL, n = 1 << NL, np = n + 1, N = np * np;
   // a coarse cell of the target configuration (256 x 256 coarse mesh), or a 2:1 rectangle for kind 3
   const double H = 1.0 / 256, X0 = 37 * H, Y0 = 101 * H, HY = kind == 3 ? 0.5 * H : H;
   double       corners[8] = {X0, Y0, X0 + H, Y0, X0, Y0 + HY, X0 + H, Y0 + HY};
@@ -196,7 +199,7 @@ main(int argc, char **argv)
         bref[j] += pj[a] * S[ST_F * N + a];
     }
 
-  // ---- the kernel, 512 emulated threads
+  // ---- the kernel, 512 (NL = 6) or 128 (NL = 5) emulated threads
   std::vector<double>  phi((size_t)4 * N, -777.0), M(16, -777.0), b(4, -777.0), res(4, -1);
   std::vector<int32_t> iters(4, -5);
   int32_t              fail[2] = {INT_MAX, 0};
@@ -204,12 +207,12 @@ main(int argc, char **argv)
   P.corners = corners, P.q1coef = q1, P.phi = phi.data(), P.M = M.data(), P.b = b.data();
   P.iters = iters.data(), P.res = res.data(), P.fail = fail, P.fail_base = 0, P.tol2 = 1e-24, P.max_iter = max_iter, P.n_cells = 1;
   P.rhs_value = f, P.coef = coef, P.flavor = flavor;
-  constexpr int T = fused::Cfg::THREADS;
+  constexpr int T = fused::Cfg<NL>::THREADS;
   emu::Cluster  cl;
   cl.bar = std::make_unique<std::barrier<>>(T);
   cl.ctas.resize(1);
   cl.ctas[0].bar = std::make_unique<std::barrier<>>(T);
-  cl.ctas[0].smem.assign(fused::Cfg::smem_bytes / 8 + 8, NAN); // poison: the kernel must initialise what it reads
+  cl.ctas[0].smem.assign(fused::Cfg<NL>::smem_bytes / 8 + 8, NAN); // poison: the kernel must initialise what it reads
   for (int w = 0; w < T / 32; ++w)
     cl.ctas[0].warps.emplace_back(new emu::Warp);
   std::vector<std::thread> th;
@@ -218,11 +221,11 @@ main(int argc, char **argv)
       emu::t_cluster = &cl, emu::t_rank = 0;
       threadIdx.x = t, blockIdx.x = 0, blockDim.x = T, gridDim.x = 1;
       if (flavor == 1)
-        fused::solve_fused_kernel<1>(P);
+        fused::solve_fused_kernel<NL, 1>(P);
       else if (flavor == 2)
-        fused::solve_fused_kernel<2>(P);
+        fused::solve_fused_kernel<NL, 2>(P);
       else
-        fused::solve_fused_kernel<0>(P);
+        fused::solve_fused_kernel<NL, 0>(P);
     });
   for (auto &t : th)
     t.join();

@@ -334,7 +334,7 @@ def test_tensor_memory_kernel_matches_default_kernel(msb, oracle):
         if variant == 0:   # + exact solve of the 7x7 coarse level: a stronger preconditioner
             assert (itb <= ita).all() and itb.mean() < ita.mean()
         else:
-            assert np.abs(ita - itb).max() <= 1
+            assert np.all(itb <= ita + 1) and itb.mean() < ita.mean() - 2
         assert _rel(Mb, Ma) < 1e-10 and _rel(bb, ba) < 1e-10
         for x, y in zip(pa, pb):
             assert _rel(y, x) < 1e-10
@@ -651,20 +651,22 @@ def test_unsymmetric_coefficient_table_is_rejected(msb, oracle):
 
 
 # ---------------------------------------------------------------------------- the fused one-kernel stage (n = 64)
-def test_fused_stage_equals_the_three_kernel_path(msb, oracle):
-    """Default at n = 64 on axis-aligned cells: assembly, the four solves and the element matrices of a cell in
+@pytest.mark.parametrize("l", [6, 5])
+def test_fused_stage_equals_the_three_kernel_path(msb, oracle, l):
+    """Default at n = 64 and n = 32 on axis-aligned cells: assembly, the four solves and the element matrices of a cell in
     ONE kernel (msb_solve_fused.cu).  Variant 9 is the round-1 path (assemble_kernel -> solve_bpx_tm_kernel ->
-    element_matrix_kernel) with the same preconditioner: same iteration counts, same bases / M / b to solver
-    accuracy, ONE launch instead of three."""
+    element_matrix_kernel) with the same preconditioner: same bases / M / b to solver accuracy, ONE launch
+    instead of three.  The fused stage starts each solve from the coarse Q1 shape function instead of zero
+    (msb_solve_fused.cu, step (a)): never more iterations than the three-kernel path, 4-5 fewer of 26 here."""
     cd, co = _coeffs(msb, oracle, msb.COEFF_PERIODIC, (1.0 / 64, 0.9999))
     cor = msb.coarse_corners(8, 40000, 40000 + 300)
-    with msb.BasisShard(6, cor, cd, variant=9) as a, msb.BasisShard(6, cor, cd) as b:
+    with msb.BasisShard(l, cor, cd, variant=9) as a, msb.BasisShard(l, cor, cd) as b:
         a.run(1e-12, 5000)
         b.run(1e-12, 5000)
         ita, ra = a.iteration_counts()
         itb, rb = b.iteration_counts()
         assert np.all(ra <= 1e-12) and np.all(rb <= 1e-12)
-        assert np.abs(ita - itb).max() <= 1
+        assert np.all(itb <= ita + 1) and itb.mean() < ita.mean() - 2
         Ma, ba = a.element_matrices()
         Mb, bb = b.element_matrices()
         assert _rel(Mb, Ma) < 1e-10 and _rel(bb, ba) < 1e-10
@@ -675,12 +677,13 @@ def test_fused_stage_equals_the_three_kernel_path(msb, oracle):
 
 @pytest.mark.parametrize("kind,par,seed,r", [
     (0, (), 0, 3), (1, (1.0 / 64, 0.9999), 0, 8), (2, (2.0 ** -12, 0.2, 1e4, 1.0), 1234, 8), (3, (2.5,), 0, 4)])
-def test_fused_stage_against_the_oracle_every_coefficient_kind(msb, oracle, kind, par, seed, r):
+@pytest.mark.parametrize("l", [6, 5])
+def test_fused_stage_against_the_oracle_every_coefficient_kind(msb, oracle, kind, par, seed, r, l):
     cd, co = _coeffs(msb, oracle, kind, par, seed)
     total = 4 ** r
     cor = msb.coarse_corners(r, total // 3, total // 3 + 3)
-    ref = oracle.run_cells(6, cor, co, rhs_value=3.5, n_threads=3)
-    with msb.BasisShard(6, cor, cd, rhs_value=3.5) as sh:
+    ref = oracle.run_cells(l, cor, co, rhs_value=3.5, n_threads=3)
+    with msb.BasisShard(l, cor, cd, rhs_value=3.5) as sh:
         sh.run(1e-12, 5000)
         assert sh.run_stats()["launches"] == 1
         it, res = sh.iteration_counts()
@@ -692,8 +695,8 @@ def test_fused_stage_against_the_oracle_every_coefficient_kind(msb, oracle, kind
             assert _rel(M[c], ref["M"][c]) < TOL_MB and _rel(b[c], ref["b"][c]) < TOL_MB
         # the operator-level accessors assemble the HBM stencil on demand
         import scipy.sparse as sp
-        rowptr, col, val, F = oracle.assemble(6, cor[1], co, rhs_value=3.5)
-        N = oracle.n_dofs(6)
+        rowptr, col, val, F = oracle.assemble(l, cor[1], co, rhs_value=3.5)
+        N = oracle.n_dofs(l)
         K = sp.csr_matrix((val, col.astype(np.int64), rowptr.astype(np.int64)), shape=(N, N))
         x = np.random.default_rng(3).standard_normal(N)
         # (5e-12: at H = 1/256 the sine arguments are ~1e2 and a(x) comes close to 1e-4, so the last bits of the
@@ -788,11 +791,12 @@ def test_independent_restatement_on_gpu(msb, oracle, name):
             assert abs(np.linalg.norm(phis[ib]) - g["phi_norms"][ib]) < TOL_PHI * g["phi_norms"][ib]
 
 
-@pytest.mark.parametrize("l,cells", [(6, 4500), (6, 7), (5, 60)])
+@pytest.mark.parametrize("l,cells", [(6, 4500), (6, 7), (5, 700), (4, 60)])
 def test_run_with_bases_equals_run_then_get_bases(msb, oracle, l, cells):
     """msb_run_with_bases (chunks of cells; reordering + device->host copy of chunk k behind the solves of chunk k+1)
     delivers bit for bit what msb_run + msb_get_bases deliver: more cells than one chunk (28 x 148 = 4144) with a
-    ragged last chunk, fewer cells than a chunk, and the fallback for shards that do not run the fused stage (l = 5)."""
+    ragged last chunk, fewer cells than a chunk, the 32 x 32 instantiation of the fused stage (l = 5) and the fallback for
+    shards that do not run the fused stage (l = 4)."""
     cd, _ = _coeffs(msb, oracle, msb.COEFF_PERIODIC, (1.0 / 64, 0.9999))
     cor = msb.coarse_corners(8, 20000, 20000 + cells)
     with msb.BasisShard(l, cor, cd) as sh:

@@ -179,13 +179,16 @@ namespace msb
 #pragma unroll
       for (int off = 4; off > 0; off >>= 1)
         t += __shfl_xor_sync(0xffffffffu, t, off);
+      // layout [warp / 8][value][warp % 8]: the four stores of a warp fall into different banks and the second
+      // stage reads 32 consecutive doubles (buf holds max(32, 4 NWARP) entries); [value][warp] was a 4-way
+      // conflict on both sides
       if ((lane & 7) == 0)
-        buf[(lane >> 3) * NWARP + warp] = t;
+        buf[(warp >> 3) * 32 + lane + (warp & 7)] = t;
       __syncthreads();
-      const int g = lane >> 3, w = lane & 7;
-      double    u = w < NWARP ? buf[g * NWARP + w] : 0.0;
+      const int w = lane & 7;
+      double    u = w < NWARP ? buf[lane] : 0.0;
       if (w + 8 < NWARP)
-        u += buf[g * NWARP + w + 8];
+        u += buf[32 + lane];
 #pragma unroll
       for (int off = 4; off > 0; off >>= 1)
         u += __shfl_xor_sync(0xffffffffu, u, off);
@@ -728,7 +731,10 @@ namespace msb
                         {
                           if (8 * c + jj >= X::CH)
                             continue;
-                          const int j = min(48, q7 * X::CH + 8 * c + jj);
+                          // (entries beyond the 49th belong to the padding lanes: their matrix entries are zero
+                          //  and they read the zero halo row 8 of the 9 x 9 level -- clamping them to entry 48 put
+                          //  a second address into the banks of five of the seven loads, profiles/r02e_*)
+                          const int j = q7 * X::CH + 8 * c + jj;
                           double    u[NRHS];
                           ldv<NRHS>(V1, (1 + j / 7) * 9 + 1 + j % 7, u);
 #pragma unroll

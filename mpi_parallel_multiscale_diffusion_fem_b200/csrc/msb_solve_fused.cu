@@ -305,7 +305,7 @@ namespace msb
                   xq += px * Nv[vv];
                   yq += py * Nv[vv];
                 }
-              (isx ? tsx : tsy)[u] = P.coef.sine_term(isx ? xq : yq);
+              (isx ? tsx : tsy)[q * n + k] = P.coef.sine_term(isx ? xq : yq); // [Gauss point][column]: conflict-free reads
             }
           __syncthreads();
         }
@@ -326,7 +326,7 @@ namespace msb
                 constexpr double G0 = 0.21132486540518711775, G1 = 0.78867513459481288225;
                 double           a00, a01, a10, a11;
                 if (separable)
-                  P.coef.from_sines(tsx[4 * ix + q], tsy[4 * iy + q], a00, a01, a10, a11);
+                  P.coef.from_sines(tsx[q * n + ix], tsy[q * n + iy], a00, a01, a10, a11);
                 else
                   P.coef(crn[0] + (ix + ((q & 1) ? G1 : G0)) * hx, crn[1] + (iy + ((q >> 1) ? G1 : G0)) * hy, a00, a01,
                          a10, a11);

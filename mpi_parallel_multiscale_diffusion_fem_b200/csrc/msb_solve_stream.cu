@@ -165,8 +165,10 @@ namespace msb
     di[i] = 1.0 / a[0];
   }
 
-  // r = b = -K_IB g_B on interior rows, 0 on constrained rows (condense);
-  // x = g on the boundary, 0 inside; p = 0; partial r.r into parity 0
+  // Initial guess x_0 = g, the coarse Q1 shape function, on ALL nodes (boundary: the Dirichlet data of
+  // condense; interior: the exact solution for a constant coefficient -- 11 % fewer iterations
+  // on cfg5, 9 % on the reference's default run, scripts/precond_experiment.py);
+  // r_0 = b - K_II g_I = -(K g) on interior rows, 0 on constrained rows; p = 0; partial r.r into parity 0
   __global__ void __launch_bounds__(STREAM_THREADS)
   stream_init_kernel(StreamParams P)
   {
@@ -179,26 +181,24 @@ namespace msb
       {
         const int  jx = t % np, jy = t / np;
         const bool bd = jx == 0 || jy == 0 || jx == n || jy == n;
-        double     rv[4] = {0, 0, 0, 0}, xv[4] = {0, 0, 0, 0};
-        if (bd)
-          {
-            double px, py;
-            fine_vertex(c, n, jx, jy, px, py);
+        double     rv[4] = {0, 0, 0, 0}, xv[4];
+        {
+          double px, py;
+          fine_vertex(c, n, jx, jy, px, py);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              xv[k] = basis_q1_value(q1, k, px, py);
-          }
-        else if (jx == 1 || jy == 1 || jx == n - 1 || jy == n - 1)
+          for (int k = 0; k < 4; ++k)
+            xv[k] = basis_q1_value(q1, k, px, py);
+        }
+        if (!bd)
           {
+#pragma unroll
             for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
               for (int dx = -1; dx <= 1; ++dx)
                 {
-                  const int bx = jx + dx, by = jy + dy;
-                  if ((dx == 0 && dy == 0) || !(bx == 0 || bx == n || by == 0 || by == n))
-                    continue;
                   const double kij = bpx::sten_get(S, np, N, jx, jy, dx, dy);
                   double       px, py;
-                  fine_vertex(c, n, bx, by, px, py);
+                  fine_vertex(c, n, jx + dx, jy + dy, px, py);
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
                     rv[k] -= kij * basis_q1_value(q1, k, px, py);

@@ -220,19 +220,15 @@ main(int argc, char **argv)
         py = corners[1] + s * (corners[3] - corners[1]) + t * (corners[5] - corners[1]);
         return q1[0 * 4 + ib] + q1[1 * 4 + ib] * px + q1[2 * 4 + ib] * py + q1[3 * 4 + ib] * px * py;
       };
+      // initial guess: the coarse Q1 shape function on every node, r_0 = -(K g) on interior rows (as the kernel)
       for (int y = 0; y <= n; ++y)
         for (int xx = 0; xx <= n; ++xx)
-          if (xx == 0 || y == 0 || xx == n || y == n)
-            x[y * np + xx] = g(xx, y);
+          x[y * np + xx] = g(xx, y);
       for (int y = 1; y < n; ++y)
         for (int xx = 1; xx < n; ++xx)
           for (int ey = -1; ey <= 1; ++ey)
             for (int ex = -1; ex <= 1; ++ex)
-              {
-                const int bx = xx + ex, by = y + ey;
-                if (bx == 0 || by == 0 || bx == n || by == n)
-                  r[y * np + xx] -= sget(S, np, xx, y, ex, ey) * x[by * np + bx];
-              }
+              r[y * np + xx] -= sget(S, np, xx, y, ex, ey) * x[(y + ey) * np + xx + ex];
       auto dot = [&](const std::vector<double> &a, const std::vector<double> &b) {
         double s = 0;
         for (int y = 1; y < n; ++y)

@@ -89,3 +89,29 @@ def test_emulated_banded_inverse_of_the_7x7_level(tmp_path):
     for contrast in ("1", "1e4", "1e6"):
         p = subprocess.run([exe, contrast], capture_output=True, text=True, timeout=300)
         assert p.returncode == 0, p.stdout + p.stderr
+
+
+_FUSED_EXE = {}
+
+
+@pytest.mark.parametrize("nl,kind,flavour", [(6, 1, 0), (6, 0, 1), (6, 2, 2), (5, 1, 0), (5, 2, 0), (5, 3, 0)])
+def test_emulated_fused_stage_equals_a_plain_host_solve(tmp_path_factory, nl, kind, flavour):
+    """scripts/emu/fused_emu.cpp compiles msb_solve_fused.cu UNCHANGED for the host (512 OS threads for the 64 x 64
+    instantiation, 128 for the 32 x 32 one, shared / tensor memory NaN-poisoned) and compares the whole stage of one
+    coarse cell -- on-chip assembly, the initial guess x_0 = g, 2 x 2 multilevel PCG solves, the element-matrix
+    epilogue -- with a plain host implementation of the reference's sequence (basis.tpp:159-285, 450-465):
+    coefficient kinds reference / periodic / inclusions / constant, the three residual flavours."""
+    if shutil.which("g++") is None or not os.path.isdir(CUDA_INC):
+        pytest.skip("needs g++ and the CUDA headers")
+    if nl not in _FUSED_EXE:   # one build per instantiation
+        exe = str(tmp_path_factory.mktemp("emu_fused") / ("fused_emu%d" % nl))
+        subprocess.check_call(
+            ["g++", "-O1", "-std=c++20", "-pthread", "-DMSB_EMU", "-DEMU_NL=%d" % nl, "-I" + CUDA_INC,
+             "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "mpi_parallel_multiscale_diffusion_fem_b200", "csrc"),
+             os.path.join(ROOT, "scripts", "emu", "fused_emu.cpp"), "-o", exe])
+        _FUSED_EXE[nl] = exe
+    exe = _FUSED_EXE[nl]
+    p = subprocess.run([exe, str(kind), "500", str(flavour)], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and p.stdout.rstrip().endswith("OK"), p.stdout + p.stderr
+    its = [int(m) for m in re.findall(r"basis \d: iters (\d+)", p.stdout)]
+    assert len(its) == 4 and (max(its) == 0 if kind == 3 else 10 <= max(its) <= 45)   # constant coefficient: x_0 = g is exact

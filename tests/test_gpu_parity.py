@@ -334,7 +334,7 @@ def test_tensor_memory_kernel_matches_default_kernel(msb, oracle):
         if variant == 0:   # + exact solve of the 7x7 coarse level: a stronger preconditioner
             assert (itb <= ita).all() and itb.mean() < ita.mean()
         else:
-            assert np.all(itb <= ita + 1) and itb.mean() < ita.mean() - 2
+            assert np.abs(ita - itb).max() <= 1
         assert _rel(Mb, Ma) < 1e-10 and _rel(bb, ba) < 1e-10
         for x, y in zip(pa, pb):
             assert _rel(y, x) < 1e-10

@@ -679,8 +679,10 @@ namespace msb
 
   // TC_, TR_ > 0: the tile dimensions as compile-time constants (the index arithmetic of the loops below
   // divides by the tile width); 0: run-time P.tc, P.tr
-  template <int TC_, int TR_>
-  __global__ void __launch_bounds__(STREAM_THREADS)
+  // U, U2: nodes per thread and pass of phase 1 / phase 2 (loads in flight per thread); MINB: CTAs per SM the register
+  // allocation is bounded for (profiles/r02e_*: at 2 CTAs per SM both kernels wait on the long scoreboard)
+  template <int TC_, int TR_, int U = 3, int U2 = 2, int MINB = 2>
+  __global__ void __launch_bounds__(STREAM_THREADS, MINB)
   stream_ka_kernel(StreamParams P)
   {
     extern __shared__ double sp[]; // [4][H][W]: p_new on the tile + halo, then [4][CH][CW]: level-1 z_1 around the tile
@@ -711,7 +713,6 @@ namespace msb
     const double *__restrict__ r_in = P.r_in;
     const double *__restrict__ p_in = P.p_in;
     double *__restrict__       p_out = P.p_out;
-    constexpr int U = 3;
     for (int base = 0; base < WH; base += U * STREAM_THREADS)
       {
         double rv[U][4], pv[U][4], kcv[U];
@@ -766,7 +767,6 @@ namespace msb
     double    acc[4] = {0, 0, 0, 0};
     const int tw = g.x1 - g.x0, th = g.y1 - g.y0;
     double *__restrict__ qo = P.q;
-    constexpr int U2 = 2;
     for (int base = 0; base < tw * th; base += U2 * STREAM_THREADS)
       {
         double kf[U2][9];
@@ -820,8 +820,8 @@ namespace msb
   }
 
   // P.it == 0: initialisation pass (no update: alpha = 0, q is not read)
-  template <int TC_, int TR_>
-  __global__ void __launch_bounds__(STREAM_THREADS)
+  template <int TC_, int TR_, int U = 2, int MINB = 2>
+  __global__ void __launch_bounds__(STREAM_THREADS, MINB)
   stream_kb_kernel(StreamParams P)
   {
     extern __shared__ double sr[]; // [4][tr+1][tc+1]: the new residual on the tile + upper / right halo
@@ -845,7 +845,6 @@ namespace msb
     const double *__restrict__ q_in = P.q;
     double *__restrict__       r_out = P.r_out;
     double *__restrict__       x_io  = P.x;
-    constexpr int U = 2;
     for (int base = 0; base < WH; base += U * STREAM_THREADS)
       {
         double rv[U][4], qv[U][4], pv[U][4], xv[U][4], kcv[U];
@@ -1235,8 +1234,23 @@ namespace msb
         const size_t smem_a = sizeof(double) * 4 * ((size_t)(P.tc + 2) * (P.tr + 2) + (size_t)(P.tc / 2 + 2) * (P.tr / 2 + 2));
         const size_t smem_b = sizeof(double) * 4 * (size_t)(P.tc + 1) * (P.tr + 1);
         const bool   std_tile = P.tc == 128 && P.tr == 8;
-        auto         ka = std_tile ? stream_ka_kernel<128, 8> : stream_ka_kernel<0, 0>;
-        auto         kb = std_tile ? stream_kb_kernel<128, 8> : stream_kb_kernel<0, 0>;
+        // One node per thread and pass at 3 CTAs per SM (80 registers): measured on 1184 cells of cfg5 (ms per step,
+        // profiles/r02e_ab_stream.txt): 3/2 nodes at 2 CTAs (128 registers, the first version) 268.0, 2/1 nodes at 3 CTAs
+        // 235.6, 1/1 at 3 CTAs 234.8, 1/1 at 4 CTAs (64 registers, KB spills) 244.9.  ncu of the first version:
+        // both kernels wait on the long scoreboard at 16 warps per SM (KA 3.1 TB/s, KB 4.6 TB/s of DRAM traffic).
+        void (*ka)(StreamParams) = std_tile ? stream_ka_kernel<128, 8, 1, 1, 3> : stream_ka_kernel<0, 0>;
+        void (*kb)(StreamParams) = std_tile ? stream_kb_kernel<128, 8, 1, 3> : stream_kb_kernel<0, 0>;
+        if (std_tile && s.variant >= 20 && s.variant < 30) // A/B of loads in flight per thread vs CTAs per SM
+          {
+            switch (s.variant)
+              {
+                case 20: ka = stream_ka_kernel<128, 8, 3, 2, 2>, kb = stream_kb_kernel<128, 8, 2, 2>; break;
+                case 21: ka = stream_ka_kernel<128, 8, 2, 1, 3>, kb = stream_kb_kernel<128, 8, 1, 3>; break;
+                case 22: ka = stream_ka_kernel<128, 8, 1, 1, 4>, kb = stream_kb_kernel<128, 8, 1, 4>; break;
+                case 23: ka = stream_ka_kernel<128, 8, 1, 1, 4>; break;
+                default: break;
+              }
+          }
         TRY(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
         TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
         const int p1_blocks = P.nblk < 8 ? P.nblk : 8;

@@ -55,6 +55,22 @@ for step in "$@"; do
       spec="${step#wl:}"; name="${spec%%:*}"; var=0; [[ "$spec" == *:* ]] && var="${spec#*:}"
       timeout 900 $PY bench.py --workload $name --variant $var --no-cpu-baseline --no-bases > gpurun_out/bench_${name}_v$var.json 2> gpurun_out/bench_${name}_v$var.err
       $PY -c "import json; d=json.load(open('gpurun_out/bench_${name}_v$var.json')); print('$name v$var: %.1f k solves/s, %.3f ms/step, kernel %.3f ms, k=%.2f, model frac %.3f, clocks %s' % (d['value']/1e3, d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['mean_pcg_iterations'], d['roofline']['frac'], d['clocks']))" || tail -3 gpurun_out/bench_${name}_v$var.err ;;
+    ncuwl:*)
+      # ncuwl:WORKLOAD:CELLS:KERNEL_REGEX[:SKIP] -- ncu --set full of one launch of a kernel of another workload
+      IFS=: read -r _ name cells rx skip <<< "$step"
+      timeout 900 ncu --set full --import-source on --clock-control none -k regex:"$rx" -s ${skip:-20} -c 1 -f -o gpurun_out/ncu_${name}_${rx} $PY bench.py --workload $name --cells $cells --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_${name}.log 2>&1
+      ncu -i gpurun_out/ncu_${name}_${rx}.ncu-rep --page raw --csv > gpurun_out/ncu_${name}_${rx}.csv 2>/dev/null; ls -la gpurun_out/ncu_${name}_${rx}.* ;;
+    launches:*)
+      # launches:WORKLOAD:CELLS -- ncu launch list (durations) of one step
+      IFS=: read -r _ name cells <<< "$step"
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${name}_${cells}.csv $PY bench.py --workload $name --cells $cells --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/launches_${name}.log 2>&1; tail -3 gpurun_out/launches_${name}_${cells}.csv ;;
+    abw:*)
+      # abw:WORKLOAD:CELLS:V1,V2,... -- A/B of kernel variants on a slice of any workload
+      IFS=: read -r _ name cells vs <<< "$step"
+      for v in $(echo "$vs" | tr ',' ' '); do
+        timeout 300 $PY bench.py --workload $name --cells $cells --steps 3 --warmup 3 --variant $v --no-cpu-baseline --no-e2e > gpurun_out/abw_${name}_${cells}_v$v.json 2> gpurun_out/abw_${name}_v$v.err
+        $PY -c "import json; d=json.load(open('gpurun_out/abw_${name}_${cells}_v$v.json')); print('$name[$cells] variant $v: %.2f k solves/s, %.3f ms/step, k=%.2f, model frac %.3f, %s' % (d['value']/1e3, d['ms_per_step'], d['config']['mean_pcg_iterations'], d['roofline']['frac'], d['clocks']['reasons']))" || tail -3 gpurun_out/abw_${name}_v$v.err
+      done ;;
     *) echo "unknown step $step" ;;
   esac
 done

@@ -126,7 +126,12 @@ int msb_set_cells(msb_handle h, const double *corners, const double *coeff_table
  * assemble_global_element_matrix).  tol_abs / max_iter are SolverControl's
  * arguments (basis.tpp:297: 1000, 1e-12; the stopping rule is the reference's:
  * absolute l2 norm of the unpreconditioned residual of the condensed system,
- * tested every iteration). */
+ * tested every iteration).  Initial guess: the reference starts SolverCG from the
+ * zero vector (basis.tpp:152 reinit, :304); the fused, cluster, streamed and dim-3
+ * kernels start from the coarse Q1 shape function g itself (the Dirichlet data
+ * extended into the cell: the exact solution for a constant coefficient), which
+ * changes the iteration counts msb_get_iteration_counts reports (0 is possible),
+ * not the converged bases. */
 int msb_run(msb_handle h, double tol_abs, int32_t max_iter);
 
 /* Same, enqueued on `cuda_stream`; pair with msb_sync.  The shared-memory and cluster

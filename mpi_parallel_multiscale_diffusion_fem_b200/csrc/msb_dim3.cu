@@ -853,16 +853,21 @@ namespace msb
     // `by` interior rows (all x) and marches over `zc` z-planes; four plane slots hold the 8
     // bases of planes z-1, z, z+1 and the one being prefetched, so every p value is read from
     // HBM/L2 (zc+2)/zc times instead of 27 and the 216 neighbour reads per node are conflict-free
-    // LDS.  Coefficients (27 per node, shared by the 8 bases) stay in global memory / L1.
+    // LDS.  The bases are interleaved in PAIRS inside a plane slot ([pair][node][2]): the neighbour reads
+    // are 108 LDS.128 instead of 216 LDS.64 -- the crossbar moves 128-bit accesses at twice the byte rate
+    // (scripts/probes/onchip_peaks.cu), and this kernel sat at 70 % of the 64-bit wavefront peak
+    // (profiles/r02e_ncu_3d_k2m_before.csv).  Coefficients (27 per node, shared by the 8 bases) stay in
+    // global memory / L1.
     template <int MINB>
     __global__ void __launch_bounds__(THREADS, MINB)
     k2m_kernel(Params3 P)
     {
-      extern __shared__ double sp[]; // [4][NB][(by+2)*np]
+      extern __shared__ __align__(16) double sp[]; // [4][NB / 2][(by+2)*np][2]
       const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y, blk = blockIdx.x;
       const int par = (P.it - 1) & 1;
       __shared__ int    sdone[NB];
       __shared__ double sbuf[(THREADS / 32) * NB];
+      static_assert(NB % 2 == 0, "bases are staged in pairs");
       if (cell_done(P, cell, par, sdone))
         return;
       const int     ys = blk % P.nys, zi = blk / P.nys;
@@ -882,10 +887,11 @@ namespace msb
           {
             if (sdone[k])
               continue;
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(sp + (size_t)((z & 3) * NB + k) * psz);
-            const double  *sg  = pg + (size_t)k * N + src;
+            const unsigned dst =
+              (unsigned)__cvta_generic_to_shared(sp + (size_t)((z & 3) * NB + (k & ~1)) * psz + (k & 1));
+            const double *sg = pg + (size_t)k * N + src;
             for (int i = threadIdx.x; i < cnt; i += THREADS)
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * i), "l"(sg + i) : "memory");
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 16u * i), "l"(sg + i) : "memory");
           }
       };
 
@@ -910,31 +916,36 @@ namespace msb
           asm volatile("cp.async.commit_group;" ::: "memory");
           if (!active)
             continue;
-          const int     t  = (z * np + y) * np + x;
-          const double *s0 = sp + (size_t)(z & 3) * NB * psz + sb;
-          double        yv[NB], pc[NB];
+          const int      t  = (z * np + y) * np + x;
+          const double2 *s2 = reinterpret_cast<const double2 *>(sp); // [slot][pair][node]
+          const double2 *s0 = s2 + (size_t)(z & 3) * (NB / 2) * psz + sb;
+          double         yv[NB], pc[NB];
           {
             const double kc = S[t];
 #pragma unroll
-            for (int k = 0; k < NB; ++k)
+            for (int kp = 0; kp < NB / 2; ++kp)
               {
-                pc[k] = s0[k * psz];
-                yv[k] = kc * pc[k];
+                const double2 v = s0[kp * psz];
+                pc[2 * kp] = v.x, pc[2 * kp + 1] = v.y;
+                yv[2 * kp] = kc * v.x, yv[2 * kp + 1] = kc * v.y;
               }
           }
 #pragma unroll
           for (int f = 1; f <= 13; ++f)
             {
-              const int     e = 13 + f, dz = e / 9 - 1, dy = (e / 3) % 3 - 1, dx = e % 3 - 1;
-              const int     o = (dz * np + dy) * np + dx, so = dy * np + dx;
-              const double  kf = S[(size_t)f * N + t], kb = S[(size_t)f * N + t - o];
-              const double *sf = sp + (size_t)((z + dz) & 3) * NB * psz + sb + so;
-              const double *sr = sp + (size_t)((z - dz) & 3) * NB * psz + sb - so;
+              const int      e = 13 + f, dz = e / 9 - 1, dy = (e / 3) % 3 - 1, dx = e % 3 - 1;
+              const int      o = (dz * np + dy) * np + dx, so = dy * np + dx;
+              const double   kf = S[(size_t)f * N + t], kb = S[(size_t)f * N + t - o];
+              const double2 *sf = s2 + (size_t)((z + dz) & 3) * (NB / 2) * psz + sb + so;
+              const double2 *sr = s2 + (size_t)((z - dz) & 3) * (NB / 2) * psz + sb - so;
 #pragma unroll
-              for (int k = 0; k < NB; ++k)
+              for (int kp = 0; kp < NB / 2; ++kp)
                 {
-                  yv[k] = fma(kf, sf[k * psz], yv[k]);
-                  yv[k] = fma(kb, sr[k * psz], yv[k]);
+                  const double2 a = sf[kp * psz], b = sr[kp * psz];
+                  yv[2 * kp]     = fma(kf, a.x, yv[2 * kp]);
+                  yv[2 * kp + 1] = fma(kf, a.y, yv[2 * kp + 1]);
+                  yv[2 * kp]     = fma(kb, b.x, yv[2 * kp]);
+                  yv[2 * kp + 1] = fma(kb, b.y, yv[2 * kp + 1]);
                 }
             }
 #pragma unroll

@@ -195,7 +195,7 @@ def test_more_than_65535_cells_3d(msb, oracle):
         sh.run(1e-12, 100)
         M, b = sh.element_matrices()
         it, res = sh.iteration_counts()
-        assert (res <= 1e-12).all() and (it >= 1).all()
+        assert (res <= 1e-12).all() and (it >= 0).all()   # (0: a single unknown whose initial guess x_0 = g is already exact)
         assert np.abs(M.sum(axis=2)).max() < 1e-12
         assert np.abs(b.sum(axis=1) - 2.0 / 64 ** 3).max() < 1e-17
         pick = [0, 65534, 65535, 65536, 69999]

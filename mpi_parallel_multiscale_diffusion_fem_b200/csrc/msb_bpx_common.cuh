@@ -395,7 +395,19 @@ namespace msb
         const int r = tid / PARTS, jl = 8 * c + i, j = (tid % PARTS) * CH + jl;
         return (r < 49 && jl < CH && j < 49) ? Gi[j * 49 + r] : 0.0;
       }
+      // the same entry from the packed lower triangle T[i (i + 1) / 2 + j], j <= i (exact7_build<THREADS, true>):
+      // half the footprint (1225 doubles).  For a fixed column the lanes below it read consecutive words and the
+      // lanes from it on read T[r (r + 1) / 2 + j]: the triangular numbers of 16 consecutive r are distinct mod 16,
+      // so a half warp touches 16 different 8-byte banks
+      __device__ static __forceinline__ double
+      fetch_tri(const double *T, int tid, int c, int i)
+      {
+        const int r = tid / PARTS, jl = 8 * c + i, j = (tid % PARTS) * CH + jl;
+        const int hi = r > j ? r : j, lo = r > j ? j : r;
+        return (r < 49 && jl < CH && j < 49) ? T[hi * (hi + 1) / 2 + lo] : 0.0;
+      }
     };
+    constexpr int EXACT7_TRI = 49 * 50 / 2; // doubles of the packed inverse
 
     // Dense inverse of the Galerkin operator of the 7x7-unknown level (9-point stencil Gl on 9x9
     // nodes, layout of Shard::d_sten) into sGi[49][49].  With it the levels below 15x15 are solved
@@ -409,10 +421,14 @@ namespace msb
     // barriers per pivot, which was 20 % of the n = 32 kernel (profiles/r01s_stage_timers_cfg4_2368.txt).
     // sBand: scratch of EXACT7_SCRATCH doubles (band storage [49 + 8][9], zero padded).
     constexpr int EXACT7_SCRATCH = (49 + 8) * 9;
-    template <int THREADS>
+    // TRI: sGi receives only the lower triangle, packed (EXACT7_TRI doubles, Exact7::fetch_tri): column c of the
+    // inverse vanishes above row c after the forward substitution, and the entries above the diagonal that the
+    // backward substitution produces are the transposes of entries other threads store.
+    template <int THREADS, bool TRI = false>
     __device__ __forceinline__ void
     exact7_build(const double *Gl, double *sGi, double *sBand, int tid)
     {
+      auto at = [](int i, int c) { return TRI ? i * (i + 1) / 2 + c : i * 49 + c; };
       constexpr int BW = 8, LD = BW + 1;
       // lower band: sBand[i * LD + b] = A(i, i - b), b = 0 .. 8, i = (Y-1) * 7 + (X-1)
       for (int t = tid; t < EXACT7_SCRATCH; t += THREADS)
@@ -492,7 +508,8 @@ namespace msb
               for (int b = BW - 1; b >= 1; --b)
                 w[b] = w[b - 1];
               w[0]            = s;
-              sGi[i * 49 + c] = s * sBand[i * LD];
+              if (!TRI || i >= c)
+                sGi[at(i, c)] = s * sBand[i * LD];
             }
 #pragma unroll
           for (int b = 0; b < BW; ++b)
@@ -500,7 +517,9 @@ namespace msb
 #pragma unroll 7
           for (int i = 48; i >= 0; --i)
             {
-              double s = sGi[i * 49 + c], s2 = 0.0;
+              if (TRI && i < c)
+                break; // (rows above the diagonal: stored by the threads of those columns)
+              double s = sGi[at(i, c)], s2 = 0.0;
 #pragma unroll
               for (int b = BW; b >= 2; b -= 2) // rows beyond 48 are the zero padding of sBand
                 {
@@ -511,8 +530,8 @@ namespace msb
 #pragma unroll
               for (int b = BW - 1; b >= 1; --b)
                 w[b] = w[b - 1];
-              w[0]            = s;
-              sGi[i * 49 + c] = s;
+              w[0]          = s;
+              sGi[at(i, c)] = s;
             }
         }
       __syncthreads();

@@ -187,7 +187,8 @@ namespace msb
     }
 
     // NL = 6: 64 x 64 local mesh, 512 threads, one CTA per SM, the inverse of the 7x7 level in tensor memory.
-    // NL = 5: 32 x 32 local mesh, 128 threads, two or three CTAs per SM, the inverse in shared memory.
+    // NL = 5: 32 x 32 local mesh, 128 threads, THREE CTAs per SM (69 KB of shared memory each: the inverse is kept as
+    // a packed lower triangle in shared memory, 9.8 instead of 19.2 KB).
     template <int NL_>
     struct Cfg
     {
@@ -215,7 +216,7 @@ namespace msb
       // shared memory, in doubles
       static constexpr int o_A = 0, o_B = o_A + 2 * n * n, o_P = o_B + 2 * n * n, o_V = o_P + NRHS * N;
       static constexpr int o_red = o_V + NRHS * CN, o_eb = o_red + RED, o_nb = o_eb + n, o_gi = o_nb + n;
-      static constexpr int o_di  = o_gi + (GI_TMEM ? 0 : 49 * 49 + 1);
+      static constexpr int o_di  = o_gi + (GI_TMEM ? 0 : EXACT7_TRI + 1); // (NL = 5: packed lower triangle)
       static constexpr size_t smem_bytes = sizeof(double) * (size_t)o_di + sizeof(float) * (size_t)CN;
       // prologue scratch inside the vector buffers (o_P .. o_red is one contiguous area)
       static constexpr int o_kc  = o_P + 5 * L::lvl_off(2); // fine diagonal, N doubles (dead before level 2 is built)
@@ -229,6 +230,7 @@ namespace msb
       static_assert(4 * 4 * n <= NRHS * CN, "Dirichlet table must fit the coarse vectors");
       static_assert((NWARP + 3) / 4 * TCOLS + MCOLS <= TMEM_COLS, "tensor memory columns");
       static_assert(smem_bytes <= 232448, "shared memory");
+      static_assert(NL == 6 || 3 * (smem_bytes + 1024) <= 233472, "NL = 5: three CTAs per SM");
     };
 
     // RMODE (A/B flavours, FusedParams::flavor; measured on 5920 target cells, profiles/r02c_ab_flavours.txt):
@@ -240,7 +242,7 @@ namespace msb
     // bpx::coarse_correction in every flavour and is not kept: the stages it removes are short, the ones it
     // fattens (all threads) are not.
     template <int NL_, int RMODE>
-    __global__ void __launch_bounds__(Cfg<NL_>::THREADS, NL_ == 6 ? 1 : 2)
+    __global__ void __launch_bounds__(Cfg<NL_>::THREADS, NL_ == 6 ? 1 : 3)
     solve_fused_kernel(FusedParams P)
     {
       constexpr bool RTMEM = RMODE == 1, QTMEM = RMODE == 2;
@@ -512,7 +514,7 @@ namespace msb
           __syncthreads();
         }
       else
-        exact7_build<THREADS>(G + 5 * L::lvl_off(L::LW + 1), smem + C::o_gi, smem + C::o_x7, tid);
+        exact7_build<THREADS, true>(G + 5 * L::lvl_off(L::LW + 1), smem + C::o_gi, smem + C::o_x7, tid);
       ST_MARK(0)
 
       // boundary nodes in walking order (4 n of them)
@@ -828,7 +830,7 @@ namespace msb
                       {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                          g[i] = X7::fetch(sGiv, tl, c, i);
+                          g[i] = X7::fetch_tri(sGiv, tl, c, i);
                       }
                   },
                   rz);

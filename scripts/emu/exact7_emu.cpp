@@ -66,5 +66,23 @@ main(int argc, char **argv)
         amax  = std::fmax(amax, std::fabs(sGi[i * 49 + j]));
       }
   printf("contrast %g: max |A Ainv - I| = %.3e, asymmetry %.3e (max entry %.3e)\n", contrast, worst, asym, amax);
-  return worst < 1e-10 && asym < 1e-12 * amax ? 0 : 1;
+  // the packed lower-triangle variant (exact7_build<T, true> + Exact7::fetch_tri) must deliver the same entries
+  std::vector<double> full(sGi, sGi + 49 * 49);
+  cl.ctas[0].smem.assign(49 * 49 + bpx::EXACT7_SCRATCH, NAN);
+  sGi = cl.ctas[0].smem.data(), sBand = sGi + 49 * 49;
+  th.clear();
+  for (int t = 0; t < T; ++t)
+    th.emplace_back([&, t] {
+      emu::t_cluster = &cl, emu::t_rank = 0;
+      threadIdx.x = t, blockDim.x = T;
+      bpx::exact7_build<T, true>(G.data(), sGi, sBand, t);
+    });
+  for (auto &t : th)
+    t.join();
+  double dtri = 0;
+  for (int r = 0; r < 49; ++r)
+    for (int j = 0; j < 49; ++j)
+      dtri = std::fmax(dtri, std::fabs(bpx::Exact7<T>::fetch_tri(sGi, r, j / 8, j % 8) - full[j * 49 + r]));
+  printf("packed variant: max difference to the full inverse %.3e\n", dtri);
+  return worst < 1e-10 && asym < 1e-12 * amax && dtri <= 1e-12 * amax ? 0 : 1;
 }

@@ -696,11 +696,43 @@ namespace msb
     const int      W = tc + 2, H = tr + 2, WH = W * H;
     const double  *St = P.sten + (size_t)cell * ST_NARR * N;
     const int      np1 = P.L.levels >= 1 ? P.L.npl[1] : 0;
-    // ---- phase 0: the level-1 correction z_1 on the coarse nodes around the tile, once per CTA (coalesced),
-    //      instead of four scattered loads per fine node and basis
+    // Both phases below are software pipelined: the global loads of pass i+1 (and the first loads of a phase, ahead of
+    // the barrier that opens it) are in flight while pass i is computed from registers / shared memory.  Without it a
+    // CTA alternated between "all loads outstanding, nothing to do" and "computing, nothing in flight"
+    // (ncu: long-scoreboard bound at 3.1-3.8 TB/s although the bytes moved equal the algorithmic ones).
     const int cx0 = (g.x0 - 1) >> 1, cy0 = (g.y0 - 1) >> 1;
     const int CW = (tc >> 1) + 2, CH = (tr >> 1) + 2, CWH = CW * CH;
     double   *sc = sp + 4 * WH;
+    const double *__restrict__ r_in = P.r_in;
+    const double *__restrict__ p_in = P.p_in;
+    double *__restrict__       p_out = P.p_out;
+    struct Load1
+    {
+      double rv[U][4], pv[U][4], kcv[U];
+      int    tt[U];
+      bool   in[U];
+    };
+    auto load1 = [&](int base, Load1 &d) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        {
+          const int idx = base + u * STREAM_THREADS + threadIdx.x;
+          const int lx = idx % W, ly = idx / W, x = g.x0 - 1 + lx, y = g.y0 - 1 + ly;
+          d.in[u] = idx < WH && x >= 1 && y >= 1 && x <= n - 1 && y <= n - 1 && x <= g.x1 && y <= g.y1;
+          d.tt[u] = d.in[u] ? y * np + x : np + 1; // (any valid interior node: loads stay unconditional)
+          d.kcv[u] = St[ST_KC * N + d.tt[u]];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            {
+              const size_t o = ((size_t)cell * 4 + k) * N + d.tt[u];
+              d.rv[u][k] = r_in[o], d.pv[u][k] = p_in[o];
+            }
+        }
+    };
+    Load1 l1a;
+    load1(0, l1a);
+    // ---- phase 0: the level-1 correction z_1 on the coarse nodes around the tile, once per CTA (coalesced),
+    //      instead of four scattered loads per fine node and basis
     if (np1 > 0)
       for (int idx = threadIdx.x; idx < 4 * CWH; idx += STREAM_THREADS)
         {
@@ -708,106 +740,109 @@ namespace msb
           sc[idx] = (cx < np1 && cy < np1) ? P.v[((size_t)cell * 4 + k) * P.L.cn + P.L.off[1] + cy * np1 + cx] : 0.0;
         }
     __syncthreads();
-    // ---- phase 1: p_new on rows y0-1 .. y1, columns x0-1 .. x1.  U nodes per thread and pass: every global
-    //      load of the pass is issued before the first use (bytes in flight are what a streaming kernel lives on)
-    const double *__restrict__ r_in = P.r_in;
-    const double *__restrict__ p_in = P.p_in;
-    double *__restrict__       p_out = P.p_out;
-    for (int base = 0; base < WH; base += U * STREAM_THREADS)
+    // ---- phase 1: p_new on rows y0-1 .. y1, columns x0-1 .. x1, U nodes per thread and pass
+    auto comp1 = [&](int base, const Load1 &d) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        {
+          const int idx = base + u * STREAM_THREADS + threadIdx.x;
+          if (idx >= WH)
+            continue;
+          double pn[4] = {0, 0, 0, 0};
+          if (d.in[u])
+            {
+              const int    x = d.tt[u] % np, y = d.tt[u] / np;
+              const bool   own = x >= g.x0 && x < g.x1 && y >= g.y0 && y < g.y1;
+              const double dinv = 1.0 / d.kcv[u];
+              const int    xl = (x >> 1) - cx0, xh = ((x + 1) >> 1) - cx0, yl = (y >> 1) - cy0, yh = ((y + 1) >> 1) - cy0;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                {
+                  const double *v1 = sc + k * CWH;
+                  const double  cv = np1 == 0 ? 0.0 :
+                                                0.25 * ((v1[yl * CW + xl] + v1[yl * CW + xh]) + (v1[yh * CW + xl] + v1[yh * CW + xh]));
+                  pn[k] = S.done[k] ? d.pv[u][k] : fma(S.beta[k], d.pv[u][k], fma(d.rv[u][k], dinv, cv));
+                  if (own && !S.done[k])
+                    p_out[((size_t)cell * 4 + k) * N + d.tt[u]] = pn[k];
+                }
+            }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            sp[k * WH + idx] = pn[k];
+        }
+    };
+    constexpr int STEP1 = U * STREAM_THREADS;
+#pragma unroll 2
+    for (int base = 0; base < WH; base += STEP1)
       {
-        double rv[U][4], pv[U][4], kcv[U];
-        int    tt[U];
-        bool   in[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          {
-            const int idx = base + u * STREAM_THREADS + threadIdx.x;
-            const int lx = idx % W, ly = idx / W, x = g.x0 - 1 + lx, y = g.y0 - 1 + ly;
-            in[u] = idx < WH && x >= 1 && y >= 1 && x <= n - 1 && y <= n - 1 && x <= g.x1 && y <= g.y1;
-            tt[u] = in[u] ? y * np + x : np + 1; // (any valid interior node: loads stay unconditional)
-            kcv[u] = St[ST_KC * N + tt[u]];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              {
-                const size_t o = ((size_t)cell * 4 + k) * N + tt[u];
-                rv[u][k] = r_in[o], pv[u][k] = p_in[o];
-              }
-          }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          {
-            const int idx = base + u * STREAM_THREADS + threadIdx.x;
-            if (idx >= WH)
-              continue;
-            double pn[4] = {0, 0, 0, 0};
-            if (in[u])
-              {
-                const int    x = tt[u] % np, y = tt[u] / np;
-                const bool   own = x >= g.x0 && x < g.x1 && y >= g.y0 && y < g.y1;
-                const double dinv = 1.0 / kcv[u];
-                const int    xl = (x >> 1) - cx0, xh = ((x + 1) >> 1) - cx0, yl = (y >> 1) - cy0, yh = ((y + 1) >> 1) - cy0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  {
-                    const double *v1 = sc + k * CWH;
-                    const double  cv = np1 == 0 ? 0.0 :
-                                                  0.25 * ((v1[yl * CW + xl] + v1[yl * CW + xh]) + (v1[yh * CW + xl] + v1[yh * CW + xh]));
-                    pn[k] = S.done[k] ? pv[u][k] : fma(S.beta[k], pv[u][k], fma(rv[u][k], dinv, cv));
-                    if (own && !S.done[k])
-                      p_out[((size_t)cell * 4 + k) * N + tt[u]] = pn[k];
-                  }
-              }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              sp[k * WH + idx] = pn[k];
-          }
+        Load1 l1b;
+        if (base + STEP1 < WH)
+          load1(base + STEP1, l1b);
+        comp1(base, l1a);
+        l1a = l1b;
       }
-    __syncthreads();
     // ---- phase 2: q = K p_new on the own nodes, partial p.q
     double    acc[4] = {0, 0, 0, 0};
     const int tw = g.x1 - g.x0, th = g.y1 - g.y0;
     double *__restrict__ qo = P.q;
-    for (int base = 0; base < tw * th; base += U2 * STREAM_THREADS)
+    struct Load2
+    {
+      double kf[U2][9];
+      int    tt[U2], cc[U2];
+      bool   ok[U2];
+    };
+    auto load2 = [&](int base, Load2 &d) {
+#pragma unroll
+      for (int u = 0; u < U2; ++u)
+        {
+          const int idx = base + u * STREAM_THREADS + threadIdx.x;
+          d.ok[u]       = idx < tw * th;
+          const int lx = d.ok[u] ? idx % tw : 0, ly = d.ok[u] ? idx / tw : 0, t = (g.y0 + ly) * np + g.x0 + lx;
+          d.tt[u] = t, d.cc[u] = (ly + 1) * W + lx + 1;
+          d.kf[u][0] = St[ST_KC * N + t], d.kf[u][1] = St[ST_KE * N + t], d.kf[u][2] = St[ST_KE * N + t - 1];
+          d.kf[u][3] = St[ST_KN * N + t], d.kf[u][4] = St[ST_KN * N + t - np];
+          d.kf[u][5] = St[ST_KD1 * N + t], d.kf[u][6] = St[ST_KD1 * N + t - np - 1];
+          d.kf[u][7] = St[ST_KD2 * N + t - 1], d.kf[u][8] = St[ST_KD2 * N + t - np];
+        }
+    };
+    Load2 l2a;
+    load2(0, l2a); // (the coefficients do not depend on p: in flight across the barrier)
+    __syncthreads();
+    auto comp2 = [&](const Load2 &d) {
+#pragma unroll
+      for (int u = 0; u < U2; ++u)
+        {
+          if (!d.ok[u])
+            continue;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            {
+              if (S.done[k])
+                continue;
+              const double *p = sp + k * WH + d.cc[u];
+              double        yv = d.kf[u][0] * p[0];
+              yv = fma(d.kf[u][1], p[1], yv);
+              yv = fma(d.kf[u][2], p[-1], yv);
+              yv = fma(d.kf[u][3], p[W], yv);
+              yv = fma(d.kf[u][4], p[-W], yv);
+              yv = fma(d.kf[u][5], p[W + 1], yv);
+              yv = fma(d.kf[u][6], p[-W - 1], yv);
+              yv = fma(d.kf[u][7], p[W - 1], yv);
+              yv = fma(d.kf[u][8], p[-W + 1], yv);
+              qo[((size_t)cell * 4 + k) * N + d.tt[u]] = yv;
+              acc[k] = fma(p[0], yv, acc[k]);
+            }
+        }
+    };
+    constexpr int STEP2 = U2 * STREAM_THREADS;
+#pragma unroll 2
+    for (int base = 0; base < tw * th; base += STEP2)
       {
-        double kf[U2][9];
-        int    tt[U2], cc[U2];
-        bool   ok[U2];
-#pragma unroll
-        for (int u = 0; u < U2; ++u)
-          {
-            const int idx = base + u * STREAM_THREADS + threadIdx.x;
-            ok[u]         = idx < tw * th;
-            const int lx = ok[u] ? idx % tw : 0, ly = ok[u] ? idx / tw : 0, t = (g.y0 + ly) * np + g.x0 + lx;
-            tt[u] = t, cc[u] = (ly + 1) * W + lx + 1;
-            kf[u][0] = St[ST_KC * N + t], kf[u][1] = St[ST_KE * N + t], kf[u][2] = St[ST_KE * N + t - 1];
-            kf[u][3] = St[ST_KN * N + t], kf[u][4] = St[ST_KN * N + t - np];
-            kf[u][5] = St[ST_KD1 * N + t], kf[u][6] = St[ST_KD1 * N + t - np - 1];
-            kf[u][7] = St[ST_KD2 * N + t - 1], kf[u][8] = St[ST_KD2 * N + t - np];
-          }
-#pragma unroll
-        for (int u = 0; u < U2; ++u)
-          {
-            if (!ok[u])
-              continue;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              {
-                if (S.done[k])
-                  continue;
-                const double *p = sp + k * WH + cc[u];
-                double        yv = kf[u][0] * p[0];
-                yv = fma(kf[u][1], p[1], yv);
-                yv = fma(kf[u][2], p[-1], yv);
-                yv = fma(kf[u][3], p[W], yv);
-                yv = fma(kf[u][4], p[-W], yv);
-                yv = fma(kf[u][5], p[W + 1], yv);
-                yv = fma(kf[u][6], p[-W - 1], yv);
-                yv = fma(kf[u][7], p[W - 1], yv);
-                yv = fma(kf[u][8], p[-W + 1], yv);
-                qo[((size_t)cell * 4 + k) * N + tt[u]] = yv;
-                acc[k] = fma(p[0], yv, acc[k]);
-              }
-          }
+        Load2 l2b;
+        if (base + STEP2 < tw * th)
+          load2(base + STEP2, l2b);
+        comp2(l2a);
+        l2a = l2b;
       }
     block_sum_to<4>(acc, sbuf);
     if (threadIdx.x == 0)
@@ -1226,6 +1261,8 @@ namespace msb
         // prologues and reductions) 1176; the round-1 kernel sequence (variant 5) 924
         P.tc  = nint < 128 ? (nint < 1 ? 1 : nint) : 128;
         P.tr  = nint < 8 ? (nint < 1 ? 1 : nint) : 8;
+        // (full-width tiles, 2 KB contiguous rows: 255 x 4 at 3 CTAs/SM 251 ms, 255 x 8 at 2 CTAs/SM 276 ms against 232 ms for
+        //  128 x 8 on a 1184-cell slice of cfg5; deferring x += alpha p into the next KA, one pass fewer: 241 ms -- not kept)
         P.ntx = (nint + P.tc - 1) / P.tc;
         while (P.ntx * ((nint + P.tr - 1) / P.tr) > STREAM_MAXBLK)
           P.tr *= 2;

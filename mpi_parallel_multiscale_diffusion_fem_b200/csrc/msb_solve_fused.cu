@@ -112,26 +112,43 @@ namespace msb
 
     // The four edge-coefficient arrays of the n x n fine cells, cell index i = y n + x:
     //   E  (x,y)-(x+1,y)    D2 (x+1,y)-(x,y+1)    N  (x,y)-(x,y+1)    D1 (x,y)-(x+1,y+1)
-    // MSB_FUSED_PAIRED = 0 (default): four planes, sA = [E | D2], sB = [N | D1]: a stencil row costs 7 LDS.64 =
-    // 14 shared-memory wavefronts per warp.  = 1: interleaved pairs sA[i] = {E, D2}, sB[i] = {N, D1}: 4 LDS.128
-    // per row, but 16 wavefronts (one of the four is half used) -- the stencil sweep runs at ~0.9 wavefronts per
-    // cycle (ncu, profiles/r02c_*), so bytes count, not instructions; kept for the A/B only.
+    // MSB_FUSED_PAIRED = 0: four planes, sA = [E | D2], sB = [N | D1]: a stencil row costs 7 LDS.64.
+    // = 1: interleaved pairs sA[i] = {E, D2}, sB[i] = {N, D1}: 4 LDS.128 per row, one of the four half used -- measured
+    // slower (profiles/r02c_ab_flavours.txt), kept for the A/B only.
+    // = 2: four planes whose ROWS are interleaved in pairs, entry (x, y) of a plane at ((y / 2) n + x) 2 + (y & 1): the
+    // thread that marches up its strip fetches the coefficients of two consecutive rows with one LDS.128 -- 35 LDS.128
+    // per strip of 8 rows instead of 59 LDS.64, every byte used.  Measured 4 % SLOWER on both instantiations (5920 cells:
+    // target 14.13 vs 13.58 ms, cfg4 7.34 vs 7.04 ms): inside this kernel a 128-bit access costs its four 128-byte
+    // wavefronts, whatever the stand-alone probe (scripts/probes/onchip_peaks.cu: 255 B/clk/SM for LDS.128) suggests.
+    // Kept for the A/B only.
 #ifndef MSB_FUSED_PAIRED
 #  define MSB_FUSED_PAIRED 0
 #endif
     template <int n>
     struct Coef
     {
-      static constexpr bool PAIRED = MSB_FUSED_PAIRED != 0;
+      static constexpr bool PAIRED = MSB_FUSED_PAIRED == 1, ROWPAIR = MSB_FUSED_PAIRED == 2;
+      __device__ static __forceinline__ int
+      rp(int i) // row-pair position of cell i = y n + x inside a plane
+      {
+        const int y = i / n, x = i % n;
+        return (((y >> 1) * n + x) << 1) + (y & 1);
+      }
       __device__ static __forceinline__ int
       e(int i)
       {
-        return PAIRED ? 2 * i : i;
+        return PAIRED ? 2 * i : (ROWPAIR ? rp(i) : i);
       }
       __device__ static __forceinline__ int
       hi(int i) // D2 in sA, D1 in sB
       {
-        return PAIRED ? 2 * i + 1 : n * n + i;
+        return PAIRED ? 2 * i + 1 : n * n + (ROWPAIR ? rp(i) : i);
+      }
+      // both rows 2 m, 2 m + 1 of column x of a plane (ROWPAIR)
+      __device__ static __forceinline__ double2
+      pair(const double *plane, int m, int x)
+      {
+        return *reinterpret_cast<const double2 *>(plane + ((m * n + x) << 1));
       }
     };
 
@@ -652,9 +669,27 @@ namespace msb
                     ldv<NRHS>(sP, Y0 * np + Xc + 1, b2);
                     // couplings towards the row below the current one, carried up the strip
                     using K = Coef<n>;
-                    double cS  = sB[K::e((Y0 - 1) * n + Xc)];       // N(X, y-1)
-                    double cSE = sA[K::hi((Y0 - 1) * n + Xc)];      // D2(X, y-1)
-                    double cSW = sB[K::hi((Y0 - 1) * n + Xc - 1)];  // D1(X-1, y-1)
+                    // ROWPAIR: the strip starts on an odd row, so rows (Y0 - 1, Y0), (Y0 + 1, Y0 + 2), ... are pairs
+                    [[maybe_unused]] double2 pE, pW, pD2, pNW, pN, pNE, pD1w;
+                    [[maybe_unused]] const int m0 = (Y0 - 1) >> 1;
+                    [[maybe_unused]] auto load_pair = [&](int m) {
+                      pE = K::pair(sA, m, Xc), pW = K::pair(sA, m, Xc - 1);
+                      pD2 = K::pair(sA + n * n, m, Xc), pNW = K::pair(sA + n * n, m, Xc - 1);
+                      pN = K::pair(sB, m, Xc);
+                      pNE = K::pair(sB + n * n, m, Xc), pD1w = K::pair(sB + n * n, m, Xc - 1);
+                    };
+                    double cS, cSE, cSW;
+                    if constexpr (K::ROWPAIR)
+                      {
+                        load_pair(m0);
+                        cS = pN.x, cSE = pD2.x, cSW = pD1w.x;
+                      }
+                    else
+                      {
+                        cS  = sB[K::e((Y0 - 1) * n + Xc)];      // N(X, y-1)
+                        cSE = sA[K::hi((Y0 - 1) * n + Xc)];     // D2(X, y-1)
+                        cSW = sB[K::hi((Y0 - 1) * n + Xc - 1)]; // D1(X-1, y-1)
+                      }
 #pragma unroll
                     for (int j = 0; j < RPT; ++j)
                       {
@@ -666,7 +701,18 @@ namespace msb
                             ldv<NRHS>(sP, (y + 1) * np + Xc, c1);
                             ldv<NRHS>(sP, (y + 1) * np + Xc + 1, c2);
                             double cE, d2o, cW, cNW, cN, cNE, d1w;
-                            if constexpr (K::PAIRED)
+                            if constexpr (K::ROWPAIR)
+                              {
+                                if (j & 1) // row Y0 + j is even: the first row of the next pair
+                                  load_pair(m0 + (j + 1) / 2);
+                                constexpr bool second = true;
+                                (void)second;
+                                if (j & 1)
+                                  cE = pE.x, cW = pW.x, d2o = pD2.x, cNW = pNW.x, cN = pN.x, cNE = pNE.x, d1w = pD1w.x;
+                                else
+                                  cE = pE.y, cW = pW.y, d2o = pD2.y, cNW = pNW.y, cN = pN.y, cNE = pNE.y, d1w = pD1w.y;
+                              }
+                            else if constexpr (K::PAIRED)
                               {
                                 double unused;
                                 ld2(sA, y * n + Xc, cE, d2o);

@@ -36,8 +36,8 @@ for step in "$@"; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 12 --csv --log-file gpurun_out/launches_target5920.csv $PY bench.py --workload target --cells 5920 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch_target.log 2>&1; tail -8 gpurun_out/launches_target5920.csv ;;
     ncu-full)
       V=${NCU_VARIANT:-0}
-      timeout 900 ncu --set full --import-source on --clock-control none -k regex:'solve_fused|solve_bpx_tm' -c 1 -f -o gpurun_out/solve_n64_v${V}_1184 $PY bench.py --workload target --cells 1184 --steps 1 --warmup 3 --variant $V --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_target.log 2>&1
-      ncu -i gpurun_out/solve_n64_v${V}_1184.ncu-rep --page raw --csv > gpurun_out/ncu_full_solve_n64_v${V}_1184.csv 2>/dev/null; ls -la gpurun_out/*.ncu-rep | tail -2 ;;
+      timeout 900 ncu --set full --import-source on --clock-control none -k regex:'solve_fused|solve_bpx_tm' -c 1 -f -o gpurun_out/solve_n64_v${V}_${NCU_CELLS:-1184} $PY bench.py --workload target --cells ${NCU_CELLS:-1184} --steps 1 --warmup 3 --variant $V --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_target.log 2>&1
+      ncu -i gpurun_out/solve_n64_v${V}_${NCU_CELLS:-1184}.ncu-rep --page raw --csv > gpurun_out/ncu_full_solve_n64_v${V}_${NCU_CELLS:-1184}.csv 2>/dev/null; ls -la gpurun_out/*.ncu-rep | tail -2 ;;
     timers)
       MSB_LIBRARY=$PWD/mpi_parallel_multiscale_diffusion_fem_b200/libmsfem_basis_prof.so timeout 300 $PY scripts/stage_timers.py target 1184 ${TIMER_VARIANT:-0} 2>&1 | tee gpurun_out/stage_timers_target_1184_v${TIMER_VARIANT:-0}.txt ;;
     ab:*)

@@ -12,6 +12,10 @@
 #   timers           clock64 stage timers of the target solve kernel (profiling build)
 #   ab:V1,V2,..      bench.py --variant V for each V on 5920 target cells (A/B of kernel variants)
 #   wl:NAME[:VAR]    bench.py --workload NAME [--variant VAR]
+#   abw:NAME:CELLS:V1,V2   A/B of variants on a slice of any workload
+#   ncuwl:NAME:CELLS:REGEX[:SKIP]   ncu --set full of one launch of a kernel of another workload
+#   launches:NAME:CELLS    ncu launch list of one step of a workload slice
+#   (NCU_CELLS=5920 ncu-full captures a launch larger than the L2, so that dram__bytes shows the real traffic)
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 PY=python

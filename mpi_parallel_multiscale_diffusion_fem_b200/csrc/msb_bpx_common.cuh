@@ -376,6 +376,44 @@ namespace msb
       }
     };
 
+    // Full weighting of coarse node (cx, cy) from a finer level vector Vf ([node][NRHS], npf = 2^m + 1 >= 9 nodes per row).
+    // The lanes of a quarter warp read every second node of a row: with 16-byte nodes (NRHS = 2) that is a 32-byte
+    // stride, lanes cx and cx + 4 in the same banks -- a 2-way conflict on each of the nine loads (three quarters of the
+    // conflict wavefronts that were left in the fused n = 64 kernel, profiles/r02f_*).  A row is 16 bytes longer than a
+    // multiple of 128, and so is one step in x: the lanes with rot = 1 (cx in 5..8, 13..16) visit the nine points of
+    // the window ONE POSITION AHEAD in the lexicographic order, which puts them an odd multiple of 16 bytes away from
+    // the other lanes in eight of the nine load instructions (the ninth pairs (1,1) with (-1,-1)).  Weighted
+    // accumulation in three partial sums instead of three row sums: the result differs from the unrotated order in the
+    // last bits only (the preconditioner stays a fixed linear operator).
+    template <int NRHS>
+    __device__ __forceinline__ void
+    full_weighting_rot(const double *Vf, int npf, int cx, int cy, int rot, double (&acc)[NRHS])
+    {
+      double part[3][NRHS];
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int k = 0; k < NRHS; ++k)
+          part[q][k] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+        {
+          constexpr int AY[10] = {-1, -1, -1, 0, 0, 0, 1, 1, 1, -1}, DX[10] = {-1, 0, 1, -1, 0, 1, -1, 0, 1, -1};
+          const int     ay = rot ? AY[i + 1] : AY[i], dx = rot ? DX[i + 1] : DX[i];
+          const double  w0 = (AY[i] == 0 ? 1.0 : 0.5) * (DX[i] == 0 ? 1.0 : 0.5);
+          const double  w1 = (AY[i + 1] == 0 ? 1.0 : 0.5) * (DX[i + 1] == 0 ? 1.0 : 0.5);
+          const double  w  = rot ? w1 : w0;
+          double        v[NRHS];
+          ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx + dx, v);
+#pragma unroll
+          for (int k = 0; k < NRHS; ++k)
+            part[i % 3][k] = fma(w, v[k], part[i % 3][k]);
+        }
+#pragma unroll
+      for (int k = 0; k < NRHS; ++k)
+        acc[k] = (part[0][k] + part[1][k]) + part[2][k];
+    }
+
     // mark(i): optional stage-timer hook (a no-op lambda in production builds).
     // How the 49 x 49 inverse is spread over threads for the matvec: row r = tid / PARTS, the
     // columns of a row in PARTS contiguous pieces of CH entries, fetched in NCHK chunks of 8.
@@ -569,22 +607,28 @@ namespace msb
             const int cx = 1 + (t & (W - 1)), cy = 1 + (t >> LG);
             if (cx > W - 1 || cy > W - 1)
               continue;
-            // three independent row sums, then combined (short dependency chains)
-            double row[3][NRHS], acc[NRHS];
-#pragma unroll
-            for (int ay = -1; ay <= 1; ++ay)
+            double acc[NRHS];
+            if constexpr (NRHS == 2 && npf >= 9)
+              full_weighting_rot<NRHS>(Vf, npf, cx, cy, ((cx - 1) >> 2) & 1, acc);
+            else
               {
-                double a[NRHS], b[NRHS], c[NRHS];
-                ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx - 1, a);
-                ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx, b);
-                ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx + 1, c);
+                // three independent row sums, then combined (short dependency chains)
+                double row[3][NRHS];
+#pragma unroll
+                for (int ay = -1; ay <= 1; ++ay)
+                  {
+                    double a[NRHS], b[NRHS], c[NRHS];
+                    ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx - 1, a);
+                    ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx, b);
+                    ldv<NRHS>(Vf, (2 * cy + ay) * npf + 2 * cx + 1, c);
+#pragma unroll
+                    for (int k = 0; k < NRHS; ++k)
+                      row[ay + 1][k] = fma(0.5, a[k] + c[k], b[k]);
+                  }
 #pragma unroll
                 for (int k = 0; k < NRHS; ++k)
-                  row[ay + 1][k] = fma(0.5, a[k] + c[k], b[k]);
+                  acc[k] = fma(0.5, row[0][k] + row[2][k], row[1][k]);
               }
-#pragma unroll
-            for (int k = 0; k < NRHS; ++k)
-              acc[k] = fma(0.5, row[0][k] + row[2][k], row[1][k]);
             stv<NRHS>(Vl, cy * npl + cx, acc);
           }
       };
@@ -717,21 +761,27 @@ namespace msb
                   if (tid < 49)
                     {
                       const int cx = 1 + tid % 7, cy = 1 + tid / 7;
-                      double    row[3][NRHS], o[NRHS];
-#pragma unroll
-                      for (int ay = -1; ay <= 1; ++ay)
+                      double    o[NRHS];
+                      if constexpr (NRHS == 2)
+                        full_weighting_rot<NRHS>(VB, npB, cx, cy, ((cx - 1) >> 2) & 1, o);
+                      else
                         {
-                          double a[NRHS], b[NRHS], c[NRHS];
-                          ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx - 1, a);
-                          ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx, b);
-                          ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx + 1, c);
+                          double row[3][NRHS];
+#pragma unroll
+                          for (int ay = -1; ay <= 1; ++ay)
+                            {
+                              double a[NRHS], b[NRHS], c[NRHS];
+                              ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx - 1, a);
+                              ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx, b);
+                              ldv<NRHS>(VB, (2 * cy + ay) * npB + 2 * cx + 1, c);
+#pragma unroll
+                              for (int k = 0; k < NRHS; ++k)
+                                row[ay + 1][k] = fma(0.5, a[k] + c[k], b[k]);
+                            }
 #pragma unroll
                           for (int k = 0; k < NRHS; ++k)
-                            row[ay + 1][k] = fma(0.5, a[k] + c[k], b[k]);
+                            o[k] = fma(0.5, row[0][k] + row[2][k], row[1][k]);
                         }
-#pragma unroll
-                      for (int k = 0; k < NRHS; ++k)
-                        o[k] = fma(0.5, row[0][k] + row[2][k], row[1][k]);
                       stv<NRHS>(V1, cy * 9 + cx, o);
                     }
                   named_barrier<1, 32 * X::WARPS>();

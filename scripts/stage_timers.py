@@ -88,13 +88,14 @@ def main():
                       14: "prologue: Galerkin levels 2..5", 0: "prologue: exact 7x7 inverse -> TMEM",
                       1: "Dirichlet table + rhs init (per pass)", 8: "reduce r.z, |r| (+ level-1 barrier)",
                       9: "fine prolong + x, p update (+barrier)", 10: "epilogue (phi, M, b)"})
-        names.update({7: "B: r_7 direct from level 1 (thread 0)", 15: "B: named barrier 1 (wait for warps 8-12)",
-                      1: "B: 7x7 matvec (+ rhs init once per pass)", 6: "B: barrier 2, store, block barrier"})
-        order = [12, 13, 14, 0, 2, 3, 4, 5, 7, 15, 1, 6, 11, 8, 9, 10]
+        names.update({1: "pass init: x0 = g, halo, coarse vectors (once per pass)",
+                      6: "7x7 level: restriction, exact solve, block barrier",
+                      7: "15x15 level: scaling + interpolation from 7x7"})
+        order = [12, 13, 14, 0, 1, 2, 3, 4, 5, 6, 7, 11, 8, 9, 10]
     for idx in order:
         nm, c = names[idx], cyc[idx]
         per_it = c / group_its
-        print("  %-34s %5.1f%%   %8.0f cycles/iteration" % (nm, 100 * c / tot, per_it))
+        print("  %-52s %5.1f%%   %8.0f cycles/iteration" % (nm, 100 * c / tot, per_it))
 
 
 if __name__ == "__main__":

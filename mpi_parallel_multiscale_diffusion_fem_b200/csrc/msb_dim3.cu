@@ -903,59 +903,92 @@ namespace msb
       for (int k = 0; k < NB; ++k)
         acc[k] = 0.0;
 
+      // Plane sweep: the thread of column (x, y) visits the planes s = z0-1 .. z1 ONCE each and scatters plane s into
+      // three running sums -- q of its nodes in the planes s-1 (couplings with dz = +1: complete after this step), s
+      // (dz = 0) and s+1 (dz = -1).  Each staged p value is then read from shared memory once per column instead of
+      // three times (as dz = +1, 0, -1 of three different nodes): 36 LDS.128 per node instead of 108; the 27
+      // coefficient loads per node are the same ones, regrouped.  (profiles/r02g_ncu_3d_k2m_592.csv: the gather form
+      // sat at 65 % of the LSU wavefront peak.)
+      double yA[NB], yB[NB], yC[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        yA[k] = yB[k] = yC[k] = 0.0;
+      const double2 *s2 = reinterpret_cast<const double2 *>(sp); // [slot][pair][node]
+      const int      NP2 = np * np;
+
       load_plane(z0 - 1);
       load_plane(z0);
       load_plane(z0 + 1);
       asm volatile("cp.async.commit_group;" ::: "memory");
-      for (int z = z0; z < z1; ++z)
+      for (int s = z0 - 1; s <= z1; ++s)
         {
           asm volatile("cp.async.wait_group 0;" ::: "memory");
-          __syncthreads(); // planes z-1, z, z+1 have landed; everyone is done with plane z-2
-          if (z + 1 < z1)
-            load_plane(z + 2);
+          __syncthreads(); // planes up to s+1 have landed; everyone is done with plane s-2
+          if (s + 2 <= z1)
+            load_plane(s + 2);
           asm volatile("cp.async.commit_group;" ::: "memory");
           if (!active)
             continue;
-          const int      t  = (z * np + y) * np + x;
-          const double2 *s2 = reinterpret_cast<const double2 *>(sp); // [slot][pair][node]
-          const double2 *s0 = s2 + (size_t)(z & 3) * (NB / 2) * psz + sb;
-          double         yv[NB], pc[NB];
-          {
-            const double kc = S[t];
+          const bool ownA = s - 1 >= z0, ownB = s >= z0 && s < z1, ownC = s + 1 < z1; // (uniform over the CTA)
+          const int  ts = (s * np + y) * np + x;                                        // this column's node in plane s
+          const double2 *ps = s2 + (size_t)(s & 3) * (NB / 2) * psz + sb;
 #pragma unroll
-            for (int kp = 0; kp < NB / 2; ++kp)
+          for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx)
               {
-                const double2 v = s0[kp * psz];
-                pc[2 * kp] = v.x, pc[2 * kp + 1] = v.y;
-                yv[2 * kp] = kc * v.x, yv[2 * kp + 1] = kc * v.y;
-              }
-          }
+                const int so = dy * np + dx;
+                // the symmetric stencil stores the diagonal (array 0) and the 13 forward couplings e = 13 + f,
+                // e = (dz+1) 9 + (dy+1) 3 + (dx+1); a backward coupling is the forward one of the neighbour
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int fA = 5 + (dy + 1) * 3 + (dx + 1);         // node (s-1) -> (dx, dy, +1): forward, stored at the node
+                const int fC = 5 + (-dy + 1) * 3 + (-dx + 1);       // node (s+1) -> (dx, dy, -1): forward of the neighbour
+                const int eB = 9 + (dy + 1) * 3 + (dx + 1);         // node (s)   -> (dx, dy, 0)
+                const int fB = eB > 13 ? eB - 13 : (eB < 13 ? 13 - eB : 0); // |offset| index; (-dx,-dy,0) has e' = 26 - eB
+                double kA = 0.0, kB = 0.0, kC = 0.0;
+                if (ownA)
+                  kA = S[(size_t)fA * N + ts - NP2];
+                if (ownB)
+                  kB = eB >= 13 ? S[(size_t)fB * N + ts] : S[(size_t)fB * N + ts + so];
+                if (ownC)
+                  kC = S[(size_t)fC * N + ts + so];
 #pragma unroll
-          for (int f = 1; f <= 13; ++f)
+                for (int kp = 0; kp < NB / 2; ++kp)
+                  {
+                    const double2 v = ps[kp * psz + so];
+                    yA[2 * kp]     = fma(kA, v.x, yA[2 * kp]);
+                    yA[2 * kp + 1] = fma(kA, v.y, yA[2 * kp + 1]);
+                    yB[2 * kp]     = fma(kB, v.x, yB[2 * kp]);
+                    yB[2 * kp + 1] = fma(kB, v.y, yB[2 * kp + 1]);
+                    yC[2 * kp]     = fma(kC, v.x, yC[2 * kp]);
+                    yC[2 * kp + 1] = fma(kC, v.y, yC[2 * kp + 1]);
+                  }
+              }
+          if (ownA)
             {
-              const int      e = 13 + f, dz = e / 9 - 1, dy = (e / 3) % 3 - 1, dx = e % 3 - 1;
-              const int      o = (dz * np + dy) * np + dx, so = dy * np + dx;
-              const double   kf = S[(size_t)f * N + t], kb = S[(size_t)f * N + t - o];
-              const double2 *sf = s2 + (size_t)((z + dz) & 3) * (NB / 2) * psz + sb + so;
-              const double2 *sr = s2 + (size_t)((z - dz) & 3) * (NB / 2) * psz + sb - so;
+              // plane s-1 is complete: q and the p.q partial (its centre values are still staged in slot (s-1) & 3)
+              const int      t  = ts - NP2;
+              const double2 *pm = s2 + (size_t)((s - 1) & 3) * (NB / 2) * psz + sb;
 #pragma unroll
               for (int kp = 0; kp < NB / 2; ++kp)
                 {
-                  const double2 a = sf[kp * psz], b = sr[kp * psz];
-                  yv[2 * kp]     = fma(kf, a.x, yv[2 * kp]);
-                  yv[2 * kp + 1] = fma(kf, a.y, yv[2 * kp + 1]);
-                  yv[2 * kp]     = fma(kb, b.x, yv[2 * kp]);
-                  yv[2 * kp + 1] = fma(kb, b.y, yv[2 * kp + 1]);
+                  const double2 pc = pm[kp * psz];
+                  if (!sdone[2 * kp])
+                    {
+                      qg[(size_t)(2 * kp) * N + t] = yA[2 * kp];
+                      acc[2 * kp]                  = fma(pc.x, yA[2 * kp], acc[2 * kp]);
+                    }
+                  if (!sdone[2 * kp + 1])
+                    {
+                      qg[(size_t)(2 * kp + 1) * N + t] = yA[2 * kp + 1];
+                      acc[2 * kp + 1]                  = fma(pc.y, yA[2 * kp + 1], acc[2 * kp + 1]);
+                    }
                 }
             }
 #pragma unroll
           for (int k = 0; k < NB; ++k)
-            {
-              if (sdone[k])
-                continue;
-              qg[(size_t)k * N + t] = yv[k];
-              acc[k]                = fma(pc[k], yv[k], acc[k]);
-            }
+            yA[k] = yB[k], yB[k] = yC[k], yC[k] = 0.0;
         }
       __syncthreads();
       block_sum_to<NB>(acc, sbuf);

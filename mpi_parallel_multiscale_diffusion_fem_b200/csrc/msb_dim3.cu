@@ -1696,6 +1696,8 @@ namespace msb
       P.zc             = (nin + max_zc - 1) / max_zc;
       if (P.zc < 8)
         P.zc = 8;
+      if (nin < 16 && s.variant != 7) // a whole column per CTA when it is short: no halo planes inside the cell (variant 7: chunks of 8)
+        P.zc = nin;
     }
     P.nblk2 = P.nys * ((nin + P.zc - 1) / P.zc);
     const size_t k2_smem = sizeof(double) * 4 * NB * (size_t)(P.by + 2) * s.np;

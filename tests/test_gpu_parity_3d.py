@@ -226,6 +226,26 @@ def test_alternative_3d_kernels_agree_with_the_default(msb, oracle, variant):
             assert _rel(a.basis(c, 5), b.basis(c, 5)) < 1e-10
 
 
+@pytest.mark.parametrize("variant", [1, 7])
+def test_k2_tilings_agree_at_16_cubed(msb, oracle, variant):
+    """n = 16: the default K2 sweeps a whole z-column per CTA (one CTA per cell); variant 7 marches two z-chunks of 8
+    planes (halo planes inside the cell), variant 1 is the untiled kernel.  Same sums up to their order."""
+    from mpi_parallel_multiscale_diffusion_fem_b200.binding import coeff_desc
+    cor = msb.coarse_corners3(2, 5, 5 + 12)
+    cd = coeff_desc(msb.COEFF_REFERENCE)
+    with msb.BasisShard(4, cor, cd, dim=3) as a, msb.BasisShard(4, cor, cd, dim=3, variant=variant) as b:
+        a.run()
+        b.run()
+        ia, ra = a.iteration_counts()
+        ib, _ = b.iteration_counts()
+        assert (ra <= 1e-12).all() and np.abs(ia - ib).max() <= 1
+        Ma, ba = a.element_matrices()
+        Mb, bb = b.element_matrices()
+        assert _rel(Ma, Mb) < 1e-10 and _rel(ba, bb) < 1e-10
+        for c in (0, 11):
+            assert _rel(a.basis(c, 3), b.basis(c, 3)) < 1e-10
+
+
 def test_largest_accepted_3d_local_mesh_l6(msb, oracle):
     """msb_create accepts n_refine_local = 6 for dim 3 (64^3 fine hexahedra, 274 625 DoFs per solve): DoF map
     bit-exact, the 8 bases / M / b of one coarse cell against the oracle, partition of unity."""

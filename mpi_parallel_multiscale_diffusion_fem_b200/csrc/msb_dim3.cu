@@ -729,25 +729,36 @@ namespace msb
         }
     }
 
-    // K1: bookkeeping of the previous iteration, then p = z + beta p
+    // K1: bookkeeping of the previous iteration, then p = z + beta p -- and the x update of the PREVIOUS iteration,
+    // x += alpha_{it-1} p_{it-1}: K1 reads the old direction anyway, so K3 need not read p (nor read and write x) just for
+    // that: 15 instead of 16 vector passes per iteration.  alpha_{it-1} is re-derived from the stored (r.z) and the same
+    // p.q partials K3 used (the same bits).  It applies to the solves that RAN iteration it-1: not yet recorded as
+    // converged before it (CTA 0 records `iters = it-1` in this very launch while the others read: both values mean "ran").
+    // FLUSH: after the loop, only the x update of the last executed iteration (P.it = that iteration + 1).
+    template <bool FLUSH>
     __global__ void __launch_bounds__(THREADS)
     k1_kernel(Params3 P)
     {
       const int n = P.n, np = n + 1, N = np * np * np, cell = blockIdx.y, blk = blockIdx.x;
       const int par = (P.it - 1) & 1;
-      __shared__ double sbeta[NB];
+      __shared__ double sbeta[NB], sxa[NB];
       __shared__ int    sdone[NB];
       if ((threadIdx.x >> 5) < NB)
         {
           const int    k = threadIdx.x >> 5, sidx = cell * NB + k;
           const double rr = warp_sum_part(part_ptr(P.part, sidx, par, 2), P.nblk);
           const double rz = warp_sum_part(part_ptr(P.part, sidx, par, 0), P.nblk);
+          double       pqp = 1.0;
+          if (P.it >= 2)
+            pqp = warp_sum_part(part_ptr(P.part, sidx, par, 1), P.nblk2);
           if ((threadIdx.x & 31) == 0)
             {
-              const int dn = (P.iters[sidx] >= 0) || (rr <= P.tol2);
-              sdone[k]     = dn;
-              sbeta[k]     = P.it == 1 ? 0.0 : rz / P.rzprev[sidx];
-              if (blk == 0 && dn && P.iters[sidx] < 0)
+              const int itp = P.iters[sidx];
+              sxa[k]        = (P.it >= 2 && (itp < 0 || itp == P.it - 1)) ? P.rzprev[sidx] / pqp : 0.0;
+              const int dn  = (itp >= 0) || (rr <= P.tol2);
+              sdone[k]      = dn;
+              sbeta[k]      = P.it == 1 ? 0.0 : rz / P.rzprev[sidx];
+              if (blk == 0 && dn && itp < 0)
                 {
                   P.iters[sidx] = P.it - 1;
                   P.res[sidx]   = sqrt(rr);
@@ -755,11 +766,11 @@ namespace msb
             }
         }
       __syncthreads();
-      int all = 1;
+      int all = 1, anyx = 0;
 #pragma unroll
       for (int k = 0; k < NB; ++k)
-        all &= sdone[k];
-      if (all)
+        all &= sdone[k], anyx |= sxa[k] != 0.0;
+      if ((all || FLUSH) && !anyx)
         return;
       const int t0 = blk * P.chunk, t1 = min(N, t0 + P.chunk);
       for (int t = t0 + threadIdx.x; t < t1; t += THREADS)
@@ -769,17 +780,24 @@ namespace msb
           if (on_boundary3(jx, jy, jz, n))
             continue;
           // all loads first (unconditional: memory-level parallelism), predicated stores after
-          double pv[NB], zv[NB];
+          double pv[NB], zv[NB], xv[NB];
 #pragma unroll
           for (int k = 0; k < NB; ++k)
             {
               const size_t o = ((size_t)cell * NB + k) * N + t;
-              pv[k] = P.p[o], zv[k] = P.z[o];
+              pv[k] = P.p[o];
+              zv[k] = (FLUSH || all) ? 0.0 : P.z[o];
+              xv[k] = anyx ? P.x[o] : 0.0;
             }
 #pragma unroll
           for (int k = 0; k < NB; ++k)
-            if (!sdone[k])
-              P.p[((size_t)cell * NB + k) * N + t] = fma(sbeta[k], pv[k], zv[k]);
+            {
+              const size_t o = ((size_t)cell * NB + k) * N + t;
+              if (sxa[k] != 0.0)
+                P.x[o] = fma(sxa[k], pv[k], xv[k]);
+              if (!FLUSH && !sdone[k])
+                P.p[o] = fma(sbeta[k], pv[k], zv[k]);
+            }
         }
     }
 
@@ -1070,7 +1088,7 @@ namespace msb
         }
     }
 
-    // K3: alpha = rz/pq ; x += alpha p ; r -= alpha q ; partial r.r
+    // K3: alpha = rz/pq ; r -= alpha q ; partial r.r   (x += alpha p is deferred to K1 of the next iteration)
     __global__ void __launch_bounds__(THREADS)
     k3_kernel(Params3 P)
     {
@@ -1112,12 +1130,12 @@ namespace msb
           decode3(t, np, jx, jy, jz);
           if (on_boundary3(jx, jy, jz, n))
             continue;
-          double pv[NB], qv[NB], rv[NB], xv[NB];
+          double qv[NB], rv[NB];
 #pragma unroll
           for (int k = 0; k < NB; ++k)
             {
               const size_t o = ((size_t)cell * NB + k) * N + t;
-              pv[k] = P.p[o], qv[k] = P.q[o], rv[k] = P.r[o], xv[k] = P.x[o];
+              qv[k] = P.q[o], rv[k] = P.r[o];
             }
 #pragma unroll
           for (int k = 0; k < NB; ++k)
@@ -1125,8 +1143,7 @@ namespace msb
               if (sdone[k])
                 continue;
               const size_t o  = ((size_t)cell * NB + k) * N + t;
-              const double a  = salpha[k];
-              P.x[o]          = fma(a, pv[k], xv[k]);
+              const double a  = salpha[k]; // (x += a p: K1 of the next iteration / the flush launch)
               const double rn = fma(-a, qv[k], rv[k]);
               P.r[o]          = rn;
               acc[k]          = fma(rn, rn, acc[k]);
@@ -1840,7 +1857,7 @@ namespace msb
           }
         ++it;
         P.it = it;
-        for_slices([&](const Params3 &Q, int nc) { k1_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
+        for_slices([&](const Params3 &Q, int nc) { k1_kernel<false><<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
         if (k2_whole)
           for_slices([&](const Params3 &Q, int nc) { k2w_kernel<<<dim3(1, nc), THREADS, k2w_smem, st>>>(Q); });
         else if (k2_tiled)
@@ -1854,6 +1871,12 @@ namespace msb
           for_slices([&](const Params3 &Q, int nc) { k2_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
         for_slices([&](const Params3 &Q, int nc) { k3_kernel<<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
         precondition(it & 1);
+      }
+    if (it >= 1)
+      {
+        // the deferred x update of the last executed iteration
+        P.it = it + 1;
+        for_slices([&](const Params3 &Q, int nc) { k1_kernel<true><<<dim3(P.nblk, nc), THREADS, 0, st>>>(Q); });
       }
     P.it = it;
     finalize3_kernel<<<(n_solves + 7) / 8, 256, 0, st>>>(P, n_solves, s.d_fail);

@@ -194,7 +194,7 @@ def kernel_name(dim, l, variant, tier):
         if l in (5, 6) and (variant == 0 or 10 <= variant <= 12):
             return "solve_fused_kernel (assembly + 4 solves + element matrices in one launch)"
         return "solve_bpx_tm_kernel" if (l == 6 and variant in (5, 7, 9)) else "solve_bpx_kernel"
-    if (l == 7 and variant == 0) or (variant in (3, 4) and 5 <= l <= 7):
+    if (l == 7 and variant in (0, 8)) or (variant in (3, 4) and 5 <= l <= 7):
         return "solve_cluster_kernel"
     return "stream_k* (HBM-streamed)"
 

@@ -207,6 +207,8 @@ namespace msb
       double        tol2;
       int           max_iter;
       int           cn;
+      int           cell0; // first cell of this launch
+      int           split; // 1: one cluster per (cell, pass) instead of one per cell (the tail of a small shard)
     };
 
     // NBP = bases per pass.  TM = false: NBP = 2, coefficients in shared memory, x and q in registers.
@@ -299,7 +301,10 @@ namespace msb
 #endif
       cg::cluster_group cluster = cg::this_cluster();
       const int rank = (int)cluster.block_rank();
-      const int cell = blockIdx.x / CS;
+      // split launches (the tail of a shard whose last wave of clusters would leave most SMs idle): cluster -> (cell, pass)
+      const int cid     = blockIdx.x / CS;
+      const int cell    = P.cell0 + (P.split ? cid / (4 / NBP) : cid);
+      const int pass_lo = P.split ? cid % (4 / NBP) : 0, pass_hi = P.split ? pass_lo + 1 : 4 / NBP;
       const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
       const int jx = tid & (n - 1), g = tid >> L; // column, group of 4 rows
       const int y0 = rank * ROWS;
@@ -431,7 +436,7 @@ namespace msb
           v[k] = __shfl_sync(0xffffffffu, s, k * CS);
       };
 
-      for (int pass = 0; pass < 4 / NBP; ++pass)
+      for (int pass = pass_lo; pass < pass_hi; ++pass)
         {
           double x[TM ? 1 : NBP][4], r[NBP][4], z[NBP][4]; // TM: x lives in tensor memory
           double rr[NBP], rz[NBP], beta[NBP];
@@ -1051,9 +1056,11 @@ namespace msb
     }
 
 #ifndef MSB_EMU
+    // n_clusters = cells of the launch (P.split = 0) or cells x passes (P.split = 1).  max_active != nullptr: only
+    // report how many clusters of this kernel are co-resident on the device.
     template <int L, int NBP, bool TM>
     static cudaError_t
-    launch(const Params &P, int n_cells, cudaStream_t st)
+    launch(const Params &P, int n_clusters, cudaStream_t st, int *max_active = nullptr)
     {
       using Y = Lay<L, NBP, TM>;
       cudaError_t e = cudaFuncSetAttribute(solve_cluster_kernel<L, NBP, TM>,
@@ -1061,7 +1068,7 @@ namespace msb
       if (e != cudaSuccess)
         return e;
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim            = dim3((unsigned)(Y::CS * n_cells), 1, 1);
+      cfg.gridDim            = dim3((unsigned)(Y::CS * (n_clusters > 0 ? n_clusters : 1)), 1, 1);
       cfg.blockDim           = dim3(Y::T, 1, 1);
       cfg.dynamicSmemBytes   = Y::smem_bytes;
       cfg.stream             = st;
@@ -1072,6 +1079,8 @@ namespace msb
       at[0].val.clusterDim.z = 1;
       cfg.attrs              = at;
       cfg.numAttrs           = 1;
+      if (max_active)
+        return cudaOccupancyMaxActiveClusters(max_active, solve_cluster_kernel<L, NBP, TM>, &cfg);
       return cudaLaunchKernelEx(&cfg, solve_cluster_kernel<L, NBP, TM>, P);
     }
 #endif
@@ -1103,21 +1112,61 @@ namespace msb
     P.tol2     = tol * tol;
     P.max_iter = max_iter;
     P.cn       = (int)streamed_coarse_nodes(s.l);
-    cudaError_t e = cudaErrorInvalidValue;
-    switch (s.l)
+    P.cell0    = 0;
+    P.split    = 0;
+    auto run = [&](bool tm, const clus::Params &Q, int n_clusters, int *max_active) -> cudaError_t {
+      switch (s.l)
+        {
+          case 5:
+            return tm ? clus::launch<5, 4, true>(Q, n_clusters, st, max_active) : clus::launch<5, 2, false>(Q, n_clusters, st, max_active);
+          case 6:
+            return tm ? clus::launch<6, 4, true>(Q, n_clusters, st, max_active) : clus::launch<6, 2, false>(Q, n_clusters, st, max_active);
+          case 7:
+            return tm ? clus::launch<7, 4, true>(Q, n_clusters, st, max_active) : clus::launch<7, 2, false>(Q, n_clusters, st, max_active);
+        }
+      return cudaErrorInvalidValue;
+    };
+    // Tail balancing.  Only `ma` clusters are co-resident (15 on this B200: 120 of its 148 SMs), so a shard runs in
+    // ceil(cells / ma) waves and a short last wave leaves most of the GPU idle -- the reference's own default run has
+    // 64 cells: 4 full waves + 4 clusters.  The cells of a short last wave go to TWO clusters each, one per pair of bases
+    // (the two-bases flavour, one pass per cluster): the wave then takes ~0.55 of a full one (cfg1: 95.8 -> 103.1 k solves/s).
+    int tail = 0;
+    if (tmem && s.variant != 8) // (variant 8: no tail balancing, for the A/B)
       {
-        case 5:
-          e = tmem ? clus::launch<5, 4, true>(P, s.n_cells, st) : clus::launch<5, 2, false>(P, s.n_cells, st);
-          break;
-        case 6:
-          e = tmem ? clus::launch<6, 4, true>(P, s.n_cells, st) : clus::launch<6, 2, false>(P, s.n_cells, st);
-          break;
-        case 7:
-          e = tmem ? clus::launch<7, 4, true>(P, s.n_cells, st) : clus::launch<7, 2, false>(P, s.n_cells, st);
-          break;
+        static int  ma_of_l[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // (one device type per process: queried once per local-mesh size)
+        int         ma = ma_of_l[s.l];
+        cudaError_t eq = cudaSuccess;
+        if (ma == 0)
+          {
+            eq = run(true, P, 1, &ma);
+            if (eq == cudaSuccess)
+              ma_of_l[s.l] = ma;
+          }
+        if (eq == cudaSuccess && ma > 0)
+          {
+            const int t = s.n_cells % ma;
+            if (t > 0 && 2 * t <= ma)
+              tail = t;
+          }
+        else
+          (void)cudaGetLastError();
       }
-    if (e == cudaSuccess)
-      ++*n_launches;
+    cudaError_t e = cudaSuccess;
+    if (s.n_cells - tail > 0)
+      {
+        e = run(tmem, P, s.n_cells - tail, nullptr);
+        if (e == cudaSuccess)
+          ++*n_launches;
+      }
+    if (e == cudaSuccess && tail > 0)
+      {
+        clus::Params Q = P;
+        Q.cell0        = s.n_cells - tail;
+        Q.split        = 1;
+        e              = run(false, Q, 2 * tail, nullptr);
+        if (e == cudaSuccess)
+          ++*n_launches;
+      }
     return e;
   }
 #endif

@@ -1081,11 +1081,11 @@ namespace msb
     return L;
   }
 
-  // n = 128 runs the cluster kernel by default; variants 3 / 4 request it for n = 32, 64 too
+  // n = 128 runs the cluster kernel by default (variant 8: without the tail balancing); variants 3 / 4 request it for n = 32, 64 too
   bool
   streamed_tier_uses_cluster(int l, int variant)
   {
-    return cluster_tier_supported(l) && ((l == 7 && variant == 0) || variant == 3 || variant == 4);
+    return cluster_tier_supported(l) && ((l == 7 && (variant == 0 || variant == 8)) || variant == 3 || variant == 4);
   }
 
   size_t

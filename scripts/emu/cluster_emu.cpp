@@ -142,7 +142,7 @@ main(int argc, char **argv)
   int32_t fail[2] = {INT_MAX, 0};
   clus::Params P;
   P.corners = corners, P.q1coef = q1, P.sten = S.data(), P.dinv = dinv.data(), P.phi = phi.data();
-  P.iters = iters.data(), P.res = res.data(), P.fail = fail, P.tol2 = 1e-24, P.max_iter = 500, P.cn = cn;
+  P.iters = iters.data(), P.res = res.data(), P.fail = fail, P.tol2 = 1e-24, P.max_iter = 500, P.cn = cn, P.cell0 = 0, P.split = 0;
 
   size_t smem_doubles =
     tm ? (l == 5 ? clus::Lay<5, 4, true>::total : l == 6 ? clus::Lay<6, 4, true>::total : clus::Lay<7, 4, true>::total) :

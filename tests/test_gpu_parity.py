@@ -650,6 +650,30 @@ def test_unsymmetric_coefficient_table_is_rejected(msb, oracle):
     assert e.value.code == -1
 
 
+def test_cluster_tier_tail_balancing(msb, oracle):
+    """A shard whose last wave of clusters is short (cells mod co-resident clusters <= half a wave) sends the cells of
+    that wave to two clusters each, one per pair of bases (msb_solve_cluster.cu, launch_solve_cluster).  19 cells at
+    n = 128: one full wave of 15 + 4 tail cells on a B200.  Variant 8 switches the balancing off: same iteration counts,
+    same bases / M / b to solver accuracy; and the tail cells against the oracle."""
+    cd, co = _coeffs(msb, oracle, msb.COEFF_REFERENCE)
+    cor = msb.coarse_corners(3, 0, 19)
+    with msb.BasisShard(7, cor, cd) as a, msb.BasisShard(7, cor, cd, variant=8) as b:
+        a.run(1e-12, 5000)
+        b.run(1e-12, 5000)
+        ita, ra = a.iteration_counts()
+        itb, rb = b.iteration_counts()
+        assert np.all(ra <= 1e-12) and np.all(rb <= 1e-12) and np.abs(ita - itb).max() <= 1
+        Ma, ba = a.element_matrices()
+        Mb, bb = b.element_matrices()
+        assert _rel(Ma, Mb) < 1e-10 and _rel(ba, bb) < 1e-10
+        assert a.run_stats()["launches"] == b.run_stats()["launches"] + 1      # main launch + tail launch
+        ref = oracle.run_cells(7, cor[17:19], co, n_threads=2)
+        for c in (17, 18):
+            for ib in range(4):
+                assert _rel(a.basis(c, ib), ref["phi"][c - 17][ib]) < TOL_PHI
+            assert _rel(Ma[c], ref["M"][c - 17]) < TOL_MB
+
+
 # ---------------------------------------------------------------------------- the fused one-kernel stage (n = 64)
 @pytest.mark.parametrize("l", [6, 5])
 def test_fused_stage_equals_the_three_kernel_path(msb, oracle, l):

@@ -112,7 +112,7 @@ all_rectangles(const double *corners, size_t n_cells)
 static bool
 fused_eligible(const Shard &s)
 {
-  return s.dim == 2 && (s.l == 5 || s.l == 6) && s.tier == MSB_TIER_SMEM && (s.variant == 0 || (s.variant >= 10 && s.variant <= 12)) &&
+  return s.dim == 2 && (s.l == 5 || s.l == 6) && s.tier == MSB_TIER_SMEM && (s.variant == 0 || (s.variant >= 10 && s.variant <= 13)) &&
          s.aligned &&
          s.coeff.kind != MSB_COEFF_TABLE;
 }

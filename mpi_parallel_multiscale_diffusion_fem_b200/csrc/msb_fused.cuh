@@ -22,6 +22,7 @@ namespace msb
     int           n_cells;
     double        rhs_value;
     int           flavor; // A/B: 0 default, 1 residual in tensor memory, 2 q through tensor memory (variants 10-12)
+    int           split;  // 1: one CTA per (cell, pair of bases) instead of one per cell (the short last wave of a small shard)
     CoeffEval     coef;
   };
 

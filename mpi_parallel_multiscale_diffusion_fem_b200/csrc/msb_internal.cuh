@@ -134,7 +134,7 @@ namespace msb
   cudaError_t launch_stage_fused(const Shard &s, double tol, int max_iter, cudaStream_t st, int *n_launches);
   // the same for the cells [c0, c0 + nc) of the shard only (pipelined msb_run_with_bases)
   cudaError_t launch_stage_fused_range(const Shard &s, int c0, int nc, double tol, int max_iter, cudaStream_t st,
-                                       int *n_launches);
+                                       int *n_launches, bool split = false);
   size_t      streamed_coarse_nodes(int l);
   size_t      streamed_galerkin_scratch_doubles(int l, int n_cells);
 

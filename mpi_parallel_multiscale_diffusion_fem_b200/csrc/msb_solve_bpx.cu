@@ -614,9 +614,11 @@ namespace msb
   }
   // the fused one-kernel stage (msb_solve_fused.cu) for the cells [c0, c0 + nc) of the shard
   cudaError_t
-  launch_stage_fused_range(const Shard &s, int c0, int nc, double tol, int max_iter, cudaStream_t st, int *n_launches)
+  launch_stage_fused_range(const Shard &s, int c0, int nc, double tol, int max_iter, cudaStream_t st, int *n_launches,
+                           bool split)
   {
     FusedParams P;
+    P.split     = split ? 1 : 0;
     P.corners   = s.d_corners + 8 * (size_t)c0;
     P.q1coef    = s.d_q1coef + 16 * (size_t)c0;
     P.phi       = s.d_phi + (size_t)c0 * 4 * s.N;
@@ -630,7 +632,7 @@ namespace msb
     P.max_iter  = max_iter;
     P.n_cells   = nc;
     P.rhs_value = s.rhs_value;
-    P.flavor    = s.variant >= 10 && s.variant <= 12 ? s.variant - 10 : 0;
+    P.flavor    = s.variant >= 10 && s.variant <= 12 ? s.variant - 10 : 0; // (13: flavour 0 without tail balancing)
     P.coef      = make_coeff_eval(s.coeff);
     ++*n_launches;
     return launch_solve_fused(P, s.l, st);
@@ -639,6 +641,29 @@ namespace msb
   cudaError_t
   launch_stage_fused(const Shard &s, double tol, int max_iter, cudaStream_t st, int *n_launches)
   {
-    return launch_stage_fused_range(s, 0, s.n_cells, tol, max_iter, st, n_launches);
+    // Tail balancing (as in the cluster tier): `slots` CTAs are co-resident (one per SM at n = 64, three at n = 32); when
+    // the last wave of a shard is at most half full, its cells go to two CTAs each, one per pair of bases, and the wave
+    // takes ~0.6 of a full one.  Matters for shards of a few waves (cfg2: 1024 cells on 444 slots); the 443 waves of the
+    // target workload end in a wave that is more than half full and stay ONE launch.  Variant 13: off (A/B).
+    int tail = 0;
+    if (s.variant != 13)
+      {
+        static int sms = 0;
+        if (sms == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device) != cudaSuccess)
+          sms = 0, (void)cudaGetLastError();
+        const int slots = sms * (s.l == 5 ? 3 : 1);
+        if (slots > 0)
+          {
+            const int t = s.n_cells % slots;
+            if (t > 0 && 2 * t <= slots)
+              tail = t;
+          }
+      }
+    cudaError_t e = cudaSuccess;
+    if (s.n_cells - tail > 0)
+      e = launch_stage_fused_range(s, 0, s.n_cells - tail, tol, max_iter, st, n_launches, false);
+    if (e == cudaSuccess && tail > 0)
+      e = launch_stage_fused_range(s, s.n_cells - tail, tail, tol, max_iter, st, n_launches, true);
+    return e;
   }
 } // namespace msb

@@ -258,7 +258,9 @@ namespace msb
     // both interpolated straight back: two block barriers instead of five) was 3 % SLOWER than
     // bpx::coarse_correction in every flavour and is not kept: the stages it removes are short, the ones it
     // fattens (all threads) are not.
-    template <int NL_, int RMODE>
+    // SPLIT: one CTA per (cell, pair of bases) for the short last wave of a small shard (launch_stage_fused); a template
+    // parameter, not a run-time flag: with run-time loop bounds the ordinary kernel was 1.8 % slower on the target workload.
+    template <int NL_, int RMODE, bool SPLIT = false>
     __global__ void __launch_bounds__(Cfg<NL_>::THREADS, NL_ == 6 ? 1 : 3)
     solve_fused_kernel(FusedParams P)
     {
@@ -289,7 +291,10 @@ namespace msb
       double *tsx  = smem + C::o_tab, *tsy = tsx + 4 * n;
 
       const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-      const int cell = blockIdx.x;
+      // split launches (the short last wave of a small shard, launch_stage_fused): CTA -> (cell, pair of bases); the
+      // prologue is then paid by both CTAs of a cell
+      const int cell   = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+      const int grp_lo = SPLIT ? (int)(blockIdx.x & 1) : 0, grp_hi = SPLIT ? grp_lo + 1 : 4 / Cfg<NL_>::NRHS;
 
       const double *crn = P.corners + 8 * (size_t)cell;
       const double *q1  = P.q1coef + 16 * (size_t)cell;
@@ -577,7 +582,7 @@ namespace msb
       };
 
 #pragma unroll 1
-      for (int grp = 0; grp < 4 / NRHS; ++grp)
+      for (int grp = grp_lo; grp < grp_hi; ++grp)
         {
           const int rhs0 = grp * NRHS;
           // (a) Initial guess: the coarse Q1 shape function itself, x_0 = g on the interior nodes (the exact
@@ -1145,10 +1150,12 @@ namespace msb
           default:
             kern = solve_fused_kernel<NL, 0>;
         }
+      if (P.split) // (split launches always run flavour 0)
+        kern = solve_fused_kernel<NL, 0, true>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
       if (e != cudaSuccess)
         return e;
-      kern<<<P.n_cells, C::THREADS, C::smem_bytes, st>>>(P);
+      kern<<<P.split ? 2 * P.n_cells : P.n_cells, C::THREADS, C::smem_bytes, st>>>(P);
       return cudaGetLastError();
     }
   } // namespace fused

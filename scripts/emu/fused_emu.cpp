@@ -206,7 +206,7 @@ main(int argc, char **argv)
   FusedParams          P;
   P.corners = corners, P.q1coef = q1, P.phi = phi.data(), P.M = M.data(), P.b = b.data();
   P.iters = iters.data(), P.res = res.data(), P.fail = fail, P.fail_base = 0, P.tol2 = 1e-24, P.max_iter = max_iter, P.n_cells = 1;
-  P.rhs_value = f, P.coef = coef, P.flavor = flavor;
+  P.rhs_value = f, P.coef = coef, P.flavor = flavor, P.split = 0;
   constexpr int T = fused::Cfg<NL>::THREADS;
   emu::Cluster  cl;
   cl.bar = std::make_unique<std::barrier<>>(T);

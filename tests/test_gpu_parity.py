@@ -696,7 +696,9 @@ def test_fused_stage_equals_the_three_kernel_path(msb, oracle, l):
         assert _rel(Mb, Ma) < 1e-10 and _rel(bb, ba) < 1e-10
         pa, pb = a.bases(), b.bases()
         assert _rel(pb, pa) < 1e-10
-        assert a.run_stats()["launches"] == 3 and b.run_stats()["launches"] == 1
+        # (300 cells at n = 64: two full waves of 148 one-CTA-per-SM cells + 4 tail cells, which go to a second launch
+        #  with one CTA per pair of bases; at n = 32 the 300 cells are less than one wave of 444 CTAs: one launch)
+        assert a.run_stats()["launches"] == 3 and b.run_stats()["launches"] == (2 if l == 6 else 1)
 
 
 @pytest.mark.parametrize("kind,par,seed,r", [
@@ -777,6 +779,26 @@ def test_fused_stage_no_convergence_and_zero_iterations(msb, oracle):
         assert sh.failure()[0] == -1
         M, _ = sh.element_matrices()
         assert np.abs(M.sum(axis=2)).max() < 1e-9
+
+
+@pytest.mark.parametrize("l,cells", [(6, 150), (5, 450)])
+def test_fused_stage_tail_balancing(msb, oracle, l, cells):
+    """The cells of a short last wave go to two CTAs each, one per pair of bases (launch_stage_fused): 150 cells at
+    n = 64 = one wave of 148 + 2, 450 cells at n = 32 = one wave of 444 + 6.  Variant 13 switches it off: the same
+    iteration counts, bases, M and b BIT FOR BIT (a CTA computes its pair of bases independently of the other pair)."""
+    cd, _ = _coeffs(msb, oracle, msb.COEFF_PERIODIC, (1.0 / 64, 0.9999))
+    cor = msb.coarse_corners(8, 30000, 30000 + cells)
+    with msb.BasisShard(l, cor, cd) as a, msb.BasisShard(l, cor, cd, variant=13) as b:
+        a.run(1e-12, 5000)
+        b.run(1e-12, 5000)
+        assert a.run_stats()["launches"] == 2 and b.run_stats()["launches"] == 1
+        ita, _ = a.iteration_counts()
+        itb, _ = b.iteration_counts()
+        assert np.array_equal(ita, itb)
+        Ma, ba = a.element_matrices()
+        Mb, bb = b.element_matrices()
+        assert np.array_equal(Ma, Mb) and np.array_equal(ba, bb)
+        assert np.array_equal(a.bases(cells - 2, 2), b.bases(cells - 2, 2))
 
 
 # ---------------------------------------------------------------------------- the second, independent restatement
